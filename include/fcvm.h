@@ -1,0 +1,196 @@
+/*
+ * fcvm.h — C ABI of the B200-native viewpoint visibility / coverage-pruning path.
+ *
+ * This is the drop-in boundary behind FC-Planner's `predrecon::ViewpointManager`
+ * (reference: FC-Planner/src/viewpoint_manager/include/viewpoint_manager/viewpoint_manager.h:180-193).
+ * Every manager-level entry point below replaces exactly one public method of that class;
+ * the file:line of the method it replaces is quoted next to it.  A thin C++ shim with the
+ * reference's own signatures (fc-planner_b200/shim/viewpoint_manager_shim.hpp) and a ctypes
+ * mirror (fc-planner_b200/manager.py) forward to these symbols.  See INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; host pointers in, host pointers out unless a name ends
+ *     in `_dev` / a parameter is documented as a device pointer;
+ *   - return 0 on success, a negative FCVM_E* code on failure; the message is available
+ *     from fcvm_last_error(); nothing throws across the ABI (the reference's convention is
+ *     "ROS_ERROR + return", viewpoint_manager.cpp:93-96, 112-116, 124-128, 173-174);
+ *   - single-threaded contract per handle, as the reference (stateful RayCaster /
+ *     PerceptionUtils members, viewpoint_manager.h:214-216);
+ *   - there is NO CPU fallback: every call that evaluates visibility fails with
+ *     FCVM_ENODEVICE when no CUDA device is usable.
+ */
+#ifndef FCVM_H_
+#define FCVM_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FCVM_ABI_VERSION 1
+
+/* error codes */
+#define FCVM_OK          0
+#define FCVM_EINVAL     -1   /* bad argument / empty input (reference: ROS_ERROR + return)   */
+#define FCVM_ENOTREADY  -2   /* TaskState::isReady() false (viewpoint_manager.h:102-125)     */
+#define FCVM_ENODEVICE  -3   /* no usable CUDA device: the product path has no CPU fallback  */
+#define FCVM_ECUDA      -4   /* a CUDA runtime call or kernel failed                          */
+#define FCVM_ECAP       -5   /* caller buffer too small; required size returned where stated */
+#define FCVM_EINTERNAL  -6
+
+/* attitude_type (viewpoint_manager.cpp:45, 50-54, 951-952, 771) */
+#define FCVM_ATTITUDE_OTHER 0
+#define FCVM_ATTITUDE_YAW   1
+#define FCVM_ATTITUDE_ALL   2
+
+/* evaluator kinds, SURVEY.md section 3.3 */
+#define FCVM_STAGE_E1 1  /* getPose pass 1:  FOV + BiRC(discard first) + range            (cpp:355-425) */
+#define FCVM_STAGE_E2 2  /* getPose pass 2:  E1 set ∧ FOV' + offset walk + BiRC(discard)   (cpp:457-498) */
+#define FCVM_STAGE_E3 3  /* gravitation:     FOV + BiRC(discard first), no range re-check  (cpp:817-886) */
+#define FCVM_STAGE_E4 4  /* updateViewpointInfo: FOV + offset walk + BiRC(no discard)      (cpp:533-618) */
+
+/*
+ * Everything the reference reads from the ROS parameter server on this path
+ * (viewpoint_manager.cpp:35-47, perception_utils.cpp:32-37, sdf_map.cpp:128-136),
+ * plus the injected seed that replaces its two wall-clock seeded random sites
+ * (viewpoint_manager.cpp:962-977 and 249-255).
+ */
+typedef struct fcvm_params {
+  double visible_range;        /* viewpoint_manager/visible_range (also HC map inflation)  */
+  double viewpoints_distance;  /* viewpoint_manager/viewpoints_distance  (dist_vp)          */
+  double fov_h, fov_w;         /* degrees                                                    */
+  double pitch_upper, pitch_lower; /* degrees                                               */
+  double ground_pos;           /* viewpoint_manager/GroundPos                                */
+  double safe_height;          /* viewpoint_manager/safeHeight                               */
+  double safe_radius;          /* viewpoint_manager/safe_radius                              */
+  double top_angle, left_angle, right_angle; /* perception_utils/*, radians                 */
+  double max_dist;             /* perception_utils/max_dist                                  */
+  double vis_dist;             /* perception_utils/vis_dist (visualisation only; unused)     */
+  double resolution;           /* hcmap/resolution                                           */
+  int32_t z_ground;            /* viewpoint_manager/zGround                                  */
+  int32_t attitude;            /* FCVM_ATTITUDE_*                                            */
+  int32_t max_iter_num;        /* viewpoint_manager/max_iter_num                             */
+  int32_t pose_update;         /* viewpoint_manager/pose_update                              */
+  uint64_t seed;               /* injected seed for uncNeighVps + the <=100 random sample    */
+  int32_t device;              /* CUDA device ordinal                                        */
+  int32_t host_threads;        /* threads for the per-viewpoint host reductions; 0 = auto    */
+} fcvm_params;
+
+typedef struct fcvm fcvm_t;
+
+/* ---------------------------------------------------------------- manager level ---- */
+
+int         fcvm_abi_version(void);
+const char* fcvm_last_error(void);
+
+/* ViewpointManager() + init(nh)                 viewpoint_manager.cpp:25-62 */
+fcvm_t* fcvm_create(const fcvm_params* p);
+/* ~ViewpointManager()                           viewpoint_manager.cpp:28-30 */
+void    fcvm_destroy(fcvm_t* h);
+/* reset()                                       viewpoint_manager.cpp:64-72 */
+int     fcvm_reset(fcvm_t* h);
+/* setMapPointCloud(cloud)                       viewpoint_manager.cpp:74-89
+ * xyz: n packed float triples.  Builds the occupancy grid (sdf_map.cpp:122-188),
+ * uploads it bit-packed, builds the map-cloud nearest-neighbour index. */
+int     fcvm_set_map_cloud(fcvm_t* h, const float* xyz, int64_t n);
+/* setModel(cloud)                               viewpoint_manager.cpp:91-108 */
+int     fcvm_set_model(fcvm_t* h, const float* xyz, int64_t n);
+/* setNormals(map<Vector3d,Vector3d>)            viewpoint_manager.cpp:110-120
+ * n (key, value) pairs; key = exact double coordinates, std::map insert semantics. */
+int     fcvm_set_normals(fcvm_t* h, const double* pt_xyz, const double* normal_xyz, int64_t n);
+/* setInitViewpoints(PointNormal cloud)          viewpoint_manager.cpp:122-141
+ * pos_dir: n rows of 6 floats (x, y, z, normal_x, normal_y, normal_z). */
+int     fcvm_set_init_viewpoints(fcvm_t* h, const float* pos_dir, int64_t n);
+/* updateViewpoints()                            viewpoint_manager.cpp:143-330 */
+int     fcvm_update(fcvm_t* h);
+/* getUpdatedViewpoints(vector<SingleViewpoint>&) viewpoint_manager.cpp:1133-1136
+ * returns the number of final viewpoints; fills at most cap entries
+ * (vp_id[i], pose5[5*i..], vox_count[i]).  Any output pointer may be NULL. */
+int64_t fcvm_get_viewpoints(fcvm_t* h, int32_t* vp_id, double* pose5, int32_t* vox_count, int64_t cap);
+/* getUncoveredModelCloud(cloud&)                viewpoint_manager.cpp:1138-1144 */
+int64_t fcvm_get_uncovered(fcvm_t* h, float* xyz, int64_t cap);
+
+/* ---------------------------------------------------------------- parity taps ------- */
+
+/* state mirrors of VPI / MCI (viewpoint_manager.h:128-158); each returns the element count */
+int64_t fcvm_get_vps_pose(fcvm_t* h, double* pose5, int64_t cap_rows);
+int64_t fcvm_get_vps_voxcount(fcvm_t* h, int32_t* out, int64_t cap);
+int64_t fcvm_get_vps_contri(fcvm_t* h, int32_t* out, int64_t cap);
+int64_t fcvm_get_cover_state(fcvm_t* h, uint8_t* covered, int32_t* cover_contrib, int32_t* contrib_id, int64_t cap);
+
+/* grid geometry as initHCMap derives it: origin[3], voxel_num[3]; bits = occupancy in the
+ * reference's x-major order, 1 bit per voxel (LSB first), cap_bytes >= ceil(G/8). */
+int     fcvm_get_grid(fcvm_t* h, double* origin3, int32_t* voxel_num3, uint8_t* bits, int64_t cap_bytes);
+
+/* Event log of every evaluator launch, in execution order, for mask-level parity:
+ * enable before the calls to be traced.  Entry i has stage[i], vp_id[i] and a bitset row of
+ * fcvm_trace_words() 32-bit words (bit j of the row = model point j visible). */
+int     fcvm_trace_enable(fcvm_t* h, int32_t on);
+int64_t fcvm_trace_count(fcvm_t* h);
+int64_t fcvm_trace_words(fcvm_t* h);
+int     fcvm_trace_get(fcvm_t* h, int64_t i, int32_t* stage, int32_t* vp_id, double* pose5, uint32_t* row_words);
+
+/* counters accumulated since create/reset (all evaluators):
+ * [0] pair tests (insideFOV calls)   [1] rays (BiRC invocations)   [2] voxel lookups
+ * [3] offset-walk lookups            [4] step-cap trips (must be 0) [5] kernels launched
+ * [6] viewpoint evaluations          [7] safety_check lookups (host) */
+#define FCVM_NCOUNTERS 8
+int     fcvm_get_counters(fcvm_t* h, int64_t* out8);
+
+/* ---------------------------------------------------------------- evaluator level ---- */
+
+/*
+ * One evaluator pass over a batch of poses against the resident model cloud and grid:
+ * the batched form of the loops at viewpoint_manager.cpp:358-425 (E1), 457-498 (E2),
+ * 822-875 (E3), 546-586 (E4).  pose5: n x (x, y, z, pitch, yaw) host doubles.
+ * Outputs (host, each may be NULL): count[n] = visible points per pose;
+ * rows = n x fcvm_trace_words() bitset words.  restrict_rows (E2 only, may be NULL otherwise)
+ * = n x words input bitsets whose set bits are the only points considered.
+ * Timed end to end by bench.py (host->device copy, kernel, device->host copy).
+ */
+int fcvm_evaluate(fcvm_t* h, int32_t stage, const double* pose5, int64_t n,
+                  const uint32_t* restrict_rows, int32_t* count, uint32_t* rows);
+
+/* Same pass on poses that are already resident: uploads nothing, downloads nothing, leaves the
+ * bitset rows and counts on the device.  fcvm_stage_poses copies/derives the per-pose device
+ * record (position + 4 world-frame FOV normals) once; fcvm_evaluate_resident can then be
+ * launched repeatedly on `stream` (a cudaStream_t passed as void*, NULL = the handle's stream).
+ * rays_out (host, may be NULL) is only read back when sync != 0. */
+int fcvm_stage_poses(fcvm_t* h, const double* pose5, int64_t n);
+int fcvm_evaluate_resident(fcvm_t* h, int32_t stage, void* stream, int32_t sync, int64_t* rays_out);
+/* device pointers of the resident batch: rows (n x words uint32), counts (n int32) */
+int fcvm_resident_buffers(fcvm_t* h, void** rows_dev, void** count_dev, int64_t* n, int64_t* words);
+
+/* Ownership pass (viewpoint_manager.cpp:500-528, 589-617) over the resident batch rows in the
+ * given processing order, updating the manager's cover state; vp_ids[n] are the ids the rows
+ * stand for; order[n] = row indices in processing order (NULL = 0..n-1). */
+int fcvm_own_resident(fcvm_t* h, const int32_t* vp_ids, const int32_t* order, int64_t n);
+
+/* elapsed device time of the most recent evaluator launch(es) of this handle, in ms */
+double fcvm_last_kernel_ms(fcvm_t* h);
+
+/* --------------------------------------------------- multi-GPU (one process per GPU) - */
+
+/* Shard assignment: this handle evaluates only viewpoints [lo, hi) of every batch given to
+ * fcvm_set_init_viewpoints / the prune stages; rows of the other shards are supplied through the
+ * exchange callback below (torch.distributed NCCL all-gather in fc-planner_b200/distributed.py).
+ * world = 1 disables sharding. */
+typedef int (*fcvm_allgather_fn)(void* user, void* buf_dev, int64_t bytes_per_rank, void* stream);
+int fcvm_set_shard(fcvm_t* h, int32_t rank, int32_t world, fcvm_allgather_fn fn, void* user);
+
+/* --------------------------------------------------- host-only helpers (CPU tests) --- */
+
+/* PerceptionUtils::init + setPose_PY (perception_utils.cpp:29-96): 4 world-frame inward normals
+ * (top, bottom, left, right) for (pitch, yaw); out12 = 4 x 3 doubles. */
+int fcvm_host_fov_normals(const fcvm_params* p, double pitch, double yaw, double* out12);
+/* initHCMap geometry + voxelisation on the host, no device needed (sdf_map.cpp:122-188) */
+int fcvm_host_build_grid(const fcvm_params* p, const float* xyz, int64_t n,
+                         double* origin3, int32_t* voxel_num3, uint8_t* bits, int64_t cap_bytes);
+/* contiguous shard [lo, hi) of n items for (rank, world) */
+int fcvm_shard_range(int64_t n, int32_t rank, int32_t world, int64_t* lo, int64_t* hi);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FCVM_H_ */

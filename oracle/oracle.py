@@ -1,0 +1,239 @@
+"""ctypes front end of the CPU ORACLE (oracle/fcvm_oracle.hpp).  TEST INFRASTRUCTURE.
+
+Only tests/, bench.py's cpu_baseline / --impl reference legs and __graft_entry__.smoke() import
+this module, and only as the checker.  The product package never does.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIBS = {}
+
+c_i32p = ctypes.POINTER(ctypes.c_int32)
+c_i64p = ctypes.POINTER(ctypes.c_int64)
+c_u8p = ctypes.POINTER(ctypes.c_uint8)
+c_u32p = ctypes.POINTER(ctypes.c_uint32)
+c_f32p = ctypes.POINTER(ctypes.c_float)
+c_f64p = ctypes.POINTER(ctypes.c_double)
+
+
+def build(force=False):
+    """Compile the oracle (and oracle/_ref when /root/reference exists) with the committed Makefile."""
+    so = os.path.join(_HERE, "_build", "libfcvm_oracle.so")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < max(
+            os.path.getmtime(os.path.join(_HERE, f)) for f in ("fcvm_oracle.hpp", "oracle_capi.cpp")):
+        subprocess.run(["make", "-C", _HERE, "all"], check=True, stdout=subprocess.DEVNULL)
+    return so
+
+
+def _ptr(a, typ):
+    return None if a is None else a.ctypes.data_as(typ)
+
+
+def load(alt=False):
+    name = "libfcvm_oracle_alt.so" if alt else "libfcvm_oracle.so"
+    if name in _LIBS:
+        return _LIBS[name]
+    build()
+    lib = ctypes.CDLL(os.path.join(_HERE, "_build", name))
+    lib.orc_create.restype = ctypes.c_void_p
+    lib.orc_create.argtypes = [ctypes.c_void_p]
+    lib.orc_destroy.argtypes = [ctypes.c_void_p]
+    for fn in ("orc_get_viewpoints", "orc_get_uncovered", "orc_get_vps_pose", "orc_get_vps_voxcount", "orc_get_vps_contri",
+               "orc_get_cover_state", "orc_trace_count", "orc_trace_words", "orc_prune_order", "orc_ray_ids", "orc_biray_ids"):
+        getattr(lib, fn).restype = ctypes.c_int64
+    lib.orc_intbound.restype = ctypes.c_double
+    lib.orc_intbound.argtypes = [ctypes.c_double, ctypes.c_double]
+    lib.orc_mod.restype = ctypes.c_double
+    lib.orc_mod.argtypes = [ctypes.c_double, ctypes.c_double]
+    _LIBS[name] = lib
+    return lib
+
+
+class Oracle:
+    """The reference's ViewpointManager call sequence on numpy arrays, run by the CPU oracle."""
+
+    def __init__(self, params, alt=False):
+        self.lib = load(alt)
+        self.params = params
+        self.h = ctypes.c_void_p(self.lib.orc_create(ctypes.byref(params)))
+        self.P = 0
+
+    def close(self):
+        if self.h:
+            self.lib.orc_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- the 8-call sequence ---------------------------------------------------------------
+    def reset(self):
+        self.lib.orc_reset(self.h)
+
+    def setMapPointCloud(self, xyz):
+        xyz = np.ascontiguousarray(xyz, dtype=np.float32)
+        return self.lib.orc_set_map_cloud(self.h, _ptr(xyz, c_f32p), ctypes.c_int64(len(xyz)))
+
+    def setModel(self, xyz):
+        xyz = np.ascontiguousarray(xyz, dtype=np.float32)
+        self.P = len(xyz)
+        return self.lib.orc_set_model(self.h, _ptr(xyz, c_f32p), ctypes.c_int64(len(xyz)))
+
+    def setNormals(self, pts, normals):
+        pts = np.ascontiguousarray(pts, dtype=np.float64)
+        normals = np.ascontiguousarray(normals, dtype=np.float64)
+        return self.lib.orc_set_normals(self.h, _ptr(pts, c_f64p), _ptr(normals, c_f64p), ctypes.c_int64(len(pts)))
+
+    def setInitViewpoints(self, pos_dir):
+        pos_dir = np.ascontiguousarray(pos_dir, dtype=np.float32)
+        return self.lib.orc_set_init_viewpoints(self.h, _ptr(pos_dir, c_f32p), ctypes.c_int64(len(pos_dir)))
+
+    def updateViewpoints(self):
+        return self.lib.orc_update(self.h)
+
+    def getUpdatedViewpoints(self):
+        n = self.lib.orc_get_viewpoints(self.h, None, None, None, ctypes.c_int64(0))
+        ids = np.zeros(n, np.int32); pose = np.zeros((n, 5), np.float64); vox = np.zeros(n, np.int32)
+        self.lib.orc_get_viewpoints(self.h, _ptr(ids, c_i32p), _ptr(pose, c_f64p), _ptr(vox, c_i32p), ctypes.c_int64(n))
+        return ids, pose, vox
+
+    def getUncoveredModelCloud(self):
+        n = self.lib.orc_get_uncovered(self.h, None, ctypes.c_int64(0))
+        out = np.zeros((n, 3), np.float32)
+        self.lib.orc_get_uncovered(self.h, _ptr(out, c_f32p), ctypes.c_int64(n))
+        return out
+
+    # -- taps --------------------------------------------------------------------------------
+    def vps_pose(self):
+        n = self.lib.orc_get_vps_pose(self.h, None, ctypes.c_int64(0))
+        out = np.zeros((n, 5), np.float64)
+        self.lib.orc_get_vps_pose(self.h, _ptr(out, c_f64p), ctypes.c_int64(n))
+        return out
+
+    def vps_voxcount(self):
+        n = self.lib.orc_get_vps_voxcount(self.h, None, ctypes.c_int64(0))
+        out = np.zeros(n, np.int32)
+        self.lib.orc_get_vps_voxcount(self.h, _ptr(out, c_i32p), ctypes.c_int64(n))
+        return out
+
+    def vps_contri(self):
+        n = self.lib.orc_get_vps_contri(self.h, None, ctypes.c_int64(0))
+        out = np.zeros(n, np.int32)
+        self.lib.orc_get_vps_contri(self.h, _ptr(out, c_i32p), ctypes.c_int64(n))
+        return out
+
+    def cover_state(self):
+        n = self.lib.orc_get_cover_state(self.h, None, None, None, ctypes.c_int64(0))
+        cov = np.zeros(n, np.uint8); con = np.zeros(n, np.int32); cid = np.zeros(n, np.int32)
+        self.lib.orc_get_cover_state(self.h, _ptr(cov, c_u8p), _ptr(con, c_i32p), _ptr(cid, c_i32p), ctypes.c_int64(n))
+        return cov, con, cid
+
+    def grid(self, with_bits=True):
+        origin = np.zeros(3, np.float64); dims = np.zeros(3, np.int32)
+        self.lib.orc_get_grid(self.h, _ptr(origin, c_f64p), _ptr(dims, c_i32p), None, ctypes.c_int64(0))
+        bits = None
+        if with_bits:
+            g = int(dims[0]) * int(dims[1]) * int(dims[2])
+            bits = np.zeros((g + 7) // 8, np.uint8)
+            self.lib.orc_get_grid(self.h, None, None, _ptr(bits, c_u8p), ctypes.c_int64(len(bits)))
+        return origin, dims, bits
+
+    def trace_enable(self, on=True):
+        self.lib.orc_trace_enable(self.h, ctypes.c_int32(1 if on else 0))
+
+    def trace(self):
+        """[(stage, vp_id, pose5, row_words)] in execution order."""
+        n = self.lib.orc_trace_count(self.h)
+        words = self.lib.orc_trace_words(self.h)
+        out = []
+        for i in range(n):
+            st = ctypes.c_int32(); vid = ctypes.c_int32()
+            pose = np.zeros(5, np.float64); row = np.zeros(words, np.uint32)
+            self.lib.orc_trace_get(self.h, ctypes.c_int64(i), ctypes.byref(st), ctypes.byref(vid), _ptr(pose, c_f64p), _ptr(row, c_u32p))
+            out.append((st.value, vid.value, pose, row))
+        return out
+
+    def prune_order(self):
+        n = self.lib.orc_prune_order(self.h, None, ctypes.c_int64(0))
+        out = np.zeros(n, np.int32)
+        self.lib.orc_prune_order(self.h, _ptr(out, c_i32p), ctypes.c_int64(n))
+        return out
+
+    def counters(self):
+        out = np.zeros(8, np.int64)
+        self.lib.orc_get_counters(self.h, _ptr(out, c_i64p))
+        return out
+
+    def stage_seconds(self):
+        out = np.zeros(5, np.float64)
+        self.lib.orc_get_stage_seconds(self.h, _ptr(out, c_f64p))
+        return out
+
+    def evaluate(self, stage, pose5, restrict_rows=None, threads=1):
+        """Evaluator pass over a batch of poses -> (count[n], rows[n, words], counters[8])."""
+        pose5 = np.ascontiguousarray(pose5, dtype=np.float64).reshape(-1, 5)
+        n = len(pose5)
+        words = (self.P + 31) // 32
+        count = np.zeros(n, np.int32); rows = np.zeros((n, words), np.uint32); ctr = np.zeros(8, np.int64)
+        if restrict_rows is not None:
+            restrict_rows = np.ascontiguousarray(restrict_rows, dtype=np.uint32)
+        rc = self.lib.orc_evaluate(self.h, ctypes.c_int32(stage), _ptr(pose5, c_f64p), ctypes.c_int64(n), _ptr(restrict_rows, c_u32p),
+                                   _ptr(count, c_i32p), _ptr(rows, c_u32p), ctypes.c_int32(threads), _ptr(ctr, c_i64p))
+        if rc != 0:
+            raise RuntimeError(f"orc_evaluate failed: {rc}")
+        return count, rows, ctr
+
+    def safety_check(self, xyz):
+        xyz = np.ascontiguousarray(xyz, dtype=np.float32).reshape(-1, 3)
+        out = np.zeros(len(xyz), np.uint8)
+        self.lib.orc_safety_check(self.h, _ptr(xyz, c_f32p), ctypes.c_int64(len(xyz)), _ptr(out, c_u8p))
+        return out.astype(bool)
+
+
+# -- micro known-answer taps -----------------------------------------------------------------
+def ray_ids(res, origin, start, end, cap=4096, alt=False):
+    lib = load(alt)
+    o = np.asarray(origin, np.float64); s = np.asarray(start, np.float64); e = np.asarray(end, np.float64)
+    out = np.zeros((cap, 3), np.int32)
+    k = lib.orc_ray_ids(ctypes.c_double(res), _ptr(o, c_f64p), _ptr(s, c_f64p), _ptr(e, c_f64p), _ptr(out, c_i32p), ctypes.c_int64(cap))
+    return out[:min(k, cap)].copy()
+
+
+def biray_ids(res, origin, start, end, cap=4096, alt=False):
+    lib = load(alt)
+    o = np.asarray(origin, np.float64); s = np.asarray(start, np.float64); e = np.asarray(end, np.float64)
+    out = np.zeros((cap, 6), np.int32)
+    k = lib.orc_biray_ids(ctypes.c_double(res), _ptr(o, c_f64p), _ptr(s, c_f64p), _ptr(e, c_f64p), _ptr(out, c_i32p), ctypes.c_int64(cap))
+    return out[:min(k, cap)].copy()
+
+
+def fov_normals(params, pitch, yaw, alt=False):
+    lib = load(alt)
+    out = np.zeros(12, np.float64)
+    lib.orc_fov_normals(ctypes.byref(params), ctypes.c_double(pitch), ctypes.c_double(yaw), _ptr(out, c_f64p))
+    return out.reshape(4, 3)
+
+
+def inside_fov(params, pose5, pts, alt=False):
+    lib = load(alt)
+    pose5 = np.ascontiguousarray(pose5, np.float64); pts = np.ascontiguousarray(pts, np.float64).reshape(-1, 3)
+    out = np.zeros(len(pts), np.uint8)
+    lib.orc_inside_fov(ctypes.byref(params), _ptr(pose5, c_f64p), _ptr(pts, c_f64p), ctypes.c_int64(len(pts)), _ptr(out, c_u8p))
+    return out.astype(bool)
+
+
+def intbound(s, ds):
+    return load().orc_intbound(s, ds)
+
+
+def pitch_yaw(v):
+    v = np.ascontiguousarray(v, np.float64); out = np.zeros(2, np.float64)
+    load().orc_pitch_yaw(_ptr(v, c_f64p), _ptr(out, c_f64p))
+    return out
