@@ -1,0 +1,47 @@
+"""Builds libfcvm.so (CUDA kernels + host manager + C ABI) for sm_100a with nvcc, in-tree.
+
+    python fc-planner_b200/build.py [--force]
+
+nvcc cross-compiles without a GPU.  -fmad=false keeps every FP64 expression un-contracted on the
+device (the reference is an SSE2 build without FMA); -ffp-contract=off does the same for the host
+side of the library.  -lineinfo lets ncu's source page map back to these files.
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OUT = os.path.join(HERE, "_build", "libfcvm.so")
+SOURCES = ["fcvm_kernels.cu", "fcvm_host.cu"]
+DEPS = SOURCES + ["fcvm_device.cuh", "fcvm_kernels.h", "fcvm_geom.h", os.path.join("..", "..", "include", "fcvm.h")]
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
+    "-shared", "-Xcompiler", "-fPIC,-O3,-ffp-contract=off,-pthread", "-cudart", "static",
+]
+
+
+def needs_build():
+    if not os.path.exists(OUT):
+        return True
+    t = os.path.getmtime(OUT)
+    return any(os.path.getmtime(os.path.join(CSRC, d)) > t for d in DEPS)
+
+
+def build(force=False, verbose=False):
+    if not force and not needs_build():
+        return OUT
+    os.makedirs(os.path.dirname(OUT), exist_ok=True)
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + [os.path.join(CSRC, s) for s in SOURCES]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + r.stdout)
+    if verbose:
+        print(r.stdout)
+    return OUT
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

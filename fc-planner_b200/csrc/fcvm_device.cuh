@@ -1,0 +1,254 @@
+// fcvm_device.cuh — device-side primitives of the visibility path (sm_100a).
+//
+// Everything here computes in FP64 with the exact operation order of the reference and is
+// compiled with -fmad=false, so results are bit-identical to the CPU build of the reference
+// (x86-64 SSE2, no FMA contraction; FC-Planner/src/viewpoint_manager/CMakeLists.txt:4-8).
+// Only + - * / sqrt floor fmod trunc are used on the device; every transcendental of the path
+// (asin / atan2 / acos / sin / cos) runs on the host with the same libm as the reference.
+//
+// Reference statements restated here (paths relative to FC-Planner/src/):
+//   plan_env/src/raycast.cpp:26-43 (signum, mod, intbound), 341-345 (setParams),
+//   347-390 (input), 392-444 (biInput), 446-479 (nextId), 481-559 (biNextId);
+//   plan_env/include/plan_env/sdf_map.h:244-247 (indexToPos_hc), 367-373 (isInMap_hc),
+//   397-420 (occCheck);  active_perception/src/perception_utils.cpp:115-124 (insideFOV);
+//   viewpoint_manager/src/viewpoint_manager.cpp:386-396, 463-477, 482-492, 553-580, 844-853.
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace fcvm {
+
+// ---------------------------------------------------------------------------------------------
+// Occupancy grid in HBM/L2: 1 bit per voxel (set = occupied), bricked so that one 128-byte line
+// holds a compact 8 x 8 x 16 voxel block made of sixteen 4 x 4 x 4 sub-bricks (one uint64 each).
+// Consecutive DDA steps therefore stay inside the same 8-byte word ~3 steps out of 4 and inside
+// the same cache line far longer than in the reference's x-major `char` layout
+// (sdf_map.h:266-269: x*Ny*Nz + y*Nz + z).
+// ---------------------------------------------------------------------------------------------
+struct GridDesc {
+  const unsigned long long* bricks;  // [nsx*nsy*nsz][16]
+  int nx, ny, nz;                    // map_voxel_num_
+  int nsx, nsy, nsz;                 // line-blocks per axis: ceil(n/8), ceil(n/8), ceil(n/16)
+  double res;                        // resolution_
+  double offx, offy, offz;           // RayCaster::offset_ = 0.5 - origin/res   (raycast.cpp:344)
+  double orgx, orgy, orgz;           // map_origin_
+};
+
+__host__ __device__ __forceinline__ long long brick_word_index(int x, int y, int z, int nsy, int nsz) {
+  long long line = ((long long)(x >> 3) * nsy + (y >> 3)) * nsz + (z >> 4);
+  int word = ((((x >> 2) & 1) << 1) | ((y >> 2) & 1)) << 2 | ((z >> 2) & 3);
+  return line * 16 + word;
+}
+__host__ __device__ __forceinline__ int brick_bit_index(int x, int y, int z) {
+  return ((x & 3) << 4) | ((y & 3) << 2) | (z & 3);
+}
+
+// One-entry register cache of the last 4x4x4 sub-brick a ray touched.
+struct BrickCache {
+  long long key;
+  unsigned long long word;
+  __device__ __forceinline__ void reset() { key = -1; word = 0ull; }
+};
+
+// SDFMap::occCheck (sdf_map.h:397-420): true = inside the map AND not occupied.
+__device__ __forceinline__ bool occ_free(const GridDesc& g, int ix, int iy, int iz, BrickCache& c) {
+  if ((unsigned)ix >= (unsigned)g.nx || (unsigned)iy >= (unsigned)g.ny || (unsigned)iz >= (unsigned)g.nz) return false;
+  long long k = brick_word_index(ix, iy, iz, g.nsy, g.nsz);
+  if (k != c.key) {
+    c.key = k;
+    c.word = __ldg(g.bricks + k);
+  }
+  return ((c.word >> brick_bit_index(ix, iy, iz)) & 1ull) == 0ull;
+}
+
+// `idx = (Vector3d(x,y,z) + offset_).cast<int>()` for one axis (raycast.cpp:447-448): int -> double,
+// one add, truncation toward zero (so a value in (-1, 0) maps to voxel 0).
+__device__ __forceinline__ int to_map_index(int v, double off) { return __double2int_rz((double)v + off); }
+
+// raycast.cpp:26-43
+// mod(value, 1) = fmod(fmod(value, 1) + 1, 1).  fmod(v, 1) is exact and equals v - trunc(v), and that
+// subtraction is itself exact in FP64 for every finite v, so the two fmod calls are replaced by
+// trunc/sub pairs; the "+ 1" in between is the same rounded addition the reference performs.
+__device__ __forceinline__ double d_mod1(double value) {
+  const double a = value - trunc(value);
+  const double b = a + 1.0;
+  return b - trunc(b);
+}
+__device__ __forceinline__ double d_intbound(double s, double ds) {
+  if (ds < 0) { s = -s; ds = -ds; }       // intbound(-s, -ds): one level of recursion at most
+  s = d_mod1(s);
+  return (1 - s) / ds;                     // ds == 0 -> +inf, as on the host
+}
+__device__ __forceinline__ int d_signum(int x) { return x == 0 ? 0 : (x < 0 ? -1 : 1); }
+
+// One half-ray (or the one-directional ray) of the Amanatides-Woo marcher: position in
+// world-anchored voxel coordinates floor(p/res), target voxel, and the tMax/tDelta state derived
+// from the INTEGER voxel deltas (raycast.cpp:412-434).
+struct Marcher {
+  int x, y, z;        // current voxel (world-anchored lattice)
+  int ex, ey, ez;     // end / midpoint voxel
+  int sx, sy, sz;     // step direction
+  double tmx, tmy, tmz, tdx, tdy, tdz;
+  int ix, iy, iz;     // current voxel as a map index (maintained incrementally)
+
+  __device__ __forceinline__ void init(double fx, double fy, double fz, int tx, int ty, int tz, const GridDesc& g) {
+    x = (int)floor(fx); y = (int)floor(fy); z = (int)floor(fz);
+    ex = tx; ey = ty; ez = tz;
+    double dx = (double)(ex - x), dy = (double)(ey - y), dz = (double)(ez - z);
+    sx = d_signum(ex - x); sy = d_signum(ey - y); sz = d_signum(ez - z);
+    tmx = d_intbound(fx, dx); tmy = d_intbound(fy, dy); tmz = d_intbound(fz, dz);
+    tdx = ((double)sx) / dx; tdy = ((double)sy) / dy; tdz = ((double)sz) / dz;   // 0/0 = NaN on idle axes
+    ix = to_map_index(x, g.offx); iy = to_map_index(y, g.offy); iz = to_map_index(z, g.offz);
+  }
+  __device__ __forceinline__ bool at_end() const { return x == ex && y == ey && z == ez; }
+  __device__ __forceinline__ int manhattan() const { return abs(ex - x) + abs(ey - y) + abs(ez - z); }
+  // the branch ladder of nextId / biNextId (raycast.cpp:455-476): strict '<', z on ties and NaN
+  __device__ __forceinline__ void step(const GridDesc& g) {
+    if (tmx < tmy) {
+      if (tmx < tmz) { x += sx; tmx += tdx; ix = to_map_index(x, g.offx); }
+      else           { z += sz; tmz += tdz; iz = to_map_index(z, g.offz); }
+    } else {
+      if (tmy < tmz) { y += sy; tmy += tdy; iy = to_map_index(y, g.offy); }
+      else           { z += sz; tmz += tdz; iz = to_map_index(z, g.offz); }
+    }
+  }
+};
+
+struct RayStats {
+  unsigned int lookups;   // occCheck calls (same sequence as the reference makes)
+  unsigned int walk;      // of which inside the surface-offset walk
+  unsigned int trips;     // step-cap trips (the reference would not terminate); must stay 0
+};
+
+// Bidirectional ray cast (BiRC) exactly as the call sites drive it:
+//   biInput(a, b); [biNextId once, discarded]; while (biNextId) { f = occ(idx); r = occ(idxR);
+//   if (!f || !r) break; }  f = occ(idx);  visible = f && r.
+// a = viewpoint side (p-ray), b = target side (n-ray); both march to the midpoint voxel in lock
+// step, idx / idxR are the voxels BEFORE the step of that call.
+__device__ __forceinline__ bool birc(const GridDesc& g, double ax, double ay, double az, double bx, double by, double bz,
+                                     bool discard_first, RayStats& st) {
+  const double res = g.res;
+  // start_ = start / resolution_;  inter_ = (0.5*(start+end)) / resolution_;  end_ = end / resolution_
+  const double sxf = ax / res, syf = ay / res, szf = az / res;
+  const double mxf = (0.5 * (ax + bx)) / res, myf = (0.5 * (ay + by)) / res, mzf = (0.5 * (az + bz)) / res;
+  const double exf = bx / res, eyf = by / res, ezf = bz / res;
+  const int mx = (int)floor(mxf), my = (int)floor(myf), mz = (int)floor(mzf);
+  Marcher p, n;
+  p.init(sxf, syf, szf, mx, my, mz, g);
+  n.init(exf, eyf, ezf, mx, my, mz, g);
+  const int kp = p.manhattan(), kn = n.manhattan();
+  int budget = (kp > kn ? kp : kn) + 8;      // the reference has no cap
+  BrickCache cp, cn;
+  cp.reset(); cn.reset();
+
+  bool f = true, r = true;
+  int pix, piy, piz, nix, niy, niz;
+  // one biNextId call: report both voxels, then advance whichever side is not at the midpoint
+#define FCVM_BI_NEXT(ret)                                     \
+  {                                                           \
+    pix = p.ix; piy = p.iy; piz = p.iz;                       \
+    const bool pflag = !p.at_end();                           \
+    if (pflag) p.step(g);                                     \
+    nix = n.ix; niy = n.iy; niz = n.iz;                       \
+    const bool nflag = !n.at_end();                           \
+    if (nflag) n.step(g);                                     \
+    ret = pflag || nflag;                                     \
+  }
+  bool more;
+  if (discard_first) { FCVM_BI_NEXT(more); }
+  for (;;) {
+    FCVM_BI_NEXT(more);
+    if (!more) break;
+    if (--budget < 0) { st.trips++; break; }
+    f = occ_free(g, pix, piy, piz, cp);
+    r = occ_free(g, nix, niy, niz, cn);
+    st.lookups += 2;
+    if (!f || !r) break;
+  }
+#undef FCVM_BI_NEXT
+  f = occ_free(g, pix, piy, piz, cp);
+  st.lookups += 1;
+  return f && r;
+}
+
+// Surface-offset walk (viewpoint_manager.cpp:463-477 / 554-568): march point -> viewpoint with the
+// one-directional caster, stop at the 2nd free voxel (or at the viewpoint's voxel), return that
+// voxel's centre via indexToPos_hc (sdf_map.h:244-247).
+__device__ __forceinline__ void offset_target(const GridDesc& g, double px, double py, double pz, double vx, double vy, double vz,
+                                              double& tx, double& ty, double& tz, RayStats& st) {
+  const double res = g.res;
+  const double sxf = px / res, syf = py / res, szf = pz / res;
+  const double exf = vx / res, eyf = vy / res, ezf = vz / res;
+  Marcher m;
+  m.init(sxf, syf, szf, (int)floor(exf), (int)floor(eyf), (int)floor(ezf), g);
+  int budget = m.manhattan() + 8;
+  BrickCache c;
+  c.reset();
+  int count = 0;
+  int ix = m.ix, iy = m.iy, iz = m.iz;
+  for (;;) {
+    ix = m.ix; iy = m.iy; iz = m.iz;              // nextId reports the voxel before stepping
+    if (m.at_end()) break;                        // ... and returns false at the end voxel
+    if (--budget < 0) { st.trips++; break; }
+    m.step(g);
+    st.lookups += 1; st.walk += 1;
+    if (occ_free(g, ix, iy, iz, c)) {
+      count++;
+      if (count == 2) break;
+    }
+  }
+  tx = ((double)ix + 0.5) * res + g.orgx;
+  ty = ((double)iy + 0.5) * res + g.orgy;
+  tz = ((double)iz + 0.5) * res + g.orgz;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Per-viewpoint record: position + the four world-frame inward FOV normals (top, bottom, left,
+// right) computed on the host by PerceptionUtils::setPose_PY (perception_utils.cpp:76-96).
+// 16 doubles = 128 bytes, one line.
+// ---------------------------------------------------------------------------------------------
+struct alignas(16) VpRec {
+  double px, py, pz;
+  double n[4][3];
+  double pad;
+};
+
+struct FovConst {
+  double max_dist;        // perception_utils/max_dist
+  double md2_lo, md2_hi;  // max_dist^2 * (1 -/+ 1e-12): outside this band the sqrt is not needed
+  double plane_eps;       // |d.n| below this (unnormalised) -> take the exact normalised path
+  double visible_range;   // viewpoint_manager/visible_range (E1 only)
+};
+
+// PerceptionUtils::insideFOV (perception_utils.cpp:115-124), Eigen order:
+//   dir = p - pos; if (dir.norm() > max_dist) false; dir.normalize(); all four dir.dot(n) >= 0.
+// Fast path: the verdict of the normalised test is decided by the sign of the UNNORMALISED dot
+// product whenever that is farther from zero than any rounding error could move it (bound:
+// |err| < 1e-14 * |d|, the band used is 1e-10 * max_dist); points inside the band, and points
+// within 1e-12 relative of the range sphere, take the literal path with sqrt and three divisions.
+__device__ __forceinline__ bool inside_fov(const VpRec& v, const FovConst& fc, double qx, double qy, double qz) {
+  double dx = qx - v.px, dy = qy - v.py, dz = qz - v.pz;
+  const double n2 = (dx * dx + dy * dy) + dz * dz;
+  if (n2 > fc.md2_hi) return false;
+  bool exact = !(n2 < fc.md2_lo);
+  double s[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    s[q] = (dx * v.n[q][0] + dy * v.n[q][1]) + dz * v.n[q][2];
+    exact |= fabs(s[q]) <= fc.plane_eps;
+  }
+  if (!exact) return s[0] > 0.0 && s[1] > 0.0 && s[2] > 0.0 && s[3] > 0.0;
+  // literal path
+  const double nrm = sqrt(n2);
+  if (nrm > fc.max_dist) return false;
+  if (n2 > 0.0) { dx = dx / nrm; dy = dy / nrm; dz = dz / nrm; }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const double d = (dx * v.n[q][0] + dy * v.n[q][1]) + dz * v.n[q][2];
+    if (d < 0.0) return false;
+  }
+  return true;
+}
+
+}  // namespace fcvm

@@ -1,0 +1,1241 @@
+// fcvm_host.cu — the manager behind the C ABI (include/fcvm.h): a batched, device-resident
+// re-design of predrecon::ViewpointManager (FC-Planner/src/viewpoint_manager/src/viewpoint_manager.cpp).
+//
+// The reference evaluates one viewpoint at a time with a stateful ray caster.  Here each stage of
+// the call sequence becomes a few launches over ALL of the stage's viewpoints:
+//
+//   setInitViewpoints / round appends (getPose, cpp:332-531)
+//       host: PitchYaw(dir) -> FOV normals                (libm: host, same as the reference)
+//       K_E1 over the batch -> bitset rows                 (FOV + BiRC + range)
+//       host: ordered pitch / yaw sums over set bits       (asin / atan2 / acos: host)
+//       K_E2 restricted to the E1 rows -> rows, popc       (FOV' + offset walk + BiRC)
+//       K_own sweep in id order                            (ownership, cpp:500-528)
+//   viewpointsPrune (cpp:620-710)
+//       host: qualify, std::sort over the real unordered_map order, nearCheck / radius search,
+//             the sequential absorb flag chain and gravitation pulls (cpp:712-810)
+//       K_E3 over all gravitated viewpoints at once -> host ordered offset sums (cpp:817-886)
+//       K_E4 over the live viewpoints in unordered_map order -> popc -> K_own sweep
+//
+// There is no CPU implementation of any K_* stage in this library: without a CUDA device every
+// evaluating call fails with FCVM_ENODEVICE.
+#include <atomic>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <map>
+#include <random>
+#include <string>
+#include <thread>
+#include <unordered_map>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/fcvm.h"
+#include "fcvm_geom.h"
+#include "fcvm_kernels.h"
+
+namespace fcvm {
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+#define CU(call)                                                                                         \
+  do {                                                                                                   \
+    cudaError_t e__ = (call);                                                                            \
+    if (e__ != cudaSuccess)                                                                              \
+      return fail(e__ == cudaErrorNoDevice || e__ == cudaErrorInsufficientDriver ? FCVM_ENODEVICE : FCVM_ECUDA, \
+                  std::string(#call) + ": " + cudaGetErrorString(e__));                                   \
+  } while (0)
+
+template <class F>
+static void parallel_for(int64_t n, int threads, F&& f) {
+  if (threads <= 1 || n < 2 * threads) {
+    for (int64_t i = 0; i < n; ++i) f(i);
+    return;
+  }
+  std::atomic<int64_t> next(0);
+  std::vector<std::thread> th;
+  for (int t = 0; t < threads; ++t)
+    th.emplace_back([&] {
+      for (;;) {
+        const int64_t i0 = next.fetch_add(64);
+        if (i0 >= n) break;
+        for (int64_t i = i0; i < std::min(n, i0 + 64); ++i) f(i);
+      }
+    });
+  for (auto& t : th) t.join();
+}
+
+template <class T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    cudaError_t e = cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T));
+    if (e == cudaSuccess) cap = n;
+    return e;
+  }
+  void free() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+template <class T>
+struct PinBuf {
+  T* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFreeHost(p);
+    p = nullptr; cap = 0;
+    cudaError_t e = cudaMallocHost(&p, std::max<size_t>(n, 1) * sizeof(T));
+    if (e == cudaSuccess) cap = n;
+    return e;
+  }
+  void free() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+struct Pose5 { double v[5]; };
+struct FinalVp { int vp_id; Pose5 pose; int vox_count; };
+struct TraceEv { int stage; int vp_id; Pose5 pose; std::vector<uint32_t> row; };
+struct PtNormal { float x, y, z, nx, ny, nz; };
+
+struct D3Less {   // Vector3dCompare0, viewpoint_manager.h:53-63
+  bool operator()(const D3& a, const D3& b) const {
+    if (a.x != b.x) return a.x < b.x;
+    if (a.y != b.y) return a.y < b.y;
+    return a.z < b.z;
+  }
+};
+struct D3Hash {   // VectorHashEigenVector3d, viewpoint_manager.h:65-77
+  std::size_t operator()(const D3& v) const {
+    std::size_t seed = 0;
+    const double c[3] = {v.x, v.y, v.z};
+    for (int i = 0; i < 3; ++i) seed ^= std::hash<double>()(c[i]) + 0x9e3779b9 + (seed << 6) + (seed >> 2);
+    return seed;
+  }
+};
+struct D3Eq {
+  bool operator()(const D3& a, const D3& b) const { return a.x == b.x && a.y == b.y && a.z == b.z; }
+};
+
+}  // namespace fcvm
+
+using namespace fcvm;
+
+struct fcvm_handle {
+  fcvm_params prm;
+  // derived at init (viewpoint_manager.cpp:49-55)
+  double pitch_upper, pitch_lower, fov_base;
+  Camera cam;
+  int threads = 1;
+
+  // TaskState (viewpoint_manager.h:102-125)
+  bool map_flag = false, model_flag = false, viewpoints_flag = false, normal_flag = false;
+
+  // map
+  HostGrid grid;
+  CellIndex map_index;
+  DevBuf<unsigned long long> d_bricks;
+  // model
+  std::vector<float> model;   // xyz triples
+  int64_t P = 0, W = 0;       // W = row stride in words (multiple of 4)
+  DevBuf<float4> d_points;
+  // normals
+  std::map<D3, D3, D3Less> pt_normal_pairs;
+
+  // VPI / MCI (viewpoint_manager.h:128-158)
+  std::vector<Pose5> vps_pose;
+  std::vector<int> vps_voxcount, vps_contri;   // host mirrors; voxcount is authoritative on the device during a stage
+  int last_vps_num = 0;
+  DevBuf<int> d_cover_contrib, d_contrib_id, d_voxcount;
+  size_t voxcount_n = 0;      // logical length of vps_voxcount
+  std::vector<FinalVp> final_vps;
+  // ViewpointsPrune maps (viewpoint_manager.h:160-178).  They are members that are only ever
+  // clear()ed, never reconstructed (viewpoint_manager.cpp:622-626, h:169-177), so their bucket
+  // arrays - and with them the iteration order that decides the prune order among equal counts,
+  // the E4 processing order and the order of final_vps_ - carry over from call to
+  // call.  Only the key order of idx_viewpoints_ is observable, so it maps id -> slot here.
+  std::unordered_map<D3, int, D3Hash, D3Eq> inverse_idx;
+  std::unordered_map<int, int> idx_slot;
+  std::unordered_map<int, int> idx_ctrl_voxels;
+
+  // device scratch for a batch
+  DevBuf<VpRec> d_recs;
+  DevBuf<uint32_t> d_rows1, d_rows2;
+  DevBuf<int> d_count;
+  DevBuf<int4> d_sched;
+  DevBuf<unsigned long long> d_counters;
+  PinBuf<uint32_t> h_rows;
+  PinBuf<int> h_count;
+  PinBuf<VpRec> h_recs;
+  int64_t resident_n = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  double last_kernel_ms = 0.0;
+  bool device_ok = false;
+
+  // taps
+  bool trace_on = false;
+  std::vector<TraceEv> trace;
+  int64_t counters[FCVM_NCOUNTERS] = {0, 0, 0, 0, 0, 0, 0, 0};
+  int64_t unc_calls = 0, sample_calls = 0;
+
+  // sharding
+  int rank = 0, world = 1;
+  fcvm_allgather_fn gather = nullptr;
+  void* gather_user = nullptr;
+};
+
+namespace fcvm {
+
+// ------------------------------------------------------------------------------------------------
+// device bring-up (lazy: creating a handle and the host-only helpers work without a GPU)
+// ------------------------------------------------------------------------------------------------
+static int ensure_device(fcvm_handle* h) {
+  if (h->device_ok) return FCVM_OK;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(FCVM_ENODEVICE, std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
+                                    " (this library has no CPU fallback)");
+  CU(cudaSetDevice(h->prm.device));
+  CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CU(cudaEventCreate(&h->ev0));
+  CU(cudaEventCreate(&h->ev1));
+  CU(h->d_counters.reserve(8));
+  CU(cudaMemset(h->d_counters.p, 0, 8 * sizeof(unsigned long long)));
+  h->device_ok = true;
+  return FCVM_OK;
+}
+
+static void fill_grid_desc(const fcvm_handle* h, GridDesc& g) {
+  const HostGrid& hg = h->grid;
+  g.bricks = h->d_bricks.p;
+  g.nx = hg.dims[0]; g.ny = hg.dims[1]; g.nz = hg.dims[2];
+  g.nsx = hg.ns[0]; g.nsy = hg.ns[1]; g.nsz = hg.ns[2];
+  g.res = hg.res;
+  // RayCaster::setParams (raycast.cpp:341-345): offset_ = half_ - origin / resolution_
+  g.offx = 0.5 - hg.origin[0] / hg.res;
+  g.offy = 0.5 - hg.origin[1] / hg.res;
+  g.offz = 0.5 - hg.origin[2] / hg.res;
+  g.orgx = hg.origin[0]; g.orgy = hg.origin[1]; g.orgz = hg.origin[2];
+}
+
+static void fill_fov_const(const fcvm_handle* h, FovConst& f) {
+  f.max_dist = h->prm.max_dist;
+  const double md2 = h->prm.max_dist * h->prm.max_dist;
+  f.md2_lo = md2 * (1.0 - 1e-12);
+  f.md2_hi = md2 * (1.0 + 1e-12);
+  f.plane_eps = 1e-10 * std::max(h->prm.max_dist, 1.0);
+  f.visible_range = h->prm.visible_range;
+}
+
+// choose the CTA decomposition: tiles of points x chunks of viewpoints, aiming at >= 4 waves of
+// 148 SMs x 2 resident CTAs when the problem is large enough and at enough CTAs to fill the chip
+// when it is small.
+static void choose_tiling(int64_t P, int64_t V, int& tile_pts, int& vp_per_cta) {
+  tile_pts = P >= 8 * EVAL_MAX_TILE ? EVAL_MAX_TILE : (P >= 4096 ? 1024 : 512);
+  const int64_t tiles = (P + tile_pts - 1) / tile_pts;
+  const int64_t target_ctas = 148 * 2 * 4;
+  int64_t chunks = std::max<int64_t>(1, std::min<int64_t>((target_ctas + tiles - 1) / tiles, (V + EVAL_WARPS - 1) / EVAL_WARPS));
+  int64_t per = (V + chunks - 1) / chunks;
+  per = std::max<int64_t>(per, 1);
+  while ((V + per - 1) / per > 65535) per *= 2;
+  vp_per_cta = (int)per;
+}
+
+// One evaluator launch over recs[0..n) already on the device -> rows (zeroed here).  Adds the
+// kernel's counters to the handle when `count_stats`.
+static int launch_stage(fcvm_handle* h, int stage, const VpRec* d_recs, int64_t n, uint32_t* d_rows, const uint32_t* d_restrict,
+                        cudaStream_t s, bool count_stats) {
+  EvalArgs a;
+  fill_grid_desc(h, a.grid);
+  fill_fov_const(h, a.fov);
+  a.points = h->d_points.p;
+  a.P = h->P;
+  a.recs = d_recs;
+  a.V = n;
+  a.rows = d_rows;
+  a.restrict_rows = d_restrict;
+  a.words = h->W;
+  choose_tiling(h->P, n, a.tile_pts, a.vp_per_cta);
+  a.counters = count_stats ? h->d_counters.p : nullptr;
+  CU(cudaMemsetAsync(d_rows, 0, (size_t)n * h->W * sizeof(uint32_t), s));
+  CU(launch_eval(stage, a, s));
+  h->counters[5] += 1;
+  h->counters[6] += n;
+  return FCVM_OK;
+}
+
+static int fetch_counters(fcvm_handle* h) {
+  unsigned long long c[8];
+  CU(cudaMemcpyAsync(c, h->d_counters.p, sizeof(c), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaMemsetAsync(h->d_counters.p, 0, sizeof(c), h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  for (int k = 0; k < 5; ++k) h->counters[k] += (int64_t)c[k];
+  return FCVM_OK;
+}
+
+// rows per batch chunk so that one rows buffer stays <= 1 GiB
+static int64_t chunk_rows(const fcvm_handle* h, int64_t n) {
+  const int64_t per = std::max<int64_t>(1, (int64_t)(1ll << 30) / (h->W * 4));
+  return std::min(n, per);
+}
+
+// Evaluate `stage` for recs (host) [0..n): upload, launch, optional exchange across ranks, download
+// rows into rows_out (n x W, host) and/or counts.  d_rows_keep: leave rows on the device in this
+// buffer (must hold n x W words).
+static int eval_batch(fcvm_handle* h, int stage, const VpRec* recs, int64_t n, const uint32_t* restrict_host, uint32_t* rows_out,
+                      int* count_out, DevBuf<uint32_t>& d_rows, bool restrict_resident = false) {
+  int rc = ensure_device(h);
+  if (rc) return rc;
+  if (n == 0) return FCVM_OK;
+  const int64_t W = h->W;
+  // pad the batch to a multiple of the world size so that shards are equal (NCCL all-gather)
+  const int64_t per_rank = (n + h->world - 1) / h->world;
+  const int64_t n_pad = per_rank * h->world;
+  CU(h->d_recs.reserve((size_t)n_pad));
+  CU(d_rows.reserve((size_t)n_pad * W));
+  CU(h->d_count.reserve((size_t)n_pad));
+  CU(cudaMemcpyAsync(h->d_recs.p, recs, (size_t)n * sizeof(VpRec), cudaMemcpyHostToDevice, h->stream));
+  const uint32_t* d_restrict = nullptr;
+  if (stage == FCVM_STAGE_E2) {
+    DevBuf<uint32_t>& other = (&d_rows == &h->d_rows1) ? h->d_rows2 : h->d_rows1;
+    if (restrict_resident) {
+      // the E1 rows of this very batch are still in the other rows buffer
+      if (other.cap < (size_t)n_pad * W) return fail(FCVM_EINTERNAL, "resident E1 rows missing");
+    } else {
+      if (!restrict_host) return fail(FCVM_EINVAL, "E2 needs the E1 rows to restrict to");
+      CU(other.reserve((size_t)n_pad * W));
+      CU(cudaMemcpyAsync(other.p, restrict_host, (size_t)n * W * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+    }
+    d_restrict = other.p;
+  }
+  const int64_t lo = std::min(n, per_rank * h->rank), hi = std::min(n, per_rank * (h->rank + 1));
+  CU(cudaEventRecord(h->ev0, h->stream));
+  if (h->world > 1) CU(cudaMemsetAsync(d_rows.p, 0, (size_t)n_pad * W * sizeof(uint32_t), h->stream));
+  if (hi > lo) {
+    rc = launch_stage(h, stage, h->d_recs.p + lo, hi - lo, d_rows.p + lo * W, d_restrict ? d_restrict + lo * W : nullptr, h->stream, true);
+    if (rc) return rc;
+  }
+  CU(cudaEventRecord(h->ev1, h->stream));
+  if (h->world > 1) {
+    if (!h->gather) return fail(FCVM_EINVAL, "world > 1 but no all-gather callback set");
+    if (h->gather(h->gather_user, d_rows.p, per_rank * W * (int64_t)sizeof(uint32_t), h->stream) != 0)
+      return fail(FCVM_EINTERNAL, "all-gather callback failed");
+  }
+  CU(launch_popc_rows(d_rows.p, n, W, h->d_count.p, h->stream));
+  h->counters[5] += 1;
+  if (rows_out) CU(cudaMemcpyAsync(rows_out, d_rows.p, (size_t)n * W * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+  if (count_out) CU(cudaMemcpyAsync(count_out, h->d_count.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  rc = fetch_counters(h);   // synchronises the stream
+  if (rc) return rc;
+  float ms = 0.f;
+  CU(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+  h->last_kernel_ms = ms;
+  return FCVM_OK;
+}
+
+// Ownership sweep over rows resident in d_rows (n rows), processed in `order` (row indices), rows
+// standing for viewpoint ids vp_ids[row] with popcounts count[row].
+static int own_sweep(fcvm_handle* h, const DevBuf<uint32_t>& d_rows, const std::vector<int>& order, const std::vector<int>& vp_ids,
+                     const int* count) {
+  std::vector<int4> sched;
+  int max_id = -1;
+  for (int r : order) {
+    if (count[r] <= 0) continue;     // `if (contribute_voxel_num > 0)` cpp:500 / `== 0 return` cpp:586
+    sched.push_back(make_int4(r, vp_ids[(size_t)r], count[r], 0));
+    h->vps_contri[(size_t)vp_ids[(size_t)r]] = count[r];
+    max_id = std::max(max_id, vp_ids[(size_t)r]);
+  }
+  if (sched.empty()) return FCVM_OK;
+  if ((size_t)max_id >= h->voxcount_n) return fail(FCVM_EINTERNAL, "vps_voxcount shorter than a viewpoint id");
+  CU(h->d_sched.reserve(sched.size()));
+  CU(cudaMemcpyAsync(h->d_sched.p, sched.data(), sched.size() * sizeof(int4), cudaMemcpyHostToDevice, h->stream));
+  CU(launch_own_sweep(d_rows.p, h->W, h->d_sched.p, (int)sched.size(), h->last_vps_num, h->P, h->d_cover_contrib.p, h->d_contrib_id.p,
+                      h->d_voxcount.p, h->stream));
+  h->counters[5] += 1;
+  CU(cudaStreamSynchronize(h->stream));
+  return FCVM_OK;
+}
+
+// vps_voxcount lives on the device while stages run; these move it
+static int voxcount_resize(fcvm_handle* h, size_t n) {   // grow with zeros, keep contents
+  if (n <= h->voxcount_n) { h->voxcount_n = n; return FCVM_OK; }
+  if (n > h->d_voxcount.cap) {
+    DevBuf<int> nb;
+    CU(nb.reserve(std::max(n, h->d_voxcount.cap * 2)));
+    if (h->voxcount_n) CU(cudaMemcpy(nb.p, h->d_voxcount.p, h->voxcount_n * sizeof(int), cudaMemcpyDeviceToDevice));
+    h->d_voxcount.free();
+    h->d_voxcount = nb;
+  }
+  CU(cudaMemset(h->d_voxcount.p + h->voxcount_n, 0, (n - h->voxcount_n) * sizeof(int)));
+  h->voxcount_n = n;
+  return FCVM_OK;
+}
+static int voxcount_download(fcvm_handle* h, std::vector<int>& out) {
+  out.assign(h->voxcount_n, 0);
+  if (h->voxcount_n) CU(cudaMemcpy(out.data(), h->d_voxcount.p, h->voxcount_n * sizeof(int), cudaMemcpyDeviceToHost));
+  return FCVM_OK;
+}
+static int voxcount_upload(fcvm_handle* h, const std::vector<int>& in) {
+  int rc = voxcount_resize(h, 0);
+  if (rc) return rc;
+  rc = voxcount_resize(h, in.size());
+  if (rc) return rc;
+  if (!in.empty()) CU(cudaMemcpy(h->d_voxcount.p, in.data(), in.size() * sizeof(int), cudaMemcpyHostToDevice));
+  return FCVM_OK;
+}
+static int cover_reset(fcvm_handle* h) {   // MCI reset, cpp:178-183
+  CU(h->d_cover_contrib.reserve((size_t)h->P));
+  CU(h->d_contrib_id.reserve((size_t)h->P));
+  CU(cudaMemset(h->d_cover_contrib.p, 0, (size_t)h->P * sizeof(int)));
+  CU(cudaMemset(h->d_contrib_id.p, 0xff, (size_t)h->P * sizeof(int)));   // -1
+  return FCVM_OK;
+}
+
+static void record(fcvm_handle* h, int stage, int vp_id, const Pose5& pose, const uint32_t* row) {
+  TraceEv e;
+  e.stage = stage; e.vp_id = vp_id; e.pose = pose;
+  e.row.assign(row, row + h->W);
+  h->trace.push_back(std::move(e));
+}
+
+template <class F>
+static void for_each_bit(const uint32_t* row, int64_t words, F&& f) {
+  for (int64_t w = 0; w < words; ++w) {
+    uint32_t x = row[w];
+    while (x) {
+      const int b = __builtin_ctz(x);
+      x &= x - 1;
+      f((int)(w * 32 + b));
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// viewpointSafetyCheck / nearCheck (viewpoint_manager.cpp:889-946)
+// ------------------------------------------------------------------------------------------------
+static bool near_check(fcvm_handle* h, const D3& pos, int vox_num) {
+  if (!(std::isfinite(pos.x) && std::isfinite(pos.y) && std::isfinite(pos.z))) return false;
+  if (h->map_index.size() == 0) return false;            // PCL throws on an empty tree; the reference catches
+  const float q[3] = {(float)pos.x, (float)pos.y, (float)pos.z};
+  // dist = sqrt(nn_d2) (float overload); preserve unless dist < safe_radius or vox_num <= 1
+  if (vox_num <= 1) return false;
+  return !h->map_index.any_closer_than(q, h->prm.safe_radius);
+}
+static bool viewpoint_safety_check(fcvm_handle* h, float vx, float vy, float vz) {
+  const fcvm_params& p = h->prm;
+  if (p.z_ground && vz < p.ground_pos + p.safe_height) return false;
+  const double res = h->grid.res, sr = p.safe_radius;
+  const int safe_voxel = (int)std::floor(0.5 * sr / res);
+  if (safe_voxel <= 0) return false;   // reference: infinite loop
+  for (int i = 0; vx - sr + i * res < vx + sr; i = i + safe_voxel)
+    for (int j = 0; vy - sr + j * res < vy + sr; j = j + safe_voxel)
+      for (int k = 0; vz - sr + k * res < vz + sr; k = k + safe_voxel) {
+        h->counters[7]++;
+        if (!h->grid.safety_check(vx - sr + i * res, vy - sr + j * res, vz - sr + k * res)) return false;
+      }
+  return near_check(h, D3{vx, vy, vz}, 2);
+}
+
+// ------------------------------------------------------------------------------------------------
+// getPose over a batch (viewpoint_manager.cpp:332-531).  ids[i] = viewpoint id of candidate i.
+// poses_out[i] receives the returned pose; ownership and vps_contri/voxcount are updated.
+// ------------------------------------------------------------------------------------------------
+static int get_pose_batch(fcvm_handle* h, const std::vector<D3>& pos, const std::vector<D3>& dir, int first_id, std::vector<Pose5>& poses_out) {
+  const int64_t n = (int64_t)pos.size();
+  poses_out.assign((size_t)n, Pose5());
+  if (n == 0) return FCVM_OK;
+  const int64_t W = h->W, P = h->P;
+  const double vr = h->prm.visible_range;
+  int rc;
+  for (int64_t c0 = 0; c0 < n; c0 += chunk_rows(h, n)) {
+    const int64_t cn = std::min(chunk_rows(h, n), n - c0);
+    std::vector<D3> fs((size_t)cn), fy((size_t)cn);
+    std::vector<double> ip((size_t)cn), iy((size_t)cn);
+    CU(h->h_recs.reserve((size_t)cn));
+    CU(h->h_rows.reserve((size_t)cn * W));
+    CU(h->h_count.reserve((size_t)cn));
+    for (int64_t i = 0; i < cn; ++i) {
+      // fov_sample_ray = dir.normalized(); fov_yaw_ray = (x, y, 0).normalized(); init_py = PitchYaw
+      fs[(size_t)i] = normalized3(dir[(size_t)(c0 + i)]);
+      fy[(size_t)i] = normalized3(D3{fs[(size_t)i].x, fs[(size_t)i].y, 0.0});
+      pitch_yaw(fs[(size_t)i], ip[(size_t)i], iy[(size_t)i]);
+      const D3& p = pos[(size_t)(c0 + i)];
+      h->cam.fill(h->h_recs.p[i], p.x, p.y, p.z, ip[(size_t)i], iy[(size_t)i]);
+      poses_out[(size_t)(c0 + i)] = Pose5{{p.x, p.y, p.z, ip[(size_t)i], iy[(size_t)i]}};
+    }
+    std::vector<int> ids((size_t)cn), order((size_t)cn);
+    for (int64_t i = 0; i < cn; ++i) { ids[(size_t)i] = first_id + (int)(c0 + i); order[(size_t)i] = (int)i; }
+
+    if (!h->prm.pose_update) {
+      // getPose with pose_update == false delegates to updateViewpointInfo (cpp:347-353): E4 + ownership
+      rc = eval_batch(h, FCVM_STAGE_E4, h->h_recs.p, cn, nullptr, h->trace_on ? h->h_rows.p : nullptr, h->h_count.p, h->d_rows1);
+      if (rc) return rc;
+      if (h->trace_on)
+        for (int64_t i = 0; i < cn; ++i) record(h, 4, ids[(size_t)i], poses_out[(size_t)(c0 + i)], h->h_rows.p + i * W);
+      rc = own_sweep(h, h->d_rows1, order, ids, h->h_count.p);
+      if (rc) return rc;
+      continue;
+    }
+
+    // ---- E1 ------------------------------------------------------------------------------
+    rc = eval_batch(h, FCVM_STAGE_E1, h->h_recs.p, cn, nullptr, h->h_rows.p, h->h_count.p, h->d_rows1);
+    if (rc) return rc;
+    if (h->trace_on)
+      for (int64_t i = 0; i < cn; ++i) record(h, 1, ids[(size_t)i], poses_out[(size_t)(c0 + i)], h->h_rows.p + i * W);
+
+    // ---- ordered pitch / yaw averages (cpp:398-447), libm on the host ---------------------
+    std::vector<char> has_free((size_t)cn, 0);
+    const float* M = h->model.data();
+    const double pu = h->pitch_upper * M_PI / 180.0, pl = h->pitch_lower * M_PI / 180.0;
+    parallel_for(cn, h->threads, [&](int64_t i) {
+      if (h->h_count.p[i] == 0) return;     // free_num == 0: pose stays (pos, init_py), no E2 (cpp:427-436)
+      const D3 vp = pos[(size_t)(c0 + i)];
+      double avg_pitch = 0.0, avg_yaw = 0.0;
+      int free_num = 0;
+      for_each_bit(h->h_rows.p + i * W, (P + 31) / 32, [&](int j) {
+        const D3 cand{M[3 * j], M[3 * j + 1], M[3 * j + 2]};
+        const D3 d = sub3(cand, vp);
+        const D3 ray_dir = normalized3(d);
+        double pitch, yaw;
+        pitch_yaw(ray_dir, pitch, yaw);
+        warp_angle(pitch);
+        warp_angle(yaw);
+        avg_pitch += pitch;
+        const double yaw_vec = std::min(std::max(dot3(fs[(size_t)i], ray_dir), -1.0), 1.0);
+        double yawoff = std::acos(yaw_vec);
+        // ray_dir_yaw.cross(fov_yaw_ray)[2] with the UNnormalised ray_dir_yaw (cpp:399-401, A.9)
+        if (d.x * fy[(size_t)i].y - d.y * fy[(size_t)i].x < 0) yawoff = -yawoff;
+        avg_yaw += yawoff;
+        free_num++;
+      });
+      (void)vr;
+      avg_pitch = avg_pitch / free_num;
+      avg_yaw = avg_yaw / free_num;
+      avg_yaw = iy[(size_t)i] + avg_yaw;
+      warp_angle(avg_pitch);
+      warp_angle(avg_yaw);
+      if (avg_pitch > pu) avg_pitch = pu;
+      if (avg_pitch < pl) avg_pitch = pl;
+      poses_out[(size_t)(c0 + i)].v[3] = avg_pitch;
+      poses_out[(size_t)(c0 + i)].v[4] = avg_yaw;
+      has_free[(size_t)i] = 1;
+      h->cam.fill(h->h_recs.p[i], vp.x, vp.y, vp.z, avg_pitch, avg_yaw);
+    });
+
+    // ---- E2 on the E1 sets (cpp:457-498) ---------------------------------------------------
+    // viewpoints with free_num == 0 have all-zero E1 rows, so they contribute nothing here
+    rc = eval_batch(h, FCVM_STAGE_E2, h->h_recs.p, cn, nullptr, h->trace_on ? h->h_rows.p : nullptr, h->h_count.p, h->d_rows2, true);
+    if (rc) return rc;
+    if (h->trace_on)
+      for (int64_t i = 0; i < cn; ++i)
+        if (has_free[(size_t)i]) record(h, 2, ids[(size_t)i], poses_out[(size_t)(c0 + i)], h->h_rows.p + i * W);
+    rc = own_sweep(h, h->d_rows2, order, ids, h->h_count.p);
+    if (rc) return rc;
+  }
+  return FCVM_OK;
+}
+
+// updateViewpointInfo over a batch in processing order (viewpoint_manager.cpp:533-618)
+static int update_info_batch(fcvm_handle* h, const std::vector<int>& ids, const std::vector<Pose5>& poses) {
+  const int64_t n = (int64_t)ids.size();
+  const int64_t W = h->W;
+  int rc;
+  for (int64_t c0 = 0; c0 < n; c0 += chunk_rows(h, n)) {
+    const int64_t cn = std::min(chunk_rows(h, n), n - c0);
+    CU(h->h_recs.reserve((size_t)cn));
+    CU(h->h_count.reserve((size_t)cn));
+    if (h->trace_on) CU(h->h_rows.reserve((size_t)cn * W));
+    std::vector<int> cid((size_t)cn), order((size_t)cn);
+    for (int64_t i = 0; i < cn; ++i) {
+      const Pose5& p = poses[(size_t)(c0 + i)];
+      h->cam.fill(h->h_recs.p[i], p.v[0], p.v[1], p.v[2], p.v[3], p.v[4]);
+      cid[(size_t)i] = ids[(size_t)(c0 + i)];
+      order[(size_t)i] = (int)i;
+    }
+    rc = eval_batch(h, FCVM_STAGE_E4, h->h_recs.p, cn, nullptr, h->trace_on ? h->h_rows.p : nullptr, h->h_count.p, h->d_rows1);
+    if (rc) return rc;
+    if (h->trace_on)
+      for (int64_t i = 0; i < cn; ++i) record(h, 4, cid[(size_t)i], poses[(size_t)(c0 + i)], h->h_rows.p + i * W);
+    rc = own_sweep(h, h->d_rows1, order, cid, h->h_count.p);
+    if (rc) return rc;
+  }
+  return FCVM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// viewpointsPrune (viewpoint_manager.cpp:620-710) with updatePoseGravitation (712-887) split into
+// the sequential host flag chain and one batched E3 launch.
+// ------------------------------------------------------------------------------------------------
+static int viewpoints_prune(fcvm_handle* h, const std::vector<Pose5>& vps_pose, const std::vector<int>& sub_voxcount) {
+  const fcvm_params& prm = h->prm;
+  auto& inverse_idx = h->inverse_idx;
+  auto& idx_slot = h->idx_slot;
+  auto& idx_ctrl_voxels = h->idx_ctrl_voxels;
+  inverse_idx.clear();
+  idx_slot.clear();
+  idx_ctrl_voxels.clear();
+  std::vector<int> slot_id;
+  std::vector<Pose5> slot_pose;
+  std::vector<char> live, query;
+  std::vector<float> vp_cloud;
+
+  for (int i = h->last_vps_num; i < (int)vps_pose.size(); ++i) {
+    if (sub_voxcount[(size_t)i] > 0) {
+      const Pose5& q = vps_pose[(size_t)i];
+      const float fx = (float)q.v[0], fyy = (float)q.v[1], fz = (float)q.v[2];
+      vp_cloud.push_back(fx); vp_cloud.push_back(fyy); vp_cloud.push_back(fz);
+      inverse_idx[D3{fx, fyy, fz}] = i;
+      idx_slot[i] = (int)slot_id.size();
+      idx_ctrl_voxels[i] = sub_voxcount[(size_t)i];
+      slot_id.push_back(i);
+      slot_pose.push_back(q);
+      live.push_back(1);
+      query.push_back(0);
+    }
+  }
+  if (vp_cloud.empty()) return FCVM_OK;   // "No need prune viewpoints!" cpp:651-655
+
+  // sort by ctrl voxels, descending, over the unordered_map's own iteration order (cpp:658-662)
+  std::vector<std::pair<int, int>> ctrlVector(idx_ctrl_voxels.begin(), idx_ctrl_voxels.end());
+  std::sort(ctrlVector.begin(), ctrlVector.end(), [](const std::pair<int, int>& a, const std::pair<int, int>& b) { return a.second > b.second; });
+
+  CellIndex vps_tree;
+  const double bubble_radius = 0.55 * prm.viewpoints_distance * std::tan(h->fov_base);
+  vps_tree.build(vp_cloud.data(), (int64_t)slot_id.size(), bubble_radius);
+
+  const double pitch_bound = 0.3 * prm.fov_h * M_PI / 180.0;
+  const double yaw_bound = 0.3 * prm.fov_w * M_PI / 180.0;
+
+  struct Grav { int slot; D3 up; double upi, uy; };
+  std::vector<Grav> grav;
+  std::vector<int> neigh;
+  for (const auto& pr : ctrlVector) {
+    const int c = pr.first;
+    const int cs = idx_slot.find(c)->second;
+    const Pose5 cur_pose = slot_pose[(size_t)cs];
+    const D3 cur_position{cur_pose.v[0], cur_pose.v[1], cur_pose.v[2]};
+    const int cur_vox = idx_ctrl_voxels.find(c)->second;
+    if (!near_check(h, cur_position, cur_vox)) { live[(size_t)cs] = 0; continue; }
+    const float q[3] = {(float)cur_pose.v[0], (float)cur_pose.v[1], (float)cur_pose.v[2]};
+    vps_tree.radius_search(q, bubble_radius, neigh);
+    if (!(live[(size_t)cs] && (int)neigh.size() > 1)) continue;
+
+    // ---- updatePoseGravitation, host part (cpp:714-810) -----------------------------------
+    query[(size_t)cs] = 1;
+    const double cur_pitch = cur_pose.v[3], cur_yaw = cur_pose.v[4];
+    std::vector<int> updated;   // slots
+    for (int id_ : neigh) {
+      const D3 key{vp_cloud[3 * (size_t)id_], vp_cloud[3 * (size_t)id_ + 1], vp_cloud[3 * (size_t)id_ + 2]};
+      const int index_finder = inverse_idx.find(key)->second;
+      const int ms = idx_slot.find(index_finder)->second;
+      const Pose5& inner_pose = slot_pose[(size_t)ms];
+      const int inner_vox = idx_ctrl_voxels.find(index_finder)->second;
+      if (inner_vox > cur_vox) continue;
+      double diff_yaw = std::fabs(cur_pose.v[4] - inner_pose.v[4]);
+      warp_angle(diff_yaw);
+      double diff_pitch = std::fabs(cur_pose.v[3] - inner_pose.v[3]);
+      warp_angle(diff_pitch);
+      const bool update_flag = std::fabs(diff_pitch) < pitch_bound && std::fabs(diff_yaw) < yaw_bound;
+      if (update_flag && !query[(size_t)ms]) {
+        live[(size_t)ms] = 0;
+        updated.push_back(ms);
+      }
+    }
+    D3 up = cur_position;
+    double upi = cur_pitch, uy = cur_yaw;
+    for (int ms : updated) {
+      const double grav_factor = (double)idx_ctrl_voxels.find(slot_id[(size_t)ms])->second / (double)cur_vox;
+      const Pose5& o = slot_pose[(size_t)ms];
+      const D3 pull{grav_factor * (o.v[0] - cur_position.x), grav_factor * (o.v[1] - cur_position.y), grav_factor * (o.v[2] - cur_position.z)};
+      up = D3{up.x + pull.x, up.y + pull.y, up.z + pull.z};
+      double off; int flag, dirn;
+      if (prm.attitude == FCVM_ATTITUDE_ALL) {
+        wrapped_diff(o.v[3], cur_pitch, off, flag, dirn);
+        upi = upi + grav_factor * flag * dirn * off;
+      }
+      wrapped_diff(o.v[4], cur_yaw, off, flag, dirn);
+      uy = uy + grav_factor * flag * dirn * off;
+    }
+    if (prm.z_ground && up.z < prm.ground_pos + prm.safe_height) up.z = prm.ground_pos + prm.safe_height + 0.1;
+    Pose5& dst = slot_pose[(size_t)cs];
+    if (viewpoint_safety_check(h, (float)up.x, (float)up.y, (float)up.z)) {
+      dst.v[0] = up.x; dst.v[1] = up.y; dst.v[2] = up.z;
+    } else {
+      dst.v[0] = cur_position.x; dst.v[1] = cur_position.y; dst.v[2] = cur_position.z;
+    }
+    if (!prm.pose_update) {
+      dst.v[3] = upi; dst.v[4] = uy;
+    } else {
+      grav.push_back(Grav{cs, up, upi, uy});   // E3 uses `updated_position` even if it was reverted (cpp:821, 844)
+    }
+  }
+
+  // ---- E3 for every gravitated viewpoint in one batch (cpp:817-886) ---------------------------
+  if (!grav.empty()) {
+    const int64_t W = h->W, P = h->P;
+    const float* M = h->model.data();
+    const double pu = h->pitch_upper * M_PI / 180.0, pl = h->pitch_lower * M_PI / 180.0;
+    const int64_t n = (int64_t)grav.size();
+    for (int64_t c0 = 0; c0 < n; c0 += chunk_rows(h, n)) {
+      const int64_t cn = std::min(chunk_rows(h, n), n - c0);
+      CU(h->h_recs.reserve((size_t)cn));
+      CU(h->h_rows.reserve((size_t)cn * W));
+      for (int64_t i = 0; i < cn; ++i) {
+        const Grav& gq = grav[(size_t)(c0 + i)];
+        h->cam.fill(h->h_recs.p[i], gq.up.x, gq.up.y, gq.up.z, gq.upi, gq.uy);
+      }
+      int rc = eval_batch(h, FCVM_STAGE_E3, h->h_recs.p, cn, nullptr, h->h_rows.p, nullptr, h->d_rows1);
+      if (rc) return rc;
+      parallel_for(cn, h->threads, [&](int64_t i) {
+        const Grav& gq = grav[(size_t)(c0 + i)];
+        double avg_pitch = gq.upi, avg_yaw = gq.uy;
+        for_each_bit(h->h_rows.p + i * W, (P + 31) / 32, [&](int j) {
+          const D3 cand{M[3 * j], M[3 * j + 1], M[3 * j + 2]};
+          const D3 ray_dir = normalized3(sub3(cand, gq.up));
+          double pitch, yaw, off; int flag, dirn;
+          pitch_yaw(ray_dir, pitch, yaw);
+          warp_angle(pitch);
+          warp_angle(yaw);
+          wrapped_diff(pitch, gq.upi, off, flag, dirn);
+          avg_pitch = avg_pitch + flag * dirn * off;
+          wrapped_diff(yaw, gq.uy, off, flag, dirn);
+          avg_yaw = avg_yaw + flag * dirn * off;
+        });
+        double updated_pitch = avg_pitch, updated_yaw = avg_yaw;
+        if (updated_pitch > pu) updated_pitch = pu;
+        if (updated_pitch < pl) updated_pitch = pl;
+        warp_angle(updated_pitch);
+        warp_angle(updated_yaw);
+        slot_pose[(size_t)gq.slot].v[3] = updated_pitch;
+        slot_pose[(size_t)gq.slot].v[4] = updated_yaw;
+      });
+      if (h->trace_on)
+        for (int64_t i = 0; i < cn; ++i) {
+          const Grav& gq = grav[(size_t)(c0 + i)];
+          record(h, 3, slot_id[(size_t)gq.slot], Pose5{{gq.up.x, gq.up.y, gq.up.z, gq.upi, gq.uy}}, h->h_rows.p + i * W);
+        }
+    }
+  }
+
+  // ---- E4 + ownership for the live ones, in unordered_map iteration order (cpp:693-697) -------
+  std::vector<int> ids;
+  std::vector<Pose5> poses;
+  for (auto& kv : idx_slot)
+    if (live[(size_t)kv.second]) { ids.push_back(kv.first); poses.push_back(slot_pose[(size_t)kv.second]); }
+  int rc = update_info_batch(h, ids, poses);
+  if (rc) return rc;
+  rc = voxcount_download(h, h->vps_voxcount);
+  if (rc) return rc;
+  for (auto& kv : idx_slot)       // cpp:699-709
+    if (live[(size_t)kv.second] && h->vps_voxcount[(size_t)kv.first] > 0)
+      h->final_vps.push_back(FinalVp{kv.first, slot_pose[(size_t)kv.second], h->vps_voxcount[(size_t)kv.first]});
+  return FCVM_OK;
+}
+
+// uncNeighVps (viewpoint_manager.cpp:948-1131) with injected seeds: engine k of call c is seeded
+// with seed + 8*c + k (k = 0..3 pitch, 4..7 yaw)
+static void unc_neigh_vps(fcvm_handle* h, const float pt[3], const float nrm[3], std::vector<PtNormal>& out) {
+  const fcvm_params& prm = h->prm;
+  double max_pitch_range = 40.0, max_yaw_range = 40.0;
+  if (prm.attitude == FCVM_ATTITUDE_YAW) max_pitch_range = 0;
+  double op, oy;
+  pitch_yaw(D3{nrm[0], nrm[1], nrm[2]}, op, oy);
+  const uint64_t base = prm.seed + 8ull * (uint64_t)h->unc_calls++;
+  double rand_p[4], rand_y[4];
+  std::uniform_real_distribution<double> dist_p(0.0, max_pitch_range * M_PI / 180.0);
+  for (int k = 0; k < 4; ++k) {
+    std::default_random_engine g;
+    g.seed((std::default_random_engine::result_type)(base + (uint64_t)k));
+    rand_p[k] = dist_p(g);
+  }
+  std::uniform_real_distribution<double> dist_y(0.0, max_yaw_range * M_PI / 180.0);
+  for (int k = 0; k < 4; ++k) {
+    std::default_random_engine g;
+    g.seed((std::default_random_engine::result_type)(base + 4ull + (uint64_t)k));
+    rand_y[k] = dist_y(g);
+  }
+  static const int sp[8] = {+1, -1, +1, -1, +1, -1, +1, -1};
+  static const int sy[8] = {+1, -1, +1, -1, -1, +1, -1, +1};
+  PtNormal cand[8];
+  for (int q = 0; q < 8; ++q) {
+    const int k = q & 3;
+    const double pitch = sp[q] > 0 ? op + rand_p[k] : op - rand_p[k];
+    const double yaw = sy[q] > 0 ? oy + rand_y[k] : oy - rand_y[k];
+    const D3 vec = py_to_vec(pitch, yaw);
+    cand[q] = PtNormal{(float)(pt[0] + prm.viewpoints_distance * vec.x), (float)(pt[1] + prm.viewpoints_distance * vec.y),
+                       (float)(pt[2] + prm.viewpoints_distance * vec.z), (float)(-vec.x), (float)(-vec.y), (float)(-vec.z)};
+  }
+  out.clear();
+  for (int q = 0; q < 8; ++q)
+    if (viewpoint_safety_check(h, cand[q].x, cand[q].y, cand[q].z)) out.push_back(cand[q]);
+}
+
+// stand-in for pcl::RandomSample (cpp:249-255): selection sampling driven by minstd_rand0(seed + phi + call#)
+static std::vector<PtNormal> random_sample(fcvm_handle* h, const std::vector<PtNormal>& in, int sample) {
+  std::minstd_rand0 g((std::minstd_rand0::result_type)(h->prm.seed + 0x9e3779b9ull + (uint64_t)h->sample_calls++));
+  std::vector<PtNormal> out;
+  size_t N = in.size(), n = (size_t)sample, index = 0;
+  while (n > 0 && index < in.size()) {
+    const float U = (float)((double)g() / 2147483646.0);
+    if ((float)N * U <= (float)n) { out.push_back(in[index]); --n; }
+    ++index; --N;
+  }
+  return out;
+}
+
+static int set_init_viewpoints_impl(fcvm_handle* h, const std::vector<PtNormal>& vps) {
+  if (vps.empty()) return fail(FCVM_EINVAL, "Input viewpoints Fail!! Input viewpoint is empty!!!");
+  if (!h->map_flag || !h->model_flag) return fail(FCVM_ENOTREADY, "setInitViewpoints needs the map and the model first");
+  int rc = ensure_device(h);
+  if (rc) return rc;
+  const size_t n = vps.size();
+  // cpp:129-131: resize (keeps earlier contents if called twice)
+  rc = voxcount_resize(h, std::max(h->voxcount_n, n));
+  if (rc) return rc;
+  if (h->vps_contri.size() < n) h->vps_contri.resize(n, 0);
+  h->vps_pose.resize(n);
+  std::vector<D3> pos(n), dir(n);
+  for (size_t i = 0; i < n; ++i) {
+    pos[i] = D3{vps[i].x, vps[i].y, vps[i].z};
+    dir[i] = D3{vps[i].nx, vps[i].ny, vps[i].nz};
+  }
+  std::vector<Pose5> poses;
+  rc = get_pose_batch(h, pos, dir, 0, poses);
+  if (rc) return rc;
+  h->vps_pose = poses;
+  h->viewpoints_flag = true;
+  return FCVM_OK;
+}
+
+static int update_impl(fcvm_handle* h) {
+  int rc = ensure_device(h);
+  if (rc) return rc;
+  const fcvm_params& prm = h->prm;
+  const float* M = h->model.data();
+  if (!h->viewpoints_flag) {
+    // "No input viewpoints!! Use normals gengerate viewpoints!!" (cpp:145-171)
+    if (!h->map_flag || !h->model_flag || !h->normal_flag) return fail(FCVM_ENOTREADY, "Not ready: map, model and normals are required");
+    std::vector<PtNormal> vps;
+    for (int64_t i = 0; i < h->P; ++i) {
+      auto it = h->pt_normal_pairs.find(D3{M[3 * i], M[3 * i + 1], M[3 * i + 2]});
+      if (it == h->pt_normal_pairs.end()) continue;    // reference: unchecked dereference
+      const D3 nd = it->second;
+      const float vx = (float)(M[3 * i] + prm.viewpoints_distance * nd.x);
+      const float vy = (float)(M[3 * i + 1] + prm.viewpoints_distance * nd.y);
+      const float vz = (float)(M[3 * i + 2] + prm.viewpoints_distance * nd.z);
+      if (!viewpoint_safety_check(h, vx, vy, vz)) continue;
+      vps.push_back(PtNormal{vx, vy, vz, (float)(-nd.x), (float)(-nd.y), (float)(-nd.z)});
+    }
+    rc = set_init_viewpoints_impl(h, vps);
+    if (rc && rc != FCVM_EINVAL) return rc;
+  }
+  if (!(h->map_flag && h->model_flag && h->viewpoints_flag && h->normal_flag)) return fail(FCVM_ENOTREADY, "[ViewpointManager] Not ready");
+
+  // cpp:176-187
+  std::vector<int> temp_vps_voxcount;
+  rc = cover_reset(h);
+  if (rc) return rc;
+  rc = voxcount_download(h, temp_vps_voxcount);
+  if (rc) return rc;
+  rc = voxcount_upload(h, std::vector<int>(std::max((size_t)h->P, h->vps_pose.size()), 0));   // resize(P) in the reference; A.9
+  if (rc) return rc;
+  rc = viewpoints_prune(h, h->vps_pose, temp_vps_voxcount);
+  if (rc) return rc;
+
+  auto uncovered = [&](std::vector<int>& ids) -> int {
+    std::vector<int> cid((size_t)h->P);
+    CU(cudaMemcpy(cid.data(), h->d_contrib_id.p, (size_t)h->P * sizeof(int), cudaMemcpyDeviceToHost));
+    ids.clear();
+    for (int i = 0; i < (int)h->P; ++i)
+      if (cid[(size_t)i] < 0) ids.push_back(i);
+    return FCVM_OK;
+  };
+  std::vector<int> uncoveredID;
+  rc = uncovered(uncoveredID);
+  if (rc) return rc;
+
+  // cpp:206-221: candidate library for the uncovered points
+  std::unordered_map<int, std::vector<PtNormal>> uncVpsLib;
+  for (int p : uncoveredID) {
+    auto it = h->pt_normal_pairs.find(D3{M[3 * p], M[3 * p + 1], M[3 * p + 2]});
+    const D3 nd = it == h->pt_normal_pairs.end() ? D3{0, 0, 1} : it->second;
+    const float nrm[3] = {(float)nd.x, (float)nd.y, (float)nd.z};
+    unc_neigh_vps(h, &M[3 * p], nrm, uncVpsLib[p]);
+  }
+
+  int unc_iter = 0, last_unc_num = -1;
+  while ((int)uncoveredID.size() > 0 && unc_iter < prm.max_iter_num && last_unc_num != (int)uncoveredID.size()) {
+    last_unc_num = (int)uncoveredID.size();
+    std::vector<PtNormal> cand;
+    for (int p : uncoveredID)
+      for (auto& u : uncVpsLib[p]) cand.push_back(u);
+    if ((int)cand.size() > 100) cand = random_sample(h, cand, 100);
+
+    // snapshot of MCI (cpp:272-274)
+    DevBuf<int> snap_contrib, snap_id;
+    CU(snap_contrib.reserve((size_t)h->P));
+    CU(snap_id.reserve((size_t)h->P));
+    CU(cudaMemcpy(snap_contrib.p, h->d_cover_contrib.p, (size_t)h->P * sizeof(int), cudaMemcpyDeviceToDevice));
+    CU(cudaMemcpy(snap_id.p, h->d_contrib_id.p, (size_t)h->P * sizeof(int), cudaMemcpyDeviceToDevice));
+
+    const int oriVpNum = (int)h->vps_pose.size();
+    h->last_vps_num = oriVpNum;
+    rc = voxcount_resize(h, h->voxcount_n + cand.size());
+    if (rc) return rc;
+    h->vps_contri.resize(h->vps_contri.size() + cand.size(), 0);
+    if (h->vps_contri.size() < (size_t)oriVpNum + cand.size()) h->vps_contri.resize((size_t)oriVpNum + cand.size(), 0);
+    std::vector<int> before_vps_voxcount;
+    rc = voxcount_download(h, before_vps_voxcount);
+    if (rc) return rc;
+
+    std::vector<D3> pos(cand.size()), dir(cand.size());
+    for (size_t i = 0; i < cand.size(); ++i) {
+      pos[i] = D3{cand[i].x, cand[i].y, cand[i].z};
+      dir[i] = D3{cand[i].nx, cand[i].ny, cand[i].nz};
+    }
+    std::vector<Pose5> pose_set_unc;
+    rc = get_pose_batch(h, pos, dir, oriVpNum, pose_set_unc);
+    if (rc) { snap_contrib.free(); snap_id.free(); return rc; }
+    h->vps_pose.insert(h->vps_pose.end(), pose_set_unc.begin(), pose_set_unc.end());
+
+    // restore MCI, swap the voxcounts (cpp:304-309)
+    CU(cudaMemcpy(h->d_cover_contrib.p, snap_contrib.p, (size_t)h->P * sizeof(int), cudaMemcpyDeviceToDevice));
+    CU(cudaMemcpy(h->d_contrib_id.p, snap_id.p, (size_t)h->P * sizeof(int), cudaMemcpyDeviceToDevice));
+    snap_contrib.free();
+    snap_id.free();
+    rc = voxcount_download(h, temp_vps_voxcount);
+    if (rc) return rc;
+    rc = voxcount_upload(h, before_vps_voxcount);
+    if (rc) return rc;
+    rc = viewpoints_prune(h, h->vps_pose, temp_vps_voxcount);
+    if (rc) return rc;
+    rc = uncovered(uncoveredID);
+    if (rc) return rc;
+    unc_iter++;
+  }
+  return voxcount_download(h, h->vps_voxcount);
+}
+
+}  // namespace fcvm
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+extern "C" {
+
+int fcvm_abi_version(void) { return FCVM_ABI_VERSION; }
+const char* fcvm_last_error(void) { return g_err.c_str(); }
+
+fcvm_t* fcvm_create(const fcvm_params* p) {
+  if (!p) { fail(FCVM_EINVAL, "null params"); return nullptr; }
+  fcvm_handle* h = new fcvm_handle();
+  h->prm = *p;
+  h->pitch_upper = p->pitch_upper;
+  h->pitch_lower = p->pitch_lower;
+  if (p->attitude == FCVM_ATTITUDE_YAW) { h->pitch_upper = 0.0; h->pitch_lower = 0.0; }   // cpp:50-54
+  h->fov_base = std::min(p->fov_h, p->fov_w) * M_PI / 360.0;                               // cpp:55
+  h->cam.init(*p);
+  int t = p->host_threads > 0 ? p->host_threads : (int)std::thread::hardware_concurrency();
+  h->threads = std::max(1, std::min(t, 64));
+  return h;
+}
+
+void fcvm_destroy(fcvm_t* h) {
+  if (!h) return;
+  h->d_bricks.free(); h->d_points.free(); h->d_cover_contrib.free(); h->d_contrib_id.free(); h->d_voxcount.free();
+  h->d_recs.free(); h->d_rows1.free(); h->d_rows2.free(); h->d_count.free(); h->d_sched.free(); h->d_counters.free();
+  h->h_rows.free(); h->h_count.free(); h->h_recs.free();
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+int fcvm_reset(fcvm_t* h) {   // cpp:64-72
+  if (!h) return fail(FCVM_EINVAL, "null handle");
+  h->map_flag = h->model_flag = h->viewpoints_flag = h->normal_flag = false;
+  h->vps_pose.clear(); h->vps_voxcount.clear(); h->vps_contri.clear();
+  h->last_vps_num = 0; h->voxcount_n = 0;
+  h->pt_normal_pairs.clear();
+  h->final_vps.clear();
+  h->inverse_idx.clear(); h->idx_slot.clear(); h->idx_ctrl_voxels.clear();   // VPP.reset(): clear(), buckets kept
+  h->map_index = CellIndex();
+  h->trace.clear();
+  for (int k = 0; k < FCVM_NCOUNTERS; ++k) h->counters[k] = 0;
+  h->unc_calls = 0; h->sample_calls = 0;
+  if (h->device_ok && h->P > 0) return cover_reset(h);
+  return FCVM_OK;
+}
+
+int fcvm_set_map_cloud(fcvm_t* h, const float* xyz, int64_t n) {   // cpp:74-89
+  if (!h || !xyz || n <= 0) return fail(FCVM_EINVAL, "empty map cloud");
+  int rc = ensure_device(h);
+  if (rc) return rc;
+  h->grid.build(h->prm, xyz, n);
+  if (h->grid.voxels() <= 0) return fail(FCVM_EINVAL, "degenerate grid");
+  h->map_index.build(xyz, n, std::max(h->prm.safe_radius, 4 * h->prm.resolution));
+  CU(h->d_bricks.reserve(h->grid.bricks.size()));
+  CU(cudaMemcpy(h->d_bricks.p, h->grid.bricks.data(), h->grid.bricks.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice));
+  h->map_flag = true;
+  return FCVM_OK;
+}
+
+int fcvm_set_model(fcvm_t* h, const float* xyz, int64_t n) {   // cpp:91-108
+  if (!h || !xyz || n <= 0) return fail(FCVM_EINVAL, "[ViewpointManager] Input model is empty!!");
+  int rc = ensure_device(h);
+  if (rc) return rc;
+  h->model.assign(xyz, xyz + 3 * n);
+  const bool grown = n != h->P;
+  h->P = n;
+  h->W = ((n + 31) / 32 + 3) / 4 * 4;
+  // one extra tile of slack so the TMA bulk copy of the last tile never needs a tail case
+  std::vector<float4> pts((size_t)n);
+  for (int64_t i = 0; i < n; ++i) pts[(size_t)i] = make_float4(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], 0.f);
+  CU(h->d_points.reserve((size_t)n));
+  CU(cudaMemcpy(h->d_points.p, pts.data(), (size_t)n * sizeof(float4), cudaMemcpyHostToDevice));
+  if (grown || !h->model_flag) {   // MCI resize (keeps values when the size is unchanged, like vector::resize)
+    rc = cover_reset(h);
+    if (rc) return rc;
+  }
+  h->model_flag = true;
+  return FCVM_OK;
+}
+
+int fcvm_set_normals(fcvm_t* h, const double* pt, const double* nrm, int64_t n) {   // cpp:110-120
+  if (!h || !pt || !nrm || n <= 0) return fail(FCVM_EINVAL, "[ViewpointManager] Input normal Fail!! Input normal is empty!!!");
+  h->pt_normal_pairs.clear();
+  for (int64_t i = 0; i < n; ++i)
+    h->pt_normal_pairs.insert(std::make_pair(D3{pt[3 * i], pt[3 * i + 1], pt[3 * i + 2]}, D3{nrm[3 * i], nrm[3 * i + 1], nrm[3 * i + 2]}));
+  h->normal_flag = true;
+  return FCVM_OK;
+}
+
+int fcvm_set_init_viewpoints(fcvm_t* h, const float* pos_dir, int64_t n) {   // cpp:122-141
+  if (!h || !pos_dir || n <= 0) return fail(FCVM_EINVAL, "[ViewpointManager] Input viewpoints Fail!! Input viewpoint is empty!!!");
+  std::vector<PtNormal> v((size_t)n);
+  for (int64_t i = 0; i < n; ++i)
+    v[(size_t)i] = PtNormal{pos_dir[6 * i], pos_dir[6 * i + 1], pos_dir[6 * i + 2], pos_dir[6 * i + 3], pos_dir[6 * i + 4], pos_dir[6 * i + 5]};
+  return set_init_viewpoints_impl(h, v);
+}
+
+int fcvm_update(fcvm_t* h) {   // cpp:143-330
+  if (!h) return fail(FCVM_EINVAL, "null handle");
+  return update_impl(h);
+}
+
+int64_t fcvm_get_viewpoints(fcvm_t* h, int32_t* vp_id, double* pose5, int32_t* vox_count, int64_t cap) {
+  if (!h) return fail(FCVM_EINVAL, "null handle");
+  const int64_t n = (int64_t)h->final_vps.size();
+  for (int64_t i = 0; i < n && i < cap; ++i) {
+    if (vp_id) vp_id[i] = h->final_vps[(size_t)i].vp_id;
+    if (pose5) for (int k = 0; k < 5; ++k) pose5[5 * i + k] = h->final_vps[(size_t)i].pose.v[k];
+    if (vox_count) vox_count[i] = h->final_vps[(size_t)i].vox_count;
+  }
+  return n;
+}
+
+int64_t fcvm_get_uncovered(fcvm_t* h, float* xyz, int64_t cap) {   // cpp:1138-1144
+  if (!h) return fail(FCVM_EINVAL, "null handle");
+  if (!h->device_ok || h->P == 0) return 0;
+  std::vector<int> cid((size_t)h->P);
+  if (cudaMemcpy(cid.data(), h->d_contrib_id.p, (size_t)h->P * sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess)
+    return fail(FCVM_ECUDA, "download of contrib_id failed");
+  int64_t n = 0;
+  for (int64_t i = 0; i < h->P; ++i)
+    if (cid[(size_t)i] < 0) {
+      if (xyz && n < cap) { xyz[3 * n] = h->model[3 * (size_t)i]; xyz[3 * n + 1] = h->model[3 * (size_t)i + 1]; xyz[3 * n + 2] = h->model[3 * (size_t)i + 2]; }
+      ++n;
+    }
+  return n;
+}
+
+int64_t fcvm_get_vps_pose(fcvm_t* h, double* pose5, int64_t cap_rows) {
+  if (!h) return fail(FCVM_EINVAL, "null handle");
+  for (int64_t i = 0; i < (int64_t)h->vps_pose.size() && i < cap_rows; ++i)
+    for (int k = 0; k < 5; ++k) pose5[5 * i + k] = h->vps_pose[(size_t)i].v[k];
+  return (int64_t)h->vps_pose.size();
+}
+int64_t fcvm_get_vps_voxcount(fcvm_t* h, int32_t* out, int64_t cap) {
+  if (!h) return fail(FCVM_EINVAL, "null handle");
+  if (h->device_ok) { int rc = voxcount_download(h, h->vps_voxcount); if (rc) return rc; }
+  for (int64_t i = 0; i < (int64_t)h->vps_voxcount.size() && i < cap; ++i) out[i] = h->vps_voxcount[(size_t)i];
+  return (int64_t)h->vps_voxcount.size();
+}
+int64_t fcvm_get_vps_contri(fcvm_t* h, int32_t* out, int64_t cap) {
+  if (!h) return fail(FCVM_EINVAL, "null handle");
+  for (int64_t i = 0; i < (int64_t)h->vps_contri.size() && i < cap; ++i) out[i] = h->vps_contri[(size_t)i];
+  return (int64_t)h->vps_contri.size();
+}
+int64_t fcvm_get_cover_state(fcvm_t* h, uint8_t* covered, int32_t* cover_contrib, int32_t* contrib_id, int64_t cap) {
+  if (!h) return fail(FCVM_EINVAL, "null handle");
+  if (!h->device_ok || h->P == 0 || cap <= 0) return h->P;
+  std::vector<int> cc((size_t)h->P), ci((size_t)h->P);
+  if (cudaMemcpy(cc.data(), h->d_cover_contrib.p, (size_t)h->P * sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess ||
+      cudaMemcpy(ci.data(), h->d_contrib_id.p, (size_t)h->P * sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess)
+    return fail(FCVM_ECUDA, "download of cover state failed");
+  for (int64_t i = 0; i < h->P && i < cap; ++i) {
+    if (covered) covered[i] = ci[(size_t)i] >= 0 ? 1 : 0;
+    if (cover_contrib) cover_contrib[i] = cc[(size_t)i];
+    if (contrib_id) contrib_id[i] = ci[(size_t)i];
+  }
+  return h->P;
+}
+
+int fcvm_get_grid(fcvm_t* h, double* origin3, int32_t* voxel_num3, uint8_t* bits, int64_t cap_bytes) {
+  if (!h || !h->grid.ready) return fail(FCVM_ENOTREADY, "no map");
+  for (int c = 0; c < 3; ++c) { if (origin3) origin3[c] = h->grid.origin[c]; if (voxel_num3) voxel_num3[c] = h->grid.dims[c]; }
+  if (bits) {
+    if (cap_bytes < (h->grid.voxels() + 7) / 8) return fail(FCVM_ECAP, "grid buffer too small");
+    h->grid.export_xmajor(bits);
+  }
+  return FCVM_OK;
+}
+
+int fcvm_trace_enable(fcvm_t* h, int32_t on) { if (!h) return FCVM_EINVAL; h->trace_on = on != 0; if (!on) h->trace.clear(); return FCVM_OK; }
+int64_t fcvm_trace_count(fcvm_t* h) { return h ? (int64_t)h->trace.size() : 0; }
+int64_t fcvm_trace_words(fcvm_t* h) { return h ? h->W : 0; }
+int fcvm_trace_get(fcvm_t* h, int64_t i, int32_t* stage, int32_t* vp_id, double* pose5, uint32_t* row_words) {
+  if (!h || i < 0 || i >= (int64_t)h->trace.size()) return fail(FCVM_EINVAL, "trace index out of range");
+  const TraceEv& e = h->trace[(size_t)i];
+  if (stage) *stage = e.stage;
+  if (vp_id) *vp_id = e.vp_id;
+  if (pose5) for (int k = 0; k < 5; ++k) pose5[k] = e.pose.v[k];
+  if (row_words) std::memcpy(row_words, e.row.data(), e.row.size() * sizeof(uint32_t));
+  return FCVM_OK;
+}
+int fcvm_get_counters(fcvm_t* h, int64_t* out8) {
+  if (!h || !out8) return fail(FCVM_EINVAL, "null");
+  for (int k = 0; k < FCVM_NCOUNTERS; ++k) out8[k] = h->counters[k];
+  return FCVM_OK;
+}
+
+// ---------------------------------------------------------------- evaluator level
+int fcvm_evaluate(fcvm_t* h, int32_t stage, const double* pose5, int64_t n, const uint32_t* restrict_rows, int32_t* count, uint32_t* rows) {
+  if (!h || !pose5 || n <= 0 || stage < 1 || stage > 4) return fail(FCVM_EINVAL, "bad arguments");
+  if (!h->map_flag || !h->model_flag) return fail(FCVM_ENOTREADY, "evaluate needs the map and the model");
+  int rc = ensure_device(h);
+  if (rc) return rc;
+  const int64_t W = h->W;
+  for (int64_t c0 = 0; c0 < n; c0 += chunk_rows(h, n)) {
+    const int64_t cn = std::min(chunk_rows(h, n), n - c0);
+    CU(h->h_recs.reserve((size_t)cn));
+    parallel_for(cn, h->threads, [&](int64_t i) {
+      const double* p = pose5 + 5 * (c0 + i);
+      h->cam.fill(h->h_recs.p[i], p[0], p[1], p[2], p[3], p[4]);
+    });
+    rc = eval_batch(h, stage, h->h_recs.p, cn, restrict_rows ? restrict_rows + c0 * W : nullptr, rows ? rows + c0 * W : nullptr,
+                    count ? count + c0 : nullptr, h->d_rows1);
+    if (rc) return rc;
+  }
+  return FCVM_OK;
+}
+
+int fcvm_stage_poses(fcvm_t* h, const double* pose5, int64_t n) {
+  if (!h || !pose5 || n <= 0) return fail(FCVM_EINVAL, "bad arguments");
+  if (!h->map_flag || !h->model_flag) return fail(FCVM_ENOTREADY, "needs the map and the model");
+  int rc = ensure_device(h);
+  if (rc) return rc;
+  CU(h->h_recs.reserve((size_t)n));
+  parallel_for(n, h->threads, [&](int64_t i) { h->cam.fill(h->h_recs.p[i], pose5[5 * i], pose5[5 * i + 1], pose5[5 * i + 2], pose5[5 * i + 3], pose5[5 * i + 4]); });
+  CU(h->d_recs.reserve((size_t)n));
+  CU(h->d_rows1.reserve((size_t)n * h->W));
+  CU(h->d_count.reserve((size_t)n));
+  CU(cudaMemcpyAsync(h->d_recs.p, h->h_recs.p, (size_t)n * sizeof(VpRec), cudaMemcpyHostToDevice, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  h->resident_n = n;
+  return FCVM_OK;
+}
+
+int fcvm_evaluate_resident(fcvm_t* h, int32_t stage, void* stream, int32_t sync, int64_t* rays_out) {
+  if (!h || stage < 1 || stage > 4 || stage == FCVM_STAGE_E2) return fail(FCVM_EINVAL, "bad stage (E2 needs restrict rows: use fcvm_evaluate)");
+  if (h->resident_n <= 0) return fail(FCVM_ENOTREADY, "no resident batch: call fcvm_stage_poses first");
+  cudaStream_t s = stream ? (cudaStream_t)stream : h->stream;
+  CU(cudaEventRecord(h->ev0, s));
+  int rc = launch_stage(h, stage, h->d_recs.p, h->resident_n, h->d_rows1.p, nullptr, s, sync != 0);
+  if (rc) return rc;
+  CU(launch_popc_rows(h->d_rows1.p, h->resident_n, h->W, h->d_count.p, s));
+  h->counters[5] += 1;
+  CU(cudaEventRecord(h->ev1, s));
+  if (sync) {
+    CU(cudaStreamSynchronize(s));
+    const int64_t rays_before = h->counters[1];
+    if (s != h->stream) CU(cudaStreamSynchronize(h->stream));
+    rc = fetch_counters(h);
+    if (rc) return rc;
+    if (rays_out) *rays_out = h->counters[1] - rays_before;
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    h->last_kernel_ms = ms;
+  }
+  return FCVM_OK;
+}
+
+int fcvm_resident_buffers(fcvm_t* h, void** rows_dev, void** count_dev, int64_t* n, int64_t* words) {
+  if (!h) return fail(FCVM_EINVAL, "null handle");
+  if (rows_dev) *rows_dev = h->d_rows1.p;
+  if (count_dev) *count_dev = h->d_count.p;
+  if (n) *n = h->resident_n;
+  if (words) *words = h->W;
+  return FCVM_OK;
+}
+
+int fcvm_own_resident(fcvm_t* h, const int32_t* vp_ids, const int32_t* order, int64_t n) {
+  if (!h || !vp_ids || n <= 0 || n > h->resident_n) return fail(FCVM_EINVAL, "bad arguments");
+  std::vector<int> cnt((size_t)n), ids(vp_ids, vp_ids + n), ord((size_t)n);
+  CU(cudaMemcpy(cnt.data(), h->d_count.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost));
+  int max_id = 0;
+  for (int64_t i = 0; i < n; ++i) { ord[(size_t)i] = order ? order[i] : (int)i; max_id = std::max(max_id, ids[(size_t)i]); }
+  int rc = voxcount_resize(h, std::max(h->voxcount_n, (size_t)max_id + 1));
+  if (rc) return rc;
+  if (h->vps_contri.size() < (size_t)max_id + 1) h->vps_contri.resize((size_t)max_id + 1, 0);
+  return own_sweep(h, h->d_rows1, ord, ids, cnt.data());
+}
+
+double fcvm_last_kernel_ms(fcvm_t* h) { return h ? h->last_kernel_ms : 0.0; }
+
+int fcvm_set_shard(fcvm_t* h, int32_t rank, int32_t world, fcvm_allgather_fn fn, void* user) {
+  if (!h || world < 1 || rank < 0 || rank >= world) return fail(FCVM_EINVAL, "bad shard");
+  if (world > 1 && !fn) return fail(FCVM_EINVAL, "world > 1 needs an all-gather callback");
+  h->rank = rank; h->world = world; h->gather = fn; h->gather_user = user;
+  return FCVM_OK;
+}
+
+// ---------------------------------------------------------------- host-only helpers
+int fcvm_host_fov_normals(const fcvm_params* p, double pitch, double yaw, double* out12) {
+  if (!p || !out12) return fail(FCVM_EINVAL, "null");
+  Camera c;
+  c.init(*p);
+  double n[4][3];
+  c.world_normals(pitch, yaw, n);
+  for (int q = 0; q < 4; ++q) for (int i = 0; i < 3; ++i) out12[3 * q + i] = n[q][i];
+  return FCVM_OK;
+}
+
+int fcvm_host_build_grid(const fcvm_params* p, const float* xyz, int64_t n, double* origin3, int32_t* voxel_num3, uint8_t* bits, int64_t cap_bytes) {
+  if (!p || !xyz || n <= 0) return fail(FCVM_EINVAL, "empty cloud");
+  HostGrid g;
+  g.build(*p, xyz, n);
+  for (int c = 0; c < 3; ++c) { if (origin3) origin3[c] = g.origin[c]; if (voxel_num3) voxel_num3[c] = g.dims[c]; }
+  if (bits) {
+    if (cap_bytes < (g.voxels() + 7) / 8) return fail(FCVM_ECAP, "grid buffer too small");
+    g.export_xmajor(bits);
+  }
+  return FCVM_OK;
+}
+
+int fcvm_shard_range(int64_t n, int32_t rank, int32_t world, int64_t* lo, int64_t* hi) {
+  if (world < 1 || rank < 0 || rank >= world || n < 0) return fail(FCVM_EINVAL, "bad shard");
+  const int64_t per = (n + world - 1) / world;
+  if (lo) *lo = std::min(n, per * rank);
+  if (hi) *hi = std::min(n, per * (rank + 1));
+  return FCVM_OK;
+}
+
+}  // extern "C"

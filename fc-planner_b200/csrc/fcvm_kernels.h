@@ -1,0 +1,37 @@
+// fcvm_kernels.h — host-visible launch interface of the sm_100a kernels (fcvm_kernels.cu).
+#pragma once
+
+#include <cstddef>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "fcvm_device.cuh"
+
+namespace fcvm {
+
+#define EVAL_WARPS 8
+#define EVAL_MAX_TILE 2048
+
+struct EvalArgs {
+  GridDesc grid;
+  FovConst fov;
+  const float4* points;            // model cloud, float4 (x, y, z, 0) like pcl::PointXYZ; P entries
+  long long P;
+  const VpRec* recs;               // V viewpoint records
+  long long V;
+  uint32_t* rows;                  // V x words bitset rows, zeroed by the caller
+  const uint32_t* restrict_rows;   // E2 only: V x words rows of the E1 pass
+  long long words;                 // row stride in 32-bit words (multiple of 4)
+  int tile_pts;                    // points per CTA tile (multiple of 32, <= EVAL_MAX_TILE)
+  int vp_per_cta;                  // viewpoints per CTA (grid.y = ceil(V / vp_per_cta))
+  unsigned long long* counters;    // [0] pair tests [1] rays [2] lookups [3] walk lookups [4] cap trips; may be null
+};
+
+size_t eval_smem_bytes(int tile_pts);
+cudaError_t launch_eval(int stage, const EvalArgs& a, cudaStream_t s);
+cudaError_t launch_popc_rows(const uint32_t* rows, long long n, long long words, int* count, cudaStream_t s);
+// sched[t] = {row index, viewpoint id, contribute_voxel_num, 0} in processing order, rows with 0 omitted
+cudaError_t launch_own_sweep(const uint32_t* rows, long long words, const int4* sched, int nsched, int last_vps_num, long long P,
+                             int* cover_contrib, int* contrib_id, int* voxcount, cudaStream_t s);
+
+}  // namespace fcvm

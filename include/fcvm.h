@@ -77,7 +77,7 @@ typedef struct fcvm_params {
   int32_t host_threads;        /* threads for the per-viewpoint host reductions; 0 = auto    */
 } fcvm_params;
 
-typedef struct fcvm fcvm_t;
+typedef struct fcvm_handle fcvm_t;
 
 /* ---------------------------------------------------------------- manager level ---- */
 

@@ -583,7 +583,10 @@ class ViewpointManager {
     TS = TaskState();
     VPI = ViewpointsInfo();
     MCI = ModelCloudInfo();
-    VPP = ViewpointsPrune();
+    // VPP.reset() clear()s the maps (viewpoint_manager.h:169-177): their bucket arrays, hence the
+    // iteration order of later insertions, survive a reset
+    VPP.inverse_idx_.clear(); VPP.idx_viewpoints_.clear(); VPP.idx_ctrl_voxels_.clear();
+    VPP.idx_live_state_.clear(); VPP.idx_query_state_.clear(); VPP.final_vps_.clear();
     map_cloud_kdtree_ = FloatCloudSearch();
     unc_calls_ = 0; sample_calls_ = 0;
   }

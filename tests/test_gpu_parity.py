@@ -1,0 +1,157 @@
+"""GPU parity: the CUDA path through the C ABI against the CPU oracle on the same seeded inputs.
+
+Bar: bit-exact.  Masks, counts, ownership state and the selected viewpoint set are integers and
+must be identical; poses are FP64 produced by the same libm on the host from identical masks, so
+they must be identical bit for bit as well (tolerance = 0).
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk(small_plant, oracle_mod, **over):
+    from fc_planner_b200.manager import ViewpointManager
+    prm = small_plant["params"].copy(**over)
+    vm = ViewpointManager(prm)
+    orc = oracle_mod.Oracle(prm)
+    for m in (vm, orc):
+        m.setMapPointCloud(small_plant["points"])
+        m.setModel(small_plant["points"])
+        m.setNormals(small_plant["points"].astype(np.float64), small_plant["normals"])
+    return vm, orc, prm
+
+
+def _perturbed_poses(small_plant, n=300, seed=3):
+    from fc_planner_b200 import scenes
+    poses = scenes.poses_from_viewpoints(small_plant["viewpoints"][:n])
+    rng = np.random.default_rng(seed)
+    poses[:, :3] += rng.normal(0, 0.3, (len(poses), 3))        # arbitrary doubles, not float-rounded
+    poses[:, 3:] += rng.normal(0, 0.2, (len(poses), 2))
+    return poses
+
+
+@pytest.mark.parametrize("stage", [1, 3, 4])
+def test_evaluator_masks_bit_exact(small_plant, oracle_mod, stage):
+    vm, orc, _ = _mk(small_plant, oracle_mod)
+    poses = _perturbed_poses(small_plant)
+    c0 = vm.counters()
+    cnt, rows = vm.evaluate(stage, poses)
+    c1 = vm.counters() - c0
+    ocnt, orows, octr = orc.evaluate(stage, poses)
+    W = orows.shape[1]
+    assert np.array_equal(rows[:, :W], orows)
+    assert not rows[:, W:].any()
+    assert np.array_equal(cnt, ocnt)
+    assert cnt.sum() > 1000                       # the case is not vacuous
+    # algorithmic counters: pair tests, rays, voxel lookups, walk lookups identical; no cap trips
+    assert c1[0] == octr[0] and c1[1] == octr[1] and c1[2] == octr[2] and c1[3] == octr[3]
+    assert c1[4] == 0 and octr[4] == 0
+
+
+def test_e2_restricted_to_e1_rows(small_plant, oracle_mod):
+    vm, orc, _ = _mk(small_plant, oracle_mod)
+    poses = _perturbed_poses(small_plant)
+    _, rows1 = vm.evaluate(1, poses)
+    poses2 = poses.copy()
+    poses2[:, 3:] += 0.05                          # E2 runs with the averaged pose, i.e. a different FOV
+    c0 = vm.counters()
+    cnt2, rows2 = vm.evaluate(2, poses2, restrict_rows=rows1)
+    c1 = vm.counters() - c0
+    W = (orc.P + 31) // 32
+    ocnt2, orows2, octr = orc.evaluate(2, poses2, restrict_rows=rows1[:, :W])
+    assert np.array_equal(rows2[:, :W], orows2)
+    assert np.array_equal(cnt2, ocnt2)
+    assert (rows2 & ~rows1).sum() == 0            # E2 is a subset of E1
+    assert np.array_equal(c1[:5], octr[:5])
+
+
+def _compare_state(vm, orc):
+    assert np.array_equal(vm.vps_pose(), orc.vps_pose())                    # FP64, bit-exact
+    ov = orc.vps_voxcount(); gv = vm.vps_voxcount()
+    n = min(len(ov), len(gv))
+    assert np.array_equal(gv[:n], ov[:n]) and not gv[n:].any() and not ov[n:].any()
+    assert np.array_equal(vm.vps_contri(), orc.vps_contri())
+    gc, oc = vm.cover_state(), orc.cover_state()
+    assert np.array_equal(gc[0], oc[0])
+    assert np.array_equal(gc[1], oc[1])
+    assert np.array_equal(gc[2], oc[2])
+
+
+def _trace_dict(tr, W):
+    d = {}
+    for st, vid, pose, row in tr:
+        d.setdefault((st, vid), []).append((pose.copy(), row[:W].copy()))
+    return d
+
+
+@pytest.mark.parametrize("pose_update", [1, 0])
+def test_set_init_viewpoints(small_plant, oracle_mod, pose_update):
+    vm, orc, _ = _mk(small_plant, oracle_mod, pose_update=pose_update)
+    vm.trace_enable(); orc.trace_enable()
+    vm.setInitViewpoints(small_plant["viewpoints"]); orc.setInitViewpoints(small_plant["viewpoints"])
+    _compare_state(vm, orc)
+    W = (orc.P + 31) // 32
+    gt, ot = _trace_dict(vm.trace(), W), _trace_dict(orc.trace(), W)
+    assert gt.keys() == ot.keys()
+    for k in ot:
+        assert len(gt[k]) == len(ot[k])
+        for (gp, gr), (op, orow) in zip(gt[k], ot[k]):
+            assert np.array_equal(gp, op), k
+            assert np.array_equal(gr, orow), k
+
+
+@pytest.mark.parametrize("init", ["explicit", "from_normals"])
+def test_update_viewpoints_full_sequence(small_plant, oracle_mod, init):
+    """reset -> setMapPointCloud -> setModel -> setNormals -> [setInitViewpoints] -> updateViewpoints
+    -> getUpdatedViewpoints -> getUncoveredModelCloud (hcplanner.cpp:709-716)."""
+    vm, orc, _ = _mk(small_plant, oracle_mod)
+    vm.trace_enable(); orc.trace_enable()
+    if init == "explicit":
+        vm.setInitViewpoints(small_plant["viewpoints"]); orc.setInitViewpoints(small_plant["viewpoints"])
+    assert vm.updateViewpoints() == 0 and orc.updateViewpoints() == 0
+    _compare_state(vm, orc)
+    gi, gp, gx = vm.final_arrays()
+    oi, op, ox = orc.getUpdatedViewpoints()
+    assert len(oi) > 5
+    assert np.array_equal(gi, oi)            # the selected viewpoint set, in the reference's order
+    assert np.array_equal(gp, op)            # poses bit-exact
+    assert np.array_equal(gx, ox)
+    assert np.array_equal(vm.getUncoveredModelCloud(), orc.getUncoveredModelCloud())
+    W = (orc.P + 31) // 32
+    gt, ot = _trace_dict(vm.trace(), W), _trace_dict(orc.trace(), W)
+    assert gt.keys() == ot.keys()
+    bad = 0
+    for k in ot:
+        assert len(gt[k]) == len(ot[k]), k
+        for (gpz, gr), (opz, orow) in zip(gt[k], ot[k]):
+            bad += int(not np.array_equal(gr, orow)) + int(not np.array_equal(gpz, opz))
+    assert bad == 0
+    gc, oc = vm.counters(), orc.counters()
+    assert gc[4] == 0 and oc[4] == 0          # no marcher cap trips on either side
+    assert gc[1] == oc[1] and gc[2] == oc[2]  # same rays, same voxel lookups
+    assert gc[7] == oc[7]                      # same safety_check lookups
+
+
+def test_second_update_after_reset_matches(small_plant, oracle_mod):
+    """reset() keeps the prune maps' bucket arrays (clear(), not reconstruction): a second run on the
+    same handle must still match the oracle handle that went through the same history."""
+    vm, orc, _ = _mk(small_plant, oracle_mod)
+    for m in (vm, orc):
+        m.updateViewpoints()
+        m.reset()
+        m.setMapPointCloud(small_plant["points"]); m.setModel(small_plant["points"])
+        m.setNormals(small_plant["points"].astype(np.float64), small_plant["normals"])
+        m.setInitViewpoints(small_plant["viewpoints"][:150])
+        m.updateViewpoints()
+    gi, gp, gx = vm.final_arrays()
+    oi, op, ox = orc.getUpdatedViewpoints()
+    assert np.array_equal(gi, oi) and np.array_equal(gp, op) and np.array_equal(gx, ox)
+
+
+def test_error_convention(small_plant):
+    from fc_planner_b200.manager import ViewpointManager
+    vm = ViewpointManager(small_plant["params"])
+    assert vm.setModel(np.zeros((0, 3), np.float32)) == -1          # "Input model is empty!!" -> log + return
+    assert vm.updateViewpoints() == -2                               # TaskState not ready
+    assert len(vm.getUpdatedViewpoints()) == 0
