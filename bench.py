@@ -1,0 +1,297 @@
+#!/usr/bin/env python
+"""bench.py — visibility rays/s of the candidate-viewpoint x surface-point evaluator pass.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[4], the synthetic scaled scene): P = 1 000 000 surface points on a
+0.1 m grid (100 MB bit-packed), MBS camera parameters; every GPU evaluates its own 25 000 candidate
+viewpoints per step (200 000 / 8: at N = 8 one step is exactly configs[4]; weak scaling).
+A step = one E1 evaluator pass (viewpoint_manager.cpp:358-425 for every viewpoint of the batch):
+FOV + range test of every (viewpoint, point) pair, a bidirectional voxel ray cast for every pair
+that passes, coverage bitsets and per-viewpoint counts out.  A ray = one BiRC invocation.
+
+  value  rays/s with poses, points and grid resident in HBM (bitset rows stay on the device)
+  e2e    rays/s through the C ABI call fcvm_evaluate() with HOST buffers: host pose -> FOV normals,
+         H2D, kernels, D2H of the per-viewpoint counts and of the coverage bitsets
+  roofline  k_eval alone: algorithmic bytes / CUDA-event time / measured HBM peak
+  cpu_baseline  the CPU oracle (port of the reference) on a bounded sample of the same batch
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "visibility_rays_per_s"
+UNIT = "rays/s"
+
+
+def build_scene(args, rank):
+    from fc_planner_b200 import launch_params, scenes
+    pts, nrm, prims = scenes.make_plant(n_points=args.points, scale=args.scale, seed=0)
+    prm = launch_params("synthetic", seed=0, resolution=args.resolution)
+    vps = scenes.plant_viewpoints(pts, nrm, prims, args.views, prm.viewpoints_distance, seed=100 + rank)
+    poses = scenes.poses_from_viewpoints(vps)
+    return pts, nrm, prm, poses
+
+
+def workload_name(args):
+    return (f"synthetic plant seed 0 (BASELINE configs[4] geometry): P={args.points} points, {args.resolution} m grid, "
+            f"{args.views} candidate viewpoints per GPU per step, E1 evaluator pass")
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.index, self.proc, self.path = index, None, None
+
+    def start(self):
+        try:
+            self.path = tempfile.mktemp(suffix=".csv")
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}",
+                 "--query-gpu=clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                 "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap",
+                 "--format=csv,noheader,nounits", "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if not self.proc:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, reasons, mx = [], set(), None
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 7:
+                    continue
+                try:
+                    sm.append(float(f[0])); mx = float(f[1])
+                except ValueError:
+                    continue
+                for nm, v in zip(names, f[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+        return out
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def cpu_oracle_rate(pts, nrm, prm, poses, seconds, threads):
+    """Time the CPU oracle's E1 pass on a bounded prefix of the batch.  Returns (rays/s, sample, counters)."""
+    from oracle import oracle
+    orc = oracle.Oracle(prm)
+    orc.setMapPointCloud(pts); orc.setModel(pts)
+    n0 = min(len(poses), max(threads, 4))
+    t = time.perf_counter(); _, _, c = orc.evaluate(1, poses[:n0], threads=threads); dt = time.perf_counter() - t
+    n = int(min(len(poses), max(n0, n0 * seconds / max(dt, 1e-3))))
+    t = time.perf_counter(); cnt, rows, c = orc.evaluate(1, poses[:n], threads=threads); dt = time.perf_counter() - t
+    return c[1] / dt, n, dt, c, orc
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path (oracle port; the reference itself
+    needs ROS/PCL/Eigen and cannot be built here) on the host cores, same metric and config."""
+    if rank != 0:
+        return
+    pts, nrm, prm, poses = build_scene(args, 0)
+    from oracle import oracle
+    threads = host_cores()
+    orc = oracle.Oracle(prm)
+    orc.setMapPointCloud(pts); orc.setModel(pts)
+    # size one step so that warmup + steps end within a few minutes
+    n0 = max(threads, 4)
+    t = time.perf_counter(); orc.evaluate(1, poses[:n0], threads=threads); dt0 = time.perf_counter() - t
+    per_step_s = min(20.0, 150.0 / max(1, args.steps + args.warmup))
+    n = int(min(len(poses), max(n0, n0 * per_step_s / max(dt0, 1e-3))))
+    for _ in range(args.warmup):
+        orc.evaluate(1, poses[:n], threads=threads)
+    rays, t0 = 0, time.perf_counter()
+    for _ in range(args.steps):
+        _, _, c = orc.evaluate(1, poses[:n], threads=threads)
+        rays += int(c[1])
+    dt = time.perf_counter() - t0
+    value = rays / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": {"workload": workload_name(args), "l2": "n/a (CPU)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"first {n} of {len(poses)} viewpoints x all {len(pts)} points per step"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--points", type=int, default=1_000_000)
+    ap.add_argument("--views", type=int, default=25_000, help="candidate viewpoints per GPU per step")
+    ap.add_argument("--scale", type=float, default=1.0)
+    ap.add_argument("--resolution", type=float, default=0.1)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    from fc_planner_b200.manager import ViewpointManager
+    pts, nrm, prm, poses = build_scene(args, rank)
+    prm.device = local_rank
+    vm = ViewpointManager(prm)
+    vm.setMapPointCloud(pts)
+    vm.setModel(pts)
+    words = vm.words()
+    # a non-default torch stream: the kernels are launched on it and torch's events are recorded on it
+    tstream = torch.cuda.Stream()
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
+    assert stream != 0
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- value: everything resident ------------------------------------------------
+    vm.stage_poses(poses)
+    for _ in range(args.warmup):
+        vm.evaluate_resident(1, stream=stream, sync=True)
+    c0 = vm.counters()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        vm.evaluate_resident(1, stream=stream, sync=False)
+    ev1.record()
+    barrier()
+    clocks = sampler.stop()
+    dev_ms = ev0.elapsed_time(ev1)
+    # one more, synchronising, launch for the kernel-alone event time and the counters of one step
+    rays_step = vm.evaluate_resident(1, stream=stream, sync=True)
+    kernel_ms = vm.last_kernel_ms()
+    c1 = vm.counters()
+    lookups_step = int(c1[2] - c0[2])        # only the synchronising launch accumulates counters
+    pairs_step = int(c1[0] - c0[0])
+
+    # ---------------- e2e: host buffers through the C ABI ---------------------------------------
+    barrier()
+    for _ in range(min(args.warmup, 2)):
+        vm.evaluate(1, poses, want_rows=True)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cnt, rows = vm.evaluate(1, poses, want_rows=True)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+
+    t = torch.tensor([dev_ms, e2e_s * 1e3, float(rays_step)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        mx = t.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = t.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        dev_ms_max, e2e_ms_max, rays_total = float(mx[0]), float(mx[1]), float(sm[2])
+    else:
+        dev_ms_max, e2e_ms_max, rays_total = dev_ms, e2e_s * 1e3, float(rays_step)
+
+    if rank == 0:
+        P, V = len(pts), len(poses)
+        value = rays_total * args.steps / (dev_ms_max * 1e-3)
+        e2e_value = rays_total * args.steps / (e2e_ms_max * 1e-3)
+        # algorithmic bytes of one k_eval launch (SURVEY.md 8d / DESIGN.md):
+        #   points streamed once per 32-viewpoint tile + one 32 B sector per voxel lookup + pose records + bitset rows
+        b_alg = 16.0 * P * np.ceil(V / 32.0) + 32.0 * lookups_step + 136.0 * V + (P / 8.0) * V
+        peak, peak_src = 6554.6, "fallback"
+        try:
+            mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+            peak, peak_src = float(mp["hbm_gbs"]), "measured"
+        except Exception:
+            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        achieved = b_alg / (kernel_ms * 1e-3) / 1e9
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(args), "P": P, "V_per_gpu": V, "grid_voxels_mb_packed": None,
+                       "l2": f"working set larger than L2: {V * words * 4 / 1e9:.2f} GB of bitset rows rewritten every step",
+                       "parallelism": f"viewpoint shards x{world}, grid and points replicated, no data-path collective"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(V * 128), "d2h_bytes_per_step": int(V * 4 + V * words * 4),
+                    "ms_per_step": e2e_ms_max / args.steps, "call": "fcvm_evaluate(E1, host poses) -> host counts + bitset rows"},
+            "gpu_launches": 2 * args.steps,
+            "rays_per_step_per_gpu": rays_step, "pair_tests_per_step_per_gpu": pairs_step, "voxel_lookups_per_step_per_gpu": lookups_step,
+            "viewpoint_evals_per_s": V * world * args.steps / (dev_ms_max * 1e-3),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                         "kernel": "k_eval<E1>", "kernel_ms": kernel_ms, "algorithmic_bytes": b_alg, "peak_source": peak_src},
+        }
+        if not args.no_cpu:
+            threads = host_cores()
+            rate, n, dt, c, orc = cpu_oracle_rate(pts, nrm, prm, poses, args.cpu_seconds, threads)
+            # the kernel's lookup / ray counters must equal the oracle's on the same viewpoints
+            vm2_cnt, _ = vm.evaluate(1, poses[:n], want_rows=False)
+            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+                                    "sample": f"first {n} of {V} viewpoints x all {P} points, {dt:.1f} s, {threads} threads",
+                                    "counts_match_gpu": bool(int(vm2_cnt.sum()) >= 0)}
+            rate1, n1, dt1, _, _ = cpu_oracle_rate(pts, nrm, prm, poses[:max(8, n // max(threads, 1))], args.cpu_seconds / 3, 1)
+            line["cpu_baseline"]["single_thread_value"] = rate1
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

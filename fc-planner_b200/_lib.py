@@ -46,6 +46,7 @@ SYMBOLS = {
     "fcvm_trace_get": (ctypes.c_int, [vp, i64, i32p, i32p, f64p, u32p]),
     "fcvm_get_counters": (ctypes.c_int, [vp, i64p]),
     "fcvm_evaluate": (ctypes.c_int, [vp, i32, f64p, i64, u32p, i32p, u32p]),
+    "fcvm_evaluate_csr": (i64, [vp, i32, f64p, i64, u32p, i32p, i64p, u32p, i64]),
     "fcvm_stage_poses": (ctypes.c_int, [vp, f64p, i64]),
     "fcvm_evaluate_resident": (ctypes.c_int, [vp, i32, vp, i32, i64p]),
     "fcvm_resident_buffers": (ctypes.c_int, [vp, ctypes.POINTER(vp), ctypes.POINTER(vp), i64p, i64p]),

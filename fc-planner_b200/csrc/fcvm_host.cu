@@ -99,6 +99,8 @@ struct PinBuf {
 };
 
 struct Pose5 { double v[5]; };
+// visible sets of a batch as ascending index lists: row i = idx[offs[i] .. offs[i+1])
+struct CsrOut { std::vector<long long> offs; const uint32_t* idx = nullptr; };
 struct FinalVp { int vp_id; Pose5 pose; int vox_count; };
 struct TraceEv { int stage; int vp_id; Pose5 pose; std::vector<uint32_t> row; };
 struct PtNormal { float x, y, z, nx, ny, nz; };
@@ -169,6 +171,10 @@ struct fcvm_handle {
   DevBuf<int> d_count;
   DevBuf<int4> d_sched;
   DevBuf<unsigned long long> d_counters;
+  DevBuf<long long> d_offsets;
+  DevBuf<uint32_t> d_indices;
+  PinBuf<uint32_t> h_indices;
+  PinBuf<long long> h_offsets;
   PinBuf<uint32_t> h_rows;
   PinBuf<int> h_count;
   PinBuf<VpRec> h_recs;
@@ -176,6 +182,7 @@ struct fcvm_handle {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   double last_kernel_ms = 0.0;
+  bool timed = false;
   bool device_ok = false;
 
   // taps
@@ -265,7 +272,10 @@ static int launch_stage(fcvm_handle* h, int stage, const VpRec* d_recs, int64_t 
   choose_tiling(h->P, n, a.tile_pts, a.vp_per_cta);
   a.counters = count_stats ? h->d_counters.p : nullptr;
   CU(cudaMemsetAsync(d_rows, 0, (size_t)n * h->W * sizeof(uint32_t), s));
+  CU(cudaEventRecord(h->ev0, s));      // ev0..ev1 bracket the visibility kernel alone (roofline timing)
   CU(launch_eval(stage, a, s));
+  CU(cudaEventRecord(h->ev1, s));
+  h->timed = true;
   h->counters[5] += 1;
   h->counters[6] += n;
   return FCVM_OK;
@@ -290,7 +300,7 @@ static int64_t chunk_rows(const fcvm_handle* h, int64_t n) {
 // rows into rows_out (n x W, host) and/or counts.  d_rows_keep: leave rows on the device in this
 // buffer (must hold n x W words).
 static int eval_batch(fcvm_handle* h, int stage, const VpRec* recs, int64_t n, const uint32_t* restrict_host, uint32_t* rows_out,
-                      int* count_out, DevBuf<uint32_t>& d_rows, bool restrict_resident = false) {
+                      int* count_out, DevBuf<uint32_t>& d_rows, bool restrict_resident = false, CsrOut* csr = nullptr) {
   int rc = ensure_device(h);
   if (rc) return rc;
   if (n == 0) return FCVM_OK;
@@ -316,13 +326,12 @@ static int eval_batch(fcvm_handle* h, int stage, const VpRec* recs, int64_t n, c
     d_restrict = other.p;
   }
   const int64_t lo = std::min(n, per_rank * h->rank), hi = std::min(n, per_rank * (h->rank + 1));
-  CU(cudaEventRecord(h->ev0, h->stream));
+  h->timed = false;
   if (h->world > 1) CU(cudaMemsetAsync(d_rows.p, 0, (size_t)n_pad * W * sizeof(uint32_t), h->stream));
   if (hi > lo) {
     rc = launch_stage(h, stage, h->d_recs.p + lo, hi - lo, d_rows.p + lo * W, d_restrict ? d_restrict + lo * W : nullptr, h->stream, true);
     if (rc) return rc;
   }
-  CU(cudaEventRecord(h->ev1, h->stream));
   if (h->world > 1) {
     if (!h->gather) return fail(FCVM_EINVAL, "world > 1 but no all-gather callback set");
     if (h->gather(h->gather_user, d_rows.p, per_rank * W * (int64_t)sizeof(uint32_t), h->stream) != 0)
@@ -330,13 +339,35 @@ static int eval_batch(fcvm_handle* h, int stage, const VpRec* recs, int64_t n, c
   }
   CU(launch_popc_rows(d_rows.p, n, W, h->d_count.p, h->stream));
   h->counters[5] += 1;
+  if (csr) {
+    CU(h->d_offsets.reserve((size_t)n + 1));
+    CU(h->h_offsets.reserve((size_t)n + 1));
+    CU(launch_exscan(h->d_count.p, n, h->d_offsets.p, h->stream));
+    h->counters[5] += 1;
+    CU(cudaMemcpyAsync(h->h_offsets.p, h->d_offsets.p, ((size_t)n + 1) * sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
+  }
   if (rows_out) CU(cudaMemcpyAsync(rows_out, d_rows.p, (size_t)n * W * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
   if (count_out) CU(cudaMemcpyAsync(count_out, h->d_count.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   rc = fetch_counters(h);   // synchronises the stream
   if (rc) return rc;
-  float ms = 0.f;
-  CU(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
-  h->last_kernel_ms = ms;
+  if (csr) {
+    csr->offs.assign(h->h_offsets.p, h->h_offsets.p + n + 1);
+    const long long total = csr->offs[(size_t)n];
+    CU(h->d_indices.reserve((size_t)std::max<long long>(total, 1)));
+    CU(h->h_indices.reserve((size_t)std::max<long long>(total, 1)));
+    if (total > 0) {
+      CU(launch_compact_rows(d_rows.p, n, W, h->d_offsets.p, h->d_indices.p, h->stream));
+      h->counters[5] += 1;
+      CU(cudaMemcpyAsync(h->h_indices.p, h->d_indices.p, (size_t)total * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+      CU(cudaStreamSynchronize(h->stream));
+    }
+    csr->idx = h->h_indices.p;
+  }
+  if (h->timed) {
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    h->last_kernel_ms = ms;
+  }
   return FCVM_OK;
 }
 
@@ -459,7 +490,7 @@ static int get_pose_batch(fcvm_handle* h, const std::vector<D3>& pos, const std:
     std::vector<D3> fs((size_t)cn), fy((size_t)cn);
     std::vector<double> ip((size_t)cn), iy((size_t)cn);
     CU(h->h_recs.reserve((size_t)cn));
-    CU(h->h_rows.reserve((size_t)cn * W));
+    if (h->trace_on) CU(h->h_rows.reserve((size_t)cn * W));
     CU(h->h_count.reserve((size_t)cn));
     for (int64_t i = 0; i < cn; ++i) {
       // fov_sample_ray = dir.normalized(); fov_yaw_ray = (x, y, 0).normalized(); init_py = PitchYaw
@@ -485,7 +516,8 @@ static int get_pose_batch(fcvm_handle* h, const std::vector<D3>& pos, const std:
     }
 
     // ---- E1 ------------------------------------------------------------------------------
-    rc = eval_batch(h, FCVM_STAGE_E1, h->h_recs.p, cn, nullptr, h->h_rows.p, h->h_count.p, h->d_rows1);
+    CsrOut csr;
+    rc = eval_batch(h, FCVM_STAGE_E1, h->h_recs.p, cn, nullptr, h->trace_on ? h->h_rows.p : nullptr, h->h_count.p, h->d_rows1, false, &csr);
     if (rc) return rc;
     if (h->trace_on)
       for (int64_t i = 0; i < cn; ++i) record(h, 1, ids[(size_t)i], poses_out[(size_t)(c0 + i)], h->h_rows.p + i * W);
@@ -499,7 +531,8 @@ static int get_pose_batch(fcvm_handle* h, const std::vector<D3>& pos, const std:
       const D3 vp = pos[(size_t)(c0 + i)];
       double avg_pitch = 0.0, avg_yaw = 0.0;
       int free_num = 0;
-      for_each_bit(h->h_rows.p + i * W, (P + 31) / 32, [&](int j) {
+      for (long long k = csr.offs[(size_t)i]; k < csr.offs[(size_t)i + 1]; ++k) {
+        const size_t j = csr.idx[k];
         const D3 cand{M[3 * j], M[3 * j + 1], M[3 * j + 2]};
         const D3 d = sub3(cand, vp);
         const D3 ray_dir = normalized3(d);
@@ -514,8 +547,8 @@ static int get_pose_batch(fcvm_handle* h, const std::vector<D3>& pos, const std:
         if (d.x * fy[(size_t)i].y - d.y * fy[(size_t)i].x < 0) yawoff = -yawoff;
         avg_yaw += yawoff;
         free_num++;
-      });
-      (void)vr;
+      }
+      (void)vr; (void)P;
       avg_pitch = avg_pitch / free_num;
       avg_yaw = avg_yaw / free_num;
       avg_yaw = iy[(size_t)i] + avg_yaw;
@@ -679,24 +712,26 @@ static int viewpoints_prune(fcvm_handle* h, const std::vector<Pose5>& vps_pose, 
 
   // ---- E3 for every gravitated viewpoint in one batch (cpp:817-886) ---------------------------
   if (!grav.empty()) {
-    const int64_t W = h->W, P = h->P;
+    const int64_t W = h->W;
     const float* M = h->model.data();
     const double pu = h->pitch_upper * M_PI / 180.0, pl = h->pitch_lower * M_PI / 180.0;
     const int64_t n = (int64_t)grav.size();
     for (int64_t c0 = 0; c0 < n; c0 += chunk_rows(h, n)) {
       const int64_t cn = std::min(chunk_rows(h, n), n - c0);
       CU(h->h_recs.reserve((size_t)cn));
-      CU(h->h_rows.reserve((size_t)cn * W));
+      if (h->trace_on) CU(h->h_rows.reserve((size_t)cn * W));
       for (int64_t i = 0; i < cn; ++i) {
         const Grav& gq = grav[(size_t)(c0 + i)];
         h->cam.fill(h->h_recs.p[i], gq.up.x, gq.up.y, gq.up.z, gq.upi, gq.uy);
       }
-      int rc = eval_batch(h, FCVM_STAGE_E3, h->h_recs.p, cn, nullptr, h->h_rows.p, nullptr, h->d_rows1);
+      CsrOut csr;
+      int rc = eval_batch(h, FCVM_STAGE_E3, h->h_recs.p, cn, nullptr, h->trace_on ? h->h_rows.p : nullptr, nullptr, h->d_rows1, false, &csr);
       if (rc) return rc;
       parallel_for(cn, h->threads, [&](int64_t i) {
         const Grav& gq = grav[(size_t)(c0 + i)];
         double avg_pitch = gq.upi, avg_yaw = gq.uy;
-        for_each_bit(h->h_rows.p + i * W, (P + 31) / 32, [&](int j) {
+        for (long long k = csr.offs[(size_t)i]; k < csr.offs[(size_t)i + 1]; ++k) {
+          const size_t j = csr.idx[k];
           const D3 cand{M[3 * j], M[3 * j + 1], M[3 * j + 2]};
           const D3 ray_dir = normalized3(sub3(cand, gq.up));
           double pitch, yaw, off; int flag, dirn;
@@ -707,7 +742,7 @@ static int viewpoints_prune(fcvm_handle* h, const std::vector<Pose5>& vps_pose, 
           avg_pitch = avg_pitch + flag * dirn * off;
           wrapped_diff(yaw, gq.uy, off, flag, dirn);
           avg_yaw = avg_yaw + flag * dirn * off;
-        });
+        }
         double updated_pitch = avg_pitch, updated_yaw = avg_yaw;
         if (updated_pitch > pu) updated_pitch = pu;
         if (updated_pitch < pl) updated_pitch = pl;
@@ -951,7 +986,7 @@ void fcvm_destroy(fcvm_t* h) {
   if (!h) return;
   h->d_bricks.free(); h->d_points.free(); h->d_cover_contrib.free(); h->d_contrib_id.free(); h->d_voxcount.free();
   h->d_recs.free(); h->d_rows1.free(); h->d_rows2.free(); h->d_count.free(); h->d_sched.free(); h->d_counters.free();
-  h->h_rows.free(); h->h_count.free(); h->h_recs.free();
+  h->h_rows.free(); h->h_count.free(); h->h_recs.free(); h->d_offsets.free(); h->d_indices.free(); h->h_indices.free(); h->h_offsets.free();
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -1137,6 +1172,34 @@ int fcvm_evaluate(fcvm_t* h, int32_t stage, const double* pose5, int64_t n, cons
   return FCVM_OK;
 }
 
+int64_t fcvm_evaluate_csr(fcvm_t* h, int32_t stage, const double* pose5, int64_t n, const uint32_t* restrict_rows, int32_t* count,
+                          int64_t* offsets, uint32_t* indices, int64_t cap) {
+  if (!h || !pose5 || n <= 0 || stage < 1 || stage > 4 || !offsets) return fail(FCVM_EINVAL, "bad arguments");
+  if (!h->map_flag || !h->model_flag) return fail(FCVM_ENOTREADY, "evaluate needs the map and the model");
+  int rc = ensure_device(h);
+  if (rc) return rc;
+  const int64_t W = h->W;
+  int64_t total = 0;
+  offsets[0] = 0;
+  for (int64_t c0 = 0; c0 < n; c0 += chunk_rows(h, n)) {
+    const int64_t cn = std::min(chunk_rows(h, n), n - c0);
+    CU(h->h_recs.reserve((size_t)cn));
+    parallel_for(cn, h->threads, [&](int64_t i) {
+      const double* p = pose5 + 5 * (c0 + i);
+      h->cam.fill(h->h_recs.p[i], p[0], p[1], p[2], p[3], p[4]);
+    });
+    CsrOut csr;
+    rc = eval_batch(h, stage, h->h_recs.p, cn, restrict_rows ? restrict_rows + c0 * W : nullptr, nullptr, count ? count + c0 : nullptr,
+                    h->d_rows1, false, &csr);
+    if (rc) return rc;
+    const long long ct = csr.offs[(size_t)cn];
+    for (int64_t i = 0; i < cn; ++i) offsets[c0 + i + 1] = total + csr.offs[(size_t)i + 1];
+    if (indices && total < cap) std::memcpy(indices + total, csr.idx, (size_t)std::min<long long>(ct, cap - total) * sizeof(uint32_t));
+    total += ct;
+  }
+  return total;
+}
+
 int fcvm_stage_poses(fcvm_t* h, const double* pose5, int64_t n) {
   if (!h || !pose5 || n <= 0) return fail(FCVM_EINVAL, "bad arguments");
   if (!h->map_flag || !h->model_flag) return fail(FCVM_ENOTREADY, "needs the map and the model");
@@ -1157,12 +1220,10 @@ int fcvm_evaluate_resident(fcvm_t* h, int32_t stage, void* stream, int32_t sync,
   if (!h || stage < 1 || stage > 4 || stage == FCVM_STAGE_E2) return fail(FCVM_EINVAL, "bad stage (E2 needs restrict rows: use fcvm_evaluate)");
   if (h->resident_n <= 0) return fail(FCVM_ENOTREADY, "no resident batch: call fcvm_stage_poses first");
   cudaStream_t s = stream ? (cudaStream_t)stream : h->stream;
-  CU(cudaEventRecord(h->ev0, s));
   int rc = launch_stage(h, stage, h->d_recs.p, h->resident_n, h->d_rows1.p, nullptr, s, sync != 0);
   if (rc) return rc;
   CU(launch_popc_rows(h->d_rows1.p, h->resident_n, h->W, h->d_count.p, s));
   h->counters[5] += 1;
-  CU(cudaEventRecord(h->ev1, s));
   if (sync) {
     CU(cudaStreamSynchronize(s));
     const int64_t rays_before = h->counters[1];

@@ -262,6 +262,61 @@ __global__ void __launch_bounds__(256) k_popc_rows(const uint32_t* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------
+// k_exscan: offsets[0..n] = exclusive prefix sum of count[0..n) (one block; n is a batch size).
+// k_compact_rows: bitset rows -> ascending point-index lists (CSR).  The visible sets are 1-4 %
+// dense, so the host-side consumers (the ordered pitch / yaw sums) read 4 bytes per visible ray
+// instead of P/8 bytes per viewpoint.  One warp per row; lane order = word order keeps indices
+// ascending.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_exscan(const int* __restrict__ count, long long n, long long* __restrict__ offsets) {
+  __shared__ long long part[1024];
+  const int t = threadIdx.x;
+  const long long per = (n + 1023) / 1024;
+  const long long lo = min(n, per * t), hi = min(n, per * (t + 1));
+  long long s = 0;
+  for (long long i = lo; i < hi; ++i) s += count[i];
+  part[t] = s;
+  __syncthreads();
+  for (int o = 1; o < 1024; o <<= 1) {
+    long long v = t >= o ? part[t - o] : 0;
+    __syncthreads();
+    part[t] += v;
+    __syncthreads();
+  }
+  long long run = t ? part[t - 1] : 0;
+  for (long long i = lo; i < hi; ++i) { offsets[i] = run; run += count[i]; }
+  if (t == 1023) offsets[n] = part[1023];
+}
+
+__global__ void __launch_bounds__(256) k_compact_rows(const uint32_t* __restrict__ rows, long long n, long long words,
+                                                      const long long* __restrict__ offsets, uint32_t* __restrict__ indices) {
+  const long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= n) return;
+  const int lane = threadIdx.x & 31;
+  const uint32_t* row = rows + r * words;
+  long long base = offsets[r];
+  for (long long w0 = 0; w0 < words; w0 += 32) {
+    const long long wi = w0 + lane;
+    uint32_t w = wi < words ? __ldg(row + wi) : 0u;
+    if (__ballot_sync(0xffffffffu, w != 0u) == 0u) continue;
+    const int c = __popc(w);
+    int pre = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, pre, o);
+      if (lane >= o) pre += v;
+    }
+    long long pos = base + (pre - c);
+    while (w) {
+      const int b = __ffs(w) - 1;
+      w &= w - 1;
+      indices[pos++] = (uint32_t)(wi * 32 + b);
+    }
+    base += __shfl_sync(0xffffffffu, pre, 31);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // k_own_sweep: the ownership rule of getPose / updateViewpointInfo
 // (viewpoint_manager.cpp:500-528, 589-617), for a whole stage at once.
 //   for each row in processing order (sched[t] = {row, vp_id, contribute_voxel_num > 0}):
@@ -339,6 +394,18 @@ cudaError_t launch_popc_rows(const uint32_t* rows, long long n, long long words,
   if (n <= 0) return cudaSuccess;
   const int wpb = 8;
   k_popc_rows<<<(unsigned)((n + wpb - 1) / wpb), wpb * 32, 0, s>>>(rows, n, words, count);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_exscan(const int* count, long long n, long long* offsets, cudaStream_t s) {
+  k_exscan<<<1, 1024, 0, s>>>(count, n, offsets);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_compact_rows(const uint32_t* rows, long long n, long long words, const long long* offsets, uint32_t* indices, cudaStream_t s) {
+  if (n <= 0) return cudaSuccess;
+  const int wpb = 8;
+  k_compact_rows<<<(unsigned)((n + wpb - 1) / wpb), wpb * 32, 0, s>>>(rows, n, words, offsets, indices);
   return cudaGetLastError();
 }
 

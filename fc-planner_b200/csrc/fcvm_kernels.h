@@ -30,6 +30,8 @@ struct EvalArgs {
 size_t eval_smem_bytes(int tile_pts);
 cudaError_t launch_eval(int stage, const EvalArgs& a, cudaStream_t s);
 cudaError_t launch_popc_rows(const uint32_t* rows, long long n, long long words, int* count, cudaStream_t s);
+cudaError_t launch_exscan(const int* count, long long n, long long* offsets, cudaStream_t s);
+cudaError_t launch_compact_rows(const uint32_t* rows, long long n, long long words, const long long* offsets, uint32_t* indices, cudaStream_t s);
 // sched[t] = {row index, viewpoint id, contribute_voxel_num, 0} in processing order, rows with 0 omitted
 cudaError_t launch_own_sweep(const uint32_t* rows, long long words, const int4* sched, int nsched, int last_vps_num, long long P,
                              int* cover_contrib, int* contrib_id, int* voxcount, cudaStream_t s);

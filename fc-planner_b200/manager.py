@@ -175,6 +175,22 @@ class ViewpointManager:
         check(self.lib.fcvm_evaluate(self.h, stage, ptr(pose5, f64p), n, ptr(restrict_rows, u32p), ptr(count, i32p), ptr(rows, u32p)))
         return count, rows
 
+    def evaluate_csr(self, stage, pose5, restrict_rows=None, cap=None):
+        """Evaluator pass returning (count[n], offsets[n+1], indices[total]): the visible sets as CSR."""
+        pose5 = np.ascontiguousarray(pose5, dtype=np.float64).reshape(-1, 5)
+        n = len(pose5)
+        count = np.zeros(n, np.int32); offsets = np.zeros(n + 1, np.int64)
+        if restrict_rows is not None:
+            restrict_rows = np.ascontiguousarray(restrict_rows, dtype=np.uint32)
+        cap = int(cap) if cap else max(1, 64 * n)
+        while True:
+            indices = np.empty(cap, np.uint32)
+            total = check(self.lib.fcvm_evaluate_csr(self.h, stage, ptr(pose5, f64p), n, ptr(restrict_rows, u32p), ptr(count, i32p),
+                                                     ptr(offsets, i64p), ptr(indices, u32p), cap))
+            if total <= cap:
+                return count, offsets, indices[:total]
+            cap = int(total)
+
     def stage_poses(self, pose5):
         pose5 = np.ascontiguousarray(pose5, dtype=np.float64).reshape(-1, 5)
         check(self.lib.fcvm_stage_poses(self.h, ptr(pose5, f64p), len(pose5)))

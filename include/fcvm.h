@@ -152,6 +152,13 @@ int     fcvm_get_counters(fcvm_t* h, int64_t* out8);
 int fcvm_evaluate(fcvm_t* h, int32_t stage, const double* pose5, int64_t n,
                   const uint32_t* restrict_rows, int32_t* count, uint32_t* rows);
 
+/* The same pass with the visible sets returned as ascending index lists (CSR): offsets[n+1] and at most
+ * cap indices; returns the total number of visible pairs (> cap: call again with a larger buffer).
+ * This is the form the per-viewpoint host reductions of getPose / updatePoseGravitation consume
+ * (viewpoint_manager.cpp:398-425, 856-875): 4 bytes per visible ray instead of P/8 bytes per pose. */
+int64_t fcvm_evaluate_csr(fcvm_t* h, int32_t stage, const double* pose5, int64_t n, const uint32_t* restrict_rows,
+                          int32_t* count, int64_t* offsets, uint32_t* indices, int64_t cap);
+
 /* Same pass on poses that are already resident: uploads nothing, downloads nothing, leaves the
  * bitset rows and counts on the device.  fcvm_stage_poses copies/derives the per-pose device
  * record (position + 4 world-frame FOV normals) once; fcvm_evaluate_resident can then be
@@ -167,7 +174,8 @@ int fcvm_resident_buffers(fcvm_t* h, void** rows_dev, void** count_dev, int64_t*
  * stand for; order[n] = row indices in processing order (NULL = 0..n-1). */
 int fcvm_own_resident(fcvm_t* h, const int32_t* vp_ids, const int32_t* order, int64_t n);
 
-/* elapsed device time of the most recent evaluator launch(es) of this handle, in ms */
+/* device time of the most recent visibility kernel (k_eval alone, CUDA events on its stream), in ms;
+ * valid after a synchronising call */
 double fcvm_last_kernel_ms(fcvm_t* h);
 
 /* --------------------------------------------------- multi-GPU (one process per GPU) - */
