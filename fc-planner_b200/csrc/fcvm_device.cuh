@@ -20,31 +20,29 @@
 namespace fcvm {
 
 // ---------------------------------------------------------------------------------------------
-// Occupancy grid in HBM/L2: 1 bit per voxel (set = occupied), bricked so that one 128-byte line
-// holds a compact 8 x 8 x 16 voxel block made of sixteen 4 x 4 x 4 sub-bricks (one uint64 each).
-// Consecutive DDA steps therefore stay inside the same 8-byte word ~3 steps out of 4 and inside
-// the same cache line far longer than in the reference's x-major `char` layout
-// (sdf_map.h:266-269: x*Ny*Nz + y*Nz + z).
+// Occupancy grid in HBM/L2: 1 bit per voxel (set = occupied), stored as 4 x 4 x 4 bricks of one
+// uint64 each, bricks laid out z-fastest.  Consecutive DDA steps stay inside the same 8-byte word
+// ~3 steps out of 4 (the word is cached in registers), a 128-byte line holds a 4 x 4 x 64 column,
+// and the address arithmetic is 3 shifts + 2 IMADs.  The reference stores one `char` per voxel,
+// x-major (sdf_map.h:266-269: x*Ny*Nz + y*Nz + z).
 // ---------------------------------------------------------------------------------------------
 struct GridDesc {
-  const unsigned long long* bricks;  // [nsx*nsy*nsz][16]
+  const unsigned long long* bricks;  // [nbx*nby*nbz]
   int nx, ny, nz;                    // map_voxel_num_
-  int nsx, nsy, nsz;                 // line-blocks per axis: ceil(n/8), ceil(n/8), ceil(n/16)
+  int nbx, nby, nbz;                 // bricks per axis: ceil(n/4)
   double res;                        // resolution_
   double offx, offy, offz;           // RayCaster::offset_ = 0.5 - origin/res   (raycast.cpp:344)
   double orgx, orgy, orgz;           // map_origin_
 };
 
-__host__ __device__ __forceinline__ long long brick_word_index(int x, int y, int z, int nsy, int nsz) {
-  long long line = ((long long)(x >> 3) * nsy + (y >> 3)) * nsz + (z >> 4);
-  int word = ((((x >> 2) & 1) << 1) | ((y >> 2) & 1)) << 2 | ((z >> 2) & 3);
-  return line * 16 + word;
+__host__ __device__ __forceinline__ long long brick_word_index(int x, int y, int z, int nby, int nbz) {
+  return ((long long)(x >> 2) * nby + (y >> 2)) * nbz + (z >> 2);
 }
 __host__ __device__ __forceinline__ int brick_bit_index(int x, int y, int z) {
   return ((x & 3) << 4) | ((y & 3) << 2) | (z & 3);
 }
 
-// One-entry register cache of the last 4x4x4 sub-brick a ray touched.
+// One-entry register cache of the last brick a ray touched.
 struct BrickCache {
   long long key;
   unsigned long long word;
@@ -54,7 +52,7 @@ struct BrickCache {
 // SDFMap::occCheck (sdf_map.h:397-420): true = inside the map AND not occupied.
 __device__ __forceinline__ bool occ_free(const GridDesc& g, int ix, int iy, int iz, BrickCache& c) {
   if ((unsigned)ix >= (unsigned)g.nx || (unsigned)iy >= (unsigned)g.ny || (unsigned)iz >= (unsigned)g.nz) return false;
-  long long k = brick_word_index(ix, iy, iz, g.nsy, g.nsz);
+  long long k = brick_word_index(ix, iy, iz, g.nby, g.nbz);
   if (k != c.key) {
     c.key = k;
     c.word = __ldg(g.bricks + k);

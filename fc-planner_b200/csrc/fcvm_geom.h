@@ -93,7 +93,7 @@ struct HostGrid {
   double res = 0, res_inv = 0;
   double origin[3] = {0, 0, 0}, size[3] = {0, 0, 0};
   int dims[3] = {0, 0, 0};
-  int ns[3] = {0, 0, 0};
+  int ns[3] = {0, 0, 0};   // bricks per axis
   std::vector<unsigned long long> bricks;
   bool ready = false;
 
@@ -113,8 +113,8 @@ struct HostGrid {
       origin[c] = mn[c] - 2 * inflate;              // sdf_map.cpp:151
       dims[c] = (int)std::ceil(size[c] / res);      // sdf_map.cpp:156-157
     }
-    ns[0] = (dims[0] + 7) >> 3; ns[1] = (dims[1] + 7) >> 3; ns[2] = (dims[2] + 15) >> 4;
-    bricks.assign((size_t)ns[0] * ns[1] * ns[2] * 16, 0ull);
+    for (int c = 0; c < 3; ++c) ns[c] = (dims[c] + 3) >> 2;
+    bricks.assign((size_t)ns[0] * ns[1] * ns[2], 0ull);
     for (int64_t i = 0; i < n; ++i) {               // sdf_map.cpp:178-187
       int id[3];
       for (int c = 0; c < 3; ++c) id[c] = (int)std::floor(((double)xyz[3 * i + c] - origin[c]) * res_inv);

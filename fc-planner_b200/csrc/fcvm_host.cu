@@ -223,7 +223,7 @@ static void fill_grid_desc(const fcvm_handle* h, GridDesc& g) {
   const HostGrid& hg = h->grid;
   g.bricks = h->d_bricks.p;
   g.nx = hg.dims[0]; g.ny = hg.dims[1]; g.nz = hg.dims[2];
-  g.nsx = hg.ns[0]; g.nsy = hg.ns[1]; g.nsz = hg.ns[2];
+  g.nbx = hg.ns[0]; g.nby = hg.ns[1]; g.nbz = hg.ns[2];
   g.res = hg.res;
   // RayCaster::setParams (raycast.cpp:341-345): offset_ = half_ - origin / resolution_
   g.offx = 0.5 - hg.origin[0] / hg.res;
@@ -247,7 +247,7 @@ static void fill_fov_const(const fcvm_handle* h, FovConst& f) {
 static void choose_tiling(int64_t P, int64_t V, int& tile_pts, int& vp_per_cta) {
   tile_pts = P >= 8 * EVAL_MAX_TILE ? EVAL_MAX_TILE : (P >= 4096 ? 1024 : 512);
   const int64_t tiles = (P + tile_pts - 1) / tile_pts;
-  const int64_t target_ctas = 148 * 2 * 4;
+  const int64_t target_ctas = 148 * 2 * 24;   // many short CTAs: tiles far from a viewpoint chunk finish early
   int64_t chunks = std::max<int64_t>(1, std::min<int64_t>((target_ctas + tiles - 1) / tiles, (V + EVAL_WARPS - 1) / EVAL_WARPS));
   int64_t per = (V + chunks - 1) / chunks;
   per = std::max<int64_t>(per, 1);

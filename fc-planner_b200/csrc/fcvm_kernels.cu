@@ -9,10 +9,13 @@
 // Layout of one k_eval CTA: a tile of model points is staged ONCE into shared memory with a 1-D
 // TMA bulk copy (cp.async.bulk + mbarrier), then each warp pulls viewpoints from a CTA-local
 // counter and tests its 32 lanes' points against the viewpoint's four FOV planes and range.
-// Pairs that pass are compacted by ballot into a per-warp ray queue; whenever 32 rays are queued
-// the whole warp marches them (one ray per lane, both half-rays in lock step like the
-// reference), so the expensive divergent phase always runs with full warps.  Visible bits are
-// OR-ed into the viewpoint's bitset row in HBM.  No tensor cores: nothing here is a contraction.
+// Pairs that pass are compacted by ballot into a per-warp entry queue.  32 entries at a time are
+// turned into prepared rays (biInput at full warp width) and pushed onto a per-warp queue of ray
+// continuations in shared memory; the march loop then runs one ray per lane, both half-rays in
+// lock step like the reference, and a lane whose ray ends (blocked early, or short) pulls the next
+// continuation immediately, so the divergent phase keeps its lanes busy although ray lengths vary
+// by two orders of magnitude.  Visible bits are OR-ed into the viewpoint's bitset row in HBM.
+// No tensor cores: nothing here is a contraction.
 #include "fcvm_device.cuh"
 #include "fcvm_kernels.h"
 
@@ -51,48 +54,168 @@ __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarr
 // k_eval
 // ------------------------------------------------------------------------------------------
 constexpr int kWarps = EVAL_WARPS;
-constexpr int kQueue = 64;  // ray-queue entries per warp
+constexpr int kEntryQ = 64;   // (viewpoint, point) pairs that passed the FOV test, per warp
+constexpr int kReadyQ = 64;   // prepared / suspended rays ("continuations"), per warp
+constexpr int kContD = 12;    // doubles per continuation: tMax + tDelta of both half-rays
+constexpr int kContI = 11;    // ints per continuation
 
 struct QueueEntry {
   uint32_t vp;   // viewpoint index inside the batch
   uint32_t pt;   // point index inside the tile
 };
 
+// One half-ray on the fast path: the voxel is tracked directly as a MAP index (the conversion
+// `(int)(x + offset_)` was verified to be a pure shift over the ray's whole extent when the ray was
+// prepared), the walk is counted down instead of compared against the midpoint voxel, and the whole
+// extent was verified to lie inside the map, so the inner loop has no bounds test.
+struct Side {
+  int ix, iy, iz, rem;
+  int sx, sy, sz;
+  double tmx, tmy, tmz, tdx, tdy, tdz;
+  // One conditional step: the branch ladder of biNextId (raycast.cpp:496-518: strict '<', z on ties
+  // and NaN) evaluated as three predicates so that the updates are predicated, not branched.
+  __device__ __forceinline__ void step_if(bool go) {
+    const bool xy = tmx < tmy, xz = tmx < tmz, yz = tmy < tmz;
+    const bool selx = go && xy && xz;
+    const bool sely = go && !xy && yz;
+    const bool selz = go && !(xy && xz) && !(!xy && yz);
+    if (selx) { ix += sx; tmx += tdx; }
+    if (sely) { iy += sy; tmy += tdy; }
+    if (selz) { iz += sz; tmz += tdz; }
+    rem -= go ? 1 : 0;
+  }
+};
+
+#define CONT_DISCARD 1      // prepare only: the call sites make one biNextId call and discard it
+#define CONT_INRANGE 2      // E1: ray_length <= visible_range (ANDed into the verdict)
+
+struct Cont {
+  Side p, n;
+  uint32_t vp, pt;
+  int flags;
+};
+
+__device__ __forceinline__ int pack_dirs(const Side& a, const Side& b, int flags) {
+  return (a.sx + 1) | ((a.sy + 1) << 2) | ((a.sz + 1) << 4) | ((b.sx + 1) << 6) | ((b.sy + 1) << 8) | ((b.sz + 1) << 10) | (flags << 12);
+}
+__device__ __forceinline__ void cont_store(double* qd, int* qi, int slot, const Cont& c) {
+  qd[0 * kReadyQ + slot] = c.p.tmx; qd[1 * kReadyQ + slot] = c.p.tmy; qd[2 * kReadyQ + slot] = c.p.tmz;
+  qd[3 * kReadyQ + slot] = c.p.tdx; qd[4 * kReadyQ + slot] = c.p.tdy; qd[5 * kReadyQ + slot] = c.p.tdz;
+  qd[6 * kReadyQ + slot] = c.n.tmx; qd[7 * kReadyQ + slot] = c.n.tmy; qd[8 * kReadyQ + slot] = c.n.tmz;
+  qd[9 * kReadyQ + slot] = c.n.tdx; qd[10 * kReadyQ + slot] = c.n.tdy; qd[11 * kReadyQ + slot] = c.n.tdz;
+  qi[0 * kReadyQ + slot] = c.p.ix; qi[1 * kReadyQ + slot] = c.p.iy; qi[2 * kReadyQ + slot] = c.p.iz; qi[3 * kReadyQ + slot] = c.p.rem;
+  qi[4 * kReadyQ + slot] = c.n.ix; qi[5 * kReadyQ + slot] = c.n.iy; qi[6 * kReadyQ + slot] = c.n.iz; qi[7 * kReadyQ + slot] = c.n.rem;
+  qi[8 * kReadyQ + slot] = pack_dirs(c.p, c.n, c.flags);
+  qi[9 * kReadyQ + slot] = (int)c.vp; qi[10 * kReadyQ + slot] = (int)c.pt;
+}
+__device__ __forceinline__ void cont_load(const double* qd, const int* qi, int slot, Cont& c) {
+  c.p.tmx = qd[0 * kReadyQ + slot]; c.p.tmy = qd[1 * kReadyQ + slot]; c.p.tmz = qd[2 * kReadyQ + slot];
+  c.p.tdx = qd[3 * kReadyQ + slot]; c.p.tdy = qd[4 * kReadyQ + slot]; c.p.tdz = qd[5 * kReadyQ + slot];
+  c.n.tmx = qd[6 * kReadyQ + slot]; c.n.tmy = qd[7 * kReadyQ + slot]; c.n.tmz = qd[8 * kReadyQ + slot];
+  c.n.tdx = qd[9 * kReadyQ + slot]; c.n.tdy = qd[10 * kReadyQ + slot]; c.n.tdz = qd[11 * kReadyQ + slot];
+  c.p.ix = qi[0 * kReadyQ + slot]; c.p.iy = qi[1 * kReadyQ + slot]; c.p.iz = qi[2 * kReadyQ + slot]; c.p.rem = qi[3 * kReadyQ + slot];
+  c.n.ix = qi[4 * kReadyQ + slot]; c.n.iy = qi[5 * kReadyQ + slot]; c.n.iz = qi[6 * kReadyQ + slot]; c.n.rem = qi[7 * kReadyQ + slot];
+  const int d = qi[8 * kReadyQ + slot];
+  c.p.sx = (d & 3) - 1; c.p.sy = ((d >> 2) & 3) - 1; c.p.sz = ((d >> 4) & 3) - 1;
+  c.n.sx = ((d >> 6) & 3) - 1; c.n.sy = ((d >> 8) & 3) - 1; c.n.sz = ((d >> 10) & 3) - 1;
+  c.flags = d >> 12;
+  c.vp = (uint32_t)qi[9 * kReadyQ + slot]; c.pt = (uint32_t)qi[10 * kReadyQ + slot];
+}
+
+// occCheck on the fast path (no bounds test: the ray's extent is inside the map)
+__device__ __forceinline__ bool occ_fast(const GridDesc& g, int ix, int iy, int iz, int& ckey, unsigned long long& cword) {
+  const int k = ((ix >> 2) * g.nby + (iy >> 2)) * g.nbz + (iz >> 2);
+  if (k != ckey) {
+    ckey = k;
+    cword = __ldg(g.bricks + k);
+  }
+  return ((cword >> brick_bit_index(ix, iy, iz)) & 1ull) == 0ull;
+}
+
+// biInput (raycast.cpp:392-444) for one ray.  Returns true and fills `c` when the ray qualifies for
+// the fast path; otherwise the verdict is computed right here with the literal marcher (birc).
 template <int STAGE>
-__device__ __forceinline__ bool cast_one(const GridDesc& g, const FovConst& fc, const VpRec* __restrict__ recs, uint32_t v,
-                                         float4 q, RayStats& st) {
+__device__ __forceinline__ bool prepare_ray(const GridDesc& g, const FovConst& fc, const VpRec* __restrict__ recs, uint32_t v, uint32_t pti,
+                                            float4 q, Cont& c, bool& slow_verdict, RayStats& st) {
   const double vx = __ldg(&recs[v].px), vy = __ldg(&recs[v].py), vz = __ldg(&recs[v].pz);
   const double qx = (double)q.x, qy = (double)q.y, qz = (double)q.z;
+  double bx = qx, by = qy, bz = qz;
+  int flags = (STAGE == 4) ? 0 : CONT_DISCARD;
   if (STAGE == 1) {
-    // E1 also requires ray_length <= visible_range (viewpoint_manager.cpp:402-403), tested by the
-    // reference after the cast; the ray is marched either way so the lookup count matches.
+    // ray_length <= visible_range (viewpoint_manager.cpp:402-403), tested by the reference after the cast
     const double dx = qx - vx, dy = qy - vy, dz = qz - vz;
-    const double len = sqrt((dx * dx + dy * dy) + dz * dz);
-    const bool vis = birc(g, vx, vy, vz, qx, qy, qz, true, st);
-    return vis && (len <= fc.visible_range);
-  } else if (STAGE == 3) {
-    return birc(g, vx, vy, vz, qx, qy, qz, true, st);
+    if (sqrt((dx * dx + dy * dy) + dz * dz) <= fc.visible_range) flags |= CONT_INRANGE;
   } else {
-    double tx, ty, tz;
-    offset_target(g, qx, qy, qz, vx, vy, vz, tx, ty, tz, st);
-    return birc(g, vx, vy, vz, tx, ty, tz, STAGE == 2, st);
+    flags |= CONT_INRANGE;
   }
+  if (STAGE == 2 || STAGE == 4) offset_target(g, qx, qy, qz, vx, vy, vz, bx, by, bz, st);
+
+  const double res = g.res;
+  const double sxf = vx / res, syf = vy / res, szf = vz / res;
+  const double mxf = (0.5 * (vx + bx)) / res, myf = (0.5 * (vy + by)) / res, mzf = (0.5 * (vz + bz)) / res;
+  const double exf = bx / res, eyf = by / res, ezf = bz / res;
+  const int x0 = (int)floor(sxf), y0 = (int)floor(syf), z0 = (int)floor(szf);
+  const int mx = (int)floor(mxf), my = (int)floor(myf), mz = (int)floor(mzf);
+  const int x1 = (int)floor(exf), y1 = (int)floor(eyf), z1 = (int)floor(ezf);
+  // exact `(int)(x + offset_)` at the three corner voxels of the two half-rays
+  const int pix = to_map_index(x0, g.offx), piy = to_map_index(y0, g.offy), piz = to_map_index(z0, g.offz);
+  const int mix = to_map_index(mx, g.offx), miy = to_map_index(my, g.offy), miz = to_map_index(mz, g.offz);
+  const int nix = to_map_index(x1, g.offx), niy = to_map_index(y1, g.offy), niz = to_map_index(z1, g.offz);
+  auto inside = [&](int ix, int iy, int iz) { return (unsigned)ix < (unsigned)g.nx && (unsigned)iy < (unsigned)g.ny && (unsigned)iz < (unsigned)g.nz; };
+  // fast path <=> the map-index conversion is a pure shift between the corners (it is monotone, so
+  // equal deltas at the ends mean unit increments in between) and all corners are inside the map
+  // (the marcher never leaves the box spanned by its end voxels).
+  const bool fast = inside(pix, piy, piz) && inside(mix, miy, miz) && inside(nix, niy, niz) &&
+                    (mix - pix == mx - x0) && (miy - piy == my - y0) && (miz - piz == mz - z0) &&
+                    (mix - nix == mx - x1) && (miy - niy == my - y1) && (miz - niz == mz - z1);
+  if (!fast) {
+    slow_verdict = birc(g, vx, vy, vz, bx, by, bz, (flags & CONT_DISCARD) != 0, st) && (flags & CONT_INRANGE);
+    return false;
+  }
+  c.vp = v; c.pt = pti; c.flags = flags;
+  {
+    const int dx = mx - x0, dy = my - y0, dz = mz - z0;
+    c.p.ix = pix; c.p.iy = piy; c.p.iz = piz;
+    c.p.rem = abs(dx) + abs(dy) + abs(dz);
+    c.p.sx = d_signum(dx); c.p.sy = d_signum(dy); c.p.sz = d_signum(dz);
+    c.p.tmx = d_intbound(sxf, (double)dx); c.p.tmy = d_intbound(syf, (double)dy); c.p.tmz = d_intbound(szf, (double)dz);
+    c.p.tdx = ((double)c.p.sx) / (double)dx; c.p.tdy = ((double)c.p.sy) / (double)dy; c.p.tdz = ((double)c.p.sz) / (double)dz;
+  }
+  {
+    const int dx = mx - x1, dy = my - y1, dz = mz - z1;
+    c.n.ix = nix; c.n.iy = niy; c.n.iz = niz;
+    c.n.rem = abs(dx) + abs(dy) + abs(dz);
+    c.n.sx = d_signum(dx); c.n.sy = d_signum(dy); c.n.sz = d_signum(dz);
+    c.n.tmx = d_intbound(exf, (double)dx); c.n.tmy = d_intbound(eyf, (double)dy); c.n.tmz = d_intbound(ezf, (double)dz);
+    c.n.tdx = ((double)c.n.sx) / (double)dx; c.n.tdy = ((double)c.n.sy) / (double)dy; c.n.tdz = ((double)c.n.sz) / (double)dz;
+  }
+  if (flags & CONT_DISCARD) {
+    // `raycaster_->biNextId(idx, idx_rev);` before the loop (cpp:387, 483, 845): both sides advance
+    // one voxel (if they can), the reported voxels are not looked at
+    c.p.step_if(c.p.rem > 0);
+    c.n.step_if(c.n.rem > 0);
+    c.flags &= ~CONT_DISCARD;
+  }
+  return true;
 }
 
 template <int STAGE>
-__global__ void __launch_bounds__(kWarps * 32) k_eval(const __grid_constant__ EvalArgs a) {
+__global__ void __launch_bounds__(kWarps * 32, EVAL_MIN_CTAS) k_eval(const __grid_constant__ EvalArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
+  // [tile points][ready doubles][ready ints][entry queues]
   float4* tile = reinterpret_cast<float4*>(smem);
-  QueueEntry* queues = reinterpret_cast<QueueEntry*>(smem + (size_t)a.tile_pts * sizeof(float4));
+  double* ready_d = reinterpret_cast<double*>(smem + (size_t)a.tile_pts * sizeof(float4));
+  int* ready_i = reinterpret_cast<int*>(ready_d + (size_t)kWarps * kContD * kReadyQ);
+  QueueEntry* entries = reinterpret_cast<QueueEntry*>(ready_i + (size_t)kWarps * kContI * kReadyQ);
   __shared__ __align__(8) uint64_t bar;
   __shared__ int next_vp;
   __shared__ float red[kWarps][6];
   __shared__ double aabb[6];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const unsigned lt_mask = (1u << lane) - 1u;
   const long long tile_base = (long long)blockIdx.x * a.tile_pts;
   const int npts = (int)min((long long)a.tile_pts, a.P - tile_base);
-  // viewpoint chunk of this CTA
   const long long v_lo = (long long)blockIdx.y * a.vp_per_cta;
   const long long v_hi = min(v_lo + (long long)a.vp_per_cta, a.V);
 
@@ -141,28 +264,95 @@ __global__ void __launch_bounds__(kWarps * 32) k_eval(const __grid_constant__ Ev
 
   const GridDesc& g = a.grid;
   const FovConst& fc = a.fov;
-  QueueEntry* q = queues + warp * kQueue;
-  int qn = 0;                       // warp-uniform queue length
+  QueueEntry* eq = entries + warp * kEntryQ;
+  double* rqd = ready_d + (size_t)warp * kContD * kReadyQ;
+  int* rqi = ready_i + (size_t)warp * kContI * kReadyQ;
+  int en = 0;                       // warp-uniform entry-queue length
+  int rn = 0;                       // warp-uniform ready-queue length
   RayStats st = {0u, 0u, 0u};
   unsigned int nrays = 0;
   unsigned long long npairs = 0;
   const long long W = a.words;
 
-  // march one queued ray per lane (lanes >= cnt idle), OR visible bits into the bitset rows
-  auto flush = [&](int cnt) {
-    const int e = qn - cnt + lane;
+  auto set_bit = [&](uint32_t vp, uint32_t pt) {
+    const long long gp = tile_base + pt;
+    atomicOr(a.rows + (long long)vp * W + (gp >> 5), 1u << (gp & 31));
+  };
+
+  // Pop `cnt` (<= 32) entries, run biInput for each on its own lane at full warp width, push the
+  // rays that qualify for the fast path onto the ready queue; the rest are finished on the spot.
+  auto prepare = [&](int cnt) {
+    bool queued = false;
+    Cont c;
     if (lane < cnt) {
-      const QueueEntry qe = q[e];
-      const float4 pt = tile[qe.pt];
+      const QueueEntry qe = eq[en - cnt + lane];
       nrays++;
-      const bool vis = cast_one<STAGE>(g, fc, a.recs, qe.vp, pt, st);
-      if (vis) {
-        const long long gp = tile_base + qe.pt;
-        atomicOr(a.rows + (long long)qe.vp * W + (gp >> 5), 1u << (gp & 31));
+      bool verdict = false;
+      queued = prepare_ray<STAGE>(g, fc, a.recs, qe.vp, qe.pt, tile[qe.pt], c, verdict, st);
+      if (!queued && verdict) set_bit(qe.vp, qe.pt);
+    }
+    en -= cnt;
+    const unsigned m = __ballot_sync(0xffffffffu, queued);
+    if (queued) cont_store(rqd, rqi, rn + __popc(m & lt_mask), c);
+    rn += __popc(m);
+    __syncwarp();
+  };
+
+  // March rays from the ready queue, one per lane, both half-rays in lock step exactly as the call
+  // sites drive biNextId.  A lane whose ray ends takes the next continuation at
+  // once, so the warp stays full while rays of very different lengths finish.  Unless draining,
+  // the warp suspends (writes the rays in flight back as continuations) as soon as the queue is
+  // empty and fewer than `kKeep` lanes are busy, and goes back to testing FOV pairs.
+  auto march = [&](bool drain) {
+    constexpr int kKeep = 20;
+    Cont c;
+    bool active = false;
+    int pkey = -1, nkey = -1;
+    unsigned long long pword = 0ull, nword = 0ull;
+    for (;;) {
+      const unsigned idle = __ballot_sync(0xffffffffu, !active);
+      if (idle != 0u && rn > 0) {
+        const int r = __popc(idle & lt_mask);
+        if (!active && r < rn) {
+          cont_load(rqd, rqi, rn - 1 - r, c);
+          active = true;
+          pkey = -1; nkey = -1;
+        }
+        rn -= min(__popc(idle), rn);
+        __syncwarp();
+      }
+      const unsigned busy = __ballot_sync(0xffffffffu, active);
+      if (busy == 0u) break;
+      if (!drain && rn == 0 && __popc(busy) < kKeep) {
+        if (active) cont_store(rqd, rqi, __popc(busy & lt_mask), c);
+        rn = __popc(busy);
+        __syncwarp();
+        break;
+      }
+      if (active) {
+        // ---- one biNextId call and the loop body that follows it.  The call reports the voxels
+        // BEFORE it steps, so they are looked up first and both sides advance afterwards.
+        const bool pflag = c.p.rem > 0, nflag = c.n.rem > 0;
+        if (!(pflag || nflag)) {
+          // the call returned false: visible_flag = occCheck(idx); visible_flag_rev keeps its last (true) value
+          const bool f = occ_fast(g, c.p.ix, c.p.iy, c.p.iz, pkey, pword);
+          st.lookups += 1;
+          if (c.p.ix != c.n.ix || c.p.iy != c.n.iy || c.p.iz != c.n.iz) st.trips++;   // both sides must have met in the midpoint voxel
+          if (f && (c.flags & CONT_INRANGE)) set_bit(c.vp, c.pt);
+          active = false;
+        } else {
+          const bool f = occ_fast(g, c.p.ix, c.p.iy, c.p.iz, pkey, pword);
+          const bool r = occ_fast(g, c.n.ix, c.n.iy, c.n.iz, nkey, nword);
+          st.lookups += 2;
+          c.p.step_if(pflag);
+          c.n.step_if(nflag);
+          if (!f || !r) {
+            st.lookups += 1;                        // the re-check after the break (same voxel, same answer)
+            active = false;
+          }
+        }
       }
     }
-    qn -= cnt;
-    __syncwarp();
   };
 
   for (;;) {
@@ -174,12 +364,13 @@ __global__ void __launch_bounds__(kWarps * 32) k_eval(const __grid_constant__ Ev
 
     // viewpoint record -> registers (uniform loads)
     VpRec rec;
-    {
+    auto load_rec = [&]() {
       const double2* src = reinterpret_cast<const double2*>(a.recs + v);
       double2* dst = reinterpret_cast<double2*>(&rec);
 #pragma unroll
       for (int k = 0; k < 8; ++k) dst[k] = __ldg(src + k);
-    }
+    };
+    load_rec();
     // whole-tile cull: squared distance from the viewpoint to the tile's bounding box.  Every point
     // of a culled tile fails `dir.norm() > max_dist` in the reference, so skipping is exact.
     {
@@ -192,11 +383,11 @@ __global__ void __launch_bounds__(kWarps * 32) k_eval(const __grid_constant__ Ev
       }
     }
     const uint32_t* rrow = (STAGE == 2) ? a.restrict_rows + v * W + (tile_base >> 5) : nullptr;
-    for (int c = 0; c < npts; c += 32) {
-      const int i = c + lane;
+    for (int cb = 0; cb < npts; cb += 32) {
+      const int i = cb + lane;
       bool valid = i < npts;
       if (STAGE == 2) {
-        const uint32_t rw = __ldg(rrow + (c >> 5));   // only points E1 found visible are re-tested
+        const uint32_t rw = __ldg(rrow + (cb >> 5));   // only points E1 found visible are re-tested
         if (rw == 0u) continue;
         valid = valid && ((rw >> lane) & 1u);
       }
@@ -209,16 +400,21 @@ __global__ void __launch_bounds__(kWarps * 32) k_eval(const __grid_constant__ Ev
       const unsigned m = __ballot_sync(0xffffffffu, pass);
       if (m == 0u) continue;
       if (pass) {
-        const int pos = qn + __popc(m & ((1u << lane) - 1u));
-        q[pos].vp = (uint32_t)v;
-        q[pos].pt = (uint32_t)i;
+        const int pos = en + __popc(m & lt_mask);
+        eq[pos].vp = (uint32_t)v;
+        eq[pos].pt = (uint32_t)i;
       }
-      qn += __popc(m);
+      en += __popc(m);
       __syncwarp();
-      if (qn >= 32) flush(32);
+      if (en >= 32) {
+        prepare(32);
+        if (rn >= 32) march(false);
+        load_rec();   // re-read instead of keeping 30 registers live across the ray phases
+      }
     }
   }
-  if (qn > 0) flush(qn);   // drain (qn < 32 here)
+  if (en > 0) prepare(en);   // en < 32 here
+  march(true);
 
   // ---- counters -------------------------------------------------------------------------
   if (a.counters) {
@@ -372,7 +568,10 @@ static cudaError_t launch_eval_t(const EvalArgs& a, dim3 grid, size_t smem, cuda
   return cudaGetLastError();
 }
 
-size_t eval_smem_bytes(int tile_pts) { return (size_t)tile_pts * sizeof(float4) + (size_t)kWarps * kQueue * sizeof(QueueEntry); }
+size_t eval_smem_bytes(int tile_pts) {
+  return (size_t)tile_pts * sizeof(float4) + (size_t)kWarps * kReadyQ * (kContD * sizeof(double) + kContI * sizeof(int)) +
+         (size_t)kWarps * kEntryQ * sizeof(QueueEntry);
+}
 
 cudaError_t launch_eval(int stage, const EvalArgs& a, cudaStream_t s) {
   if (a.V <= 0 || a.P <= 0) return cudaSuccess;

@@ -9,7 +9,12 @@
 
 namespace fcvm {
 
-#define EVAL_WARPS 8
+#ifndef EVAL_WARPS
+#define EVAL_WARPS 8          // warps per k_eval CTA
+#endif
+#ifndef EVAL_MIN_CTAS
+#define EVAL_MIN_CTAS 2       // resident CTAs per SM the register allocation is tuned for
+#endif
 #define EVAL_MAX_TILE 2048
 
 struct EvalArgs {
