@@ -237,3 +237,98 @@ def pitch_yaw(v):
     v = np.ascontiguousarray(v, np.float64); out = np.zeros(2, np.float64)
     load().orc_pitch_yaw(_ptr(v, c_f64p), _ptr(out, c_f64p))
     return out
+
+
+# -- oracle/_ref: the reference's own raycast.cpp / perception_utils.cpp (built from /root/reference
+#    by the Makefile against shim/ headers; see ref_capi.cpp) --------------------------------------
+_REF = None
+
+
+def ref_path():
+    return os.path.join(_HERE, "_ref", "libfcvm_ref.so")
+
+
+def ref_available():
+    return os.path.exists(ref_path())
+
+
+def ref_load():
+    global _REF
+    if _REF is None:
+        lib = ctypes.CDLL(ref_path())
+        for fn in ("ref_mod", "ref_intbound"):
+            getattr(lib, fn).restype = ctypes.c_double
+        lib.ref_signum.restype = ctypes.c_int
+        lib.ref_signum.argtypes = [ctypes.c_int]
+        lib.ref_mod.argtypes = [ctypes.c_double, ctypes.c_double]
+        lib.ref_intbound.argtypes = [ctypes.c_double, ctypes.c_double]
+        lib.ref_ray_ids.restype = ctypes.c_int64
+        lib.ref_biray_ids.restype = ctypes.c_int64
+        lib.ref_create.restype = ctypes.c_void_p
+        lib.ref_create.argtypes = [ctypes.c_void_p]
+        lib.ref_destroy.argtypes = [ctypes.c_void_p]
+        _REF = lib
+    return _REF
+
+
+def ref_ray_ids(res, origin, start, end, cap=4096, bi=False):
+    lib = ref_load()
+    o = np.asarray(origin, np.float64); s = np.asarray(start, np.float64); e = np.asarray(end, np.float64)
+    w = 6 if bi else 3
+    out = np.zeros((cap, w), np.int32)
+    fn = lib.ref_biray_ids if bi else lib.ref_ray_ids
+    k = fn(ctypes.c_double(res), _ptr(o, c_f64p), _ptr(s, c_f64p), _ptr(e, c_f64p), _ptr(out, c_i32p), ctypes.c_int64(cap), ctypes.c_int64(cap))
+    return out[:min(k, cap)].copy()
+
+
+def ref_fov_normals(params, pitch, yaw):
+    out = np.zeros(12, np.float64)
+    ref_load().ref_fov_normals(ctypes.byref(params), ctypes.c_double(pitch), ctypes.c_double(yaw), _ptr(out, c_f64p))
+    return out.reshape(4, 3)
+
+
+def ref_inside_fov(params, pose5, pts):
+    pose5 = np.ascontiguousarray(pose5, np.float64); pts = np.ascontiguousarray(pts, np.float64).reshape(-1, 3)
+    out = np.zeros(len(pts), np.uint8)
+    ref_load().ref_inside_fov(ctypes.byref(params), _ptr(pose5, c_f64p), _ptr(pts, c_f64p), ctypes.c_int64(len(pts)), _ptr(out, c_u8p))
+    return out.astype(bool)
+
+
+class RefEvaluator:
+    """Evaluator passes E1..E4 run by the reference's RayCaster + PerceptionUtils objects."""
+
+    def __init__(self, params):
+        self.lib = ref_load()
+        self.params = params
+        self.h = ctypes.c_void_p(self.lib.ref_create(ctypes.byref(params)))
+        self.P = 0
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.lib.ref_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def setMapPointCloud(self, xyz):
+        xyz = np.ascontiguousarray(xyz, dtype=np.float32)
+        self.lib.ref_set_map_cloud(self.h, _ptr(xyz, c_f32p), ctypes.c_int64(len(xyz)))
+
+    def setModel(self, xyz):
+        xyz = np.ascontiguousarray(xyz, dtype=np.float32)
+        self.P = len(xyz)
+        self.lib.ref_set_model(self.h, _ptr(xyz, c_f32p), ctypes.c_int64(len(xyz)))
+
+    def evaluate(self, stage, pose5, restrict_rows=None):
+        pose5 = np.ascontiguousarray(pose5, dtype=np.float64).reshape(-1, 5)
+        n = len(pose5)
+        words = (self.P + 31) // 32
+        count = np.zeros(n, np.int32); rows = np.zeros((n, words), np.uint32); ctr = np.zeros(4, np.int64)
+        if restrict_rows is not None:
+            restrict_rows = np.ascontiguousarray(restrict_rows, dtype=np.uint32)
+        rc = self.lib.ref_evaluate(self.h, ctypes.c_int32(stage), _ptr(pose5, c_f64p), ctypes.c_int64(n), _ptr(restrict_rows, c_u32p),
+                                   _ptr(count, c_i32p), _ptr(rows, c_u32p), _ptr(ctr, c_i64p))
+        if rc != 0:
+            raise RuntimeError(f"ref_evaluate failed: {rc}")
+        return count, rows, ctr

@@ -1,0 +1,29 @@
+"""The CPU oracle reproduces the committed golden fixtures of the three shipped scenes (MBS, pipe,
+Christ the Redeemer; BASELINE.json configs[0..2]) bit for bit: every E1..E4 visibility mask, every
+intermediate pose, the ownership state, the pruned viewpoint set and the uncovered cloud.
+
+The fixtures were produced by tests/golden/make_golden.py from the reference's own .pcd files; this
+test guards the oracle (and the libm / libstdc++ it runs on) against drift.  Bar: bit-exact."""
+import numpy as np
+import pytest
+
+from conftest import compare_with_golden, load_golden, run_sequence
+
+
+@pytest.mark.parametrize("scene", ["mbs", "pipe", "christ"])
+def test_oracle_reproduces_golden(oracle_mod, scene):
+    prm, z = load_golden(scene)
+    orc = oracle_mod.Oracle(prm)
+    run_sequence(orc, z)
+    compare_with_golden(orc, z, orc.getUpdatedViewpoints())
+    assert np.array_equal(orc.prune_order(), z["prune_order"])
+    assert np.array_equal(orc.counters(), z["counters"])
+
+
+def test_golden_scenes_are_not_vacuous():
+    for scene, min_final in (("mbs", 100), ("pipe", 100), ("christ", 50)):
+        _, z = load_golden(scene)
+        assert len(z["final_ids"]) >= min_final
+        assert z["counters"][1] > 50_000            # rays
+        assert set(np.unique(z["trace_stage"])) == {1, 2, 3, 4}
+        assert 0 < len(z["uncovered"]) < 0.1 * len(z["model"])
