@@ -1,0 +1,213 @@
+// viewpoint_manager/viewpoint_manager.h — drop-in replacement header for FC-Planner's
+// `predrecon::ViewpointManager`, forwarding every public method to the C ABI of libfcvm.so
+// (include/fcvm.h).  Put this directory ahead of the reference's
+// viewpoint_manager/include on the include path and link libfcvm.so instead of
+// libviewpoint_manager.so: the three call sites (hcplanner.cpp:47, 709-716;
+// skeleton_viewpoint.cpp:44, 489-496; viewpoint_manager_node.cpp:130-136, 239) compile unchanged.
+//
+// Public interface mirrored (reference: viewpoint_manager/include/viewpoint_manager/viewpoint_manager.h):
+//   :53-63  Vector3dCompare0      :65-77  VectorHashEigenVector3d      :79-84  SingleViewpoint
+//   :180-193 ViewpointManager(), ~ViewpointManager(), init, reset, setModel, setMapPointCloud,
+//            setNormals, setInitViewpoints, updateViewpoints, getUpdatedViewpoints,
+//            getUncoveredModelCloud
+// Error convention as the reference: void methods, ROS_ERROR + return on bad input; nothing throws.
+// A missing CUDA device is reported the same way — the library has no CPU fallback.
+#ifndef _VIEWPOINT_MANAGER_H_
+#define _VIEWPOINT_MANAGER_H_
+
+#include <ros/ros.h>
+#include <Eigen/Eigen>
+#include <pcl/point_cloud.h>
+#include <pcl/point_types.h>
+
+#include <cstdint>
+#include <functional>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "fcvm.h"
+
+#ifndef ROS_ERROR
+#include <cstdio>
+#define ROS_ERROR(...) do { std::fprintf(stderr, "[ERROR] " __VA_ARGS__); std::fprintf(stderr, "\n"); } while (0)
+#endif
+
+namespace predrecon
+{
+  struct Vector3dCompare0
+  {
+    bool operator()(const Eigen::Vector3d &a, const Eigen::Vector3d &b) const
+    {
+      for (int k = 0; k < 2; ++k)
+        if (a(k) != b(k))
+          return a(k) < b(k);
+      return a(2) < b(2);
+    }
+  };
+
+  struct VectorHashEigenVector3d
+  {
+    std::size_t operator()(const Eigen::Vector3d &v) const
+    {
+      std::size_t seed = 0;
+      for (int i = 0; i < 3; ++i)
+        seed ^= std::hash<double>()(v(i)) + 0x9e3779b9 + (seed << 6) + (seed >> 2);
+      return seed;
+    }
+  };
+
+  struct SingleViewpoint
+  {
+    int vp_id;
+    Eigen::VectorXd pose;   // (x, y, z, pitch, yaw)
+    int vox_count;
+  };
+
+  class ViewpointManager
+  {
+  public:
+    ViewpointManager() : h_(nullptr) {}
+    ~ViewpointManager() { fcvm_destroy(h_); }
+    ViewpointManager(const ViewpointManager &) = delete;
+    ViewpointManager &operator=(const ViewpointManager &) = delete;
+
+    // viewpoint_manager.cpp:32-62 + perception_utils.cpp:32-37 + sdf_map.cpp:128-136: the same
+    // parameter names and defaults, read once here and handed to the library as a plain struct.
+    void init(ros::NodeHandle &nh)
+    {
+      fcvm_params p = fcvm_params();
+      std::string attitude;
+      bool zflag = false, pose_update = false;
+      nh.param("viewpoint_manager/visible_range", p.visible_range, -1.0);
+      nh.param("viewpoint_manager/viewpoints_distance", p.viewpoints_distance, -1.0);
+      nh.param("viewpoint_manager/fov_h", p.fov_h, -1.0);
+      nh.param("viewpoint_manager/fov_w", p.fov_w, -1.0);
+      nh.param("viewpoint_manager/pitch_upper", p.pitch_upper, -1.0);
+      nh.param("viewpoint_manager/pitch_lower", p.pitch_lower, -1.0);
+      nh.param("viewpoint_manager/zGround", zflag, false);
+      nh.param("viewpoint_manager/GroundPos", p.ground_pos, -1.0);
+      nh.param("viewpoint_manager/safeHeight", p.safe_height, -1.0);
+      nh.param("viewpoint_manager/safe_radius", p.safe_radius, -1.0);
+      nh.param("viewpoint_manager/attitude_type", attitude, std::string("null"));
+      nh.param("viewpoint_manager/max_iter_num", p.max_iter_num, -1);
+      nh.param("viewpoint_manager/pose_update", pose_update, false);
+      nh.param("perception_utils/top_angle", p.top_angle, -1.0);
+      nh.param("perception_utils/left_angle", p.left_angle, -1.0);
+      nh.param("perception_utils/right_angle", p.right_angle, -1.0);
+      nh.param("perception_utils/max_dist", p.max_dist, -1.0);
+      nh.param("perception_utils/vis_dist", p.vis_dist, -1.0);
+      nh.param("hcmap/resolution", p.resolution, -1.0);
+      int seed = 0, device = 0, threads = 0;
+      nh.param("fcvm/seed", seed, 0);             // replaces the reference's wall-clock seeds (cpp:962-977, 249-255)
+      nh.param("fcvm/device", device, 0);
+      nh.param("fcvm/host_threads", threads, 0);
+      p.z_ground = zflag ? 1 : 0;
+      p.pose_update = pose_update ? 1 : 0;
+      p.attitude = attitude == "yaw" ? FCVM_ATTITUDE_YAW : (attitude == "all" ? FCVM_ATTITUDE_ALL : FCVM_ATTITUDE_OTHER);
+      p.seed = (uint64_t)seed;
+      p.device = device;
+      p.host_threads = threads;
+      fcvm_destroy(h_);
+      h_ = fcvm_create(&p);
+      if (!h_) ROS_ERROR("[ViewpointManager] %s", fcvm_last_error());
+    }
+
+    void reset() { ok(fcvm_reset(h_)); }
+
+    void setModel(pcl::PointCloud<pcl::PointXYZ>::Ptr input_model)
+    {
+      std::vector<float> xyz;
+      pack(*input_model, xyz);
+      ok(fcvm_set_model(h_, xyz.data(), (int64_t)(xyz.size() / 3)));
+    }
+
+    void setMapPointCloud(pcl::PointCloud<pcl::PointXYZ>::Ptr input_map)
+    {
+      std::vector<float> xyz;
+      pack(*input_map, xyz);
+      ok(fcvm_set_map_cloud(h_, xyz.data(), (int64_t)(xyz.size() / 3)));
+    }
+
+    void setNormals(std::map<Eigen::Vector3d, Eigen::Vector3d, Vector3dCompare0> &pt_normal_pairs)
+    {
+      std::vector<double> k, v;
+      k.reserve(3 * pt_normal_pairs.size());
+      v.reserve(3 * pt_normal_pairs.size());
+      for (const auto &kv : pt_normal_pairs)
+        for (int i = 0; i < 3; ++i)
+        {
+          k.push_back(kv.first(i));
+          v.push_back(kv.second(i));
+        }
+      ok(fcvm_set_normals(h_, k.data(), v.data(), (int64_t)pt_normal_pairs.size()));
+    }
+
+    void setInitViewpoints(pcl::PointCloud<pcl::PointNormal>::Ptr input_normal_vps)
+    {
+      std::vector<float> rows;
+      rows.reserve(6 * input_normal_vps->points.size());
+      for (const auto &q : input_normal_vps->points)
+      {
+        const float r[6] = {q.x, q.y, q.z, q.normal_x, q.normal_y, q.normal_z};
+        rows.insert(rows.end(), r, r + 6);
+      }
+      ok(fcvm_set_init_viewpoints(h_, rows.data(), (int64_t)(rows.size() / 6)));
+    }
+
+    void updateViewpoints() { ok(fcvm_update(h_)); }
+
+    void getUpdatedViewpoints(std::vector<SingleViewpoint> &viewpoints)
+    {
+      const int64_t n = h_ ? fcvm_get_viewpoints(h_, nullptr, nullptr, nullptr, 0) : 0;
+      std::vector<int32_t> id((size_t)(n > 0 ? n : 0)), vox(id.size());
+      std::vector<double> pose(5 * id.size());
+      if (n > 0) fcvm_get_viewpoints(h_, id.data(), pose.data(), vox.data(), n);
+      viewpoints.clear();        // `viewpoints = VPP.final_vps_` (viewpoint_manager.cpp:1135)
+      for (size_t i = 0; i < id.size(); ++i)
+      {
+        SingleViewpoint s;
+        s.vp_id = id[i];
+        s.pose.resize(5);
+        for (int c = 0; c < 5; ++c) s.pose(c) = pose[5 * i + c];
+        s.vox_count = vox[i];
+        viewpoints.push_back(s);
+      }
+    }
+
+    void getUncoveredModelCloud(pcl::PointCloud<pcl::PointXYZ> &cloud)
+    {
+      const int64_t n = h_ ? fcvm_get_uncovered(h_, nullptr, 0) : 0;
+      std::vector<float> xyz(3 * (size_t)(n > 0 ? n : 0));
+      if (n > 0) fcvm_get_uncovered(h_, xyz.data(), n);
+      cloud.clear();                                   // viewpoint_manager.cpp:1140
+      for (size_t i = 0; i + 2 < xyz.size(); i += 3)
+      {
+        pcl::PointXYZ q;
+        q.x = xyz[i]; q.y = xyz[i + 1]; q.z = xyz[i + 2];
+        cloud.push_back(q);
+      }
+    }
+
+    fcvm_t *handle() { return h_; }   // evaluator-level entry points and parity taps of fcvm.h
+
+  private:
+    static void pack(const pcl::PointCloud<pcl::PointXYZ> &c, std::vector<float> &xyz)
+    {
+      xyz.clear();
+      xyz.reserve(3 * c.points.size());
+      for (const auto &q : c.points)
+      {
+        xyz.push_back(q.x); xyz.push_back(q.y); xyz.push_back(q.z);
+      }
+    }
+    void ok(int rc)
+    {
+      if (rc != FCVM_OK) ROS_ERROR("[ViewpointManager] %s (code %d)", h_ ? fcvm_last_error() : "init() was not called", rc);
+    }
+    fcvm_t *h_;
+  };
+} // namespace predrecon
+
+#endif
