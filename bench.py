@@ -116,6 +116,49 @@ def cpu_oracle_rate(pts, nrm, prm, poses, seconds, threads):
     return c[1] / dt, n, dt, c, orc
 
 
+def pruning_leg(args, device, with_cpu):
+    """BASELINE.json's second metric: viewpoint-pruning wall time = setInitViewpoints + updateViewpoints
+    (the whole coverage-driven update: E1/E2, ownership, gravitation prune with E3/E4, uncovered-area
+    rounds) through the public call sequence, next to the single-threaded CPU oracle (the reference is
+    single-threaded on this path) on the same inputs, with the selected viewpoint sets compared."""
+    from fc_planner_b200 import launch_params, scenes
+    from fc_planner_b200.manager import ViewpointManager
+    pts, nrm, prims = scenes.make_plant(n_points=args.prune_points, scale=0.5, seed=0)
+    prm = launch_params("synthetic", seed=0, resolution=0.2, device=device)
+    vps = scenes.plant_viewpoints(pts, nrm, prims, args.prune_views, prm.viewpoints_distance, seed=5)
+
+    def run(m):
+        m.reset(); m.setMapPointCloud(pts); m.setModel(pts); m.setNormals(pts.astype(np.float64), nrm)
+        t = time.perf_counter()
+        m.setInitViewpoints(vps)
+        rc = m.updateViewpoints()
+        dt = time.perf_counter() - t
+        assert rc == 0
+        return dt
+
+    # The first run on a fresh handle is the one compared with the oracle: the reference's prune maps keep
+    # their bucket arrays across reset() (viewpoint_manager.h:169-177), so the iteration order - and with it
+    # the selected set - of a handle depends on its history, and the oracle below is a fresh handle too.
+    vm = ViewpointManager(prm)
+    first_s = run(vm)                         # includes every device allocation of the handle
+    gi, gp, gx = vm.final_arrays()
+    c = vm.counters()
+    n_unc = int(len(vm.getUncoveredModelCloud()))
+    gpu_s = min(run(vm), run(vm))
+    out = {"workload": f"synthetic plant scale 0.5: P={len(pts)} points, {len(vps)} initial candidate viewpoints, 0.2 m grid, "
+                       f"max_iter_num={prm.max_iter_num}; setInitViewpoints + updateViewpoints",
+           "gpu_ms": 1e3 * gpu_s, "gpu_ms_first_call": 1e3 * first_s, "final_viewpoints": int(len(gi)), "uncovered_points": n_unc,
+           "rays": int(c[1]), "kernel_launches": int(c[5])}
+    if with_cpu:
+        from oracle import oracle
+        orc = oracle.Oracle(prm)
+        cpu_s = run(orc)
+        oi, op, ox = orc.getUpdatedViewpoints()
+        out.update({"cpu_ms": 1e3 * cpu_s, "cpu_cores": 1, "cpu_kind": "port", "speedup": cpu_s / gpu_s,
+                    "selected_set_identical": bool(np.array_equal(gi, oi) and np.array_equal(gp, op) and np.array_equal(gx, ox))})
+    return out
+
+
 def run_reference(args, rank, world):
     """--impl reference: the reference's CPU implementation of the path (oracle port; the reference itself
     needs ROS/PCL/Eigen and cannot be built here) on the host cores, same metric and config."""
@@ -163,6 +206,9 @@ def main():
     ap.add_argument("--resolution", type=float, default=0.1)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--prune-points", type=int, default=40_000)
+    ap.add_argument("--prune-views", type=int, default=4_000)
+    ap.add_argument("--no-prune", action="store_true")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -180,6 +226,8 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     from fc_planner_b200.manager import ViewpointManager
@@ -224,15 +272,22 @@ def main():
     pairs_step = int(c1[0] - c0[0])
 
     # ---------------- e2e: host buffers through the C ABI ---------------------------------------
+    # poses come from, and counts + bitset rows go to, page-locked host memory (fcvm_host_alloc);
+    # every step does the host pose -> FOV-normal conversion, H2D, the kernels and the full D2H.
+    from fc_planner_b200.manager import pinned_empty
+    h_poses = pinned_empty(poses.shape, np.float64)
+    h_poses[:] = poses
+    out = (pinned_empty((len(poses),), np.int32), pinned_empty((len(poses), words), np.uint32))
     barrier()
-    for _ in range(min(args.warmup, 2)):
-        vm.evaluate(1, poses, want_rows=True)
+    for _ in range(min(args.warmup, 3)):
+        vm.evaluate(1, h_poses, out=out)
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        cnt, rows = vm.evaluate(1, poses, want_rows=True)
+        cnt, rows = vm.evaluate(1, h_poses, out=out)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    e2e_visible = int(cnt.sum())
 
     t = torch.tensor([dev_ms, e2e_s * 1e3, float(rays_step)], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -270,7 +325,8 @@ def main():
                        "parallelism": f"viewpoint shards x{world}, grid and points replicated, no data-path collective"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(V * 128), "d2h_bytes_per_step": int(V * 4 + V * words * 4),
-                    "ms_per_step": e2e_ms_max / args.steps, "call": "fcvm_evaluate(E1, host poses) -> host counts + bitset rows"},
+                    "ms_per_step": e2e_ms_max / args.steps, "visible_pairs_per_step_per_gpu": e2e_visible,
+                    "call": "fcvm_evaluate(E1, pinned host poses) -> pinned host counts + bitset rows; rows of a finished sub-batch copy out while the next is evaluated"},
             "gpu_launches": 2 * args.steps,
             "rays_per_step_per_gpu": rays_step, "pair_tests_per_step_per_gpu": pairs_step, "voxel_lookups_per_step_per_gpu": lookups_step,
             "viewpoint_evals_per_s": V * world * args.steps / (dev_ms_max * 1e-3),
@@ -287,6 +343,8 @@ def main():
                                     "counts_match_gpu": bool(int(vm2_cnt.sum()) >= 0)}
             rate1, n1, dt1, _, _ = cpu_oracle_rate(pts, nrm, prm, poses[:max(8, n // max(threads, 1))], args.cpu_seconds / 3, 1)
             line["cpu_baseline"]["single_thread_value"] = rate1
+        if not args.no_prune:
+            line["pruning"] = pruning_leg(args, local_rank, with_cpu=not args.no_cpu)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -51,6 +51,8 @@ SYMBOLS = {
     "fcvm_evaluate_resident": (ctypes.c_int, [vp, i32, vp, i32, i64p]),
     "fcvm_resident_buffers": (ctypes.c_int, [vp, ctypes.POINTER(vp), ctypes.POINTER(vp), i64p, i64p]),
     "fcvm_own_resident": (ctypes.c_int, [vp, i32p, i32p, i64]),
+    "fcvm_host_alloc": (vp, [i64]),
+    "fcvm_host_free": (None, [vp]),
     "fcvm_last_kernel_ms": (f64, [vp]),
     "fcvm_set_shard": (ctypes.c_int, [vp, i32, i32, ALLGATHER_FN, vp]),
     "fcvm_host_fov_normals": (ctypes.c_int, [ctypes.POINTER(Params), f64, f64, f64p]),

@@ -180,6 +180,8 @@ struct fcvm_handle {
   PinBuf<VpRec> h_recs;
   int64_t resident_n = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;          // D2H of finished sub-batches while the next one is evaluated
+  std::vector<cudaEvent_t> pipe_ev;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   double last_kernel_ms = 0.0;
   bool timed = false;
@@ -211,6 +213,7 @@ static int ensure_device(fcvm_handle* h) {
                                     " (this library has no CPU fallback)");
   CU(cudaSetDevice(h->prm.device));
   CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
   CU(cudaEventCreate(&h->ev0));
   CU(cudaEventCreate(&h->ev1));
   CU(h->d_counters.reserve(8));
@@ -290,9 +293,12 @@ static int fetch_counters(fcvm_handle* h) {
   return FCVM_OK;
 }
 
-// rows per batch chunk so that one rows buffer stays <= 1 GiB
+constexpr int64_t kPipeMinRows = 1024;   // smallest sub-batch worth a launch of its own
+
+// rows per batch chunk so that one rows buffer stays <= 4 GiB (two such buffers live on the device;
+// a B200 has 180 GB, the cap only bounds the pinned staging of the traced / CSR paths)
 static int64_t chunk_rows(const fcvm_handle* h, int64_t n) {
-  const int64_t per = std::max<int64_t>(1, (int64_t)(1ll << 30) / (h->W * 4));
+  const int64_t per = std::max<int64_t>(1, (int64_t)(4ll << 30) / (h->W * 4));
   return std::min(n, per);
 }
 
@@ -328,7 +334,28 @@ static int eval_batch(fcvm_handle* h, int stage, const VpRec* recs, int64_t n, c
   const int64_t lo = std::min(n, per_rank * h->rank), hi = std::min(n, per_rank * (h->rank + 1));
   h->timed = false;
   if (h->world > 1) CU(cudaMemsetAsync(d_rows.p, 0, (size_t)n_pad * W * sizeof(uint32_t), h->stream));
-  if (hi > lo) {
+  // Single GPU with rows wanted on the host: evaluate in up to 4 sub-batches and copy each finished
+  // one out on the copy stream while the next is being evaluated (the rows dominate the transfer).
+  bool rows_streamed = false;
+  if (rows_out && h->world == 1 && n >= 2 * kPipeMinRows) {
+    const int64_t sub = std::max<int64_t>(kPipeMinRows, (n + 3) / 4);
+    size_t k = 0;
+    for (int64_t s0 = 0; s0 < n; s0 += sub, ++k) {
+      const int64_t sn = std::min(sub, n - s0);
+      rc = launch_stage(h, stage, h->d_recs.p + s0, sn, d_rows.p + s0 * W, d_restrict ? d_restrict + s0 * W : nullptr, h->stream, true);
+      if (rc) return rc;
+      if (h->pipe_ev.size() <= k) {
+        cudaEvent_t e;
+        CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        h->pipe_ev.push_back(e);
+      }
+      CU(cudaEventRecord(h->pipe_ev[k], h->stream));
+      CU(cudaStreamWaitEvent(h->copy_stream, h->pipe_ev[k], 0));
+      CU(cudaMemcpyAsync(rows_out + s0 * W, d_rows.p + s0 * W, (size_t)sn * W * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->copy_stream));
+    }
+    rows_streamed = true;
+    h->timed = false;    // ev0/ev1 bracket only the last sub-batch
+  } else if (hi > lo) {
     rc = launch_stage(h, stage, h->d_recs.p + lo, hi - lo, d_rows.p + lo * W, d_restrict ? d_restrict + lo * W : nullptr, h->stream, true);
     if (rc) return rc;
   }
@@ -346,10 +373,11 @@ static int eval_batch(fcvm_handle* h, int stage, const VpRec* recs, int64_t n, c
     h->counters[5] += 1;
     CU(cudaMemcpyAsync(h->h_offsets.p, h->d_offsets.p, ((size_t)n + 1) * sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
   }
-  if (rows_out) CU(cudaMemcpyAsync(rows_out, d_rows.p, (size_t)n * W * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+  if (rows_out && !rows_streamed) CU(cudaMemcpyAsync(rows_out, d_rows.p, (size_t)n * W * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
   if (count_out) CU(cudaMemcpyAsync(count_out, h->d_count.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   rc = fetch_counters(h);   // synchronises the stream
   if (rc) return rc;
+  if (rows_streamed) CU(cudaStreamSynchronize(h->copy_stream));
   if (csr) {
     csr->offs.assign(h->h_offsets.p, h->h_offsets.p + n + 1);
     const long long total = csr->offs[(size_t)n];
@@ -989,6 +1017,8 @@ void fcvm_destroy(fcvm_t* h) {
   h->h_rows.free(); h->h_count.free(); h->h_recs.free(); h->d_offsets.free(); h->d_indices.free(); h->h_indices.free(); h->h_offsets.free();
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
+  for (cudaEvent_t e : h->pipe_ev) cudaEventDestroy(e);
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -1267,6 +1297,15 @@ int fcvm_set_shard(fcvm_t* h, int32_t rank, int32_t world, fcvm_allgather_fn fn,
   h->rank = rank; h->world = world; h->gather = fn; h->gather_user = user;
   return FCVM_OK;
 }
+
+void* fcvm_host_alloc(int64_t bytes) {
+  void* p = nullptr;
+  if (bytes <= 0) { fail(FCVM_EINVAL, "bad size"); return nullptr; }
+  cudaError_t e = cudaMallocHost(&p, (size_t)bytes);
+  if (e != cudaSuccess) { fail(e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver ? FCVM_ENODEVICE : FCVM_ECUDA, std::string("cudaMallocHost: ") + cudaGetErrorString(e)); return nullptr; }
+  return p;
+}
+void fcvm_host_free(void* p) { if (p) cudaFreeHost(p); }
 
 // ---------------------------------------------------------------- host-only helpers
 int fcvm_host_fov_normals(const fcvm_params* p, double pitch, double yaw, double* out12) {

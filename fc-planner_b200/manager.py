@@ -163,12 +163,17 @@ class ViewpointManager:
         return out
 
     # ---- evaluator level ----------------------------------------------------------------------
-    def evaluate(self, stage, pose5, restrict_rows=None, want_rows=True):
-        """One evaluator pass over host poses -> (count[n], rows[n, words]); H2D + kernel + D2H."""
+    def evaluate(self, stage, pose5, restrict_rows=None, want_rows=True, out=None):
+        """One evaluator pass over host poses -> (count[n], rows[n, words]); H2D + kernel + D2H.
+        out = (count, rows) preallocated arrays (e.g. from pinned_empty) to receive the result."""
         pose5 = np.ascontiguousarray(pose5, dtype=np.float64).reshape(-1, 5)
         n, words = len(pose5), self.words()
-        count = np.zeros(n, np.int32)
-        rows = np.zeros((n, words), np.uint32) if want_rows else None
+        if out is not None:
+            count, rows = out
+            assert count.shape == (n,) and count.dtype == np.int32 and rows.shape == (n, words) and rows.dtype == np.uint32
+        else:
+            count = np.zeros(n, np.int32)
+            rows = np.zeros((n, words), np.uint32) if want_rows else None
         if restrict_rows is not None:
             restrict_rows = np.ascontiguousarray(restrict_rows, dtype=np.uint32)
             assert restrict_rows.shape == (n, words)
@@ -217,6 +222,36 @@ class ViewpointManager:
         cb = _lib.ALLGATHER_FN(gather_cb) if gather_cb is not None else ctypes.cast(None, _lib.ALLGATHER_FN)
         self._keep.append(cb)
         check(self.lib.fcvm_set_shard(self.h, rank, world, cb, None))
+
+
+class _Pinned:
+    def __init__(self, nbytes):
+        self.lib = _lib.load()
+        self.ptr = self.lib.fcvm_host_alloc(nbytes)
+        if not self.ptr:
+            raise _lib.FcvmError(-4, self.lib.fcvm_last_error().decode("utf-8", "replace"))
+
+    def __del__(self):
+        try:
+            self.lib.fcvm_host_free(self.ptr)
+        except Exception:
+            pass
+
+
+def pinned_empty(shape, dtype):
+    """numpy array over page-locked host memory (fcvm_host_alloc); freed with the array."""
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape))
+    owner = _Pinned(max(1, n * dtype.itemsize))
+    buf = (ctypes.c_uint8 * (n * dtype.itemsize)).from_address(owner.ptr)
+    arr = np.frombuffer(buf, dtype=dtype, count=n).reshape(shape)
+    _PINNED_OWNERS[id(buf)] = owner
+    import weakref
+    weakref.finalize(buf, _PINNED_OWNERS.pop, id(buf), None)
+    return arr
+
+
+_PINNED_OWNERS = {}
 
 
 def host_fov_normals(params, pitch, yaw):

@@ -5,7 +5,7 @@
  * (reference: FC-Planner/src/viewpoint_manager/include/viewpoint_manager/viewpoint_manager.h:180-193).
  * Every manager-level entry point below replaces exactly one public method of that class;
  * the file:line of the method it replaces is quoted next to it.  A thin C++ shim with the
- * reference's own signatures (fc-planner_b200/shim/viewpoint_manager_shim.hpp) and a ctypes
+ * reference's own signatures (fc-planner_b200/shim/viewpoint_manager/viewpoint_manager.h) and a ctypes
  * mirror (fc-planner_b200/manager.py) forward to these symbols.  See INTEGRATION.md.
  *
  * Conventions
@@ -173,6 +173,12 @@ int fcvm_resident_buffers(fcvm_t* h, void** rows_dev, void** count_dev, int64_t*
  * given processing order, updating the manager's cover state; vp_ids[n] are the ids the rows
  * stand for; order[n] = row indices in processing order (NULL = 0..n-1). */
 int fcvm_own_resident(fcvm_t* h, const int32_t* vp_ids, const int32_t* order, int64_t n);
+
+/* Page-locked host memory for the caller's input / output buffers of the evaluator-level calls:
+ * copies to and from it run at full PCIe rate and overlap with the kernels (rows of a finished
+ * sub-batch are copied out while the next sub-batch is evaluated).  Pageable buffers work too, slower. */
+void* fcvm_host_alloc(int64_t bytes);
+void  fcvm_host_free(void* p);
 
 /* device time of the most recent visibility kernel (k_eval alone, CUDA events on its stream), in ms;
  * valid after a synchronising call */

@@ -1,8 +1,11 @@
-// oracle/shim/ros/ros.h — stand-in for the one roscpp facility the reference's perception_utils.cpp
-// uses: NodeHandle::param(name, var, default).  TEST INFRASTRUCTURE (oracle/_ref build only).
-// Values come from a process-wide table filled by ref_capi.cpp (the ROS parameter server's role).
+// oracle/shim/ros/ros.h — stand-in for the roscpp facilities the reference's hot-path sources use:
+// NodeHandle::param(name, var, default) and the ROS_INFO / ROS_WARN / ROS_ERROR macros.
+// TEST INFRASTRUCTURE (oracle/_ref build only).  Values come from a process-wide table filled by
+// the ref_*capi.cpp wrappers (the ROS parameter server's role).
 #pragma once
 
+#include <cstdio>
+#include <cstdlib>
 #include <map>
 #include <string>
 
@@ -10,6 +13,10 @@ namespace ros {
 
 inline std::map<std::string, double>& shim_param_table() {
   static std::map<std::string, double> t;
+  return t;
+}
+inline std::map<std::string, std::string>& shim_string_table() {
+  static std::map<std::string, std::string> t;
   return t;
 }
 
@@ -25,6 +32,21 @@ class NodeHandle {
     var = static_cast<T>(it->second);
     return true;
   }
+  bool param(const std::string& name, std::string& var, const std::string& def) const {
+    auto it = shim_string_table().find(name);
+    if (it == shim_string_table().end()) {
+      var = def;
+      return false;
+    }
+    var = it->second;
+    return true;
+  }
 };
 
 }  // namespace ros
+
+#ifndef ROS_INFO
+#define ROS_INFO(...) do { } while (0)
+#define ROS_WARN(...) do { } while (0)
+#define ROS_ERROR(...) do { if (std::getenv("FCVM_REF_VERBOSE")) { std::fprintf(stderr, __VA_ARGS__); std::fprintf(stderr, "\n"); } } while (0)
+#endif

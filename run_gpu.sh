@@ -1,6 +1,10 @@
 set -x
-python -m pytest tests -m gpu -x -q 2>&1 | tail -8
-python bench.py --steps 2 --warmup 1 --views 4096 --no-cpu > gpurun_out/plain4.log 2>&1 && \
-ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches_r1c.csv python bench.py --steps 2 --warmup 1 --views 4096 --no-cpu > gpurun_out/ncu4.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:k_eval -s 1 -c 1 -o gpurun_out/prof_r1c python bench.py --steps 2 --warmup 1 --views 4096 --no-cpu > gpurun_out/ncu5.log 2>&1
-tail -2 gpurun_out/ncu5.log | cut -c1-200
+python bench.py --steps 3 --warmup 3 > gpurun_out/bench_r1e.json 2> gpurun_out/bench_r1e.err; echo "rc=$?"; python - <<'PY'
+import json
+d=json.load(open('gpurun_out/bench_r1e.json'))
+print({k:d[k] for k in ('value','ms_per_step','e2e','pruning')})
+PY
+tail -5 gpurun_out/bench_r1e.err
+python bench.py --steps 2 --warmup 1 --no-cpu --no-prune > gpurun_out/plain6.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:k_eval -s 1 -c 1 -o gpurun_out/prof_r1e python bench.py --steps 2 --warmup 1 --no-cpu --no-prune > gpurun_out/ncu6.log 2>&1
+tail -2 gpurun_out/ncu6.log | cut -c1-200
