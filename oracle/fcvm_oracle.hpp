@@ -6,11 +6,19 @@
 // cpu_baseline / --impl reference legs and __graft_entry__.smoke() may use it, and only as the
 // checker.  The product library (fc-planner_b200/csrc) never includes, links or calls it.
 //
-// PARITY UNPINNED: the reference ships no tests, golden vectors or fixtures for this path
-//  and cannot be built in this image (needs ROS, PCL, Eigen, FLANN).  What
-// pins this file instead: (1) line-by-line correspondence, cited below; (2) oracle/_ref builds the
-// reference's own raycast.cpp and perception_utils.cpp from /root/reference against stand-in
-// Eigen/ROS headers and tests/test_oracle_vs_ref.py compares this file with them.
+// PARITY PIN.  The reference ships no tests, golden vectors or fixtures for this path (SURVEY.md
+// section 4) and its own build (catkin + ROS + PCL + Eigen + FLANN) is impossible in this image.
+// What pins this file instead is the reference's own SOURCE, compiled by oracle/Makefile from where
+// it lies under /root/reference against stand-in third-party headers (oracle/shim/):
+//   oracle/_ref/libfcvm_ref.so    raycast.cpp + perception_utils.cpp      (tests/test_oracle_vs_ref.py)
+//   oracle/_ref/libfcvm_refvm.so  + the whole viewpoint_manager.cpp       (tests/test_oracle_vs_ref_vm.py)
+// The oracle equals both bit for bit: marcher voxel sequences, FOV verdicts, E1-E4 masks, and for
+// the full call sequence the selected viewpoints, all poses, counts, cover state, uncovered cloud
+// and lookup counts, on synthetic scenes and on the three shipped scenes (= tests/golden/*.npz).
+// STILL UNPINNED (third-party internals that exist neither here nor under /root/reference): Eigen's
+// SSE2 packet reduction order for 3-vectors (assumed (a0*b0 + a1*b1) + a2*b2),
+// FLANN's tie order, pcl::RandomSample's algorithm and the wall-clock seeds (replaced by an
+// injected seed on all sides), and sdf_map.cpp (needs PCL/ROS/OpenCV; restated in HCMap below).
 //
 // All paths are relative to /root/reference/FC-Planner/src/.
 //

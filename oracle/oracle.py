@@ -332,3 +332,113 @@ class RefEvaluator:
         if rc != 0:
             raise RuntimeError(f"ref_evaluate failed: {rc}")
         return count, rows, ctr
+
+
+# -- oracle/_ref: the reference's own viewpoint_manager.cpp (ref_vm_capi.cpp) -----------------------
+_REFVM = None
+
+
+def refvm_path():
+    return os.path.join(_HERE, "_ref", "libfcvm_refvm.so")
+
+
+def refvm_available():
+    return os.path.exists(refvm_path())
+
+
+def refvm_load():
+    global _REFVM
+    if _REFVM is None:
+        lib = ctypes.CDLL(refvm_path())
+        lib.refvm_create.restype = ctypes.c_void_p
+        lib.refvm_create.argtypes = [ctypes.c_void_p]
+        lib.refvm_destroy.argtypes = [ctypes.c_void_p]
+        for fn in ("refvm_get_viewpoints", "refvm_get_uncovered", "refvm_get_vps_pose", "refvm_get_vps_voxcount", "refvm_get_vps_contri",
+                   "refvm_get_cover_state", "refvm_lookups"):
+            getattr(lib, fn).restype = ctypes.c_int64
+        _REFVM = lib
+    return _REFVM
+
+
+class RefViewpointManager:
+    """predrecon::ViewpointManager compiled from the reference's own viewpoint_manager.cpp, driven
+    through the same call sequence as `Oracle`.  ONE instance per process at a time: the injected
+    seed counters (clock shim, RandomSample shim) are process-wide."""
+
+    def __init__(self, params):
+        self.lib = refvm_load()
+        self.params = params
+        self.h = ctypes.c_void_p(self.lib.refvm_create(ctypes.byref(params)))
+        self.P = 0
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.lib.refvm_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def reset(self):
+        self.lib.refvm_reset(self.h)
+
+    def setMapPointCloud(self, xyz):
+        xyz = np.ascontiguousarray(xyz, dtype=np.float32)
+        return self.lib.refvm_set_map_cloud(self.h, _ptr(xyz, c_f32p), ctypes.c_int64(len(xyz)))
+
+    def setModel(self, xyz):
+        xyz = np.ascontiguousarray(xyz, dtype=np.float32)
+        self.P = len(xyz)
+        return self.lib.refvm_set_model(self.h, _ptr(xyz, c_f32p), ctypes.c_int64(len(xyz)))
+
+    def setNormals(self, pts, normals):
+        pts = np.ascontiguousarray(pts, dtype=np.float64); normals = np.ascontiguousarray(normals, dtype=np.float64)
+        return self.lib.refvm_set_normals(self.h, _ptr(pts, c_f64p), _ptr(normals, c_f64p), ctypes.c_int64(len(pts)))
+
+    def setInitViewpoints(self, pos_dir):
+        pos_dir = np.ascontiguousarray(pos_dir, dtype=np.float32)
+        return self.lib.refvm_set_init_viewpoints(self.h, _ptr(pos_dir, c_f32p), ctypes.c_int64(len(pos_dir)))
+
+    def updateViewpoints(self):
+        return self.lib.refvm_update(self.h)
+
+    def getUpdatedViewpoints(self):
+        n = self.lib.refvm_get_viewpoints(self.h, None, None, None, ctypes.c_int64(0))
+        ids = np.zeros(n, np.int32); pose = np.zeros((n, 5), np.float64); vox = np.zeros(n, np.int32)
+        self.lib.refvm_get_viewpoints(self.h, _ptr(ids, c_i32p), _ptr(pose, c_f64p), _ptr(vox, c_i32p), ctypes.c_int64(n))
+        return ids, pose, vox
+
+    def getUncoveredModelCloud(self):
+        n = self.lib.refvm_get_uncovered(self.h, None, ctypes.c_int64(0))
+        out = np.zeros((n, 3), np.float32)
+        self.lib.refvm_get_uncovered(self.h, _ptr(out, c_f32p), ctypes.c_int64(n))
+        return out
+
+    def vps_pose(self):
+        n = self.lib.refvm_get_vps_pose(self.h, None, ctypes.c_int64(0))
+        out = np.zeros((n, 5), np.float64)
+        self.lib.refvm_get_vps_pose(self.h, _ptr(out, c_f64p), ctypes.c_int64(n))
+        return out
+
+    def vps_voxcount(self):
+        n = self.lib.refvm_get_vps_voxcount(self.h, None, ctypes.c_int64(0))
+        out = np.zeros(n, np.int32)
+        self.lib.refvm_get_vps_voxcount(self.h, _ptr(out, c_i32p), ctypes.c_int64(n))
+        return out
+
+    def vps_contri(self):
+        n = self.lib.refvm_get_vps_contri(self.h, None, ctypes.c_int64(0))
+        out = np.zeros(n, np.int32)
+        self.lib.refvm_get_vps_contri(self.h, _ptr(out, c_i32p), ctypes.c_int64(n))
+        return out
+
+    def cover_state(self):
+        n = self.lib.refvm_get_cover_state(self.h, None, None, None, ctypes.c_int64(0))
+        cov = np.zeros(n, np.uint8); con = np.zeros(n, np.int32); cid = np.zeros(n, np.int32)
+        self.lib.refvm_get_cover_state(self.h, _ptr(cov, c_u8p), _ptr(con, c_i32p), _ptr(cid, c_i32p), ctypes.c_int64(n))
+        return cov, con, cid
+
+    def lookups(self):
+        s = ctypes.c_int64(0)
+        occ = self.lib.refvm_lookups(self.h, ctypes.byref(s))
+        return int(occ), int(s.value)
