@@ -116,7 +116,7 @@ def cpu_oracle_rate(pts, nrm, prm, poses, seconds, threads):
     return c[1] / dt, n, dt, c, orc
 
 
-def pruning_leg(args, device, with_cpu):
+def pruning_leg(args, device, with_cpu, world=1, rank=0):
     """BASELINE.json's second metric: viewpoint-pruning wall time = setInitViewpoints + updateViewpoints
     (the whole coverage-driven update: E1/E2, ownership, gravitation prune with E3/E4, uncovered-area
     rounds) through the public call sequence, next to the single-threaded CPU oracle (the reference is
@@ -140,16 +140,35 @@ def pruning_leg(args, device, with_cpu):
     # their bucket arrays across reset() (viewpoint_manager.h:169-177), so the iteration order - and with it
     # the selected set - of a handle depends on its history, and the oracle below is a fresh handle too.
     vm = ViewpointManager(prm)
+    if world > 1:
+        # viewpoints sharded over the ranks, grid + model replicated, one NCCL all-gather of the bitset
+        # rows per evaluator stage; every rank obtains the same result (fc-planner_b200/distributed.py)
+        from fc_planner_b200 import distributed as fd
+        ex = fd.attach(vm)
     first_s = run(vm)                         # includes every device allocation of the handle
     gi, gp, gx = vm.final_arrays()
     c = vm.counters()
     n_unc = int(len(vm.getUncoveredModelCloud()))
     gpu_s = min(run(vm), run(vm))
+    if world > 1:
+        import hashlib
+        import torch
+        import torch.distributed as dist
+        gpu_s, first_s = fd.max_over_ranks([gpu_s, first_s], device="cuda")     # wall time: max over ranks
+        # every rank must have selected the same set: compare a digest of (ids, poses, vox counts)
+        dig = int.from_bytes(hashlib.sha256(gi.tobytes() + gp.tobytes() + gx.tobytes()).digest()[:7], "little")
+        t = torch.tensor([dig], dtype=torch.int64, device="cuda")
+        lo, hi = t.clone(), t.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        ranks_agree = bool(int(lo) == int(hi))
     out = {"workload": f"synthetic plant scale 0.5: P={len(pts)} points, {len(vps)} initial candidate viewpoints, 0.2 m grid, "
                        f"max_iter_num={prm.max_iter_num}; setInitViewpoints + updateViewpoints",
            "gpu_ms": 1e3 * gpu_s, "gpu_ms_first_call": 1e3 * first_s, "final_viewpoints": int(len(gi)), "uncovered_points": n_unc,
-           "rays": int(c[1]), "kernel_launches": int(c[5])}
-    if with_cpu:
+           "rays": int(c[1]), "kernel_launches": int(c[5]), "n_gpus": world,
+           "scaling": "strong (one fixed problem sharded over the ranks; latency-bound at this size)"}
+    if world > 1:
+        out.update({"ranks_agree": ranks_agree, "allgathers_per_run": ex.calls // 3, "allgather_mb_per_run": ex.bytes / 3 / 1e6})
+    if with_cpu and rank == 0:
         from oracle import oracle
         orc = oracle.Oracle(prm)
         cpu_s = run(orc)
@@ -297,6 +316,9 @@ def main():
     else:
         dev_ms_max, e2e_ms_max, rays_total = dev_ms, e2e_s * 1e3, float(rays_step)
 
+    # second metric (collective when world > 1: every rank takes part)
+    prune = None if args.no_prune else pruning_leg(args, local_rank, with_cpu=not args.no_cpu and world == 1, world=world, rank=rank)
+
     if rank == 0:
         P, V = len(pts), len(poses)
         value = rays_total * args.steps / (dev_ms_max * 1e-3)
@@ -333,7 +355,7 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "kernel": "k_eval<E1>", "kernel_ms": kernel_ms, "algorithmic_bytes": b_alg, "peak_source": peak_src},
         }
-        if not args.no_cpu:
+        if not args.no_cpu and world == 1:      # the CPU baseline is timed on rank 0 at N = 1 only
             threads = host_cores()
             rate, n, dt, c, orc = cpu_oracle_rate(pts, nrm, prm, poses, args.cpu_seconds, threads)
             # the kernel's lookup / ray counters must equal the oracle's on the same viewpoints
@@ -343,8 +365,7 @@ def main():
                                     "counts_match_gpu": bool(int(vm2_cnt.sum()) >= 0)}
             rate1, n1, dt1, _, _ = cpu_oracle_rate(pts, nrm, prm, poses[:max(8, n // max(threads, 1))], args.cpu_seconds / 3, 1)
             line["cpu_baseline"]["single_thread_value"] = rate1
-        if not args.no_prune:
-            line["pruning"] = pruning_leg(args, local_rank, with_cpu=not args.no_cpu)
+        line["pruning"] = prune
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -62,7 +62,7 @@ SYMBOLS = {
 
 
 def lib_path():
-    return os.path.join(_HERE, "_build", "libfcvm.so")
+    return os.environ.get("FCVM_LIB") or os.path.join(_HERE, "_build", "libfcvm.so")
 
 
 def load():

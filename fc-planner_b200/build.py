@@ -30,18 +30,20 @@ def needs_build():
 
 
 def build(force=False, verbose=False):
-    if not force and not needs_build():
+    if not force and not needs_build() and not os.environ.get("FCVM_OUT"):
         return OUT
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    defs = [f"-D{k}={os.environ[e]}" for e, k in (("FCVM_EVAL_WARPS", "EVAL_WARPS"), ("FCVM_EVAL_MIN_CTAS", "EVAL_MIN_CTAS")) if os.environ.get(e)]
-    cmd = [nvcc] + NVCC_FLAGS + defs + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + [os.path.join(CSRC, s) for s in SOURCES]
+    # tuning experiments: FCVM_DEFS="EVAL_UNROLL=2,EVAL_KEEP=16" FCVM_OUT=/path/variant.so (load with FCVM_LIB=...)
+    defs = ["-D" + d for d in os.environ.get("FCVM_DEFS", "").split(",") if d]
+    out = os.environ.get("FCVM_OUT", OUT)
+    cmd = [nvcc] + NVCC_FLAGS + defs + (["-Xptxas", "-v"] if verbose else []) + ["-o", out] + [os.path.join(CSRC, s) for s in SOURCES]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + r.stdout)
     if verbose:
         print(r.stdout)
-    return OUT
+    return out
 
 
 if __name__ == "__main__":

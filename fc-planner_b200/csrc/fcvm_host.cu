@@ -69,6 +69,13 @@ static void parallel_for(int64_t n, int threads, F&& f) {
   for (auto& t : th) t.join();
 }
 
+struct Stopwatch {
+  double& acc;
+  std::chrono::steady_clock::time_point t0;
+  explicit Stopwatch(double& a) : acc(a), t0(std::chrono::steady_clock::now()) {}
+  ~Stopwatch() { acc += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); }
+};
+
 template <class T>
 struct DevBuf {
   T* p = nullptr;
@@ -187,6 +194,8 @@ struct fcvm_handle {
   bool timed = false;
   bool device_ok = false;
 
+  // wall-clock split of the manager-level calls (FCVM_PROFILE=1 prints it after fcvm_update)
+  double t_eval = 0, t_own = 0, t_init = 0, t_update = 0, t_unc = 0;
   // taps
   bool trace_on = false;
   std::vector<TraceEv> trace;
@@ -250,7 +259,7 @@ static void fill_fov_const(const fcvm_handle* h, FovConst& f) {
 static void choose_tiling(int64_t P, int64_t V, int& tile_pts, int& vp_per_cta) {
   tile_pts = P >= 8 * EVAL_MAX_TILE ? EVAL_MAX_TILE : (P >= 4096 ? 1024 : 512);
   const int64_t tiles = (P + tile_pts - 1) / tile_pts;
-  const int64_t target_ctas = 148 * 2 * 24;   // many short CTAs: tiles far from a viewpoint chunk finish early
+  const int64_t target_ctas = 148 * EVAL_MIN_CTAS * EVAL_WAVES;   // many short CTAs: tiles far from a viewpoint chunk finish early
   int64_t chunks = std::max<int64_t>(1, std::min<int64_t>((target_ctas + tiles - 1) / tiles, (V + EVAL_WARPS - 1) / EVAL_WARPS));
   int64_t per = (V + chunks - 1) / chunks;
   per = std::max<int64_t>(per, 1);
@@ -310,6 +319,7 @@ static int eval_batch(fcvm_handle* h, int stage, const VpRec* recs, int64_t n, c
   int rc = ensure_device(h);
   if (rc) return rc;
   if (n == 0) return FCVM_OK;
+  Stopwatch sw(h->t_eval);
   const int64_t W = h->W;
   // pad the batch to a multiple of the world size so that shards are equal (NCCL all-gather)
   const int64_t per_rank = (n + h->world - 1) / h->world;
@@ -403,6 +413,7 @@ static int eval_batch(fcvm_handle* h, int stage, const VpRec* recs, int64_t n, c
 // standing for viewpoint ids vp_ids[row] with popcounts count[row].
 static int own_sweep(fcvm_handle* h, const DevBuf<uint32_t>& d_rows, const std::vector<int>& order, const std::vector<int>& vp_ids,
                      const int* count) {
+  Stopwatch sw(h->t_own);
   std::vector<int4> sched;
   int max_id = -1;
   for (int r : order) {
@@ -926,12 +937,14 @@ static int update_impl(fcvm_handle* h) {
 
   // cpp:206-221: candidate library for the uncovered points
   std::unordered_map<int, std::vector<PtNormal>> uncVpsLib;
+  Stopwatch* sw_unc = new Stopwatch(h->t_unc);
   for (int p : uncoveredID) {
     auto it = h->pt_normal_pairs.find(D3{M[3 * p], M[3 * p + 1], M[3 * p + 2]});
     const D3 nd = it == h->pt_normal_pairs.end() ? D3{0, 0, 1} : it->second;
     const float nrm[3] = {(float)nd.x, (float)nd.y, (float)nd.z};
     unc_neigh_vps(h, &M[3 * p], nrm, uncVpsLib[p]);
   }
+  delete sw_unc;
 
   int unc_iter = 0, last_unc_num = -1;
   while ((int)uncoveredID.size() > 0 && unc_iter < prm.max_iter_num && last_unc_num != (int)uncoveredID.size()) {
@@ -1035,6 +1048,7 @@ int fcvm_reset(fcvm_t* h) {   // cpp:64-72
   h->trace.clear();
   for (int k = 0; k < FCVM_NCOUNTERS; ++k) h->counters[k] = 0;
   h->unc_calls = 0; h->sample_calls = 0;
+  h->t_eval = h->t_own = h->t_init = h->t_update = h->t_unc = 0;
   if (h->device_ok && h->P > 0) return cover_reset(h);
   return FCVM_OK;
 }
@@ -1087,12 +1101,22 @@ int fcvm_set_init_viewpoints(fcvm_t* h, const float* pos_dir, int64_t n) {   // 
   std::vector<PtNormal> v((size_t)n);
   for (int64_t i = 0; i < n; ++i)
     v[(size_t)i] = PtNormal{pos_dir[6 * i], pos_dir[6 * i + 1], pos_dir[6 * i + 2], pos_dir[6 * i + 3], pos_dir[6 * i + 4], pos_dir[6 * i + 5]};
+  Stopwatch sw(h->t_init);
   return set_init_viewpoints_impl(h, v);
 }
 
 int fcvm_update(fcvm_t* h) {   // cpp:143-330
   if (!h) return fail(FCVM_EINVAL, "null handle");
-  return update_impl(h);
+  int rc;
+  {
+    Stopwatch sw(h->t_update);
+    rc = update_impl(h);
+  }
+  if (std::getenv("FCVM_PROFILE"))
+    std::fprintf(stderr, "[fcvm] setInitViewpoints %.1f ms, updateViewpoints %.1f ms; of which evaluator batches (H2D + kernels + D2H + sync) %.1f ms, "
+                 "ownership sweeps %.1f ms, uncovered-candidate generation %.1f ms; kernels launched %lld\n",
+                 h->t_init, h->t_update, h->t_eval, h->t_own, h->t_unc, (long long)h->counters[5]);
+  return rc;
 }
 
 int64_t fcvm_get_viewpoints(fcvm_t* h, int32_t* vp_id, double* pose5, int32_t* vox_count, int64_t cap) {

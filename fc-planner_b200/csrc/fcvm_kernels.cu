@@ -55,7 +55,8 @@ __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarr
 // ------------------------------------------------------------------------------------------
 constexpr int kWarps = EVAL_WARPS;
 constexpr int kEntryQ = 64;   // (viewpoint, point) pairs that passed the FOV test, per warp
-constexpr int kReadyQ = 64;   // prepared / suspended rays ("continuations"), per warp
+constexpr int kReadyQ = EVAL_READYQ;   // prepared / suspended rays ("continuations"), per warp; >= EVAL_KEEP - 1 + 32
+static_assert(EVAL_READYQ >= EVAL_KEEP - 1 + 32, "ready queue too small for a suspended warp plus one prepared batch");
 constexpr int kContD = 12;    // doubles per continuation: tMax + tDelta of both half-rays
 constexpr int kContI = 11;    // ints per continuation
 
@@ -304,7 +305,7 @@ __global__ void __launch_bounds__(kWarps * 32, EVAL_MIN_CTAS) k_eval(const __gri
   // the warp suspends (writes the rays in flight back as continuations) as soon as the queue is
   // empty and fewer than `kKeep` lanes are busy, and goes back to testing FOV pairs.
   auto march = [&](bool drain) {
-    constexpr int kKeep = 20;
+    constexpr int kKeep = EVAL_KEEP;
     Cont c;
     bool active = false;
     int pkey = -1, nkey = -1;
@@ -329,26 +330,31 @@ __global__ void __launch_bounds__(kWarps * 32, EVAL_MIN_CTAS) k_eval(const __gri
         __syncwarp();
         break;
       }
-      if (active) {
-        // ---- one biNextId call and the loop body that follows it.  The call reports the voxels
-        // BEFORE it steps, so they are looked up first and both sides advance afterwards.
-        const bool pflag = c.p.rem > 0, nflag = c.n.rem > 0;
-        if (!(pflag || nflag)) {
-          // the call returned false: visible_flag = occCheck(idx); visible_flag_rev keeps its last (true) value
-          const bool f = occ_fast(g, c.p.ix, c.p.iy, c.p.iz, pkey, pword);
-          st.lookups += 1;
-          if (c.p.ix != c.n.ix || c.p.iy != c.n.iy || c.p.iz != c.n.iz) st.trips++;   // both sides must have met in the midpoint voxel
-          if (f && (c.flags & CONT_INRANGE)) set_bit(c.vp, c.pt);
-          active = false;
-        } else {
-          const bool f = occ_fast(g, c.p.ix, c.p.iy, c.p.iz, pkey, pword);
-          const bool r = occ_fast(g, c.n.ix, c.n.iy, c.n.iz, nkey, nword);
-          st.lookups += 2;
-          c.p.step_if(pflag);
-          c.n.step_if(nflag);
-          if (!f || !r) {
-            st.lookups += 1;                        // the re-check after the break (same voxel, same answer)
+      // EVAL_UNROLL biNextId calls per refill / suspend check: the two ballots and the queue logic are
+      // warp-wide overhead, a lane that finishes inside the group idles for at most EVAL_UNROLL - 1 steps
+#pragma unroll
+      for (int u = 0; u < EVAL_UNROLL; ++u) {
+        if (active) {
+          // ---- one biNextId call and the loop body that follows it.  The call reports the voxels
+          // BEFORE it steps, so they are looked up first and both sides advance afterwards.
+          const bool pflag = c.p.rem > 0, nflag = c.n.rem > 0;
+          if (!(pflag || nflag)) {
+            // the call returned false: visible_flag = occCheck(idx); visible_flag_rev keeps its last (true) value
+            const bool f = occ_fast(g, c.p.ix, c.p.iy, c.p.iz, pkey, pword);
+            st.lookups += 1;
+            if (c.p.ix != c.n.ix || c.p.iy != c.n.iy || c.p.iz != c.n.iz) st.trips++;   // both sides must have met in the midpoint voxel
+            if (f && (c.flags & CONT_INRANGE)) set_bit(c.vp, c.pt);
             active = false;
+          } else {
+            const bool f = occ_fast(g, c.p.ix, c.p.iy, c.p.iz, pkey, pword);
+            const bool r = occ_fast(g, c.n.ix, c.n.iy, c.n.iz, nkey, nword);
+            st.lookups += 2;
+            c.p.step_if(pflag);
+            c.n.step_if(nflag);
+            if (!f || !r) {
+              st.lookups += 1;                        // the re-check after the break (same voxel, same answer)
+              active = false;
+            }
           }
         }
       }

@@ -15,7 +15,21 @@ namespace fcvm {
 #ifndef EVAL_MIN_CTAS
 #define EVAL_MIN_CTAS 2       // resident CTAs per SM the register allocation is tuned for
 #endif
-#define EVAL_MAX_TILE 2048
+#ifndef EVAL_KEEP
+#define EVAL_KEEP 20          // march: suspend back to the FOV phase when fewer lanes than this are busy and the queue is empty
+#endif
+#ifndef EVAL_UNROLL
+#define EVAL_UNROLL 1         // march: biNextId calls per refill / suspend check
+#endif
+#ifndef EVAL_WAVES
+#define EVAL_WAVES 24         // CTA waves (over 148 SMs x EVAL_MIN_CTAS) the tiling aims at
+#endif
+#ifndef EVAL_READYQ
+#define EVAL_READYQ 64        // ray continuations per warp in shared memory (140 B each)
+#endif
+#ifndef EVAL_MAX_TILE
+#define EVAL_MAX_TILE 2048    // points per CTA tile at large P (16 B each, staged by one TMA bulk copy)
+#endif
 
 struct EvalArgs {
   GridDesc grid;
