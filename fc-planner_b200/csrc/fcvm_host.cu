@@ -498,7 +498,10 @@ static bool near_check(fcvm_handle* h, const D3& pos, int vox_num) {
   if (vox_num <= 1) return false;
   return !h->map_index.any_closer_than(q, h->prm.safe_radius);
 }
-static bool viewpoint_safety_check(fcvm_handle* h, float vx, float vy, float vz) {
+// `lookups` receives the number of safety_check calls (the handle's counter when null; a caller-owned
+// counter when the candidates of many points are checked concurrently)
+static bool viewpoint_safety_check(fcvm_handle* h, float vx, float vy, float vz, int64_t* lookups = nullptr) {
+  int64_t& ctr = lookups ? *lookups : h->counters[7];
   const fcvm_params& p = h->prm;
   if (p.z_ground && vz < p.ground_pos + p.safe_height) return false;
   const double res = h->grid.res, sr = p.safe_radius;
@@ -507,7 +510,7 @@ static bool viewpoint_safety_check(fcvm_handle* h, float vx, float vy, float vz)
   for (int i = 0; vx - sr + i * res < vx + sr; i = i + safe_voxel)
     for (int j = 0; vy - sr + j * res < vy + sr; j = j + safe_voxel)
       for (int k = 0; vz - sr + k * res < vz + sr; k = k + safe_voxel) {
-        h->counters[7]++;
+        ctr++;
         if (!h->grid.safety_check(vx - sr + i * res, vy - sr + j * res, vz - sr + k * res)) return false;
       }
   return near_check(h, D3{vx, vy, vz}, 2);
@@ -815,13 +818,14 @@ static int viewpoints_prune(fcvm_handle* h, const std::vector<Pose5>& vps_pose, 
 
 // uncNeighVps (viewpoint_manager.cpp:948-1131) with injected seeds: engine k of call c is seeded
 // with seed + 8*c + k (k = 0..3 pitch, 4..7 yaw)
-static void unc_neigh_vps(fcvm_handle* h, const float pt[3], const float nrm[3], std::vector<PtNormal>& out) {
+static void unc_neigh_vps(const fcvm_handle* hc, const float pt[3], const float nrm[3], std::vector<PtNormal>& out, int64_t call, int64_t* lookups) {
+  fcvm_handle* h = const_cast<fcvm_handle*>(hc);   // read-only here: grid, map index, parameters
   const fcvm_params& prm = h->prm;
   double max_pitch_range = 40.0, max_yaw_range = 40.0;
   if (prm.attitude == FCVM_ATTITUDE_YAW) max_pitch_range = 0;
   double op, oy;
   pitch_yaw(D3{nrm[0], nrm[1], nrm[2]}, op, oy);
-  const uint64_t base = prm.seed + 8ull * (uint64_t)h->unc_calls++;
+  const uint64_t base = prm.seed + 8ull * (uint64_t)call;
   double rand_p[4], rand_y[4];
   std::uniform_real_distribution<double> dist_p(0.0, max_pitch_range * M_PI / 180.0);
   for (int k = 0; k < 4; ++k) {
@@ -848,7 +852,7 @@ static void unc_neigh_vps(fcvm_handle* h, const float pt[3], const float nrm[3],
   }
   out.clear();
   for (int q = 0; q < 8; ++q)
-    if (viewpoint_safety_check(h, cand[q].x, cand[q].y, cand[q].z)) out.push_back(cand[q]);
+    if (viewpoint_safety_check(h, cand[q].x, cand[q].y, cand[q].z, lookups)) out.push_back(cand[q]);
 }
 
 // stand-in for pcl::RandomSample (cpp:249-255): selection sampling driven by minstd_rand0(seed + phi + call#)
@@ -936,22 +940,32 @@ static int update_impl(fcvm_handle* h) {
   if (rc) return rc;
 
   // cpp:206-221: candidate library for the uncovered points
-  std::unordered_map<int, std::vector<PtNormal>> uncVpsLib;
-  Stopwatch* sw_unc = new Stopwatch(h->t_unc);
-  for (int p : uncoveredID) {
-    auto it = h->pt_normal_pairs.find(D3{M[3 * p], M[3 * p + 1], M[3 * p + 2]});
-    const D3 nd = it == h->pt_normal_pairs.end() ? D3{0, 0, 1} : it->second;
-    const float nrm[3] = {(float)nd.x, (float)nd.y, (float)nd.z};
-    unc_neigh_vps(h, &M[3 * p], nrm, uncVpsLib[p]);
+  // The points are independent (candidate q of the c-th call draws from engines seeded seed + 8c + k), so
+  // the library is built by all host threads; slot k belongs to uncoveredID[k] of this first list.
+  std::vector<std::vector<PtNormal>> uncVpsLib(uncoveredID.size());
+  std::vector<int> lib_slot((size_t)h->P, -1);
+  {
+    Stopwatch sw_unc(h->t_unc);
+    const int64_t n_unc = (int64_t)uncoveredID.size(), call0 = h->unc_calls;
+    h->unc_calls += n_unc;
+    for (int64_t k = 0; k < n_unc; ++k) lib_slot[(size_t)uncoveredID[(size_t)k]] = (int)k;
+    std::vector<int64_t> looks((size_t)n_unc, 0);
+    parallel_for(n_unc, h->threads, [&](int64_t k) {
+      const int p = uncoveredID[(size_t)k];
+      auto it = h->pt_normal_pairs.find(D3{M[3 * p], M[3 * p + 1], M[3 * p + 2]});
+      const D3 nd = it == h->pt_normal_pairs.end() ? D3{0, 0, 1} : it->second;
+      const float nrm[3] = {(float)nd.x, (float)nd.y, (float)nd.z};
+      unc_neigh_vps(h, &M[3 * p], nrm, uncVpsLib[(size_t)k], call0 + k, &looks[(size_t)k]);
+    });
+    for (int64_t v : looks) h->counters[7] += v;
   }
-  delete sw_unc;
 
   int unc_iter = 0, last_unc_num = -1;
   while ((int)uncoveredID.size() > 0 && unc_iter < prm.max_iter_num && last_unc_num != (int)uncoveredID.size()) {
     last_unc_num = (int)uncoveredID.size();
     std::vector<PtNormal> cand;
     for (int p : uncoveredID)
-      for (auto& u : uncVpsLib[p]) cand.push_back(u);
+      for (auto& u : uncVpsLib[(size_t)lib_slot[(size_t)p]]) cand.push_back(u);
     if ((int)cand.size() > 100) cand = random_sample(h, cand, 100);
 
     // snapshot of MCI (cpp:272-274)

@@ -16,10 +16,10 @@ namespace fcvm {
 #define EVAL_MIN_CTAS 2       // resident CTAs per SM the register allocation is tuned for
 #endif
 #ifndef EVAL_KEEP
-#define EVAL_KEEP 20          // march: suspend back to the FOV phase when fewer lanes than this are busy and the queue is empty
+#define EVAL_KEEP 24          // march: suspend back to the FOV phase when fewer lanes than this are busy and the queue is empty
 #endif
 #ifndef EVAL_UNROLL
-#define EVAL_UNROLL 1         // march: biNextId calls per refill / suspend check
+#define EVAL_UNROLL 2         // march: biNextId calls per refill / suspend check
 #endif
 #ifndef EVAL_WAVES
 #define EVAL_WAVES 24         // CTA waves (over 148 SMs x EVAL_MIN_CTAS) the tiling aims at
@@ -28,7 +28,7 @@ namespace fcvm {
 #define EVAL_READYQ 64        // ray continuations per warp in shared memory (140 B each)
 #endif
 #ifndef EVAL_MAX_TILE
-#define EVAL_MAX_TILE 2048    // points per CTA tile at large P (16 B each, staged by one TMA bulk copy)
+#define EVAL_MAX_TILE 1024    // points per CTA tile at large P (16 B each, staged by one TMA bulk copy)
 #endif
 
 struct EvalArgs {

@@ -42,14 +42,14 @@ def load_golden(scene):
     8-call sequence (tests/golden/make_golden.py)."""
     from fc_planner_b200 import launch_params
     z = np.load(os.path.join(GOLDEN, f"{scene}.npz"))
-    prm = launch_params(scene, seed=int(z["seed"]))
+    prm = launch_params({"pipe4x": "pipe"}.get(scene, scene), seed=int(z["seed"]))   # pipe4x: configs[3] substitute, see make_golden.py
     return prm, z
 
 
 def run_sequence(mgr, z, trace=True):
     """reset -> setMapPointCloud -> setModel -> setNormals -> updateViewpoints (viewpoints generated
     from the normals, viewpoint_manager.cpp:145-171) on a manager-like object."""
-    if trace:
+    if trace and len(z["trace_stage"]):
         mgr.trace_enable()
     mgr.reset()
     mgr.setMapPointCloud(z["map_cloud"])
@@ -74,7 +74,7 @@ def compare_with_golden(mgr, z, final, check_trace=True):
     c = mgr.counters()
     assert c[4] == 0                                            # no marcher cap trips
     assert c[1] == z["counters"][1] and c[2] == z["counters"][2] and c[3] == z["counters"][3]   # rays, lookups, walk lookups
-    if check_trace:
+    if check_trace and len(z["trace_stage"]):
         tr = mgr.trace()
         W = z["trace_rows"].shape[1]
         assert len(tr) == len(z["trace_stage"])

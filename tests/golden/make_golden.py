@@ -37,18 +37,22 @@ SCENES = {
     "mbs": dict(map="hierarchical_coverage_planner/data/MBSmore.pcd", model="hierarchical_coverage_planner/data/MBS.pcd", ground=-10.5),
     "pipe": dict(map="hierarchical_coverage_planner/data/pipe.pcd", model="hierarchical_coverage_planner/data/pipe.pcd", ground=None),
     "christ": dict(map="hierarchical_coverage_planner/data/christmore.pcd", model="rosa/data/christ.pcd", ground=None),
+    # BASELINE.json configs[3] names a "Pacifico" scene the reference does not ship (SURVEY.md preface): substitute =
+    # pipe with the model leaf halved (2.0 -> 1.0 m), one candidate per model point => ~4x the candidate viewpoints
+    "pipe4x": dict(map="hierarchical_coverage_planner/data/pipe.pcd", model="hierarchical_coverage_planner/data/pipe.pcd", ground=None,
+                   params="pipe", leaf=1.0, trace=False),
 }
 
 
 def build_inputs(scene):
     from scipy.spatial import cKDTree
     cfg = SCENES[scene]
-    prm = launch_params(scene, seed=20231019)
+    prm = launch_params(cfg.get("params", scene), seed=20231019)
     map_cloud = scenes.read_pcd_xyz(os.path.join(REF, cfg["map"]))
     src = scenes.read_pcd_xyz(os.path.join(REF, cfg["model"]))
     if cfg["ground"] is not None:
         src = src[src[:, 2] > cfg["ground"]]
-    model = scenes.voxel_centroids(src, model_leaf(scene))
+    model = scenes.voxel_centroids(src, cfg.get("leaf") or model_leaf(scene))
     # snap every centroid to the nearest point of the model source, so that thin surfaces keep their
     # points (the reference keeps a centroid only if its own voxel is occupied, hcplanner.cpp:150-158)
     model = src[cKDTree(src.astype(np.float64)).query(model.astype(np.float64), k=1)[1]]
@@ -81,9 +85,10 @@ def build_inputs(scene):
     return prm, map_cloud, model, normals
 
 
-def run_oracle(prm, map_cloud, model, normals, init_vps=None):
+def run_oracle(prm, map_cloud, model, normals, init_vps=None, trace=True):
     orc = oracle.Oracle(prm)
-    orc.trace_enable()
+    if trace:
+        orc.trace_enable()
     orc.reset()
     orc.setMapPointCloud(map_cloud)
     orc.setModel(model)
@@ -101,14 +106,14 @@ def run_oracle(prm, map_cloud, model, normals, init_vps=None):
         prune_order=orc.prune_order(), counters=orc.counters(),
         trace_stage=np.array([t[0] for t in tr], np.int8), trace_vp=np.array([t[1] for t in tr], np.int32),
         trace_pose=np.array([t[2] for t in tr], np.float64).reshape(-1, 5),
-        trace_rows=np.array([t[3] for t in tr], np.uint32).reshape(len(tr), -1))
+        trace_rows=np.array([t[3] for t in tr], np.uint32).reshape(len(tr), -1) if tr else np.zeros((0, 0), np.uint32))
 
 
 def main():
     names = sys.argv[1:] or list(SCENES)
     for scene in names:
         prm, map_cloud, model, normals = build_inputs(scene)
-        out = run_oracle(prm, map_cloud, model, normals)
+        out = run_oracle(prm, map_cloud, model, normals, trace=SCENES[scene].get("trace", True))
         path = os.path.join(HERE, f"{scene}.npz")
         np.savez_compressed(path, scene=scene, seed=np.uint64(prm.seed), map_cloud=map_cloud, model=model, normals=normals, **out)
         c = out["counters"]

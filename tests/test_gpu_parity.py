@@ -157,7 +157,7 @@ def test_error_convention(small_plant):
     assert len(vm.getUpdatedViewpoints()) == 0
 
 
-@pytest.mark.parametrize("scene", ["mbs", "pipe", "christ"])
+@pytest.mark.parametrize("scene", ["mbs", "pipe", "christ", "pipe4x"])
 def test_shipped_scene_matches_golden(scene):
     """BASELINE.json configs[0..2]: the full 8-call sequence on the reference's own MBS / pipe /
     Christ point clouds against the committed golden fixtures (tests/golden/*.npz, generated by the

@@ -10,7 +10,7 @@ import pytest
 from conftest import compare_with_golden, load_golden, run_sequence
 
 
-@pytest.mark.parametrize("scene", ["mbs", "pipe", "christ"])
+@pytest.mark.parametrize("scene", ["mbs", "pipe", "christ", "pipe4x"])
 def test_oracle_reproduces_golden(oracle_mod, scene):
     prm, z = load_golden(scene)
     orc = oracle_mod.Oracle(prm)
@@ -21,9 +21,10 @@ def test_oracle_reproduces_golden(oracle_mod, scene):
 
 
 def test_golden_scenes_are_not_vacuous():
-    for scene, min_final in (("mbs", 100), ("pipe", 100), ("christ", 50)):
+    for scene, min_final in (("mbs", 100), ("pipe", 100), ("christ", 50), ("pipe4x", 300)):
         _, z = load_golden(scene)
         assert len(z["final_ids"]) >= min_final
         assert z["counters"][1] > 50_000            # rays
-        assert set(np.unique(z["trace_stage"])) == {1, 2, 3, 4}
+        if scene != "pipe4x":                       # the 4x-density fixture carries no per-call masks (size)
+            assert set(np.unique(z["trace_stage"])) == {1, 2, 3, 4}
         assert 0 < len(z["uncovered"]) < 0.1 * len(z["model"])

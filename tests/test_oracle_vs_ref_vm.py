@@ -77,7 +77,7 @@ def test_second_run_on_the_same_handle_matches_reference_source(small_plant):
     _compare(ref, orc)
 
 
-@pytest.mark.parametrize("scene", ["mbs", "pipe", "christ"])
+@pytest.mark.parametrize("scene", ["mbs", "pipe", "christ", "pipe4x"])
 def test_shipped_scene_matches_reference_source(scene):
     """MBS, pipe and Christ the Redeemer (BASELINE.json configs[0..2]) from the committed golden
     inputs: the reference's own viewpoint_manager.cpp reproduces the golden outputs the oracle
