@@ -30,6 +30,7 @@ struct GridDesc {
   const unsigned long long* bricks;  // [nbx*nby*nbz]
   int nx, ny, nz;                    // map_voxel_num_
   int nbx, nby, nbz;                 // bricks per axis: ceil(n/4)
+  int nbricks;                       // nbx * nby * nbz (< 2^31: the reference addresses voxels with int)
   double res;                        // resolution_
   double offx, offy, offz;           // RayCaster::offset_ = 0.5 - origin/res   (raycast.cpp:344)
   double orgx, orgy, orgz;           // map_origin_

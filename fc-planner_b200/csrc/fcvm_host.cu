@@ -236,6 +236,7 @@ static void fill_grid_desc(const fcvm_handle* h, GridDesc& g) {
   g.bricks = h->d_bricks.p;
   g.nx = hg.dims[0]; g.ny = hg.dims[1]; g.nz = hg.dims[2];
   g.nbx = hg.ns[0]; g.nby = hg.ns[1]; g.nbz = hg.ns[2];
+  g.nbricks = (int)hg.bricks.size();
   g.res = hg.res;
   // RayCaster::setParams (raycast.cpp:341-345): offset_ = half_ - origin / resolution_
   g.offx = 0.5 - hg.origin[0] / hg.res;
@@ -1073,6 +1074,7 @@ int fcvm_set_map_cloud(fcvm_t* h, const float* xyz, int64_t n) {   // cpp:74-89
   if (rc) return rc;
   h->grid.build(h->prm, xyz, n);
   if (h->grid.voxels() <= 0) return fail(FCVM_EINVAL, "degenerate grid");
+  if (h->grid.voxels() >= (1ll << 31)) return fail(FCVM_EINVAL, "grid has 2^31 voxels or more: beyond the reference's int addressing (sdf_map.h:266-269)");
   h->map_index.build(xyz, n, std::max(h->prm.safe_radius, 4 * h->prm.resolution));
   CU(h->d_bricks.reserve(h->grid.bricks.size()));
   CU(cudaMemcpy(h->d_bricks.p, h->grid.bricks.data(), h->grid.bricks.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice));

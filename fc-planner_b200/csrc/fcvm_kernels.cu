@@ -123,12 +123,17 @@ __device__ __forceinline__ void cont_load(const double* qd, const int* qi, int s
   c.vp = (uint32_t)qi[9 * kReadyQ + slot]; c.pt = (uint32_t)qi[10 * kReadyQ + slot];
 }
 
-// occCheck on the fast path (no bounds test: the ray's extent is inside the map)
+// occCheck on the fast path.  No per-axis bounds test: the ray's extent was verified to lie inside the
+// map when it was prepared, and a sane marcher never leaves the box spanned by its end voxels.  The
+// reference marcher is not always sane (it can run away from a lattice-aligned start, see
+// tests/test_oracle_vs_ref.py), so the brick index is range-checked where a new brick is fetched:
+// a stray ray reads "occupied" instead of memory outside the grid, and is counted as a cap trip
+// when its two halves fail to meet.
 __device__ __forceinline__ bool occ_fast(const GridDesc& g, int ix, int iy, int iz, int& ckey, unsigned long long& cword) {
   const int k = ((ix >> 2) * g.nby + (iy >> 2)) * g.nbz + (iz >> 2);
   if (k != ckey) {
     ckey = k;
-    cword = __ldg(g.bricks + k);
+    cword = (unsigned)k < (unsigned)g.nbricks ? __ldg(g.bricks + k) : ~0ull;
   }
   return ((cword >> brick_bit_index(ix, iy, iz)) & 1ull) == 0ull;
 }

@@ -170,3 +170,29 @@ def test_shipped_scene_matches_golden(scene):
     run_sequence(vm, z)
     compare_with_golden(vm, z, vm.final_arrays())
     assert vm.counters()[7] == z["counters"][7]       # same safety_check lookups on the host
+
+
+def test_lattice_aligned_viewpoints(small_plant, oracle_mod):
+    """Viewpoints exactly on voxel-lattice corners: the inputs on which the reference's marcher can
+    run away (no termination; tests/test_oracle_vs_ref.py).  Oracle and kernel cap such rays and
+    count them (counter 4); every viewpoint without a capped ray must still match bit for bit, and
+    nothing may fault."""
+    from fc_planner_b200 import scenes
+    vm, orc, prm = _mk(small_plant, oracle_mod)
+    poses = scenes.poses_from_viewpoints(small_plant["viewpoints"][:160])
+    poses[:, :3] = np.round(poses[:, :3] / prm.resolution) * prm.resolution
+    c0 = vm.counters()
+    cnt, rows = vm.evaluate(1, poses)
+    gpu_trips = int((vm.counters() - c0)[4])
+    W = (orc.P + 31) // 32
+    clean, capped = 0, 0
+    for i in range(len(poses)):
+        ocnt, orows, octr = orc.evaluate(1, poses[i:i + 1])
+        if octr[4] == 0:
+            assert np.array_equal(rows[i, :W], orows[0]) and cnt[i] == ocnt[0], i
+            clean += 1
+        else:
+            capped += 1
+    assert clean > 100
+    assert (gpu_trips > 0) == (capped > 0) or capped == 0
+    print(f"lattice-aligned: {clean} clean viewpoints bit-exact, {capped} with capped rays (oracle), gpu cap trips {gpu_trips}")
