@@ -46,7 +46,7 @@ def build_scene(args, rank):
 
 def workload_name(args):
     return (f"synthetic plant seed 0 (BASELINE configs[4] geometry): P={args.points} points, {args.resolution} m grid, "
-            f"{args.views} candidate viewpoints per GPU per step, E1 evaluator pass")
+            f"{args.views} candidate viewpoints per GPU per step, E{args.stage} evaluator pass")
 
 
 class ClockSampler:
@@ -104,16 +104,16 @@ def host_cores():
         return os.cpu_count() or 1
 
 
-def cpu_oracle_rate(pts, nrm, prm, poses, seconds, threads):
+def cpu_oracle_rate(pts, nrm, prm, poses, seconds, threads, stage=1):
     """Time the CPU oracle's E1 pass on a bounded prefix of the batch.  Returns (rays/s, sample, counters)."""
     from oracle import oracle
     orc = oracle.Oracle(prm)
     orc.setMapPointCloud(pts); orc.setModel(pts)
     n0 = min(len(poses), max(threads, 4))
-    t = time.perf_counter(); _, _, c = orc.evaluate(1, poses[:n0], threads=threads); dt = time.perf_counter() - t
+    t = time.perf_counter(); _, _, c = orc.evaluate(stage, poses[:n0], threads=threads); dt = time.perf_counter() - t
     n = int(min(len(poses), max(n0, n0 * seconds / max(dt, 1e-3))))
-    t = time.perf_counter(); cnt, rows, c = orc.evaluate(1, poses[:n], threads=threads); dt = time.perf_counter() - t
-    return c[1] / dt, n, dt, c, orc
+    t = time.perf_counter(); cnt, rows, c = orc.evaluate(stage, poses[:n], threads=threads); dt = time.perf_counter() - t
+    return c[1] / dt, n, dt, c, cnt
 
 
 def pruning_leg(args, device, with_cpu, world=1, rank=0):
@@ -190,14 +190,14 @@ def run_reference(args, rank, world):
     orc.setMapPointCloud(pts); orc.setModel(pts)
     # size one step so that warmup + steps end within a few minutes
     n0 = max(threads, 4)
-    t = time.perf_counter(); orc.evaluate(1, poses[:n0], threads=threads); dt0 = time.perf_counter() - t
+    t = time.perf_counter(); orc.evaluate(args.stage, poses[:n0], threads=threads); dt0 = time.perf_counter() - t
     per_step_s = min(20.0, 150.0 / max(1, args.steps + args.warmup))
     n = int(min(len(poses), max(n0, n0 * per_step_s / max(dt0, 1e-3))))
     for _ in range(args.warmup):
-        orc.evaluate(1, poses[:n], threads=threads)
+        orc.evaluate(args.stage, poses[:n], threads=threads)
     rays, t0 = 0, time.perf_counter()
     for _ in range(args.steps):
-        _, _, c = orc.evaluate(1, poses[:n], threads=threads)
+        _, _, c = orc.evaluate(args.stage, poses[:n], threads=threads)
         rays += int(c[1])
     dt = time.perf_counter() - t0
     value = rays / dt
@@ -228,6 +228,8 @@ def main():
     ap.add_argument("--prune-points", type=int, default=40_000)
     ap.add_argument("--prune-views", type=int, default=4_000)
     ap.add_argument("--no-prune", action="store_true")
+    ap.add_argument("--stage", type=int, default=1, choices=[1, 3, 4],
+                    help="evaluator pass to time: 1 = getPose pass 1 (headline), 3 = gravitation pass, 4 = updateViewpointInfo (offset walk + BiRC)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -270,7 +272,7 @@ def main():
     # ---------------- value: everything resident ------------------------------------------------
     vm.stage_poses(poses)
     for _ in range(args.warmup):
-        vm.evaluate_resident(1, stream=stream, sync=True)
+        vm.evaluate_resident(args.stage, stream=stream, sync=True)
     c0 = vm.counters()
     sampler = ClockSampler(local_rank)
     barrier()
@@ -278,13 +280,13 @@ def main():
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(args.steps):
-        vm.evaluate_resident(1, stream=stream, sync=False)
+        vm.evaluate_resident(args.stage, stream=stream, sync=False)
     ev1.record()
     barrier()
     clocks = sampler.stop()
     dev_ms = ev0.elapsed_time(ev1)
     # one more, synchronising, launch for the kernel-alone event time and the counters of one step
-    rays_step = vm.evaluate_resident(1, stream=stream, sync=True)
+    rays_step = vm.evaluate_resident(args.stage, stream=stream, sync=True)
     kernel_ms = vm.last_kernel_ms()
     c1 = vm.counters()
     lookups_step = int(c1[2] - c0[2])        # only the synchronising launch accumulates counters
@@ -299,11 +301,11 @@ def main():
     out = (pinned_empty((len(poses),), np.int32), pinned_empty((len(poses), words), np.uint32))
     barrier()
     for _ in range(min(args.warmup, 3)):
-        vm.evaluate(1, h_poses, out=out)
+        vm.evaluate(args.stage, h_poses, out=out)
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        cnt, rows = vm.evaluate(1, h_poses, out=out)
+        cnt, rows = vm.evaluate(args.stage, h_poses, out=out)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     e2e_visible = int(cnt.sum())
@@ -353,17 +355,17 @@ def main():
             "rays_per_step_per_gpu": rays_step, "pair_tests_per_step_per_gpu": pairs_step, "voxel_lookups_per_step_per_gpu": lookups_step,
             "viewpoint_evals_per_s": V * world * args.steps / (dev_ms_max * 1e-3),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "kernel": "k_eval<E1>", "kernel_ms": kernel_ms, "algorithmic_bytes": b_alg, "peak_source": peak_src},
+                         "kernel": f"k_eval<E{args.stage}>", "kernel_ms": kernel_ms, "algorithmic_bytes": b_alg, "peak_source": peak_src},
         }
         if not args.no_cpu and world == 1:      # the CPU baseline is timed on rank 0 at N = 1 only
             threads = host_cores()
-            rate, n, dt, c, orc = cpu_oracle_rate(pts, nrm, prm, poses, args.cpu_seconds, threads)
+            rate, n, dt, c, ocnt = cpu_oracle_rate(pts, nrm, prm, poses, args.cpu_seconds, threads, args.stage)
             # the kernel's lookup / ray counters must equal the oracle's on the same viewpoints
-            vm2_cnt, _ = vm.evaluate(1, poses[:n], want_rows=False)
+            vm2_cnt, _ = vm.evaluate(args.stage, poses[:n], want_rows=False)
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
                                     "sample": f"first {n} of {V} viewpoints x all {P} points, {dt:.1f} s, {threads} threads",
-                                    "counts_match_gpu": bool(int(vm2_cnt.sum()) >= 0)}
-            rate1, n1, dt1, _, _ = cpu_oracle_rate(pts, nrm, prm, poses[:max(8, n // max(threads, 1))], args.cpu_seconds / 3, 1)
+                                    "counts_match_gpu": bool(np.array_equal(vm2_cnt, ocnt))}   # per-viewpoint visible counts, GPU vs oracle
+            rate1, n1, dt1, _, _ = cpu_oracle_rate(pts, nrm, prm, poses[:max(8, n // max(threads, 1))], args.cpu_seconds / 3, 1, args.stage)
             line["cpu_baseline"]["single_thread_value"] = rate1
         line["pruning"] = prune
         print(json.dumps(line), flush=True)

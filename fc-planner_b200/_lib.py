@@ -54,6 +54,7 @@ SYMBOLS = {
     "fcvm_host_alloc": (vp, [i64]),
     "fcvm_host_free": (None, [vp]),
     "fcvm_last_kernel_ms": (f64, [vp]),
+    "fcvm_debug_bounds_violations": (i64, [vp]),
     "fcvm_set_shard": (ctypes.c_int, [vp, i32, i32, ALLGATHER_FN, vp]),
     "fcvm_host_fov_normals": (ctypes.c_int, [ctypes.POINTER(Params), f64, f64, f64p]),
     "fcvm_host_build_grid": (ctypes.c_int, [ctypes.POINTER(Params), f32p, i64, f64p, i32p, u8p, i64]),

@@ -46,5 +46,25 @@ def build(force=False, verbose=False):
     return out
 
 
+DBG = os.path.join(HERE, "_build", "libfcvm_dbg.so")
+
+
+def build_debug(force=False):
+    """The FCVM_DEBUG_BOUNDS build (every data-dependent index of k_eval checked and counted), used by
+    tests/test_gpu_bounds.py in place of compute-sanitizer."""
+    if not force and os.path.exists(DBG) and not any(os.path.getmtime(os.path.join(CSRC, d)) > os.path.getmtime(DBG) for d in DEPS):
+        return DBG
+    old = {k: os.environ.get(k) for k in ("FCVM_DEFS", "FCVM_OUT")}
+    os.environ["FCVM_DEFS"], os.environ["FCVM_OUT"] = "FCVM_DEBUG_BOUNDS=1", DBG
+    try:
+        return build(force=True)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

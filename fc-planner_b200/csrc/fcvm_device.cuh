@@ -56,7 +56,7 @@ __device__ __forceinline__ bool occ_free(const GridDesc& g, int ix, int iy, int 
   long long k = brick_word_index(ix, iy, iz, g.nby, g.nbz);
   if (k != c.key) {
     c.key = k;
-    c.word = __ldg(g.bricks + k);
+    c.word = (unsigned long long)k < (unsigned long long)g.nbricks ? __ldg(g.bricks + k) : ~0ull;   // unreachable after the bounds test; belt and braces
   }
   return ((c.word >> brick_bit_index(ix, iy, iz)) & 1ull) == 0ull;
 }

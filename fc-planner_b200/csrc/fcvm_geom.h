@@ -207,15 +207,27 @@ struct CellIndex {
     const double r = radius * 1.0001 + 1e-6;     // cover float rounding of the distance test
     int lo[3], hi[3];
     for (int c = 0; c < 3; ++c) { lo[c] = cell_coord(q[c] - r, c); hi[c] = cell_coord(q[c] + r, c); }
-    for (int x = lo[0]; x <= hi[0]; ++x)
-      for (int y = lo[1]; y <= hi[1]; ++y)
+    const double r2 = r * r;
+    auto gap2 = [&](int k, int c) {              // squared distance from q to the slab of cell k along axis c
+      const double a = (double)mn[c] + k * cell, b = a + cell;
+      const double d = q[c] < a ? a - q[c] : (q[c] > b ? q[c] - b : 0.0);
+      return d * d;
+    };
+    for (int x = lo[0]; x <= hi[0]; ++x) {
+      const double gx = gap2(x, 0);
+      for (int y = lo[1]; y <= hi[1]; ++y) {
+        const double gxy = gx + gap2(y, 1);
+        if (gxy > r2) continue;
         for (int z = lo[2]; z <= hi[2]; ++z) {
+          if (gxy + gap2(z, 2) > r2) continue;   // the whole cell is farther than the query radius
           const int64_t k = ((int64_t)x * nc[1] + y) * nc[2] + z;
           for (int64_t e = cell_start[(size_t)k]; e < cell_start[(size_t)k + 1]; ++e) {
             const int id = order[(size_t)e];
             if (!f(id, dist2(q, &pts[3 * (size_t)id]))) return;
           }
         }
+      }
+    }
   }
   // is the (float) nearest-neighbour distance sqrt(d2) < radius ?  This is all nearCheck needs
   // (viewpoint_manager.cpp:941-943): dist = sqrt(nn_squared_distance[0]) with the float overload.

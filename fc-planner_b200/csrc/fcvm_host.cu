@@ -201,6 +201,7 @@ struct fcvm_handle {
   std::vector<TraceEv> trace;
   int64_t counters[FCVM_NCOUNTERS] = {0, 0, 0, 0, 0, 0, 0, 0};
   int64_t unc_calls = 0, sample_calls = 0;
+  int64_t bounds_violations = 0;
 
   // sharding
   int rank = 0, world = 1;
@@ -300,6 +301,7 @@ static int fetch_counters(fcvm_handle* h) {
   CU(cudaMemsetAsync(h->d_counters.p, 0, sizeof(c), h->stream));
   CU(cudaStreamSynchronize(h->stream));
   for (int k = 0; k < 5; ++k) h->counters[k] += (int64_t)c[k];
+  h->bounds_violations += (int64_t)c[5];   // only FCVM_DEBUG_BOUNDS builds ever write slot 5
   return FCVM_OK;
 }
 
@@ -1075,7 +1077,7 @@ int fcvm_set_map_cloud(fcvm_t* h, const float* xyz, int64_t n) {   // cpp:74-89
   h->grid.build(h->prm, xyz, n);
   if (h->grid.voxels() <= 0) return fail(FCVM_EINVAL, "degenerate grid");
   if (h->grid.voxels() >= (1ll << 31)) return fail(FCVM_EINVAL, "grid has 2^31 voxels or more: beyond the reference's int addressing (sdf_map.h:266-269)");
-  h->map_index.build(xyz, n, std::max(h->prm.safe_radius, 4 * h->prm.resolution));
+  h->map_index.build(xyz, n, std::max(h->prm.safe_radius / 4, 2 * h->prm.resolution));   // cells well below the nearCheck radius: far cells are culled whole
   CU(h->d_bricks.reserve(h->grid.bricks.size()));
   CU(cudaMemcpy(h->d_bricks.p, h->grid.bricks.data(), h->grid.bricks.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice));
   h->map_flag = true;
@@ -1330,6 +1332,15 @@ int fcvm_own_resident(fcvm_t* h, const int32_t* vp_ids, const int32_t* order, in
 }
 
 double fcvm_last_kernel_ms(fcvm_t* h) { return h ? h->last_kernel_ms : 0.0; }
+
+int64_t fcvm_debug_bounds_violations(fcvm_t* h) {
+#ifdef FCVM_DEBUG_BOUNDS
+  return h ? h->bounds_violations : -1;
+#else
+  (void)h;
+  return -1;    // not a checking build
+#endif
+}
 
 int fcvm_set_shard(fcvm_t* h, int32_t rank, int32_t world, fcvm_allgather_fn fn, void* user) {
   if (!h || world < 1 || rank < 0 || rank >= world) return fail(FCVM_EINVAL, "bad shard");

@@ -53,6 +53,15 @@ __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarr
 // ------------------------------------------------------------------------------------------
 // k_eval
 // ------------------------------------------------------------------------------------------
+// FCVM_DEBUG_BOUNDS builds (libfcvm_dbg.so, tests/test_gpu_bounds.py) check every data-dependent
+// index of k_eval - queue slots, tile offsets, bitset words, brick indices - and count violations in
+// counter slot 5 instead of performing the access.  compute-sanitizer is closed on this GPU pool,
+// so this is the memory-safety evidence.  Release builds compile the checks away.
+#ifdef FCVM_DEBUG_BOUNDS
+#define FCVM_CHECK(cond) ((cond) ? true : (a.counters ? (atomicAdd(a.counters + 5, 1ull), false) : false))
+#else
+#define FCVM_CHECK(cond) true
+#endif
 constexpr int kWarps = EVAL_WARPS;
 constexpr int kEntryQ = 64;   // (viewpoint, point) pairs that passed the FOV test, per warp
 constexpr int kReadyQ = EVAL_READYQ;   // prepared / suspended rays ("continuations"), per warp; >= EVAL_KEEP - 1 + 32
@@ -282,7 +291,7 @@ __global__ void __launch_bounds__(kWarps * 32, EVAL_MIN_CTAS) k_eval(const __gri
 
   auto set_bit = [&](uint32_t vp, uint32_t pt) {
     const long long gp = tile_base + pt;
-    atomicOr(a.rows + (long long)vp * W + (gp >> 5), 1u << (gp & 31));
+    if (FCVM_CHECK(vp < (uint32_t)a.V && gp < a.P && (gp >> 5) < W)) atomicOr(a.rows + (long long)vp * W + (gp >> 5), 1u << (gp & 31));
   };
 
   // Pop `cnt` (<= 32) entries, run biInput for each on its own lane at full warp width, push the
@@ -294,12 +303,14 @@ __global__ void __launch_bounds__(kWarps * 32, EVAL_MIN_CTAS) k_eval(const __gri
       const QueueEntry qe = eq[en - cnt + lane];
       nrays++;
       bool verdict = false;
-      queued = prepare_ray<STAGE>(g, fc, a.recs, qe.vp, qe.pt, tile[qe.pt], c, verdict, st);
-      if (!queued && verdict) set_bit(qe.vp, qe.pt);
+      if (FCVM_CHECK(en - cnt + lane >= 0 && en - cnt + lane < kEntryQ && qe.pt < (uint32_t)npts && qe.vp < (uint32_t)a.V)) {
+        queued = prepare_ray<STAGE>(g, fc, a.recs, qe.vp, qe.pt, tile[qe.pt], c, verdict, st);
+        if (!queued && verdict) set_bit(qe.vp, qe.pt);
+      }
     }
     en -= cnt;
     const unsigned m = __ballot_sync(0xffffffffu, queued);
-    if (queued) cont_store(rqd, rqi, rn + __popc(m & lt_mask), c);
+    if (queued && FCVM_CHECK(rn + __popc(m & lt_mask) < kReadyQ)) cont_store(rqd, rqi, rn + __popc(m & lt_mask), c);
     rn += __popc(m);
     __syncwarp();
   };
@@ -319,7 +330,7 @@ __global__ void __launch_bounds__(kWarps * 32, EVAL_MIN_CTAS) k_eval(const __gri
       const unsigned idle = __ballot_sync(0xffffffffu, !active);
       if (idle != 0u && rn > 0) {
         const int r = __popc(idle & lt_mask);
-        if (!active && r < rn) {
+        if (!active && r < rn && FCVM_CHECK(rn - 1 - r >= 0 && rn - 1 - r < kReadyQ)) {
           cont_load(rqd, rqi, rn - 1 - r, c);
           active = true;
           pkey = -1; nkey = -1;
@@ -412,8 +423,10 @@ __global__ void __launch_bounds__(kWarps * 32, EVAL_MIN_CTAS) k_eval(const __gri
       if (m == 0u) continue;
       if (pass) {
         const int pos = en + __popc(m & lt_mask);
-        eq[pos].vp = (uint32_t)v;
-        eq[pos].pt = (uint32_t)i;
+        if (FCVM_CHECK(pos < kEntryQ)) {
+          eq[pos].vp = (uint32_t)v;
+          eq[pos].pt = (uint32_t)i;
+        }
       }
       en += __popc(m);
       __syncwarp();

@@ -215,6 +215,10 @@ class ViewpointManager:
         order = None if order is None else np.ascontiguousarray(order, dtype=np.int32)
         check(self.lib.fcvm_own_resident(self.h, ptr(vp_ids, i32p), ptr(order, i32p), len(vp_ids)))
 
+    def debug_bounds_violations(self):
+        """-1 unless the loaded library is the FCVM_DEBUG_BOUNDS build (libfcvm_dbg.so)."""
+        return int(self.lib.fcvm_debug_bounds_violations(self.h))
+
     def last_kernel_ms(self):
         return float(self.lib.fcvm_last_kernel_ms(self.h))
 

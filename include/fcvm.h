@@ -184,6 +184,11 @@ void  fcvm_host_free(void* p);
  * valid after a synchronising call */
 double fcvm_last_kernel_ms(fcvm_t* h);
 
+/* Index checks of the visibility kernel: a library built with -DFCVM_DEBUG_BOUNDS (libfcvm_dbg.so)
+ * verifies every data-dependent index (queue slots, tile offsets, bitset words, brick indices) and
+ * returns the number of violations seen since create; a release build returns -1. */
+int64_t fcvm_debug_bounds_violations(fcvm_t* h);
+
 /* --------------------------------------------------- multi-GPU (one process per GPU) - */
 
 /* Shard assignment: this handle evaluates only viewpoints [lo, hi) of every batch given to
