@@ -5,7 +5,7 @@ import os
 
 import numpy as np
 
-from .params import Params
+from .params import Camera, Params
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
@@ -59,6 +59,13 @@ SYMBOLS = {
     "fcvm_host_fov_normals": (ctypes.c_int, [ctypes.POINTER(Params), f64, f64, f64p]),
     "fcvm_host_build_grid": (ctypes.c_int, [ctypes.POINTER(Params), f32p, i64, f64p, i32p, u8p, i64]),
     "fcvm_shard_range": (ctypes.c_int, [i64, i32, i32, i64p, i64p]),
+    "fcvm_cov_create": (vp, [ctypes.POINTER(Params), ctypes.POINTER(Camera)]),
+    "fcvm_cov_destroy": (None, [vp]),
+    "fcvm_cov_set_cloud": (ctypes.c_int, [vp, f32p, i64]),
+    "fcvm_cov_pinhole": (i64, [vp, f64p, i64, i64p, i32p, i64, u8p]),
+    "fcvm_cov_evaluate": (i64, [vp, f64p, i64, f64p, i64p, i32p, i64, u8p]),
+    "fcvm_cov_counters": (ctypes.c_int, [vp, i64p]),
+    "fcvm_cov_last_kernel_ms": (f64, [vp]),
 }
 
 

@@ -1,0 +1,575 @@
+// fcvm_cov.cu — pin-hole coverage evaluation on sm_100a: kernels + C ABI.
+//
+// Replaces, for whole batches of poses, the three functions of
+// FC-Planner/src/hierarchical_coverage_planner/src/hcplanner.cpp that brute-force every
+// path / trajectory pose against every point of the full cloud:
+//   CameraModelProjection :1196-1211    PinHoleCamera :1128-1194    CoverageEvaluation :1032-1126
+// and the path-coverage loop around PinHoleCamera (:250-271).
+//
+// Reference algorithm per pose: scan the cloud in index order; a point inside the FOV is projected to
+// a pixel; the pixel keeps the point with the smallest camera distance (strict '<', so the earliest
+// index wins ties); the visible set is the set of pixel occupants.  CoverageEvaluation additionally
+// clears cover_state of every occupant that is displaced during the scan (:1085), which makes the
+// per-pose `visibleCloud` depend on the scan order.
+//
+// Re-design (no sort, no per-pose image in shared memory):
+//   k_cov_scan   persistent CTAs pull poses from a counter.  A CTA owns a z-buffer slot in HBM
+//                (u64 distance bits + occupant id per pixel, 'empty' = all ones) that only ever
+//                holds the touched pixels of one pose and is restored through a touched list, so
+//                nothing is cleared per pose.  The cloud is walked in 1024-point chunks in index
+//                order; chunks whose bounding box is out of range or entirely behind one FOV
+//                plane are skipped (exact: every point of such a chunk fails insideFOV).  Inside a
+//                chunk all points are tested at once; the sequential "holds the pixel at the time
+//                of its scan" predicate of the reference is evaluated in parallel as
+//                    held(i) = d_i < zbuf_before_chunk[pix]  and  no j < i in the chunk with the
+//                              same pixel and d_j <= d_i
+//                (the second clause only runs for pixels that a shared-memory hash saw twice).
+//                Held points atomicMin the pixel; the unique held point that equals the new
+//                minimum becomes the occupant and marks the previous one displaced; the other held
+//                points mark themselves displaced.  Output: one visible bitset row and (optionally)
+//                one displaced bitset row per pose.
+//   k_cov_sweep  the order-dependent part of CoverageEvaluation across poses, one thread per
+//                32-point word column sweeping the rows in pose order:
+//                    cs &= ~displaced_k;  group_k = visible_k & ~cs;  cs |= visible_k;  ever |= visible_k
+//   rows -> CSR  with k_popc_rows / k_exscan / k_compact_rows of the visibility path.
+//
+// Arithmetic: FP64, -fmad=false, only + - * / sqrt floor on the device, Eigen's 3-term reduction order
+// (SURVEY.md A.2); sin / cos / tan of the pose and camera run on the host (fcvm_geom.h).
+// No CPU fallback: without a CUDA device every evaluating call returns FCVM_ENODEVICE.
+#include <climits>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+
+#include "fcvm_geom.h"
+#include "fcvm_hostutil.h"
+#include "fcvm_kernels.h"
+
+namespace fcvm {
+
+constexpr int kCovThreads = 256;
+constexpr int kCovPer = 4;                        // points per thread per chunk
+constexpr int kCovChunk = kCovThreads * kCovPer;  // 1024 points, walked in index order
+constexpr int kCovHash = 2048;                    // pixel-collision detector slots (per chunk)
+constexpr unsigned long long kEmpty = ~0ull;
+
+struct alignas(16) CovPose {
+  VpRec rec;          // position + 4 world FOV normals (setPose_PY)
+  double M[9];        // R_p.inverse() * R_y.inverse(), row-major (CameraModelProjection :1199-1204)
+  double pad[3];
+};
+
+struct CovConst {
+  double fx, fy;      // hcplanner/fx, fy
+  double ldc0, ldc1;  // leftdown = (-xRange, -yRange)
+  double xRes, yRes;
+  int xPixel, yPixel;
+};
+
+struct CovArgs {
+  FovConst fov;
+  CovConst cam;
+  const float4* points;
+  long long P;
+  const float* chunk_box;         // [nchunks][6] = min xyz, max xyz of each 1024-point chunk
+  int nchunks;
+  const CovPose* poses;
+  int m;
+  uint32_t* vis_rows;             // m x words, zeroed by the caller
+  uint32_t* disp_rows;            // m x words or null
+  long long words;
+  unsigned long long* zdist;      // [slots][npix]
+  int* zidx;                      // [slots][npix]
+  int* touched;                   // [slots][npix]
+  long long npix;
+  int* next_pose;                 // work counter (zeroed by the caller)
+  unsigned long long* counters;   // [0] projections [1] out-of-image [2] chunks scanned [3] duplicate-pixel slow paths
+};
+
+// (int)floor(v) as x86-64 cvttsd2si delivers it: out-of-range and NaN become INT_MIN
+__device__ __forceinline__ int floor_to_int(double v) {
+  const double f = floor(v);
+  if (!(f >= -2147483648.0 && f <= 2147483647.0)) return INT_MIN;
+  return (int)f;
+}
+
+__global__ void __launch_bounds__(kCovThreads, 2) k_cov_scan(const __grid_constant__ CovArgs a) {
+  __shared__ int s_pix[kCovChunk];
+  __shared__ double s_dist[kCovChunk];
+  __shared__ int s_hash[kCovHash];
+  __shared__ uint32_t s_live[1024];        // surviving-chunk bitmap, 32768 chunks per pass
+  __shared__ int s_pose, s_ntouched;
+
+  const int tid = threadIdx.x, lane = tid & 31;
+  unsigned long long* zdist = a.zdist + (long long)blockIdx.x * a.npix;
+  int* zidx = a.zidx + (long long)blockIdx.x * a.npix;
+  int* touched = a.touched + (long long)blockIdx.x * a.npix;
+  const FovConst& fc = a.fov;
+  const CovConst& cc = a.cam;
+  unsigned long long n_proj = 0, n_out = 0, n_chunks = 0, n_slow = 0;
+
+  for (int i = tid; i < kCovHash; i += kCovThreads) s_hash[i] = 0;
+
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) { s_pose = atomicAdd(a.next_pose, 1); s_ntouched = 0; }
+    __syncthreads();
+    const int k = s_pose;
+    if (k >= a.m) break;
+
+    CovPose ps;
+    {
+      const double2* src = reinterpret_cast<const double2*>(a.poses + k);
+      double2* dst = reinterpret_cast<double2*>(&ps);
+#pragma unroll
+      for (int q = 0; q < (int)(sizeof(CovPose) / 16); ++q) dst[q] = __ldg(src + q);
+    }
+    const VpRec& rec = ps.rec;
+    uint32_t* vrow = a.vis_rows + (long long)k * a.words;
+    uint32_t* drow = a.disp_rows ? a.disp_rows + (long long)k * a.words : nullptr;
+
+    for (int c0 = 0; c0 < a.nchunks; c0 += 32768) {
+      const int cn = min(32768, a.nchunks - c0);
+      // ---- chunk cull: out of range, or the whole box behind one FOV plane ------------------
+      __syncthreads();
+      for (int cb = 0; cb < cn; cb += kCovThreads) {
+        const int c = cb + tid;
+        bool live = false;
+        if (c < cn) {
+          const float* b = a.chunk_box + (long long)(c0 + c) * 6;
+          const double lx = (double)__ldg(b + 0) - rec.px, ly = (double)__ldg(b + 1) - rec.py, lz = (double)__ldg(b + 2) - rec.pz;
+          const double hx = (double)__ldg(b + 3) - rec.px, hy = (double)__ldg(b + 4) - rec.py, hz = (double)__ldg(b + 5) - rec.pz;
+          const double cx = fmax(fmax(lx, -hx), 0.0), cy = fmax(fmax(ly, -hy), 0.0), cz = fmax(fmax(lz, -hz), 0.0);
+          live = !((cx * cx + cy * cy) + cz * cz > fc.md2_hi * 1.000001);
+          // largest d.n over the box; a margin far above rounding keeps the skip exact
+          const double reach = fmax(fabs(lx), fabs(hx)) + fmax(fabs(ly), fabs(hy)) + fmax(fabs(lz), fabs(hz));
+          const double margin = 1e-9 * (reach + 1.0);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const double best = fmax(lx * rec.n[q][0], hx * rec.n[q][0]) + fmax(ly * rec.n[q][1], hy * rec.n[q][1]) +
+                                fmax(lz * rec.n[q][2], hz * rec.n[q][2]);
+            live = live && !(best < -margin);
+          }
+        }
+        const unsigned mask = __ballot_sync(0xffffffffu, live);
+        if (lane == 0) s_live[(cb + tid) >> 5] = mask;
+      }
+      __syncthreads();
+
+      // ---- surviving chunks in index order --------------------------------------------------
+      for (int w = 0; w < (cn + 31) / 32; ++w) {
+        uint32_t bits = s_live[w];
+        while (bits) {
+          const int c = c0 + w * 32 + (__ffs(bits) - 1);
+          bits &= bits - 1;
+          const long long base = (long long)c * kCovChunk;
+          n_chunks += (tid == 0);
+
+          // phase 1: FOV + projection of 4 points per thread
+          int pix[kCovPer];
+          double dist[kCovPer];
+          bool any = false;
+#pragma unroll
+          for (int u = 0; u < kCovPer; ++u) {
+            const int slot = u * kCovThreads + tid;
+            const long long i = base + slot;
+            pix[u] = -1;
+            dist[u] = 0.0;
+            if (i < a.P) {
+              const float4 q = __ldg(a.points + i);
+              const double qx = (double)q.x, qy = (double)q.y, qz = (double)q.z;
+              if (inside_fov(rec, fc, qx, qy, qz)) {
+                // CameraModelProjection (hcplanner.cpp:1196-1211)
+                const double dx = qx - rec.px, dy = qy - rec.py, dz = qz - rec.pz;
+                const double dd = sqrt((dx * dx + dy * dy) + dz * dz);
+                const double pc0 = (ps.M[0] * dx + ps.M[1] * dy) + ps.M[2] * dz;
+                const double pc1 = (ps.M[3] * dx + ps.M[4] * dy) + ps.M[5] * dz;
+                const double pc2 = (ps.M[6] * dx + ps.M[7] * dy) + ps.M[8] * dz;
+                const double camX = cc.fx * pc1 / (1000.0 * pc0) - cc.ldc0;
+                const double camY = cc.fy * pc2 / (1000.0 * pc0) - cc.ldc1;
+                const int xi = floor_to_int(camX / cc.xRes), yi = floor_to_int(camY / cc.yRes);
+                n_proj++;
+                if (xi >= 0 && yi >= 0) {
+                  if (xi >= cc.xPixel || yi >= cc.yPixel) n_out++;
+                  else { pix[u] = xi * cc.yPixel + yi; dist[u] = dd; any = true; }
+                }
+              }
+            }
+            s_pix[slot] = pix[u];
+            s_dist[slot] = dist[u];
+            if (pix[u] >= 0) atomicAdd(&s_hash[(pix[u] * 0x9E3779B1u) >> 21], 1);
+          }
+          if (!__syncthreads_or(any)) continue;
+
+          // phase 2: does the point hold its pixel at the time the reference scans it?
+          unsigned long long before[kCovPer];
+          bool held[kCovPer];
+#pragma unroll
+          for (int u = 0; u < kCovPer; ++u) {
+            held[u] = false;
+            before[u] = kEmpty;
+            if (pix[u] >= 0) {
+              const unsigned long long dbits = (unsigned long long)__double_as_longlong(dist[u]);
+              before[u] = __ldcg(zdist + pix[u]);
+              held[u] = dbits < before[u];
+              if (held[u] && s_hash[(pix[u] * 0x9E3779B1u) >> 21] > 1) {
+                n_slow++;
+                const int slot = u * kCovThreads + tid;
+                for (int j = 0; j < slot; ++j)
+                  if (s_pix[j] == pix[u] && s_dist[j] <= dist[u]) { held[u] = false; break; }
+              }
+            }
+          }
+          __syncthreads();
+          // phase 3: the pixel's new minimum
+#pragma unroll
+          for (int u = 0; u < kCovPer; ++u)
+            if (held[u]) atomicMin(zdist + pix[u], (unsigned long long)__double_as_longlong(dist[u]));
+          __syncthreads();
+          // phase 4: occupant hand-over; displaced marks; collision detector restored
+#pragma unroll
+          for (int u = 0; u < kCovPer; ++u) {
+            if (pix[u] < 0) continue;
+            atomicSub(&s_hash[(pix[u] * 0x9E3779B1u) >> 21], 1);
+            if (!held[u]) continue;
+            const int me = (int)(base + u * kCovThreads + tid);
+            if (__ldcg(zdist + pix[u]) == (unsigned long long)__double_as_longlong(dist[u])) {
+              if (before[u] == kEmpty) {
+                touched[atomicAdd(&s_ntouched, 1)] = pix[u];
+              } else if (drow) {
+                const int old = __ldcg(zidx + pix[u]);
+                atomicOr(drow + (old >> 5), 1u << (old & 31));
+              }
+              __stcg(zidx + pix[u], me);
+            } else if (drow) {
+              atomicOr(drow + (me >> 5), 1u << (me & 31));
+            }
+          }
+        }
+      }
+    }
+
+    // ---- occupants -> visible row; z-buffer slot back to 'empty' -----------------------------
+    __syncthreads();
+    const int nt = s_ntouched;
+    for (int t = tid; t < nt; t += kCovThreads) {
+      const int p = touched[t];
+      const int id = __ldcg(zidx + p);
+      atomicOr(vrow + (id >> 5), 1u << (id & 31));
+      __stcg(zdist + p, kEmpty);
+    }
+  }
+
+  // counters: one atomic per warp
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    n_proj += __shfl_xor_sync(0xffffffffu, n_proj, o);
+    n_out += __shfl_xor_sync(0xffffffffu, n_out, o);
+    n_chunks += __shfl_xor_sync(0xffffffffu, n_chunks, o);
+    n_slow += __shfl_xor_sync(0xffffffffu, n_slow, o);
+  }
+  if (lane == 0 && a.counters) {
+    if (n_proj) atomicAdd(a.counters + 0, n_proj);
+    if (n_out) atomicAdd(a.counters + 1, n_out);
+    if (n_chunks) atomicAdd(a.counters + 2, n_chunks);
+    if (n_slow) atomicAdd(a.counters + 3, n_slow);
+  }
+}
+
+// One thread per 32-point word column, rows swept in pose order.  disp_group: in = displaced rows,
+// out = group rows (may be null: PinHoleCamera only needs the union).  cs / ever carry over between
+// batches of one call.
+__global__ void __launch_bounds__(128) k_cov_sweep(const uint32_t* __restrict__ vis, uint32_t* disp_group, int m, long long words,
+                                                   uint32_t* __restrict__ cs_io, uint32_t* __restrict__ ever_io) {
+  const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= words) return;
+  uint32_t cs = cs_io[c], ever = ever_io[c];
+  if (disp_group) {
+    int k = 0;
+    for (; k + 4 <= m; k += 4) {
+      uint32_t v[4], d[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { v[u] = __ldg(vis + (long long)(k + u) * words + c); d[u] = disp_group[(long long)(k + u) * words + c]; }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        cs &= ~d[u];
+        disp_group[(long long)(k + u) * words + c] = v[u] & ~cs;
+        cs |= v[u];
+        ever |= v[u];
+      }
+    }
+    for (; k < m; ++k) {
+      const uint32_t v = __ldg(vis + (long long)k * words + c), d = disp_group[(long long)k * words + c];
+      cs &= ~d;
+      disp_group[(long long)k * words + c] = v & ~cs;
+      cs |= v;
+      ever |= v;
+    }
+  } else {
+    for (int k = 0; k < m; ++k) ever |= __ldg(vis + (long long)k * words + c);
+  }
+  cs_io[c] = cs;
+  ever_io[c] = ever;
+}
+
+}  // namespace fcvm
+
+// ------------------------------------------------------------------------------------------------
+using namespace fcvm;
+
+struct fcvm_cov_handle {
+  fcvm_params prm;
+  fcvm_camera camp;
+  Camera cam;            // FOV normals (PerceptionUtils)
+  CovConst cc;
+  int threads = 1;
+  int64_t P = 0, W = 0;
+  int nchunks = 0;
+  int slots = 0;
+  DevBuf<float4> d_points;
+  DevBuf<float> d_box;
+  DevBuf<CovPose> d_poses;
+  PinBuf<CovPose> h_poses;
+  DevBuf<uint32_t> d_vis, d_disp, d_cs, d_ever, d_indices;
+  DevBuf<unsigned long long> d_zdist, d_counters;
+  DevBuf<int> d_zidx, d_touched, d_next, d_count;
+  DevBuf<long long> d_offsets;
+  PinBuf<long long> h_offsets;
+  PinBuf<uint32_t> h_indices, h_words;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool device_ok = false, cloud_ok = false;
+  double last_kernel_ms = 0.0;
+  int64_t counters[6] = {0, 0, 0, 0, 0, 0};   // pair tests, projections, out of image, kernels, chunks scanned, slow paths
+};
+
+static int cov_ensure_device(fcvm_cov_handle* h) {
+  if (h->device_ok) return FCVM_OK;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(FCVM_ENODEVICE, std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
+                                    " (this library has no CPU fallback)");
+  CU(cudaSetDevice(h->prm.device));
+  CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CU(cudaEventCreate(&h->ev0));
+  CU(cudaEventCreate(&h->ev1));
+  CU(h->d_counters.reserve(4));
+  CU(cudaMemset(h->d_counters.p, 0, 4 * sizeof(unsigned long long)));
+  CU(h->d_next.reserve(1));
+  // z-buffer slots: one per resident CTA
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->prm.device);
+  const long long npix = (long long)h->cc.xPixel * h->cc.yPixel;
+  h->slots = sms * 2;
+  while (h->slots > 1 && (long long)h->slots * npix * 16 > (8ll << 30)) h->slots /= 2;
+  CU(h->d_zdist.reserve((size_t)h->slots * npix));
+  CU(h->d_zidx.reserve((size_t)h->slots * npix));
+  CU(h->d_touched.reserve((size_t)h->slots * npix));
+  CU(cudaMemset(h->d_zdist.p, 0xFF, (size_t)h->slots * npix * sizeof(unsigned long long)));
+  h->device_ok = true;
+  return FCVM_OK;
+}
+
+// One batch of poses [k0, k0 + mb): rows on the device; sweep; the requested rows as CSR appended to the outputs.
+static int cov_batch(fcvm_cov_handle* h, const double* pose5, int64_t mb, bool evaluate, int64_t* offsets, int32_t* ids, int64_t cap, int64_t& total,
+                     float& kernel_ms) {
+  const int64_t W = h->W;
+  CU(h->h_poses.reserve((size_t)mb));
+  parallel_for(mb, h->threads, [&](int64_t i) {
+    const double* p = pose5 + 5 * i;
+    CovPose& cp = h->h_poses.p[i];
+    h->cam.fill(cp.rec, p[0], p[1], p[2], p[3], p[4]);
+    camera_pose_matrix(p[3], p[4], cp.M);
+    cp.pad[0] = cp.pad[1] = cp.pad[2] = 0.0;
+  });
+  CU(h->d_poses.reserve((size_t)mb));
+  CU(h->d_vis.reserve((size_t)mb * W));
+  if (evaluate) CU(h->d_disp.reserve((size_t)mb * W));
+  CU(h->d_count.reserve((size_t)mb));
+  CU(h->d_offsets.reserve((size_t)mb + 1));
+  cudaStream_t s = h->stream;
+  CU(cudaMemcpyAsync(h->d_poses.p, h->h_poses.p, (size_t)mb * sizeof(CovPose), cudaMemcpyHostToDevice, s));
+  CU(cudaMemsetAsync(h->d_vis.p, 0, (size_t)mb * W * sizeof(uint32_t), s));
+  if (evaluate) CU(cudaMemsetAsync(h->d_disp.p, 0, (size_t)mb * W * sizeof(uint32_t), s));
+  CU(cudaMemsetAsync(h->d_next.p, 0, sizeof(int), s));
+
+  CovArgs a;
+  a.fov.max_dist = h->prm.max_dist;
+  const double md2 = h->prm.max_dist * h->prm.max_dist;
+  a.fov.md2_lo = md2 * (1.0 - 1e-12);
+  a.fov.md2_hi = md2 * (1.0 + 1e-12);
+  a.fov.plane_eps = 1e-10 * std::max(h->prm.max_dist, 1.0);
+  a.fov.visible_range = h->prm.visible_range;
+  a.cam = h->cc;
+  a.points = h->d_points.p;
+  a.P = h->P;
+  a.chunk_box = h->d_box.p;
+  a.nchunks = h->nchunks;
+  a.poses = h->d_poses.p;
+  a.m = (int)mb;
+  a.vis_rows = h->d_vis.p;
+  a.disp_rows = evaluate ? h->d_disp.p : nullptr;
+  a.words = W;
+  a.zdist = h->d_zdist.p;
+  a.zidx = h->d_zidx.p;
+  a.touched = h->d_touched.p;
+  a.npix = (long long)h->cc.xPixel * h->cc.yPixel;
+  a.next_pose = h->d_next.p;
+  a.counters = h->d_counters.p;
+  const int grid = (int)std::min<int64_t>(mb, h->slots);
+  CU(cudaEventRecord(h->ev0, s));
+  k_cov_scan<<<grid, kCovThreads, 0, s>>>(a);
+  CU(cudaGetLastError());
+  k_cov_sweep<<<(unsigned)((W + 127) / 128), 128, 0, s>>>(h->d_vis.p, evaluate ? h->d_disp.p : nullptr, (int)mb, W, h->d_cs.p, h->d_ever.p);
+  CU(cudaGetLastError());
+  const uint32_t* out_rows = evaluate ? h->d_disp.p : h->d_vis.p;
+  CU(launch_popc_rows(out_rows, mb, W, h->d_count.p, s));
+  CU(launch_exscan(h->d_count.p, mb, h->d_offsets.p, s));
+  CU(cudaEventRecord(h->ev1, s));
+  h->counters[3] += 4;
+  CU(h->h_offsets.reserve((size_t)mb + 1));
+  CU(cudaMemcpyAsync(h->h_offsets.p, h->d_offsets.p, (size_t)(mb + 1) * sizeof(long long), cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  float ms = 0.f;
+  CU(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+  kernel_ms += ms;
+  const long long ct = h->h_offsets.p[mb];
+  if (offsets)
+    for (int64_t i = 0; i < mb; ++i) offsets[i + 1] = total + h->h_offsets.p[i + 1];
+  if (ids && ct > 0 && total < cap) {
+    CU(h->d_indices.reserve((size_t)ct));
+    CU(h->h_indices.reserve((size_t)ct));
+    CU(launch_compact_rows(out_rows, mb, W, h->d_offsets.p, h->d_indices.p, s));
+    h->counters[3] += 1;
+    CU(cudaMemcpyAsync(h->h_indices.p, h->d_indices.p, (size_t)ct * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    std::memcpy(ids + total, h->h_indices.p, (size_t)std::min<long long>(ct, cap - total) * sizeof(int32_t));
+  }
+  total += ct;
+  return FCVM_OK;
+}
+
+static int64_t cov_run(fcvm_cov_handle* h, const double* pose5, int64_t m, bool evaluate, int64_t* offsets, int32_t* ids, int64_t cap, uint8_t* mark,
+                       double* rate) {
+  if (!h || (m > 0 && !pose5) || m < 0) return fail(FCVM_EINVAL, "bad arguments");
+  if (!h->cloud_ok) return fail(FCVM_ENOTREADY, "set the cloud first");
+  int rc = cov_ensure_device(h);
+  if (rc) return rc;
+  const int64_t W = h->W;
+  CU(h->d_cs.reserve((size_t)W));
+  CU(h->d_ever.reserve((size_t)W));
+  CU(cudaMemsetAsync(h->d_cs.p, 0, (size_t)W * sizeof(uint32_t), h->stream));
+  CU(cudaMemsetAsync(h->d_ever.p, 0, (size_t)W * sizeof(uint32_t), h->stream));
+  int64_t total = 0;
+  float kernel_ms = 0.f;
+  if (offsets) offsets[0] = 0;
+  const int64_t per = std::max<int64_t>(1, std::min<int64_t>((int64_t)(2ll << 30) / (W * 4), INT_MAX / 2));
+  for (int64_t k0 = 0; k0 < m; k0 += per) {
+    const int64_t mb = std::min(per, m - k0);
+    rc = cov_batch(h, pose5 + 5 * k0, mb, evaluate, offsets ? offsets + k0 : nullptr, ids, cap, total, kernel_ms);
+    if (rc) return rc;
+  }
+  h->last_kernel_ms = kernel_ms;
+  h->counters[0] += m * h->P;
+  unsigned long long c[4];
+  CU(cudaMemcpyAsync(c, h->d_counters.p, sizeof(c), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaMemsetAsync(h->d_counters.p, 0, sizeof(c), h->stream));
+  CU(h->h_words.reserve((size_t)W));
+  CU(cudaMemcpyAsync(h->h_words.p, h->d_ever.p, (size_t)W * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  h->counters[1] += (int64_t)c[0];
+  h->counters[2] += (int64_t)c[1];
+  h->counters[4] += (int64_t)c[2];
+  h->counters[5] += (int64_t)c[3];
+  int64_t truenum = 0;
+  for (int64_t i = 0; i < h->P; ++i) {
+    const uint8_t b = (uint8_t)((h->h_words.p[i >> 5] >> (i & 31)) & 1u);
+    truenum += b;
+    if (mark) mark[i] = b;
+  }
+  if (rate) *rate = (double)truenum / (double)h->P;     // hcplanner.cpp:1113-1117
+  return total;
+}
+
+extern "C" {
+
+fcvm_cov_t* fcvm_cov_create(const fcvm_params* p, const fcvm_camera* cam) {
+  if (!p || !cam) { fail(FCVM_EINVAL, "null params"); return nullptr; }
+  const int xPixel = 2 * (int)cam->cx, yPixel = 2 * (int)cam->cy;     // hcplanner.cpp:1039, :1131
+  if (xPixel <= 0 || yPixel <= 0 || (long long)xPixel * yPixel > (1ll << 28)) { fail(FCVM_EINVAL, "bad image size"); return nullptr; }
+  fcvm_cov_handle* h = new (std::nothrow) fcvm_cov_handle();
+  if (!h) { fail(FCVM_EINTERNAL, "out of memory"); return nullptr; }
+  h->prm = *p;
+  h->camp = *cam;
+  h->cam.init(*p);
+  const double xRange = cam->fx * std::tan(0.5 * cam->fov_w * M_PI / 180.0) / 1000.0;   // :1040
+  const double yRange = cam->fy * std::tan(0.5 * cam->fov_h * M_PI / 180.0) / 1000.0;   // :1041
+  h->cc.fx = cam->fx; h->cc.fy = cam->fy;
+  h->cc.ldc0 = -xRange; h->cc.ldc1 = -yRange;
+  h->cc.xPixel = xPixel; h->cc.yPixel = yPixel;
+  h->cc.xRes = 2 * xRange / xPixel; h->cc.yRes = 2 * yRange / yPixel;                   // :1044
+  const int t = p->host_threads > 0 ? p->host_threads : (int)std::thread::hardware_concurrency();
+  h->threads = std::max(1, std::min(t, 64));
+  return h;
+}
+
+void fcvm_cov_destroy(fcvm_cov_t* h) {
+  if (!h) return;
+  if (h->device_ok) {
+    cudaSetDevice(h->prm.device);
+    cudaStreamSynchronize(h->stream);
+    h->d_points.free(); h->d_box.free(); h->d_poses.free(); h->h_poses.free();
+    h->d_vis.free(); h->d_disp.free(); h->d_cs.free(); h->d_ever.free(); h->d_indices.free();
+    h->d_zdist.free(); h->d_counters.free(); h->d_zidx.free(); h->d_touched.free(); h->d_next.free(); h->d_count.free();
+    h->d_offsets.free(); h->h_offsets.free(); h->h_indices.free(); h->h_words.free();
+    cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1);
+    cudaStreamDestroy(h->stream);
+  }
+  delete h;
+}
+
+int fcvm_cov_set_cloud(fcvm_cov_t* h, const float* xyz, int64_t n) {
+  if (!h || !xyz || n <= 0) return fail(FCVM_EINVAL, "bad arguments");
+  if (n >= (1ll << 31) - kCovChunk) return fail(FCVM_EINVAL, "cloud too large (the reference indexes points with int)");
+  int rc = cov_ensure_device(h);
+  if (rc) return rc;
+  h->P = n;
+  h->W = ((n + 31) / 32 + 3) / 4 * 4;
+  h->nchunks = (int)((n + kCovChunk - 1) / kCovChunk);
+  std::vector<float4> pts((size_t)n);
+  std::vector<float> box((size_t)h->nchunks * 6);
+  parallel_for(h->nchunks, h->threads, [&](int64_t c) {
+    float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    for (int64_t i = c * kCovChunk; i < std::min<int64_t>(n, (c + 1) * kCovChunk); ++i) {
+      pts[(size_t)i] = make_float4(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], 0.f);
+      for (int d = 0; d < 3; ++d) { mn[d] = std::min(mn[d], xyz[3 * i + d]); mx[d] = std::max(mx[d], xyz[3 * i + d]); }
+    }
+    for (int d = 0; d < 3; ++d) { box[(size_t)c * 6 + d] = mn[d]; box[(size_t)c * 6 + 3 + d] = mx[d]; }
+  });
+  CU(h->d_points.reserve((size_t)n));
+  CU(h->d_box.reserve(box.size()));
+  CU(cudaMemcpy(h->d_points.p, pts.data(), (size_t)n * sizeof(float4), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(h->d_box.p, box.data(), box.size() * sizeof(float), cudaMemcpyHostToDevice));
+  h->cloud_ok = true;
+  return FCVM_OK;
+}
+
+int64_t fcvm_cov_pinhole(fcvm_cov_t* h, const double* pose5, int64_t m, int64_t* offsets, int32_t* ids, int64_t cap, uint8_t* covered) {
+  return cov_run(h, pose5, m, false, offsets, ids, cap, covered, nullptr);
+}
+
+int64_t fcvm_cov_evaluate(fcvm_cov_t* h, const double* pose5, int64_t m, double* rate, int64_t* group_offsets, int32_t* group_ids, int64_t cap,
+                          uint8_t* ever) {
+  return cov_run(h, pose5, m, true, group_offsets, group_ids, cap, ever, rate);
+}
+
+int fcvm_cov_counters(fcvm_cov_t* h, int64_t* out6) {
+  if (!h || !out6) return fail(FCVM_EINVAL, "bad arguments");
+  for (int k = 0; k < 6; ++k) out6[k] = h->counters[k];
+  return FCVM_OK;
+}
+
+double fcvm_cov_last_kernel_ms(fcvm_cov_t* h) { return h ? h->last_kernel_ms : 0.0; }
+
+}  // extern "C"

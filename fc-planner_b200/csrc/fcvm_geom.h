@@ -85,6 +85,31 @@ struct Camera {
   }
 };
 
+// Eigen::Matrix3d::inverse() (Eigen/src/LU/InverseImpl.h, size 3): cofactors times 1 / det, with
+// det = (c00*m00 + c10*m10) + c20*m20.  Used by CameraModelProjection (hcplanner.cpp:1201-1204).
+inline void inverse3(const double m[3][3], double r[3][3]) {
+  auto cof = [&](int i, int j) {
+    const int i1 = (i + 1) % 3, i2 = (i + 2) % 3, j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+    return m[i1][j1] * m[i2][j2] - m[i1][j2] * m[i2][j1];
+  };
+  const double c0 = cof(0, 0), c1 = cof(1, 0), c2 = cof(2, 0);
+  const double det = (c0 * m[0][0] + c1 * m[1][0]) + c2 * m[2][0];
+  const double invdet = 1.0 / det;
+  r[0][0] = c0 * invdet; r[0][1] = c1 * invdet; r[0][2] = c2 * invdet;
+  r[1][0] = cof(0, 1) * invdet; r[1][1] = cof(1, 1) * invdet; r[1][2] = cof(2, 1) * invdet;
+  r[2][0] = cof(0, 2) * invdet; r[2][1] = cof(1, 2) * invdet; r[2][2] = cof(2, 2) * invdet;
+}
+// R_p.inverse() * R_y.inverse() of CameraModelProjection (hcplanner.cpp:1199-1204), row-major into M[9]
+inline void camera_pose_matrix(double pitch, double yaw, double M[9]) {
+  const double Ry[3][3] = {{std::cos(yaw), -std::sin(yaw), 0.0}, {std::sin(yaw), std::cos(yaw), 0.0}, {0.0, 0.0, 1.0}};
+  const double Rp[3][3] = {{std::cos(pitch), 0.0, -std::sin(pitch)}, {0.0, 1.0, 0.0}, {std::sin(pitch), 0.0, std::cos(pitch)}};
+  double Ryi[3][3], Rpi[3][3];
+  inverse3(Ry, Ryi);
+  inverse3(Rp, Rpi);
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) M[3 * i + j] = (Rpi[i][0] * Ryi[0][j] + Rpi[i][1] * Ryi[1][j]) + Rpi[i][2] * Ryi[2][j];
+}
+
 // ---------------------------------------------------------------------------------------------
 // HC occupancy grid on the host: geometry exactly as initHCMap derives it, storage in the bricked
 // 1-bit layout the kernels read (fcvm_device.cuh).  The host copy serves safety_check.

@@ -49,6 +49,19 @@ class Params(ctypes.Structure):
         return {f: getattr(self, f) for f, _ in self._fields_}
 
 
+class Camera(ctypes.Structure):
+    """ctypes image of `fcvm_camera`: hcplanner/{fx, fy, cx, cy} (hcplanner.cpp:56-59) and the degrees
+    viewpoint_manager/{fov_h, fov_w} that CoverageEvaluation / PinHoleCamera combine with M_PI (:1040-1041)."""
+    _fields_ = [("fx", ctypes.c_double), ("fy", ctypes.c_double), ("cx", ctypes.c_double), ("cy", ctypes.c_double),
+                ("fov_h", ctypes.c_double), ("fov_w", ctypes.c_double)]
+
+
+def launch_camera(scene="mbs"):
+    """hierarchical_coverage_planner/launch/{mbs,pipe,christ}.launch:5-8 (identical in all three)."""
+    s = _SCENES[scene]
+    return Camera(fx=417.0467, fy=461.0951, cx=320.0, cy=240.0, fov_h=s["fov_h"], fov_w=s["fov_w"])
+
+
 # scene -> (fov_h, fov_w, max_dist, resolution, dist_vp, pitch_upper, pitch_lower, zGround, GroundPos,
 #           safeHeight, safe_radius, attitude, max_iter_num, pose_update, model leaf)
 # viewpoint_manager/launch/{mbs,pipe,christ}.launch; hierarchical_coverage_planner/launch/* carry the

@@ -6,4 +6,4 @@ import os as _os
 
 __path__.append(_os.path.join(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))), "fc-planner_b200"))
 
-from .params import Params, launch_params  # noqa: E402,F401
+from .params import Camera, Params, launch_camera, launch_params  # noqa: E402,F401

@@ -198,6 +198,40 @@ int64_t fcvm_debug_bounds_violations(fcvm_t* h);
 typedef int (*fcvm_allgather_fn)(void* user, void* buf_dev, int64_t bytes_per_rank, void* stream);
 int fcvm_set_shard(fcvm_t* h, int32_t rank, int32_t world, fcvm_allgather_fn fn, void* user);
 
+/* --------------------------------------------------- pin-hole coverage evaluation -------
+ * the brute-force loop that follows the viewpoint path in a real run -
+ * every path / trajectory pose x every point of the full cloud: insideFOV, pin-hole projection, a
+ * per-pixel nearest-point z-buffer (hierarchical_coverage_planner/src/hcplanner.cpp).
+ * One handle per (camera, cloud); poses are evaluated in batches on the GPU.  No CPU fallback. */
+typedef struct fcvm_camera {
+  double fx, fy, cx, cy;   /* hcplanner/{fx, fy, cx, cy}            (hcplanner.cpp:56-59) */
+  double fov_h, fov_w;     /* degrees, as viewpoint_manager/{fov_h, fov_w} (hcplanner.cpp:1040-1041 use them with M_PI) */
+} fcvm_camera;
+typedef struct fcvm_cov_handle fcvm_cov_t;
+
+/* p supplies perception_utils/{top,left,right}_angle and max_dist (PerceptionUtils::insideFOV) and device */
+fcvm_cov_t* fcvm_cov_create(const fcvm_params* p, const fcvm_camera* cam);
+void        fcvm_cov_destroy(fcvm_cov_t* c);
+/* the cloud the poses are checked against: `Fullmodel` (hcplanner.cpp:252) / `checkCloud` (:1129) */
+int         fcvm_cov_set_cloud(fcvm_cov_t* c, const float* xyz, int64_t n);
+/* PinHoleCamera (hcplanner.cpp:1128-1194) for m poses (x, y, z, pitch, yaw): the ids pose k covers are
+ * ids[offsets[k] .. offsets[k+1]) ascending (the std::set of :1191); covered[n] (may be NULL) = union over
+ * the poses, i.e. `CoverState` of the path-coverage loop (:253-261).  Returns the total number of ids
+ * (> cap: call again with a larger buffer), negative on error. */
+int64_t     fcvm_cov_pinhole(fcvm_cov_t* c, const double* pose5, int64_t m, int64_t* offsets, int32_t* ids, int64_t cap, uint8_t* covered);
+/* CoverageEvaluation (hcplanner.cpp:1032-1126) over m trajectory poses: *rate = coverage rate; the
+ * points pushed into pose k's `visibleCloud` (visible_group, :1102-1107) are
+ * group_ids[group_offsets[k] .. group_offsets[k+1]); ever[n] (may be NULL) = visible in any pose.
+ * Returns the total number of group ids (> cap: call again), negative on error. */
+int64_t     fcvm_cov_evaluate(fcvm_cov_t* c, const double* pose5, int64_t m, double* rate, int64_t* group_offsets, int32_t* group_ids,
+                              int64_t cap, uint8_t* ever);
+/* counters since create: [0] pair tests (insideFOV) [1] projections [2] out-of-image projections (undefined
+ * behaviour in the reference: unchecked Eigen index; skipped here) [3] kernels launched [4] 1024-point
+ * chunks scanned (the rest were culled whole) [5] duplicate-pixel slow paths taken */
+int         fcvm_cov_counters(fcvm_cov_t* c, int64_t* out6);
+/* device time of all kernels of the most recent pinhole / evaluate call, in ms (CUDA events) */
+double      fcvm_cov_last_kernel_ms(fcvm_cov_t* c);
+
 /* --------------------------------------------------- host-only helpers (CPU tests) --- */
 
 /* PerceptionUtils::init + setPose_PY (perception_utils.cpp:29-96): 4 world-frame inward normals

@@ -24,7 +24,7 @@ def build(force=False):
     """Compile the oracle (and oracle/_ref when /root/reference exists) with the committed Makefile."""
     so = os.path.join(_HERE, "_build", "libfcvm_oracle.so")
     if force or not os.path.exists(so) or os.path.getmtime(so) < max(
-            os.path.getmtime(os.path.join(_HERE, f)) for f in ("fcvm_oracle.hpp", "oracle_capi.cpp")):
+            os.path.getmtime(os.path.join(_HERE, f)) for f in ("fcvm_oracle.hpp", "fcvm_oracle_cov.hpp", "oracle_capi.cpp")):
         subprocess.run(["make", "-C", _HERE, "all"], check=True, stdout=subprocess.DEVNULL)
     return so
 
@@ -45,6 +45,11 @@ def load(alt=False):
     for fn in ("orc_get_viewpoints", "orc_get_uncovered", "orc_get_vps_pose", "orc_get_vps_voxcount", "orc_get_vps_contri",
                "orc_get_cover_state", "orc_trace_count", "orc_trace_words", "orc_prune_order", "orc_ray_ids", "orc_biray_ids"):
         getattr(lib, fn).restype = ctypes.c_int64
+    lib.orc_cov_create.restype = ctypes.c_void_p
+    lib.orc_cov_create.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+    lib.orc_cov_destroy.argtypes = [ctypes.c_void_p]
+    lib.orc_cov_pinhole.restype = ctypes.c_int64
+    lib.orc_cov_evaluate.restype = ctypes.c_int64
     lib.orc_intbound.restype = ctypes.c_double
     lib.orc_intbound.argtypes = [ctypes.c_double, ctypes.c_double]
     lib.orc_mod.restype = ctypes.c_double
@@ -442,3 +447,68 @@ class RefViewpointManager:
         s = ctypes.c_int64(0)
         occ = self.lib.refvm_lookups(self.h, ctypes.byref(s))
         return int(occ), int(s.value)
+
+
+# -- pin-hole coverage evaluation (fcvm_oracle_cov.hpp; hcplanner.cpp:1032-1211) -------------------
+class CameraParams(ctypes.Structure):
+    """hcplanner/{fx, fy, cx, cy} + viewpoint_manager/{fov_h, fov_w}; same layout as fcvm_camera in include/fcvm.h."""
+    _fields_ = [("fx", ctypes.c_double), ("fy", ctypes.c_double), ("cx", ctypes.c_double), ("cy", ctypes.c_double),
+                ("fov_h", ctypes.c_double), ("fov_w", ctypes.c_double)]
+
+
+class CoverageOracle:
+    def __init__(self, params, camera, alt=False):
+        self.lib = load(alt)
+        self.params, self.camera = params, camera
+        self.h = ctypes.c_void_p(self.lib.orc_cov_create(ctypes.byref(params), ctypes.byref(camera)))
+        self.n = 0
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.lib.orc_cov_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def setCloud(self, xyz):
+        xyz = np.ascontiguousarray(xyz, dtype=np.float32)
+        self.n = len(xyz)
+        self.lib.orc_cov_set_cloud(self.h, _ptr(xyz, c_f32p), ctypes.c_int64(len(xyz)))
+
+    def image(self):
+        wh = np.zeros(2, np.int32); res = np.zeros(2, np.float64)
+        self.lib.orc_cov_image(self.h, _ptr(wh, c_i32p), _ptr(res, c_f64p))
+        return int(wh[0]), int(wh[1]), float(res[0]), float(res[1])
+
+    def project(self, pose5, pts):
+        pose5 = np.ascontiguousarray(pose5, np.float64); pts = np.ascontiguousarray(pts, np.float64).reshape(-1, 3)
+        dist = np.zeros(len(pts), np.float64); xy = np.zeros((len(pts), 2), np.int32)
+        self.lib.orc_cov_project(self.h, _ptr(pose5, c_f64p), _ptr(pts, c_f64p), ctypes.c_int64(len(pts)), _ptr(dist, c_f64p), _ptr(xy, c_i32p))
+        return dist, xy
+
+    def pinhole(self, pose5, threads=1):
+        """PinHoleCamera per pose -> (offsets[m+1], ids, covered[n] union, counters[3])."""
+        pose5 = np.ascontiguousarray(pose5, dtype=np.float64).reshape(-1, 5)
+        m = len(pose5)
+        offsets = np.zeros(m + 1, np.int64); covered = np.zeros(self.n, np.uint8); ctr = np.zeros(3, np.int64)
+        total = self.lib.orc_cov_pinhole(self.h, _ptr(pose5, c_f64p), ctypes.c_int64(m), _ptr(offsets, c_i64p), None, ctypes.c_int64(0), None,
+                                         ctypes.c_int32(threads), None)
+        ids = np.zeros(total, np.int32)
+        self.lib.orc_cov_pinhole(self.h, _ptr(pose5, c_f64p), ctypes.c_int64(m), _ptr(offsets, c_i64p), _ptr(ids, c_i32p), ctypes.c_int64(total),
+                                 _ptr(covered, c_u8p), ctypes.c_int32(threads), _ptr(ctr, c_i64p))
+        return offsets, ids, covered, ctr
+
+    def CoverageEvaluation(self, pose5):
+        """-> (coverage rate, group_offsets[m+1], group_ids, ever_visible[n])."""
+        pose5 = np.ascontiguousarray(pose5, dtype=np.float64).reshape(-1, 5)
+        m = len(pose5)
+        rate = ctypes.c_double(0); offsets = np.zeros(m + 1, np.int64); ever = np.zeros(self.n, np.uint8)
+        cap = max(1, self.n * 4)
+        while True:
+            ids = np.zeros(cap, np.int32)
+            total = self.lib.orc_cov_evaluate(self.h, _ptr(pose5, c_f64p), ctypes.c_int64(m), ctypes.byref(rate), _ptr(offsets, c_i64p),
+                                              _ptr(ids, c_i32p), ctypes.c_int64(cap), _ptr(ever, c_u8p))
+            if total <= cap:
+                return rate.value, offsets, ids[:total], ever
+            cap = int(total)

@@ -2,6 +2,7 @@
 // Only tests/, bench.py's cpu_baseline / --impl reference legs and __graft_entry__.smoke()
 // load this library, as the checker.  See fcvm_oracle.hpp for the restatement and its citations.
 #include "fcvm_oracle.hpp"
+#include "fcvm_oracle_cov.hpp"
 
 #include <atomic>
 #include <thread>
@@ -242,5 +243,91 @@ int orc_safety_check(orc_handle* h, const float* xyz, int64_t n, uint8_t* out) {
   return 0;
 }
 int orc_pitch_yaw(const double* v3, double* py2) { ViewpointManager::PitchYaw(V3(v3[0], v3[1], v3[2]), py2); return 0; }
+
+// ---- pin-hole coverage evaluation (fcvm_oracle_cov.hpp; hcplanner.cpp:1032-1211) ----
+struct orc_cov_handle { CoverageEvaluator ce; };
+
+orc_cov_handle* orc_cov_create(const Params* p, const Camera* c) {
+  orc_cov_handle* h = new orc_cov_handle();
+  h->ce.init(*p, *c);
+  return h;
+}
+void orc_cov_destroy(orc_cov_handle* h) { delete h; }
+int orc_cov_set_cloud(orc_cov_handle* h, const float* xyz, int64_t n) { h->ce.setCloud(xyz, n); return 0; }
+// PinHoleCamera for m poses (optionally over `threads` std::threads; poses are independent):
+// offsets[m + 1], ids (ascending per pose, at most cap), covered[n] = union.  Returns the total count.
+int64_t orc_cov_pinhole(orc_cov_handle* h, const double* pose5, int64_t m, int64_t* offsets, int32_t* ids, int64_t cap, uint8_t* covered,
+                        int32_t threads, int64_t* counters3) {
+  std::vector<std::vector<int>> vis((size_t)m);
+  if (threads < 1) threads = 1;
+  std::vector<CovCounters> ctrs((size_t)threads);
+  std::atomic<int64_t> next(0);
+  auto work = [&](int t) {
+    CoverageEvaluator ce = h->ce;      // own scratch tables, shared read-only cloud copy
+    ce.ctr = CovCounters();
+    for (;;) {
+      const int64_t k = next.fetch_add(1);
+      if (k >= m) break;
+      ce.PinHoleCamera(pose5 + 5 * k, vis[(size_t)k]);
+    }
+    ctrs[(size_t)t] = ce.ctr;
+  };
+  if (threads == 1) work(0);
+  else {
+    std::vector<std::thread> th;
+    for (int t = 0; t < threads; ++t) th.emplace_back(work, t);
+    for (auto& t : th) t.join();
+  }
+  int64_t total = 0;
+  if (covered) for (int64_t i = 0; i < h->ce.size(); ++i) covered[i] = 0;
+  for (int64_t k = 0; k < m; ++k) {
+    if (offsets) offsets[k] = total;
+    for (int id : vis[(size_t)k]) {
+      if (ids && total < cap) ids[total] = id;
+      if (covered) covered[id] = 1;
+      ++total;
+    }
+  }
+  if (offsets) offsets[m] = total;
+  if (counters3) {
+    counters3[0] = counters3[1] = counters3[2] = 0;
+    for (auto& c : ctrs) { counters3[0] += c.pair_tests; counters3[1] += c.projections; counters3[2] += c.out_of_image; }
+  }
+  return total;
+}
+// CoverageEvaluation: returns the rate through *rate; groups as CSR; ever[n] = points visible in any pose
+int64_t orc_cov_evaluate(orc_cov_handle* h, const double* pose5, int64_t m, double* rate, int64_t* group_offsets, int32_t* group_ids, int64_t cap,
+                         uint8_t* ever) {
+  std::vector<std::vector<int>> groups;
+  std::vector<char> ev;
+  const double r = h->ce.CoverageEvaluation(pose5, m, groups, ev);
+  if (rate) *rate = r;
+  int64_t total = 0;
+  for (int64_t k = 0; k < m; ++k) {
+    if (group_offsets) group_offsets[k] = total;
+    for (int id : groups[(size_t)k]) {
+      if (group_ids && total < cap) group_ids[total] = id;
+      ++total;
+    }
+  }
+  if (group_offsets) group_offsets[m] = total;
+  if (ever) for (size_t i = 0; i < ev.size(); ++i) ever[i] = (uint8_t)ev[i];
+  return total;
+}
+// CameraModelProjection for single points (known-answer tests): out = distance, xID, yID per point
+int orc_cov_project(orc_cov_handle* h, const double* pose5, const double* pts, int64_t n, double* dist, int32_t* xy) {
+  double M[3][3];
+  CoverageEvaluator::poseMatrix(pose5, M);
+  for (int64_t i = 0; i < n; ++i) {
+    int cod[2];
+    h->ce.project(pose5, M, V3(pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]), dist[i], cod);
+    xy[2 * i] = cod[0]; xy[2 * i + 1] = cod[1];
+  }
+  return 0;
+}
+int orc_cov_image(orc_cov_handle* h, int32_t* wh, double* res2) {
+  wh[0] = h->ce.xPixel; wh[1] = h->ce.yPixel; res2[0] = h->ce.xRes; res2[1] = h->ce.yRes;
+  return 0;
+}
 
 }  // extern "C"

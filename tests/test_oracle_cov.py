@@ -1,0 +1,102 @@
+"""Pin of the coverage-evaluation oracle (oracle/fcvm_oracle_cov.hpp; hcplanner.cpp:1032-1211).
+
+1. Known answers derived by hand from the statements of CameraModelProjection / PinHoleCamera / CoverageEvaluation.
+2. The reference's OWN shipped output: solution/Traj/CloudInfo<Scene>.txt is `visible_group` of the reference's
+   CoverageEvaluation run over the poses of TrajInfo<Scene>.txt (tests/golden/make_cov_golden.py).  The oracle must
+   reproduce it up to the 6-decimal rounding of the printed poses (>= 99.9 % of the ids, every scene), and must
+   reproduce its own recorded outputs bit for bit.
+"""
+import os
+import zlib
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, load_golden
+from fc_planner_b200 import launch_camera, launch_params
+
+
+def _cov(oracle_mod, prm=None, cam=None):
+    return oracle_mod.CoverageOracle(prm or launch_params("mbs"), cam or launch_camera("mbs"))
+
+
+def test_projection_known_answers(oracle_mod):
+    ce = _cov(oracle_mod)
+    w, h, xres, yres = ce.image()
+    assert (w, h) == (640, 480)                                  # 2 * (int)cx, 2 * (int)cy
+    cam = launch_camera("mbs")
+    assert xres == 2 * (cam.fx * np.tan(0.5 * 75.0 * np.pi / 180.0) / 1000.0) / 640
+    # pitch = yaw = 0: the camera looks along +x; a point on the axis lands on the principal point
+    dist, xy = ce.project([0, 0, 0, 0, 0], [[5, 0, 0], [5, 0.001, 0], [5, 0, -0.001], [0, 3, 4]])
+    assert dist[0] == 5.0 and tuple(xy[0]) == (320, 240)
+    assert tuple(xy[1]) == (320, 240) and tuple(xy[2]) == (320, 239)
+    assert dist[3] == 5.0
+    # yaw = pi/2: looks along +y; +x is to the right of the image axis (camX uses pointCam(1) = -x)
+    dist, xy = ce.project([1, 2, 3, 0, np.pi / 2], [[1, 7, 3], [1.5, 7, 3]])
+    assert tuple(xy[0]) in ((320, 240), (319, 240)) and xy[1][0] < xy[0][0]
+
+
+def test_zbuffer_rules(oracle_mod):
+    """strict '<': nearest wins, the earliest index wins ties; CoverageEvaluation un-covers displaced occupants."""
+    ce = _cov(oracle_mod)
+    cloud = np.array([[6, 0, 0], [5, 0, 0], [5, 0, 0], [7, 0, 0], [5, 2, 0]], np.float32)   # 0..3 share the principal pixel
+    ce.setCloud(cloud)
+    pose = np.array([[0, 0, 0, 0, 0]], np.float64)
+    offs, ids, covered, ctr = ce.pinhole(pose)
+    assert ids.tolist() == [1, 4] and covered.tolist() == [0, 1, 0, 0, 1]
+    assert ctr.tolist() == [5, 5, 0]
+    # pose A sees point 0 alone (point 1.. out of range); pose B sees 0 first, then 1 displaces it; pose C = A again:
+    # point 0 was un-covered by the displacement in B, so it is pushed into C's group again
+    prm = launch_params("mbs")
+    cloud = np.array([[6, 0, 0], [-6, 0, 0]], np.float32)
+    ce.setCloud(cloud)
+    A = [0, 0, 0, 0, 0]          # looks +x from the origin: sees point 0
+    B = [8, 0, 0, 0, np.pi]      # looks -x from x = 8: point 0 at 2 m, point 1 at 14 m (out of max_dist 11)
+    rate, offs, ids, ever = ce.CoverageEvaluation(np.array([A, A, B], np.float64))
+    assert rate == 0.5 and np.diff(offs).tolist() == [1, 0, 0] and ids.tolist() == [0]
+    cloud = np.array([[6, 0, 0], [5, 0, 0]], np.float32)
+    ce.setCloud(cloud)
+    rate, offs, ids, ever = ce.CoverageEvaluation(np.array([A, A], np.float64))
+    # every pose: point 0 takes the pixel, point 1 displaces it (cover_state[0] := false), visSet = {1}
+    assert rate == 0.5 and np.diff(offs).tolist() == [1, 0] and ids.tolist() == [1]
+    C = [0, 1, 0, 0, 0]          # from the side: 0 and 1 fall on different pixels, both visible; 0 is not covered -> group {0}
+    rate, offs, ids, ever = ce.CoverageEvaluation(np.array([A, C, A, C], np.float64))
+    assert rate == 1.0 and [ids[offs[k]:offs[k + 1]].tolist() for k in range(4)] == [[1], [0], [], [0]]
+
+
+@pytest.mark.parametrize("scene", ["mbs", "pipe", "christ"])
+def test_oracle_reproduces_the_shipped_reference_output(oracle_mod, scene):
+    prm, zs = load_golden(scene)
+    z = np.load(os.path.join(GOLDEN, f"cov_{scene}.npz"))
+    ce = _cov(oracle_mod, launch_params(scene), launch_camera(scene))
+    ce.setCloud(zs["map_cloud"])
+    rate, offs, ids, ever = ce.CoverageEvaluation(z["poses"])
+    # bit-exact against the recorded oracle outputs
+    assert rate == float(z["rate"])
+    assert np.array_equal(offs, z["group_offsets"]) and np.array_equal(ids, z["group_ids"])
+    assert np.array_equal(np.packbits(ever, bitorder="little"), z["ever"])
+    # against the reference's shipped groups (poses printed with 6 decimals)
+    roffs, rids = z["ref_offsets"], z["ref_ids"]
+    same = only_ref = only_orc = 0
+    for k in range(len(z["poses"])):
+        a, b = set(ids[offs[k]:offs[k + 1]].tolist()), set(rids[roffs[k]:roffs[k + 1]].tolist())
+        same += len(a & b); only_ref += len(b - a); only_orc += len(a - b)
+    assert [same, only_ref, only_orc] == z["agreement"][:3].tolist()
+    assert z["agreement"][3] == 0                                  # every shipped point was found in the cloud
+    assert same >= 0.999 * len(rids) and only_ref + only_orc <= 1e-3 * len(rids)
+    assert len(rids) > 20_000                                      # not vacuous
+
+
+def test_pinhole_golden_and_threads(oracle_mod):
+    prm, zs = load_golden("pipe")
+    z = np.load(os.path.join(GOLDEN, "cov_pipe.npz"))
+    ce = _cov(oracle_mod, launch_params("pipe"), launch_camera("pipe"))
+    ce.setCloud(zs["map_cloud"])
+    poses = z["poses"][:2000]
+    o1, i1, c1, k1 = ce.pinhole(poses, threads=1)
+    o4, i4, c4, k4 = ce.pinhole(poses, threads=4)
+    assert np.array_equal(o1, o4) and np.array_equal(i1, i4) and np.array_equal(c1, c4) and np.array_equal(k1, k4)
+    assert np.array_equal(o1, z["pin_offsets"][:2001])
+    full = ce.pinhole(z["poses"], threads=4)
+    assert zlib.crc32(full[1].tobytes()) == int(z["pin_ids_crc"]) and np.array_equal(np.packbits(full[2], bitorder="little"), z["covered"])
+    assert np.array_equal(full[3], z["counters"])
