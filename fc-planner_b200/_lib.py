@@ -64,8 +64,10 @@ SYMBOLS = {
     "fcvm_cov_set_cloud": (ctypes.c_int, [vp, f32p, i64]),
     "fcvm_cov_pinhole": (i64, [vp, f64p, i64, i64p, i32p, i64, u8p]),
     "fcvm_cov_evaluate": (i64, [vp, f64p, i64, f64p, i64p, i32p, i64, u8p]),
+    "fcvm_cov_fetch_ids": (i64, [vp, i32p, i64]),
     "fcvm_cov_counters": (ctypes.c_int, [vp, i64p]),
     "fcvm_cov_last_kernel_ms": (f64, [vp]),
+    "fcvm_cov_last_scan_ms": (f64, [vp]),
 }
 
 

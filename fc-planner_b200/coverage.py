@@ -43,19 +43,19 @@ class CoverageEvaluator:
     def _poses(self, poseSet):
         return np.ascontiguousarray(poseSet, dtype=np.float64).reshape(-1, 5)
 
-    def PinHoleCamera(self, poseSet, cap=None):
+    def PinHoleCamera(self, poseSet):
         """-> (offsets[m+1], covered ids ascending per pose, CoverState[n] of the path loop :253-261)."""
         pose5 = self._poses(poseSet)
         m = len(pose5)
         offsets = np.zeros(m + 1, np.int64)
         covered = np.zeros(self.n, np.uint8)
-        cap = int(cap if cap is not None else max(1024, 2048 * m))
-        while True:
-            ids = np.zeros(cap, np.int32)
-            total = check(self.lib.fcvm_cov_pinhole(self.h, ptr(pose5, f64p), m, ptr(offsets, i64p), ptr(ids, i32p), cap, ptr(covered, u8p)))
-            if total <= cap:
-                return offsets, ids[:total], covered
-            cap = int(total)
+        total = check(self.lib.fcvm_cov_pinhole(self.h, ptr(pose5, f64p), m, ptr(offsets, i64p), None, 0, ptr(covered, u8p)))
+        return offsets, self._fetch(total), covered
+
+    def _fetch(self, total):
+        ids = np.zeros(int(total), np.int32)
+        assert check(self.lib.fcvm_cov_fetch_ids(self.h, ptr(ids, i32p), len(ids))) == total
+        return ids
 
     def path_coverage(self, poseSet):
         """The path-coverage loop of hcplanner.cpp:250-271 -> (coverage, CoverState[n])."""
@@ -64,7 +64,7 @@ class CoverageEvaluator:
         check(self.lib.fcvm_cov_pinhole(self.h, ptr(pose5, f64p), len(pose5), None, None, 0, ptr(covered, u8p)))
         return float(covered.sum()) / float(self.n), covered
 
-    def CoverageEvaluation(self, poseSet, cap=None):
+    def CoverageEvaluation(self, poseSet):
         """-> (coverageRate, group_offsets[m+1], group ids, ever_visible[n]); group k = the points pushed into
         `visible_group[k]` (:1102-1108)."""
         pose5 = self._poses(poseSet)
@@ -72,14 +72,8 @@ class CoverageEvaluator:
         rate = ctypes.c_double(0.0)
         offsets = np.zeros(m + 1, np.int64)
         ever = np.zeros(self.n, np.uint8)
-        cap = int(cap if cap is not None else max(1024, 4 * self.n))
-        while True:
-            ids = np.zeros(cap, np.int32)
-            total = check(self.lib.fcvm_cov_evaluate(self.h, ptr(pose5, f64p), m, ctypes.byref(rate), ptr(offsets, i64p), ptr(ids, i32p), cap,
-                                                     ptr(ever, u8p)))
-            if total <= cap:
-                return rate.value, offsets, ids[:total], ever
-            cap = int(total)
+        total = check(self.lib.fcvm_cov_evaluate(self.h, ptr(pose5, f64p), m, ctypes.byref(rate), ptr(offsets, i64p), None, 0, ptr(ever, u8p)))
+        return rate.value, offsets, self._fetch(total), ever
 
     def counters(self):
         """[pair tests, projections, out-of-image, kernels launched, chunks scanned, duplicate-pixel slow paths]"""
@@ -89,3 +83,6 @@ class CoverageEvaluator:
 
     def last_kernel_ms(self):
         return float(self.lib.fcvm_cov_last_kernel_ms(self.h))
+
+    def last_scan_ms(self):
+        return float(self.lib.fcvm_cov_last_scan_ms(self.h))

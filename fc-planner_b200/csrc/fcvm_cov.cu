@@ -23,14 +23,15 @@
 //                of its scan" predicate of the reference is evaluated in parallel as
 //                    held(i) = d_i < zbuf_before_chunk[pix]  and  no j < i in the chunk with the
 //                              same pixel and d_j <= d_i
-//                (the second clause only runs for pixels that a shared-memory hash saw twice).
+//                (the second clause walks a per-pixel chain kept in a shared-memory hash table; the chain
+//                has one member unless two points of the chunk really share a pixel).
 //                Held points atomicMin the pixel; the unique held point that equals the new
 //                minimum becomes the occupant and marks the previous one displaced; the other held
 //                points mark themselves displaced.  Output: one visible bitset row and (optionally)
 //                one displaced bitset row per pose.
-//   k_cov_sweep  the order-dependent part of CoverageEvaluation across poses, one thread per
-//                32-point word column sweeping the rows in pose order:
-//                    cs &= ~displaced_k;  group_k = visible_k & ~cs;  cs |= visible_k;  ever |= visible_k
+//   k_cov_sum /  the order-dependent part of CoverageEvaluation across poses, per 32-point word column:
+//   k_cov_apply      cs &= ~displaced_k;  group_k = visible_k & ~cs;  cs |= visible_k;  ever |= visible_k
+//                run as a two-pass segmented scan over the poses (row steps compose, see the kernels).
 //   rows -> CSR  with k_popc_rows / k_exscan / k_compact_rows of the visibility path.
 //
 // Arithmetic: FP64, -fmad=false, only + - * / sqrt floor on the device, Eigen's 3-term reduction order
@@ -83,7 +84,7 @@ struct CovArgs {
   int* touched;                   // [slots][npix]
   long long npix;
   int* next_pose;                 // work counter (zeroed by the caller)
-  unsigned long long* counters;   // [0] projections [1] out-of-image [2] chunks scanned [3] duplicate-pixel slow paths
+  unsigned long long* counters;   // [0] projections [1] out-of-image [2] chunks scanned [3] held points whose pixel was shared inside the chunk
 };
 
 // (int)floor(v) as x86-64 cvttsd2si delivers it: out-of-range and NaN become INT_MIN
@@ -94,9 +95,10 @@ __device__ __forceinline__ int floor_to_int(double v) {
 }
 
 __global__ void __launch_bounds__(kCovThreads, 2) k_cov_scan(const __grid_constant__ CovArgs a) {
-  __shared__ int s_pix[kCovChunk];
   __shared__ double s_dist[kCovChunk];
-  __shared__ int s_hash[kCovHash];
+  __shared__ short s_next[kCovChunk];      // chain of the chunk's points that share a pixel
+  __shared__ int t_key[kCovHash];          // open-addressing table pixel -> chain head (per chunk)
+  __shared__ int t_head[kCovHash];
   __shared__ uint32_t s_live[1024];        // surviving-chunk bitmap, 32768 chunks per pass
   __shared__ int s_pose, s_ntouched;
 
@@ -108,7 +110,7 @@ __global__ void __launch_bounds__(kCovThreads, 2) k_cov_scan(const __grid_consta
   const CovConst& cc = a.cam;
   unsigned long long n_proj = 0, n_out = 0, n_chunks = 0, n_slow = 0;
 
-  for (int i = tid; i < kCovHash; i += kCovThreads) s_hash[i] = 0;
+  for (int i = tid; i < kCovHash; i += kCovThreads) { t_key[i] = -1; t_head[i] = -1; }
 
   for (;;) {
     __syncthreads();
@@ -166,7 +168,7 @@ __global__ void __launch_bounds__(kCovThreads, 2) k_cov_scan(const __grid_consta
           n_chunks += (tid == 0);
 
           // phase 1: FOV + projection of 4 points per thread
-          int pix[kCovPer];
+          int pix[kCovPer], bucket[kCovPer];
           double dist[kCovPer];
           bool any = false;
 #pragma unroll
@@ -195,9 +197,18 @@ __global__ void __launch_bounds__(kCovThreads, 2) k_cov_scan(const __grid_consta
                 }
               }
             }
-            s_pix[slot] = pix[u];
             s_dist[slot] = dist[u];
-            if (pix[u] >= 0) atomicAdd(&s_hash[(pix[u] * 0x9E3779B1u) >> 21], 1);
+            bucket[u] = 0;
+            if (pix[u] >= 0) {
+              int hb = (int)((pix[u] * 0x9E3779B1u) >> 21);
+              for (;;) {
+                const int old = atomicCAS(&t_key[hb], -1, pix[u]);
+                if (old == -1 || old == pix[u]) break;
+                hb = (hb + 1) & (kCovHash - 1);
+              }
+              s_next[slot] = (short)atomicExch(&t_head[hb], slot);
+              bucket[u] = hb;
+            }
           }
           if (!__syncthreads_or(any)) continue;
 
@@ -212,11 +223,12 @@ __global__ void __launch_bounds__(kCovThreads, 2) k_cov_scan(const __grid_consta
               const unsigned long long dbits = (unsigned long long)__double_as_longlong(dist[u]);
               before[u] = __ldcg(zdist + pix[u]);
               held[u] = dbits < before[u];
-              if (held[u] && s_hash[(pix[u] * 0x9E3779B1u) >> 21] > 1) {
-                n_slow++;
+              if (held[u]) {
                 const int slot = u * kCovThreads + tid;
-                for (int j = 0; j < slot; ++j)
-                  if (s_pix[j] == pix[u] && s_dist[j] <= dist[u]) { held[u] = false; break; }
+                int j = t_head[bucket[u]];
+                n_slow += (j != slot || s_next[slot] >= 0);
+                for (; j >= 0; j = s_next[j])
+                  if (j < slot && s_dist[j] <= dist[u]) { held[u] = false; break; }
               }
             }
           }
@@ -230,7 +242,8 @@ __global__ void __launch_bounds__(kCovThreads, 2) k_cov_scan(const __grid_consta
 #pragma unroll
           for (int u = 0; u < kCovPer; ++u) {
             if (pix[u] < 0) continue;
-            atomicSub(&s_hash[(pix[u] * 0x9E3779B1u) >> 21], 1);
+            t_key[bucket[u]] = -1;
+            t_head[bucket[u]] = -1;
             if (!held[u]) continue;
             const int me = (int)(base + u * kCovThreads + tid);
             if (__ldcg(zdist + pix[u]) == (unsigned long long)__double_as_longlong(dist[u])) {
@@ -245,6 +258,7 @@ __global__ void __launch_bounds__(kCovThreads, 2) k_cov_scan(const __grid_consta
               atomicOr(drow + (me >> 5), 1u << (me & 31));
             }
           }
+          __syncthreads();      // the table is clean before the next chunk inserts
         }
       }
     }
@@ -276,40 +290,66 @@ __global__ void __launch_bounds__(kCovThreads, 2) k_cov_scan(const __grid_consta
   }
 }
 
-// One thread per 32-point word column, rows swept in pose order.  disp_group: in = displaced rows,
-// out = group rows (may be null: PinHoleCamera only needs the union).  cs / ever carry over between
-// batches of one call.
-__global__ void __launch_bounds__(128) k_cov_sweep(const uint32_t* __restrict__ vis, uint32_t* disp_group, int m, long long words,
-                                                   uint32_t* __restrict__ cs_io, uint32_t* __restrict__ ever_io) {
+// The order-dependent part of CoverageEvaluation across poses, per 32-point word column c:
+//     cs &= ~displaced_k;  group_k = visible_k & ~cs;  cs |= visible_k;  ever |= visible_k      (k in pose order)
+// One row step is the map cs -> (cs & ~d) | v; such maps compose: (cs & ~A) | B followed by a row gives
+// A' = A | d, B' = (B & ~d) | v.  So the poses are cut into segments that run in parallel:
+//   k_cov_sum    one thread per (segment, column): the segment's (A, B); its union of visible bits -> ever (atomicOr)
+//   k_cov_apply  one thread per (segment, column): cs at the segment start from the summaries of the earlier
+//                segments, then the rows of the segment for real (group rows overwrite the displaced rows);
+//                the last segment stores cs for the next batch of the call.
+__global__ void __launch_bounds__(128) k_cov_sum(const uint32_t* __restrict__ vis, const uint32_t* __restrict__ disp, int m, int seg_len,
+                                                 long long words, uint32_t* __restrict__ sumA, uint32_t* __restrict__ sumB,
+                                                 uint32_t* __restrict__ ever_io) {
   const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= words) return;
-  uint32_t cs = cs_io[c], ever = ever_io[c];
-  if (disp_group) {
-    int k = 0;
-    for (; k + 4 <= m; k += 4) {
-      uint32_t v[4], d[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) { v[u] = __ldg(vis + (long long)(k + u) * words + c); d[u] = disp_group[(long long)(k + u) * words + c]; }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        cs &= ~d[u];
-        disp_group[(long long)(k + u) * words + c] = v[u] & ~cs;
-        cs |= v[u];
-        ever |= v[u];
-      }
+  const int k0 = blockIdx.y * seg_len, k1 = min(m, k0 + seg_len);
+  uint32_t A = 0u, B = 0u, E = 0u;
+  if (disp) {
+#pragma unroll 8
+    for (int k = k0; k < k1; ++k) {
+      const uint32_t v = __ldg(vis + (long long)k * words + c), d = __ldg(disp + (long long)k * words + c);
+      A |= d;
+      B = (B & ~d) | v;
+      E |= v;
     }
-    for (; k < m; ++k) {
-      const uint32_t v = __ldg(vis + (long long)k * words + c), d = disp_group[(long long)k * words + c];
-      cs &= ~d;
-      disp_group[(long long)k * words + c] = v & ~cs;
-      cs |= v;
-      ever |= v;
-    }
+    sumA[(long long)blockIdx.y * words + c] = A;
+    sumB[(long long)blockIdx.y * words + c] = B;
   } else {
-    for (int k = 0; k < m; ++k) ever |= __ldg(vis + (long long)k * words + c);
+#pragma unroll 8
+    for (int k = k0; k < k1; ++k) E |= __ldg(vis + (long long)k * words + c);
   }
-  cs_io[c] = cs;
-  ever_io[c] = ever;
+  if (E) atomicOr(ever_io + c, E);
+}
+
+__global__ void __launch_bounds__(128) k_cov_apply(const uint32_t* __restrict__ vis, uint32_t* disp_group, int m, int seg_len, long long words,
+                                                   const uint32_t* __restrict__ sumA, const uint32_t* __restrict__ sumB,
+                                                   const uint32_t* __restrict__ cs_in, uint32_t* __restrict__ cs_out) {
+  const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= words) return;
+  const int seg = blockIdx.y;
+  const int k0 = seg * seg_len, k1 = min(m, k0 + seg_len);
+  uint32_t cs = __ldg(cs_in + c);
+  for (int s = 0; s < seg; ++s) cs = (cs & ~__ldg(sumA + (long long)s * words + c)) | __ldg(sumB + (long long)s * words + c);
+  int k = k0;
+  for (; k + 4 <= k1; k += 4) {
+    uint32_t v[4], d[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { v[u] = __ldg(vis + (long long)(k + u) * words + c); d[u] = disp_group[(long long)(k + u) * words + c]; }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      cs &= ~d[u];
+      disp_group[(long long)(k + u) * words + c] = v[u] & ~cs;
+      cs |= v[u];
+    }
+  }
+  for (; k < k1; ++k) {
+    const uint32_t v = __ldg(vis + (long long)k * words + c), d = disp_group[(long long)k * words + c];
+    cs &= ~d;
+    disp_group[(long long)k * words + c] = v & ~cs;
+    cs |= v;
+  }
+  if (seg == (int)gridDim.y - 1) cs_out[c] = cs;
 }
 
 }  // namespace fcvm
@@ -330,16 +370,17 @@ struct fcvm_cov_handle {
   DevBuf<float> d_box;
   DevBuf<CovPose> d_poses;
   PinBuf<CovPose> h_poses;
-  DevBuf<uint32_t> d_vis, d_disp, d_cs, d_ever, d_indices;
+  DevBuf<uint32_t> d_vis, d_disp, d_cs, d_cs_in, d_sumA, d_sumB, d_ever, d_indices;
   DevBuf<unsigned long long> d_zdist, d_counters;
   DevBuf<int> d_zidx, d_touched, d_next, d_count;
   DevBuf<long long> d_offsets;
   PinBuf<long long> h_offsets;
   PinBuf<uint32_t> h_indices, h_words;
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, evm = nullptr;
   bool device_ok = false, cloud_ok = false;
-  double last_kernel_ms = 0.0;
+  double last_kernel_ms = 0.0, last_scan_ms = 0.0;
+  std::vector<int32_t> last_ids;               // CSR ids of the most recent pinhole / evaluate call (fcvm_cov_fetch_ids)
   int64_t counters[6] = {0, 0, 0, 0, 0, 0};   // pair tests, projections, out of image, kernels, chunks scanned, slow paths
 };
 
@@ -354,6 +395,7 @@ static int cov_ensure_device(fcvm_cov_handle* h) {
   CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   CU(cudaEventCreate(&h->ev0));
   CU(cudaEventCreate(&h->ev1));
+  CU(cudaEventCreate(&h->evm));
   CU(h->d_counters.reserve(4));
   CU(cudaMemset(h->d_counters.p, 0, 4 * sizeof(unsigned long long)));
   CU(h->d_next.reserve(1));
@@ -373,7 +415,7 @@ static int cov_ensure_device(fcvm_cov_handle* h) {
 
 // One batch of poses [k0, k0 + mb): rows on the device; sweep; the requested rows as CSR appended to the outputs.
 static int cov_batch(fcvm_cov_handle* h, const double* pose5, int64_t mb, bool evaluate, int64_t* offsets, int32_t* ids, int64_t cap, int64_t& total,
-                     float& kernel_ms) {
+                     float& kernel_ms, float& scan_ms) {
   const int64_t W = h->W;
   CU(h->h_poses.reserve((size_t)mb));
   parallel_for(mb, h->threads, [&](int64_t i) {
@@ -421,30 +463,61 @@ static int cov_batch(fcvm_cov_handle* h, const double* pose5, int64_t mb, bool e
   CU(cudaEventRecord(h->ev0, s));
   k_cov_scan<<<grid, kCovThreads, 0, s>>>(a);
   CU(cudaGetLastError());
-  k_cov_sweep<<<(unsigned)((W + 127) / 128), 128, 0, s>>>(h->d_vis.p, evaluate ? h->d_disp.p : nullptr, (int)mb, W, h->d_cs.p, h->d_ever.p);
-  CU(cudaGetLastError());
+  CU(cudaEventRecord(h->evm, s));
+  {
+    // segments: enough (segment, column) threads to fill the chip, at least 64 rows each
+    int nseg = (int)std::max<int64_t>(1, std::min<int64_t>({(int64_t)128, (150000 + W - 1) / W, (mb + 63) / 64}));
+    const int seg_len = (int)((mb + nseg - 1) / nseg);
+    nseg = (int)((mb + seg_len - 1) / seg_len);
+    const dim3 g((unsigned)((W + 127) / 128), (unsigned)nseg);
+    if (evaluate) {
+      CU(h->d_sumA.reserve((size_t)nseg * W));
+      CU(h->d_sumB.reserve((size_t)nseg * W));
+    }
+    k_cov_sum<<<g, 128, 0, s>>>(h->d_vis.p, evaluate ? h->d_disp.p : nullptr, (int)mb, seg_len, W, h->d_sumA.p, h->d_sumB.p, h->d_ever.p);
+    CU(cudaGetLastError());
+    if (evaluate) {
+      // cs_io is read by every segment's threads and written by the last segment's: double-buffer it
+      CU(cudaMemcpyAsync(h->d_cs_in.p, h->d_cs.p, (size_t)W * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+      k_cov_apply<<<g, 128, 0, s>>>(h->d_vis.p, h->d_disp.p, (int)mb, seg_len, W, h->d_sumA.p, h->d_sumB.p, h->d_cs_in.p, h->d_cs.p);
+      CU(cudaGetLastError());
+      h->counters[3] += 1;
+    }
+  }
   const uint32_t* out_rows = evaluate ? h->d_disp.p : h->d_vis.p;
-  CU(launch_popc_rows(out_rows, mb, W, h->d_count.p, s));
-  CU(launch_exscan(h->d_count.p, mb, h->d_offsets.p, s));
+  const bool want_csr = offsets || ids;          // the path-coverage loop only needs the union
+  if (want_csr) {
+    CU(launch_popc_rows(out_rows, mb, W, h->d_count.p, s));
+    CU(launch_exscan(h->d_count.p, mb, h->d_offsets.p, s));
+    h->counters[3] += 2;
+  }
   CU(cudaEventRecord(h->ev1, s));
-  h->counters[3] += 4;
-  CU(h->h_offsets.reserve((size_t)mb + 1));
-  CU(cudaMemcpyAsync(h->h_offsets.p, h->d_offsets.p, (size_t)(mb + 1) * sizeof(long long), cudaMemcpyDeviceToHost, s));
+  h->counters[3] += 2;
+  long long ct = 0;
+  if (want_csr) {
+    CU(h->h_offsets.reserve((size_t)mb + 1));
+    CU(cudaMemcpyAsync(h->h_offsets.p, h->d_offsets.p, (size_t)(mb + 1) * sizeof(long long), cudaMemcpyDeviceToHost, s));
+  }
   CU(cudaStreamSynchronize(s));
   float ms = 0.f;
   CU(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
   kernel_ms += ms;
-  const long long ct = h->h_offsets.p[mb];
-  if (offsets)
-    for (int64_t i = 0; i < mb; ++i) offsets[i + 1] = total + h->h_offsets.p[i + 1];
-  if (ids && ct > 0 && total < cap) {
+  CU(cudaEventElapsedTime(&ms, h->ev0, h->evm));
+  scan_ms += ms;
+  if (want_csr) {
+    ct = h->h_offsets.p[mb];
+    if (offsets)
+      for (int64_t i = 0; i < mb; ++i) offsets[i + 1] = total + h->h_offsets.p[i + 1];
+  }
+  if (ct > 0) {
     CU(h->d_indices.reserve((size_t)ct));
     CU(h->h_indices.reserve((size_t)ct));
     CU(launch_compact_rows(out_rows, mb, W, h->d_offsets.p, h->d_indices.p, s));
     h->counters[3] += 1;
     CU(cudaMemcpyAsync(h->h_indices.p, h->d_indices.p, (size_t)ct * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
-    std::memcpy(ids + total, h->h_indices.p, (size_t)std::min<long long>(ct, cap - total) * sizeof(int32_t));
+    if (ids && total < cap) std::memcpy(ids + total, h->h_indices.p, (size_t)std::min<long long>(ct, cap - total) * sizeof(int32_t));
+    h->last_ids.insert(h->last_ids.end(), (const int32_t*)h->h_indices.p, (const int32_t*)h->h_indices.p + ct);
   }
   total += ct;
   return FCVM_OK;
@@ -458,19 +531,22 @@ static int64_t cov_run(fcvm_cov_handle* h, const double* pose5, int64_t m, bool 
   if (rc) return rc;
   const int64_t W = h->W;
   CU(h->d_cs.reserve((size_t)W));
+  CU(h->d_cs_in.reserve((size_t)W));
   CU(h->d_ever.reserve((size_t)W));
   CU(cudaMemsetAsync(h->d_cs.p, 0, (size_t)W * sizeof(uint32_t), h->stream));
   CU(cudaMemsetAsync(h->d_ever.p, 0, (size_t)W * sizeof(uint32_t), h->stream));
   int64_t total = 0;
-  float kernel_ms = 0.f;
+  float kernel_ms = 0.f, scan_ms = 0.f;
+  h->last_ids.clear();
   if (offsets) offsets[0] = 0;
   const int64_t per = std::max<int64_t>(1, std::min<int64_t>((int64_t)(2ll << 30) / (W * 4), INT_MAX / 2));
   for (int64_t k0 = 0; k0 < m; k0 += per) {
     const int64_t mb = std::min(per, m - k0);
-    rc = cov_batch(h, pose5 + 5 * k0, mb, evaluate, offsets ? offsets + k0 : nullptr, ids, cap, total, kernel_ms);
+    rc = cov_batch(h, pose5 + 5 * k0, mb, evaluate, offsets ? offsets + k0 : nullptr, ids, cap, total, kernel_ms, scan_ms);
     if (rc) return rc;
   }
   h->last_kernel_ms = kernel_ms;
+  h->last_scan_ms = scan_ms;
   h->counters[0] += m * h->P;
   unsigned long long c[4];
   CU(cudaMemcpyAsync(c, h->d_counters.p, sizeof(c), cudaMemcpyDeviceToHost, h->stream));
@@ -520,10 +596,10 @@ void fcvm_cov_destroy(fcvm_cov_t* h) {
     cudaSetDevice(h->prm.device);
     cudaStreamSynchronize(h->stream);
     h->d_points.free(); h->d_box.free(); h->d_poses.free(); h->h_poses.free();
-    h->d_vis.free(); h->d_disp.free(); h->d_cs.free(); h->d_ever.free(); h->d_indices.free();
+    h->d_vis.free(); h->d_disp.free(); h->d_cs.free(); h->d_cs_in.free(); h->d_sumA.free(); h->d_sumB.free(); h->d_ever.free(); h->d_indices.free();
     h->d_zdist.free(); h->d_counters.free(); h->d_zidx.free(); h->d_touched.free(); h->d_next.free(); h->d_count.free();
     h->d_offsets.free(); h->h_offsets.free(); h->h_indices.free(); h->h_words.free();
-    cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1);
+    cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1); cudaEventDestroy(h->evm);
     cudaStreamDestroy(h->stream);
   }
   delete h;
@@ -564,6 +640,13 @@ int64_t fcvm_cov_evaluate(fcvm_cov_t* h, const double* pose5, int64_t m, double*
   return cov_run(h, pose5, m, true, group_offsets, group_ids, cap, ever, rate);
 }
 
+int64_t fcvm_cov_fetch_ids(fcvm_cov_t* h, int32_t* ids, int64_t cap) {
+  if (!h || (cap > 0 && !ids)) return fail(FCVM_EINVAL, "bad arguments");
+  const int64_t n = (int64_t)h->last_ids.size();
+  if (n > 0 && cap > 0) std::memcpy(ids, h->last_ids.data(), (size_t)std::min(n, cap) * sizeof(int32_t));
+  return n;
+}
+
 int fcvm_cov_counters(fcvm_cov_t* h, int64_t* out6) {
   if (!h || !out6) return fail(FCVM_EINVAL, "bad arguments");
   for (int k = 0; k < 6; ++k) out6[k] = h->counters[k];
@@ -571,5 +654,6 @@ int fcvm_cov_counters(fcvm_cov_t* h, int64_t* out6) {
 }
 
 double fcvm_cov_last_kernel_ms(fcvm_cov_t* h) { return h ? h->last_kernel_ms : 0.0; }
+double fcvm_cov_last_scan_ms(fcvm_cov_t* h) { return h ? h->last_scan_ms : 0.0; }
 
 }  // extern "C"

@@ -217,20 +217,25 @@ int         fcvm_cov_set_cloud(fcvm_cov_t* c, const float* xyz, int64_t n);
 /* PinHoleCamera (hcplanner.cpp:1128-1194) for m poses (x, y, z, pitch, yaw): the ids pose k covers are
  * ids[offsets[k] .. offsets[k+1]) ascending (the std::set of :1191); covered[n] (may be NULL) = union over
  * the poses, i.e. `CoverState` of the path-coverage loop (:253-261).  Returns the total number of ids
- * (> cap: call again with a larger buffer), negative on error. */
+ * (> cap: fcvm_cov_fetch_ids has them all), negative on error. */
 int64_t     fcvm_cov_pinhole(fcvm_cov_t* c, const double* pose5, int64_t m, int64_t* offsets, int32_t* ids, int64_t cap, uint8_t* covered);
 /* CoverageEvaluation (hcplanner.cpp:1032-1126) over m trajectory poses: *rate = coverage rate; the
  * points pushed into pose k's `visibleCloud` (visible_group, :1102-1107) are
  * group_ids[group_offsets[k] .. group_offsets[k+1]); ever[n] (may be NULL) = visible in any pose.
- * Returns the total number of group ids (> cap: call again), negative on error. */
+ * Returns the total number of group ids (> cap: fcvm_cov_fetch_ids), negative on error. */
 int64_t     fcvm_cov_evaluate(fcvm_cov_t* c, const double* pose5, int64_t m, double* rate, int64_t* group_offsets, int32_t* group_ids,
                               int64_t cap, uint8_t* ever);
+/* the ids of the most recent fcvm_cov_pinhole / fcvm_cov_evaluate call (kept in the handle, so a caller that did
+ * not know the size calls once with ids = NULL and then fetches): copies at most cap ids, returns their number */
+int64_t     fcvm_cov_fetch_ids(fcvm_cov_t* c, int32_t* ids, int64_t cap);
 /* counters since create: [0] pair tests (insideFOV) [1] projections [2] out-of-image projections (undefined
  * behaviour in the reference: unchecked Eigen index; skipped here) [3] kernels launched [4] 1024-point
  * chunks scanned (the rest were culled whole) [5] duplicate-pixel slow paths taken */
 int         fcvm_cov_counters(fcvm_cov_t* c, int64_t* out6);
 /* device time of all kernels of the most recent pinhole / evaluate call, in ms (CUDA events) */
 double      fcvm_cov_last_kernel_ms(fcvm_cov_t* c);
+/* of which k_cov_scan (FOV + projection + z-buffer), the dominant kernel */
+double      fcvm_cov_last_scan_ms(fcvm_cov_t* c);
 
 /* --------------------------------------------------- host-only helpers (CPU tests) --- */
 

@@ -50,7 +50,7 @@ def test_shipped_trajectories_bit_exact(oracle_mod, scene):
     assert rate == float(z["rate"])
     assert np.array_equal(offs, z["group_offsets"]) and np.array_equal(ids, z["group_ids"])
     assert np.array_equal(np.packbits(ever, bitorder="little"), z["ever"])
-    p_offs, p_ids, covered = ce.PinHoleCamera(z["poses"], cap=int(z["pin_offsets"][-1]))
+    p_offs, p_ids, covered = ce.PinHoleCamera(z["poses"])
     assert np.array_equal(p_offs, z["pin_offsets"]) and zlib.crc32(p_ids.tobytes()) == int(z["pin_ids_crc"])
     assert np.array_equal(np.packbits(covered, bitorder="little"), z["covered"])
     ctr = ce.counters()
