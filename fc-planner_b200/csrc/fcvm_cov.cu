@@ -51,6 +51,10 @@ namespace fcvm {
 constexpr int kCovThreads = 256;
 constexpr int kCovPer = 4;                        // points per thread per chunk
 constexpr int kCovChunk = kCovThreads * kCovPer;  // 1024 points, walked in index order
+#ifndef COV_CTAS
+#define COV_CTAS 4          // resident CTAs per SM the register allocation is capped for
+#endif
+constexpr int kCovCtasPerSm = COV_CTAS;
 constexpr int kCovHash = 2048;                    // pixel-collision detector slots (per chunk)
 constexpr unsigned long long kEmpty = ~0ull;
 
@@ -94,13 +98,16 @@ __device__ __forceinline__ int floor_to_int(double v) {
   return (int)f;
 }
 
-__global__ void __launch_bounds__(kCovThreads, 2) k_cov_scan(const __grid_constant__ CovArgs a) {
+__global__ void __launch_bounds__(kCovThreads, kCovCtasPerSm) k_cov_scan(const __grid_constant__ CovArgs a) {
   __shared__ double s_dist[kCovChunk];
+  __shared__ int s_pix[kCovChunk];         // pixel of each point of the chunk, -1 = not in the image
   __shared__ short s_next[kCovChunk];      // chain of the chunk's points that share a pixel
+  __shared__ short s_bucket[kCovChunk];    // the table slot of the point's pixel
   __shared__ int t_key[kCovHash];          // open-addressing table pixel -> chain head (per chunk)
   __shared__ int t_head[kCovHash];
   __shared__ uint32_t s_live[1024];        // surviving-chunk bitmap, 32768 chunks per pass
   __shared__ int s_pose, s_ntouched;
+  __shared__ CovPose s_ps;
 
   const int tid = threadIdx.x, lane = tid & 31;
   unsigned long long* zdist = a.zdist + (long long)blockIdx.x * a.npix;
@@ -108,7 +115,7 @@ __global__ void __launch_bounds__(kCovThreads, 2) k_cov_scan(const __grid_consta
   int* touched = a.touched + (long long)blockIdx.x * a.npix;
   const FovConst& fc = a.fov;
   const CovConst& cc = a.cam;
-  unsigned long long n_proj = 0, n_out = 0, n_chunks = 0, n_slow = 0;
+  unsigned int n_proj = 0, n_out = 0, n_chunks = 0, n_slow = 0;
 
   for (int i = tid; i < kCovHash; i += kCovThreads) { t_key[i] = -1; t_head[i] = -1; }
 
@@ -119,13 +126,11 @@ __global__ void __launch_bounds__(kCovThreads, 2) k_cov_scan(const __grid_consta
     const int k = s_pose;
     if (k >= a.m) break;
 
-    CovPose ps;
-    {
-      const double2* src = reinterpret_cast<const double2*>(a.poses + k);
-      double2* dst = reinterpret_cast<double2*>(&ps);
-#pragma unroll
-      for (int q = 0; q < (int)(sizeof(CovPose) / 16); ++q) dst[q] = __ldg(src + q);
-    }
+    // the pose record lives in shared memory (broadcast reads): 28 doubles per thread would halve the occupancy
+    if (tid < (int)(sizeof(CovPose) / 16))
+      reinterpret_cast<double2*>(&s_ps)[tid] = __ldg(reinterpret_cast<const double2*>(a.poses + k) + tid);
+    __syncthreads();
+    const CovPose& ps = s_ps;
     const VpRec& rec = ps.rec;
     uint32_t* vrow = a.vis_rows + (long long)k * a.words;
     uint32_t* drow = a.disp_rows ? a.disp_rows + (long long)k * a.words : nullptr;
@@ -167,18 +172,15 @@ __global__ void __launch_bounds__(kCovThreads, 2) k_cov_scan(const __grid_consta
           const long long base = (long long)c * kCovChunk;
           n_chunks += (tid == 0);
 
-          // phase 1: FOV + projection of 4 points per thread
-          int pix[kCovPer], bucket[kCovPer];
-          double dist[kCovPer];
+          // phase 1: FOV + projection of 4 points per thread.  All per-point state lives in shared memory and the
+          // loops over a thread's points are not unrolled: registers buy occupancy here, the kernel waits on L2.
           bool any = false;
-#pragma unroll
+#pragma unroll 1
           for (int u = 0; u < kCovPer; ++u) {
             const int slot = u * kCovThreads + tid;
-            const long long i = base + slot;
-            pix[u] = -1;
-            dist[u] = 0.0;
-            if (i < a.P) {
-              const float4 q = __ldg(a.points + i);
+            int px = -1;
+            if (base + slot < a.P) {
+              const float4 q = __ldg(a.points + base + slot);
               const double qx = (double)q.x, qy = (double)q.y, qz = (double)q.z;
               if (inside_fov(rec, fc, qx, qy, qz)) {
                 // CameraModelProjection (hcplanner.cpp:1196-1211)
@@ -192,68 +194,74 @@ __global__ void __launch_bounds__(kCovThreads, 2) k_cov_scan(const __grid_consta
                 const int xi = floor_to_int(camX / cc.xRes), yi = floor_to_int(camY / cc.yRes);
                 n_proj++;
                 if (xi >= 0 && yi >= 0) {
-                  if (xi >= cc.xPixel || yi >= cc.yPixel) n_out++;
-                  else { pix[u] = xi * cc.yPixel + yi; dist[u] = dd; any = true; }
+                  if (xi >= cc.xPixel || yi >= cc.yPixel) {
+                    n_out++;
+                  } else {
+                    px = xi * cc.yPixel + yi;
+                    any = true;
+                    s_dist[slot] = dd;
+                    int hb = (int)((px * 0x9E3779B1u) >> 21);
+                    for (;;) {
+                      const int old = atomicCAS(&t_key[hb], -1, px);
+                      if (old == -1 || old == px) break;
+                      hb = (hb + 1) & (kCovHash - 1);
+                    }
+                    s_next[slot] = (short)atomicExch(&t_head[hb], slot);
+                    s_bucket[slot] = (short)hb;
+                  }
                 }
               }
             }
-            s_dist[slot] = dist[u];
-            bucket[u] = 0;
-            if (pix[u] >= 0) {
-              int hb = (int)((pix[u] * 0x9E3779B1u) >> 21);
-              for (;;) {
-                const int old = atomicCAS(&t_key[hb], -1, pix[u]);
-                if (old == -1 || old == pix[u]) break;
-                hb = (hb + 1) & (kCovHash - 1);
-              }
-              s_next[slot] = (short)atomicExch(&t_head[hb], slot);
-              bucket[u] = hb;
-            }
+            s_pix[slot] = px;
           }
           if (!__syncthreads_or(any)) continue;
 
           // phase 2: does the point hold its pixel at the time the reference scans it?
-          unsigned long long before[kCovPer];
-          bool held[kCovPer];
-#pragma unroll
+          unsigned held = 0u, fresh = 0u;          // bit u: point u holds its pixel / the pixel was empty before this chunk
+#pragma unroll 1
           for (int u = 0; u < kCovPer; ++u) {
-            held[u] = false;
-            before[u] = kEmpty;
-            if (pix[u] >= 0) {
-              const unsigned long long dbits = (unsigned long long)__double_as_longlong(dist[u]);
-              before[u] = __ldcg(zdist + pix[u]);
-              held[u] = dbits < before[u];
-              if (held[u]) {
-                const int slot = u * kCovThreads + tid;
-                int j = t_head[bucket[u]];
-                n_slow += (j != slot || s_next[slot] >= 0);
-                for (; j >= 0; j = s_next[j])
-                  if (j < slot && s_dist[j] <= dist[u]) { held[u] = false; break; }
-              }
+            const int slot = u * kCovThreads + tid;
+            const int px = s_pix[slot];
+            if (px < 0) continue;
+            const double dd = s_dist[slot];
+            const unsigned long long before = __ldcg(zdist + px);
+            if (before == kEmpty) fresh |= 1u << u;
+            if ((unsigned long long)__double_as_longlong(dd) < before) {
+              bool h = true;
+              int j = t_head[s_bucket[slot]];
+              n_slow += (j != slot || s_next[slot] >= 0);
+              for (; j >= 0; j = s_next[j])
+                if (j < slot && s_dist[j] <= dd) { h = false; break; }
+              if (h) held |= 1u << u;
             }
           }
           __syncthreads();
           // phase 3: the pixel's new minimum
-#pragma unroll
-          for (int u = 0; u < kCovPer; ++u)
-            if (held[u]) atomicMin(zdist + pix[u], (unsigned long long)__double_as_longlong(dist[u]));
-          __syncthreads();
-          // phase 4: occupant hand-over; displaced marks; collision detector restored
-#pragma unroll
+#pragma unroll 1
           for (int u = 0; u < kCovPer; ++u) {
-            if (pix[u] < 0) continue;
-            t_key[bucket[u]] = -1;
-            t_head[bucket[u]] = -1;
-            if (!held[u]) continue;
-            const int me = (int)(base + u * kCovThreads + tid);
-            if (__ldcg(zdist + pix[u]) == (unsigned long long)__double_as_longlong(dist[u])) {
-              if (before[u] == kEmpty) {
-                touched[atomicAdd(&s_ntouched, 1)] = pix[u];
+            const int slot = u * kCovThreads + tid;
+            if ((held >> u) & 1u) atomicMin(zdist + s_pix[slot], (unsigned long long)__double_as_longlong(s_dist[slot]));
+          }
+          __syncthreads();
+          // phase 4: occupant hand-over; displaced marks; the chain table is wiped
+#pragma unroll 1
+          for (int u = 0; u < kCovPer; ++u) {
+            const int slot = u * kCovThreads + tid;
+            const int px = s_pix[slot];
+            if (px < 0) continue;
+            const int hb = s_bucket[slot];
+            t_key[hb] = -1;
+            t_head[hb] = -1;
+            if (!((held >> u) & 1u)) continue;
+            const int me = (int)(base + slot);
+            if (__ldcg(zdist + px) == (unsigned long long)__double_as_longlong(s_dist[slot])) {
+              if ((fresh >> u) & 1u) {
+                touched[atomicAdd(&s_ntouched, 1)] = px;
               } else if (drow) {
-                const int old = __ldcg(zidx + pix[u]);
+                const int old = __ldcg(zidx + px);
                 atomicOr(drow + (old >> 5), 1u << (old & 31));
               }
-              __stcg(zidx + pix[u], me);
+              __stcg(zidx + px, me);
             } else if (drow) {
               atomicOr(drow + (me >> 5), 1u << (me & 31));
             }
@@ -283,10 +291,10 @@ __global__ void __launch_bounds__(kCovThreads, 2) k_cov_scan(const __grid_consta
     n_slow += __shfl_xor_sync(0xffffffffu, n_slow, o);
   }
   if (lane == 0 && a.counters) {
-    if (n_proj) atomicAdd(a.counters + 0, n_proj);
-    if (n_out) atomicAdd(a.counters + 1, n_out);
-    if (n_chunks) atomicAdd(a.counters + 2, n_chunks);
-    if (n_slow) atomicAdd(a.counters + 3, n_slow);
+    if (n_proj) atomicAdd(a.counters + 0, (unsigned long long)n_proj);
+    if (n_out) atomicAdd(a.counters + 1, (unsigned long long)n_out);
+    if (n_chunks) atomicAdd(a.counters + 2, (unsigned long long)n_chunks);
+    if (n_slow) atomicAdd(a.counters + 3, (unsigned long long)n_slow);
   }
 }
 
@@ -403,7 +411,7 @@ static int cov_ensure_device(fcvm_cov_handle* h) {
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->prm.device);
   const long long npix = (long long)h->cc.xPixel * h->cc.yPixel;
-  h->slots = sms * 2;
+  h->slots = sms * kCovCtasPerSm;
   while (h->slots > 1 && (long long)h->slots * npix * 16 > (8ll << 30)) h->slots /= 2;
   CU(h->d_zdist.reserve((size_t)h->slots * npix));
   CU(h->d_zidx.reserve((size_t)h->slots * npix));

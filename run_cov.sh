@@ -1,4 +1,4 @@
-timeout 900 python -m pytest tests/test_gpu_cov.py -x -q 2>&1 | tail -15
+timeout 900 python -m pytest tests/test_gpu_cov.py -x -q 2>&1 | tail -5
 cat > /tmp/covtime.py <<'PY'
 import os, time, numpy as np, sys
 sys.path.insert(0, os.getcwd()); sys.path.insert(0, 'tests')
@@ -10,9 +10,7 @@ for scene in ('mbs', 'pipe', 'christ'):
     ce = CoverageEvaluator(launch_params(scene), launch_camera(scene)); ce.setCloud(zs['map_cloud'])
     for it in range(3):
         t = time.time(); r = ce.CoverageEvaluation(z['poses']); w = time.time() - t
-        print(scene, 'evaluate wall ms', round(w * 1e3, 2), 'kernels ms', round(ce.last_kernel_ms(), 3), 'scan ms', round(ce.last_scan_ms(), 3), 'rate', r[0])
-    t = time.time(); r = ce.path_coverage(z['poses']); print(scene, 'path_coverage wall ms', round((time.time() - t) * 1e3, 2), 'kernels', round(ce.last_kernel_ms(), 3), 'scan', round(ce.last_scan_ms(), 3))
-    print(scene, 'counters', ce.counters().tolist())
+    print(os.environ.get('FCVM_LIB', 'default')[-14:], scene, 'evaluate wall ms', round(w * 1e3, 2), 'kernels ms', round(ce.last_kernel_ms(), 3), 'scan ms', round(ce.last_scan_ms(), 3), 'rate', r[0])
 PY
-timeout 300 python /tmp/covtime.py 2>&1 | tail -20
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_cov_scan -c 1 -o gpurun_out/prof_cov_r1b python /tmp/covtime.py > gpurun_out/ncu_cov.log 2>&1; tail -3 gpurun_out/ncu_cov.log
+timeout 300 python /tmp/covtime.py 2>&1 | tail -4
+for c in 2 3; do FCVM_LIB=$PWD/fc-planner_b200/_variants/cov_ctas$c.so timeout 300 python /tmp/covtime.py 2>&1 | tail -3; done
