@@ -178,6 +178,62 @@ def pruning_leg(args, device, with_cpu, world=1, rank=0):
     return out
 
 
+def coverage_leg(args, device, with_cpu):
+    """the planner's pin-hole coverage evaluation (hcplanner.cpp:1032-1211) over the reference's
+    own shipped MBS trajectory (9 311 poses x the 75 620-point full cloud; tests/golden/cov_mbs.npz), through the public
+    call with host buffers, next to the single-threaded CPU oracle (the reference runs this loop on one thread)."""
+    from fc_planner_b200 import launch_camera, launch_params
+    from fc_planner_b200.coverage import CoverageEvaluator
+    g = os.path.join(ROOT, "tests", "golden")
+    try:
+        cloud = np.load(os.path.join(g, "mbs.npz"))["map_cloud"]
+        z = np.load(os.path.join(g, "cov_mbs.npz"))
+    except Exception as e:                                   # fixtures missing: say so instead of inventing a workload
+        return {"unavailable": f"fixture not found: {e}"}
+    prm, cam = launch_params("mbs", device=device), launch_camera("mbs")
+    poses = z["poses"]
+    ce = CoverageEvaluator(prm, cam)
+    ce.setCloud(cloud)
+    ce.CoverageEvaluation(poses)                             # allocations
+    best, kern, scan = 1e9, 0.0, 0.0
+    for _ in range(5):
+        t = time.perf_counter(); rate, offs, ids, ever = ce.CoverageEvaluation(poses); dt = time.perf_counter() - t
+        if dt < best:
+            best, kern, scan = dt, ce.last_kernel_ms(), ce.last_scan_ms()
+    c0 = ce.counters()
+    ce.CoverageEvaluation(poses)
+    c = ce.counters() - c0
+    m, n = len(poses), len(cloud)
+    # algorithmic bytes of one k_cov_scan launch: one 16-B PointXYZ per insideFOV call + the three image-table entries
+    # (state 8 B, distance 8 B, point id 4 B) per projection + the two bitset rows per pose
+    b_alg = 16.0 * c[0] + 20.0 * c[1] + 2.0 * m * (n / 8.0)
+    peak = 6554.6
+    try:
+        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        pass
+    out = {"workload": f"MBS shipped trajectory: {m} poses x {n} points, 640x480 pin-hole image; CoverageEvaluation (rate + visible_group per pose)",
+           "gpu_ms": 1e3 * best, "kernel_ms": kern, "scan_kernel_ms": scan, "coverage_rate": rate, "group_ids": int(len(ids)),
+           "pair_tests": int(c[0]), "projections": int(c[1]), "chunks_scanned": int(c[4]), "chunks_total": int(m * ((n + 1023) // 1024)),
+           "pair_tests_per_s": c[0] / (scan * 1e-3), "kernel_launches": int(c[3]),
+           "matches_fixture": bool(rate == float(z["rate"]) and np.array_equal(offs, z["group_offsets"]) and np.array_equal(ids, z["group_ids"])),
+           "reference_output_agreement": {"same": int(z["agreement"][0]), "only_reference": int(z["agreement"][1]),
+                                          "only_ours": int(z["agreement"][2]),
+                                          "note": "vs the reference's shipped solution/Traj/CloudInfoMBS.txt; its poses are printed with 6 decimals"},
+           "roofline": {"bound": "hbm", "kernel": "k_cov_scan", "achieved": b_alg / (scan * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                        "frac": b_alg / (scan * 1e-3) / 1e9 / peak, "algorithmic_bytes": b_alg,
+                        "note": "algorithmic = what the reference loop touches; whole 1024-point chunks are culled exactly, so fewer bytes move"}}
+    if with_cpu:
+        from oracle import oracle
+        orc = oracle.CoverageOracle(prm, cam)
+        orc.setCloud(cloud)
+        t = time.perf_counter(); o_rate, o_offs, o_ids, o_ever = orc.CoverageEvaluation(poses); cpu_s = time.perf_counter() - t
+        out.update({"cpu_ms": 1e3 * cpu_s, "cpu_cores": 1, "cpu_kind": "port", "speedup": cpu_s / best,
+                    "identical_to_oracle": bool(rate == o_rate and np.array_equal(offs, o_offs) and np.array_equal(ids, o_ids)
+                                                and np.array_equal(ever, o_ever))})
+    return out
+
+
 def run_reference(args, rank, world):
     """--impl reference: the reference's CPU implementation of the path (oracle port; the reference itself
     needs ROS/PCL/Eigen and cannot be built here) on the host cores, same metric and config."""
@@ -228,6 +284,7 @@ def main():
     ap.add_argument("--prune-points", type=int, default=40_000)
     ap.add_argument("--prune-views", type=int, default=4_000)
     ap.add_argument("--no-prune", action="store_true")
+    ap.add_argument("--no-cov", action="store_true")
     ap.add_argument("--stage", type=int, default=1, choices=[1, 3, 4],
                     help="evaluator pass to time: 1 = getPose pass 1 (headline), 3 = gravitation pass, 4 = updateViewpointInfo (offset walk + BiRC)")
     args = ap.parse_args()
@@ -368,6 +425,8 @@ def main():
             rate1, n1, dt1, _, _ = cpu_oracle_rate(pts, nrm, prm, poses[:max(8, n // max(threads, 1))], args.cpu_seconds / 3, 1, args.stage)
             line["cpu_baseline"]["single_thread_value"] = rate1
         line["pruning"] = prune
+        if not args.no_cov:
+            line["coverage_evaluation"] = coverage_leg(args, local_rank, with_cpu=not args.no_cpu and world == 1)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -40,6 +40,7 @@ SYMBOLS = {
     "fcvm_get_vps_contri": (i64, [vp, i32p, i64]),
     "fcvm_get_cover_state": (i64, [vp, u8p, i32p, i32p, i64]),
     "fcvm_get_grid": (ctypes.c_int, [vp, f64p, i32p, u8p, i64]),
+    "fcvm_safety_check": (ctypes.c_int, [vp, f32p, i64, u8p]),
     "fcvm_trace_enable": (ctypes.c_int, [vp, i32]),
     "fcvm_trace_count": (i64, [vp]),
     "fcvm_trace_words": (i64, [vp]),

@@ -122,16 +122,10 @@ struct HostGrid {
   std::vector<unsigned long long> bricks;
   bool ready = false;
 
-  void build(const fcvm_params& p, const float* xyz, int64_t n) {
+  // geometry from the float bounding box of the map cloud (pcl::getMinMax3D), sdf_map.cpp:144-157
+  void set_geometry(const fcvm_params& p, const float mn[3], const float mx[3]) {
     res = p.resolution;
     const double inflate = p.visible_range;
-    float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};   // pcl::getMinMax3D
-    for (int64_t i = 0; i < n; ++i)
-      for (int c = 0; c < 3; ++c) {
-        const float v = xyz[3 * i + c];
-        mn[c] = std::min(mn[c], v);
-        mx[c] = std::max(mx[c], v);
-      }
     res_inv = 1 / res;
     for (int c = 0; c < 3; ++c) {
       size[c] = 4 * inflate + mx[c] - mn[c];        // sdf_map.cpp:146-148 (double + float - float)
@@ -139,6 +133,19 @@ struct HostGrid {
       dims[c] = (int)std::ceil(size[c] / res);      // sdf_map.cpp:156-157
     }
     for (int c = 0; c < 3; ++c) ns[c] = (dims[c] + 3) >> 2;
+    bricks.clear();
+    ready = true;
+  }
+  // host-side build (the CPU-only helper fcvm_host_build_grid; the product path voxelises on the device)
+  void build(const fcvm_params& p, const float* xyz, int64_t n) {
+    float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};   // pcl::getMinMax3D
+    for (int64_t i = 0; i < n; ++i)
+      for (int c = 0; c < 3; ++c) {
+        const float v = xyz[3 * i + c];
+        mn[c] = std::min(mn[c], v);
+        mx[c] = std::max(mx[c], v);
+      }
+    set_geometry(p, mn, mx);
     bricks.assign((size_t)ns[0] * ns[1] * ns[2], 0ull);
     for (int64_t i = 0; i < n; ++i) {               // sdf_map.cpp:178-187
       int id[3];
@@ -146,8 +153,8 @@ struct HostGrid {
       if (in_map(id[0], id[1], id[2]))              // reference: unchecked write
         bricks[(size_t)brick_word_index(id[0], id[1], id[2], ns[1], ns[2])] |= 1ull << brick_bit_index(id[0], id[1], id[2]);
     }
-    ready = true;
   }
+  size_t nbricks() const { return (size_t)ns[0] * ns[1] * ns[2]; }
   bool in_map(int x, int y, int z) const {          // sdf_map.h:367-373
     return !(x < 0 || y < 0 || z < 0 || x > dims[0] - 1 || y > dims[1] - 1 || z > dims[2] - 1);
   }

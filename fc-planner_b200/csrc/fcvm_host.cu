@@ -86,9 +86,20 @@ struct fcvm_handle {
   bool map_flag = false, model_flag = false, viewpoints_flag = false, normal_flag = false;
 
   // map
-  HostGrid grid;
-  CellIndex map_index;
+  HostGrid grid;                               // geometry; the bricks live on the device (downloaded on demand for the parity tap)
   DevBuf<unsigned long long> d_bricks;
+  // map cloud on the device + its uniform cell index (nearCheck), built by fcvm_map.cu
+  DevBuf<float> d_map_xyz;
+  DevBuf<float4> d_map_sorted;
+  DevBuf<long long> d_cell_start;
+  DevBuf<int> d_cell_count;
+  DevBuf<float> d_minmax;
+  CellGeom cells;
+  int64_t n_map = 0;
+  // batched safety checks
+  DevBuf<float> d_cand;
+  DevBuf<uint8_t> d_ok;
+  DevBuf<unsigned long long> d_looks;
   // model
   std::vector<float> model;   // xyz triples
   int64_t P = 0, W = 0;       // W = row stride in words (multiple of 4)
@@ -177,7 +188,7 @@ static void fill_grid_desc(const fcvm_handle* h, GridDesc& g) {
   g.bricks = h->d_bricks.p;
   g.nx = hg.dims[0]; g.ny = hg.dims[1]; g.nz = hg.dims[2];
   g.nbx = hg.ns[0]; g.nby = hg.ns[1]; g.nbz = hg.ns[2];
-  g.nbricks = (int)hg.bricks.size();
+  g.nbricks = (int)hg.nbricks();
   g.res = hg.res;
   // RayCaster::setParams (raycast.cpp:341-345): offset_ = half_ - origin / resolution_
   g.offx = 0.5 - hg.origin[0] / hg.res;
@@ -433,30 +444,46 @@ static void for_each_bit(const uint32_t* row, int64_t words, F&& f) {
 // ------------------------------------------------------------------------------------------------
 // viewpointSafetyCheck / nearCheck (viewpoint_manager.cpp:889-946)
 // ------------------------------------------------------------------------------------------------
-static bool near_check(fcvm_handle* h, const D3& pos, int vox_num) {
-  if (!(std::isfinite(pos.x) && std::isfinite(pos.y) && std::isfinite(pos.z))) return false;
-  if (h->map_index.size() == 0) return false;            // PCL throws on an empty tree; the reference catches
-  const float q[3] = {(float)pos.x, (float)pos.y, (float)pos.z};
-  // dist = sqrt(nn_d2) (float overload); preserve unless dist < safe_radius or vox_num <= 1
-  if (vox_num <= 1) return false;
-  return !h->map_index.any_closer_than(q, h->prm.safe_radius);
-}
-// `lookups` receives the number of safety_check calls (the handle's counter when null; a caller-owned
-// counter when the candidates of many points are checked concurrently)
-static bool viewpoint_safety_check(fcvm_handle* h, float vx, float vy, float vz, int64_t* lookups = nullptr) {
-  int64_t& ctr = lookups ? *lookups : h->counters[7];
+// Both run on the device for whole batches of candidate positions (k_safety, fcvm_map.cu): mode 0 = viewpointSafetyCheck
+// (ground test, lattice of safety_check probes with the reference's early exit, nearCheck with vox_num = 2), mode 1 =
+// nearCheck alone.  counters[7] advances by the number of safety_check probes the reference would have made.
+static int safety_batch(fcvm_handle* h, const std::vector<float>& xyz, int mode, std::vector<uint8_t>& ok) {
+  const int64_t n = (int64_t)xyz.size() / 3;
+  ok.assign((size_t)n, 0);
+  if (n == 0) return FCVM_OK;
   const fcvm_params& p = h->prm;
-  if (p.z_ground && vz < p.ground_pos + p.safe_height) return false;
-  const double res = h->grid.res, sr = p.safe_radius;
-  const int safe_voxel = (int)std::floor(0.5 * sr / res);
-  if (safe_voxel <= 0) return false;   // reference: infinite loop
-  for (int i = 0; vx - sr + i * res < vx + sr; i = i + safe_voxel)
-    for (int j = 0; vy - sr + j * res < vy + sr; j = j + safe_voxel)
-      for (int k = 0; vz - sr + k * res < vz + sr; k = k + safe_voxel) {
-        ctr++;
-        if (!h->grid.safety_check(vx - sr + i * res, vy - sr + j * res, vz - sr + k * res)) return false;
-      }
-  return near_check(h, D3{vx, vy, vz}, 2);
+  CU(h->d_cand.reserve((size_t)3 * n));
+  CU(h->d_ok.reserve((size_t)n));
+  CU(h->d_looks.reserve(1));
+  cudaStream_t s = h->stream;
+  CU(cudaMemcpyAsync(h->d_cand.p, xyz.data(), (size_t)3 * n * sizeof(float), cudaMemcpyHostToDevice, s));
+  CU(cudaMemsetAsync(h->d_looks.p, 0, sizeof(unsigned long long), s));
+  SafetyArgs a;
+  for (int c = 0; c < 3; ++c) { a.geom.org[c] = h->grid.origin[c]; a.geom.dims[c] = h->grid.dims[c]; a.geom.nb[c] = h->grid.ns[c]; }
+  a.geom.res_inv = h->grid.res_inv;
+  a.bricks = h->d_bricks.p;
+  a.cells = h->cells;
+  a.cell_start = h->d_cell_start.p;
+  a.sorted = h->d_map_sorted.p;
+  a.n_map = h->n_map;
+  a.sr = p.safe_radius;
+  a.res = h->grid.res;
+  a.safe_voxel = (int)std::floor(0.5 * p.safe_radius / h->grid.res);
+  a.z_ground = p.z_ground;
+  a.ground_limit = p.ground_pos + p.safe_height;
+  a.mode = mode;
+  a.cand = h->d_cand.p;
+  a.n = n;
+  a.ok = h->d_ok.p;
+  a.lookups = h->d_looks.p;
+  CU(launch_safety(a, s));
+  h->counters[5] += 1;
+  unsigned long long looks = 0;
+  CU(cudaMemcpyAsync(ok.data(), h->d_ok.p, (size_t)n, cudaMemcpyDeviceToHost, s));
+  CU(cudaMemcpyAsync(&looks, h->d_looks.p, sizeof(looks), cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  h->counters[7] += (int64_t)looks;
+  return FCVM_OK;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -631,16 +658,26 @@ static int viewpoints_prune(fcvm_handle* h, const std::vector<Pose5>& vps_pose, 
   const double pitch_bound = 0.3 * prm.fov_h * M_PI / 180.0;
   const double yaw_bound = 0.3 * prm.fov_w * M_PI / 180.0;
 
+  // nearCheck of every candidate's own position (cpp:678-682): the poses read here are never modified before their
+  // own turn in the chain below, so the checks are independent and run as one device batch
+  std::vector<uint8_t> near_ok;
+  {
+    int rc = safety_batch(h, vp_cloud, 1, near_ok);
+    if (rc) return rc;
+  }
+
   struct Grav { int slot; D3 up; double upi, uy; };
   std::vector<Grav> grav;
   std::vector<int> neigh;
+  struct Pulled { int slot; D3 up; D3 cur; };
+  std::vector<Pulled> pulled;                 // positions whose viewpointSafetyCheck (cpp:805-810) is resolved after the chain
   for (const auto& pr : ctrlVector) {
     const int c = pr.first;
     const int cs = idx_slot.find(c)->second;
     const Pose5 cur_pose = slot_pose[(size_t)cs];
     const D3 cur_position{cur_pose.v[0], cur_pose.v[1], cur_pose.v[2]};
     const int cur_vox = idx_ctrl_voxels.find(c)->second;
-    if (!near_check(h, cur_position, cur_vox)) { live[(size_t)cs] = 0; continue; }
+    if (!(cur_vox > 1 && near_ok[(size_t)cs])) { live[(size_t)cs] = 0; continue; }     // nearCheck(cur_position, cur_vox)
     const float q[3] = {(float)cur_pose.v[0], (float)cur_pose.v[1], (float)cur_pose.v[2]};
     vps_tree.radius_search(q, bubble_radius, neigh);
     if (!(live[(size_t)cs] && (int)neigh.size() > 1)) continue;
@@ -683,15 +720,27 @@ static int viewpoints_prune(fcvm_handle* h, const std::vector<Pose5>& vps_pose, 
     }
     if (prm.z_ground && up.z < prm.ground_pos + prm.safe_height) up.z = prm.ground_pos + prm.safe_height + 0.1;
     Pose5& dst = slot_pose[(size_t)cs];
-    if (viewpoint_safety_check(h, (float)up.x, (float)up.y, (float)up.z)) {
-      dst.v[0] = up.x; dst.v[1] = up.y; dst.v[2] = up.z;
-    } else {
-      dst.v[0] = cur_position.x; dst.v[1] = cur_position.y; dst.v[2] = cur_position.z;
-    }
+    // keep the pulled position only if it is safe (cpp:805-810).  Nothing later in the chain reads the position of a
+    // viewpoint that has been queried, so all these checks are resolved together below.
+    pulled.push_back(Pulled{cs, up, cur_position});
     if (!prm.pose_update) {
       dst.v[3] = upi; dst.v[4] = uy;
     } else {
       grav.push_back(Grav{cs, up, upi, uy});   // E3 uses `updated_position` even if it was reverted (cpp:821, 844)
+    }
+  }
+
+  if (!pulled.empty()) {
+    std::vector<float> q;
+    q.reserve(3 * pulled.size());
+    for (const Pulled& pl : pulled) { q.push_back((float)pl.up.x); q.push_back((float)pl.up.y); q.push_back((float)pl.up.z); }
+    std::vector<uint8_t> safe;
+    int rc = safety_batch(h, q, 0, safe);
+    if (rc) return rc;
+    for (size_t i = 0; i < pulled.size(); ++i) {
+      const D3& src = safe[i] ? pulled[i].up : pulled[i].cur;
+      Pose5& dst = slot_pose[(size_t)pulled[i].slot];
+      dst.v[0] = src.x; dst.v[1] = src.y; dst.v[2] = src.z;
     }
   }
 
@@ -761,8 +810,8 @@ static int viewpoints_prune(fcvm_handle* h, const std::vector<Pose5>& vps_pose, 
 
 // uncNeighVps (viewpoint_manager.cpp:948-1131) with injected seeds: engine k of call c is seeded
 // with seed + 8*c + k (k = 0..3 pitch, 4..7 yaw)
-static void unc_neigh_vps(const fcvm_handle* hc, const float pt[3], const float nrm[3], std::vector<PtNormal>& out, int64_t call, int64_t* lookups) {
-  fcvm_handle* h = const_cast<fcvm_handle*>(hc);   // read-only here: grid, map index, parameters
+// The 8 candidates are produced here; their viewpointSafetyCheck (cpp:1060-1128) runs on the device for all points at once.
+static void unc_neigh_vps(const fcvm_handle* h, const float pt[3], const float nrm[3], PtNormal cand[8], int64_t call) {
   const fcvm_params& prm = h->prm;
   double max_pitch_range = 40.0, max_yaw_range = 40.0;
   if (prm.attitude == FCVM_ATTITUDE_YAW) max_pitch_range = 0;
@@ -784,7 +833,6 @@ static void unc_neigh_vps(const fcvm_handle* hc, const float pt[3], const float 
   }
   static const int sp[8] = {+1, -1, +1, -1, +1, -1, +1, -1};
   static const int sy[8] = {+1, -1, +1, -1, -1, +1, -1, +1};
-  PtNormal cand[8];
   for (int q = 0; q < 8; ++q) {
     const int k = q & 3;
     const double pitch = sp[q] > 0 ? op + rand_p[k] : op - rand_p[k];
@@ -793,9 +841,6 @@ static void unc_neigh_vps(const fcvm_handle* hc, const float pt[3], const float 
     cand[q] = PtNormal{(float)(pt[0] + prm.viewpoints_distance * vec.x), (float)(pt[1] + prm.viewpoints_distance * vec.y),
                        (float)(pt[2] + prm.viewpoints_distance * vec.z), (float)(-vec.x), (float)(-vec.y), (float)(-vec.z)};
   }
-  out.clear();
-  for (int q = 0; q < 8; ++q)
-    if (viewpoint_safety_check(h, cand[q].x, cand[q].y, cand[q].z, lookups)) out.push_back(cand[q]);
 }
 
 // stand-in for pcl::RandomSample (cpp:249-255): selection sampling driven by minstd_rand0(seed + phi + call#)
@@ -843,7 +888,8 @@ static int update_impl(fcvm_handle* h) {
   if (!h->viewpoints_flag) {
     // "No input viewpoints!! Use normals gengerate viewpoints!!" (cpp:145-171)
     if (!h->map_flag || !h->model_flag || !h->normal_flag) return fail(FCVM_ENOTREADY, "Not ready: map, model and normals are required");
-    std::vector<PtNormal> vps;
+    std::vector<PtNormal> all, vps;
+    std::vector<float> q;
     for (int64_t i = 0; i < h->P; ++i) {
       auto it = h->pt_normal_pairs.find(D3{M[3 * i], M[3 * i + 1], M[3 * i + 2]});
       if (it == h->pt_normal_pairs.end()) continue;    // reference: unchecked dereference
@@ -851,9 +897,14 @@ static int update_impl(fcvm_handle* h) {
       const float vx = (float)(M[3 * i] + prm.viewpoints_distance * nd.x);
       const float vy = (float)(M[3 * i + 1] + prm.viewpoints_distance * nd.y);
       const float vz = (float)(M[3 * i + 2] + prm.viewpoints_distance * nd.z);
-      if (!viewpoint_safety_check(h, vx, vy, vz)) continue;
-      vps.push_back(PtNormal{vx, vy, vz, (float)(-nd.x), (float)(-nd.y), (float)(-nd.z)});
+      all.push_back(PtNormal{vx, vy, vz, (float)(-nd.x), (float)(-nd.y), (float)(-nd.z)});
+      q.push_back(vx); q.push_back(vy); q.push_back(vz);
     }
+    std::vector<uint8_t> safe;
+    rc = safety_batch(h, q, 0, safe);                  // viewpointSafetyCheck of every candidate (cpp:159-160), one launch
+    if (rc) return rc;
+    for (size_t i = 0; i < all.size(); ++i)
+      if (safe[i]) vps.push_back(all[i]);
     rc = set_init_viewpoints_impl(h, vps);
     if (rc && rc != FCVM_EINVAL) return rc;
   }
@@ -892,15 +943,25 @@ static int update_impl(fcvm_handle* h) {
     const int64_t n_unc = (int64_t)uncoveredID.size(), call0 = h->unc_calls;
     h->unc_calls += n_unc;
     for (int64_t k = 0; k < n_unc; ++k) lib_slot[(size_t)uncoveredID[(size_t)k]] = (int)k;
-    std::vector<int64_t> looks((size_t)n_unc, 0);
+    std::vector<PtNormal> cand8((size_t)8 * n_unc);
+    std::vector<float> q((size_t)24 * n_unc);
     parallel_for(n_unc, h->threads, [&](int64_t k) {
       const int p = uncoveredID[(size_t)k];
       auto it = h->pt_normal_pairs.find(D3{M[3 * p], M[3 * p + 1], M[3 * p + 2]});
       const D3 nd = it == h->pt_normal_pairs.end() ? D3{0, 0, 1} : it->second;
       const float nrm[3] = {(float)nd.x, (float)nd.y, (float)nd.z};
-      unc_neigh_vps(h, &M[3 * p], nrm, uncVpsLib[(size_t)k], call0 + k, &looks[(size_t)k]);
+      unc_neigh_vps(h, &M[3 * p], nrm, &cand8[(size_t)8 * k], call0 + k);
+      for (int c = 0; c < 8; ++c) {
+        const PtNormal& u = cand8[(size_t)8 * k + c];
+        q[(size_t)24 * k + 3 * c] = u.x; q[(size_t)24 * k + 3 * c + 1] = u.y; q[(size_t)24 * k + 3 * c + 2] = u.z;
+      }
     });
-    for (int64_t v : looks) h->counters[7] += v;
+    std::vector<uint8_t> safe;
+    rc = safety_batch(h, q, 0, safe);
+    if (rc) return rc;
+    for (int64_t k = 0; k < n_unc; ++k)
+      for (int c = 0; c < 8; ++c)
+        if (safe[(size_t)8 * k + c]) uncVpsLib[(size_t)k].push_back(cand8[(size_t)8 * k + c]);
   }
 
   int unc_iter = 0, last_unc_num = -1;
@@ -982,6 +1043,8 @@ fcvm_t* fcvm_create(const fcvm_params* p) {
 
 void fcvm_destroy(fcvm_t* h) {
   if (!h) return;
+  h->d_map_xyz.free(); h->d_map_sorted.free(); h->d_cell_start.free(); h->d_cell_count.free(); h->d_minmax.free();
+  h->d_cand.free(); h->d_ok.free(); h->d_looks.free();
   h->d_bricks.free(); h->d_points.free(); h->d_cover_contrib.free(); h->d_contrib_id.free(); h->d_voxcount.free();
   h->d_recs.free(); h->d_rows1.free(); h->d_rows2.free(); h->d_count.free(); h->d_sched.free(); h->d_counters.free();
   h->h_rows.free(); h->h_count.free(); h->h_recs.free(); h->d_offsets.free(); h->d_indices.free(); h->h_indices.free(); h->h_offsets.free();
@@ -1001,7 +1064,7 @@ int fcvm_reset(fcvm_t* h) {   // cpp:64-72
   h->pt_normal_pairs.clear();
   h->final_vps.clear();
   h->inverse_idx.clear(); h->idx_slot.clear(); h->idx_ctrl_voxels.clear();   // VPP.reset(): clear(), buckets kept
-  h->map_index = CellIndex();
+  h->n_map = 0;
   h->trace.clear();
   for (int k = 0; k < FCVM_NCOUNTERS; ++k) h->counters[k] = 0;
   h->unc_calls = 0; h->sample_calls = 0;
@@ -1012,14 +1075,62 @@ int fcvm_reset(fcvm_t* h) {   // cpp:64-72
 
 int fcvm_set_map_cloud(fcvm_t* h, const float* xyz, int64_t n) {   // cpp:74-89
   if (!h || !xyz || n <= 0) return fail(FCVM_EINVAL, "empty map cloud");
-  int rc = ensure_device(h);
+  double t_dev = 0, t_grid = 0, t_index = 0;
+  int rc;
+  { Stopwatch sw(t_dev); rc = ensure_device(h); }
   if (rc) return rc;
-  h->grid.build(h->prm, xyz, n);
-  if (h->grid.voxels() <= 0) return fail(FCVM_EINVAL, "degenerate grid");
-  if (h->grid.voxels() >= (1ll << 31)) return fail(FCVM_EINVAL, "grid has 2^31 voxels or more: beyond the reference's int addressing (sdf_map.h:266-269)");
-  h->map_index.build(xyz, n, std::max(h->prm.safe_radius / 4, 2 * h->prm.resolution));   // cells well below the nearCheck radius: far cells are culled whole
-  CU(h->d_bricks.reserve(h->grid.bricks.size()));
-  CU(cudaMemcpy(h->d_bricks.p, h->grid.bricks.data(), h->grid.bricks.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice));
+  cudaStream_t s = h->stream;
+  {
+    // initHCMap on the device (sdf_map.cpp:140-187): bounding box, geometry, one bit per occupied voxel
+    Stopwatch sw(t_grid);
+    CU(h->d_map_xyz.reserve((size_t)3 * n));
+    CU(cudaMemcpyAsync(h->d_map_xyz.p, xyz, (size_t)3 * n * sizeof(float), cudaMemcpyHostToDevice, s));
+    const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(296, (n + 255) / 256));
+    CU(h->d_minmax.reserve((size_t)6 * blocks));
+    CU(launch_cloud_minmax(h->d_map_xyz.p, n, h->d_minmax.p, blocks, s));
+    std::vector<float> part((size_t)6 * blocks);
+    CU(cudaMemcpyAsync(part.data(), h->d_minmax.p, part.size() * sizeof(float), cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    for (int b = 0; b < blocks; ++b)
+      for (int c = 0; c < 3; ++c) { mn[c] = std::min(mn[c], part[(size_t)6 * b + c]); mx[c] = std::max(mx[c], part[(size_t)6 * b + 3 + c]); }
+    h->grid.set_geometry(h->prm, mn, mx);
+    if (h->grid.voxels() <= 0) return fail(FCVM_EINVAL, "degenerate grid");
+    if (h->grid.voxels() >= (1ll << 31)) return fail(FCVM_EINVAL, "grid has 2^31 voxels or more: beyond the reference's int addressing (sdf_map.h:266-269)");
+    MapGeom g;
+    for (int c = 0; c < 3; ++c) { g.org[c] = h->grid.origin[c]; g.dims[c] = h->grid.dims[c]; g.nb[c] = h->grid.ns[c]; }
+    g.res_inv = h->grid.res_inv;
+    CU(h->d_bricks.reserve(h->grid.nbricks()));
+    CU(cudaMemsetAsync(h->d_bricks.p, 0, h->grid.nbricks() * sizeof(unsigned long long), s));
+    CU(launch_voxelise(h->d_map_xyz.p, n, g, h->d_bricks.p, s));
+    h->counters[5] += 2;
+
+    // uniform cell index over the map cloud for nearCheck: cells well below the radius so that far cells are never visited
+    Stopwatch sw2(t_index);
+    CellGeom& cg = h->cells;
+    cg.cell = std::max(std::max(h->prm.safe_radius / 4, 2 * h->prm.resolution), 1e-6);
+    for (int c = 0; c < 3; ++c) cg.mn[c] = mn[c];
+    for (;;) {
+      double tot = 1;
+      for (int c = 0; c < 3; ++c) { cg.nc[c] = (int)std::floor(((double)mx[c] - mn[c]) / cg.cell) + 1; tot *= cg.nc[c]; }
+      if (tot <= 4.0e6) break;
+      cg.cell *= 1.5;
+    }
+    const int64_t ncell = (int64_t)cg.nc[0] * cg.nc[1] * cg.nc[2];
+    CU(h->d_cell_count.reserve((size_t)ncell));
+    CU(h->d_cell_start.reserve((size_t)ncell + 1));
+    CU(h->d_map_sorted.reserve((size_t)n));
+    CU(cudaMemsetAsync(h->d_cell_count.p, 0, (size_t)ncell * sizeof(int), s));
+    CU(launch_cell_count(h->d_map_xyz.p, n, cg, h->d_cell_count.p, s));
+    CU(launch_exscan(h->d_cell_count.p, ncell, h->d_cell_start.p, s));
+    CU(cudaMemsetAsync(h->d_cell_count.p, 0, (size_t)ncell * sizeof(int), s));
+    CU(launch_cell_fill(h->d_map_xyz.p, n, cg, h->d_cell_start.p, h->d_cell_count.p, h->d_map_sorted.p, s));
+    h->counters[5] += 3;
+    CU(cudaStreamSynchronize(s));
+    h->n_map = n;
+  }
+  if (std::getenv("FCVM_PROFILE"))
+    std::fprintf(stderr, "[fcvm] setMapPointCloud: device bring-up %.1f ms, upload + grid + cell index on the device %.1f ms\n", t_dev, t_grid);
   h->map_flag = true;
   return FCVM_OK;
 }
@@ -1140,8 +1251,23 @@ int fcvm_get_grid(fcvm_t* h, double* origin3, int32_t* voxel_num3, uint8_t* bits
   for (int c = 0; c < 3; ++c) { if (origin3) origin3[c] = h->grid.origin[c]; if (voxel_num3) voxel_num3[c] = h->grid.dims[c]; }
   if (bits) {
     if (cap_bytes < (h->grid.voxels() + 7) / 8) return fail(FCVM_ECAP, "grid buffer too small");
+    h->grid.bricks.resize(h->grid.nbricks());
+    CU(cudaMemcpy(h->grid.bricks.data(), h->d_bricks.p, h->grid.nbricks() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     h->grid.export_xmajor(bits);
+    h->grid.bricks.clear();
+    h->grid.bricks.shrink_to_fit();
   }
+  return FCVM_OK;
+}
+
+int fcvm_safety_check(fcvm_t* h, const float* xyz, int64_t n, uint8_t* ok) {
+  if (!h || !xyz || n <= 0 || !ok) return fail(FCVM_EINVAL, "bad arguments");
+  if (!h->map_flag) return fail(FCVM_ENOTREADY, "safety check needs the map");
+  std::vector<float> q(xyz, xyz + 3 * n);
+  std::vector<uint8_t> out;
+  int rc = safety_batch(h, q, 0, out);
+  if (rc) return rc;
+  std::memcpy(ok, out.data(), (size_t)n);
   return FCVM_OK;
 }
 

@@ -55,4 +55,40 @@ cudaError_t launch_compact_rows(const uint32_t* rows, long long n, long long wor
 cudaError_t launch_own_sweep(const uint32_t* rows, long long words, const int4* sched, int nsched, int last_vps_num, long long P,
                              int* cover_contrib, int* contrib_id, int* voxcount, cudaStream_t s);
 
+
+// ---- map side (fcvm_map.cu) --------------------------------------------------------------------
+struct MapGeom {            // SDFMap geometry as initHCMap derives it (sdf_map.cpp:144-157)
+  double org[3];            // map_origin_
+  double res_inv;           // 1 / resolution_
+  int dims[3];              // map_voxel_num_
+  int nb[3];                // bricks per axis
+};
+struct CellGeom {           // uniform cell index over the map cloud
+  float mn[3];
+  double cell;
+  int nc[3];
+};
+struct SafetyArgs {
+  MapGeom geom;
+  const unsigned long long* bricks;
+  CellGeom cells;
+  const long long* cell_start;     // [ncell + 1]
+  const float4* sorted;            // map points grouped by cell
+  long long n_map;
+  double sr, res;                  // safe_radius, resolution_
+  int safe_voxel;                  // floor(0.5 * safe_radius / res)
+  int z_ground;
+  double ground_limit;             // GroundZPos + safeHeight
+  int mode;                        // 0 = viewpointSafetyCheck (lattice + nearCheck), 1 = nearCheck only
+  const float* cand;               // n x (x, y, z) float, as pcl::PointXYZ holds them
+  long long n;
+  uint8_t* ok;                     // [n]
+  unsigned long long* lookups;     // += safety_check probes made (reference order, early exit included)
+};
+cudaError_t launch_cloud_minmax(const float* xyz, long long n, float* partial, int blocks, cudaStream_t s);
+cudaError_t launch_voxelise(const float* xyz, long long n, const MapGeom& g, unsigned long long* bricks, cudaStream_t s);
+cudaError_t launch_cell_count(const float* xyz, long long n, const CellGeom& cg, int* count, cudaStream_t s);
+cudaError_t launch_cell_fill(const float* xyz, long long n, const CellGeom& cg, const long long* start, int* fill, float4* sorted, cudaStream_t s);
+cudaError_t launch_safety(const SafetyArgs& a, cudaStream_t s);
+
 }  // namespace fcvm

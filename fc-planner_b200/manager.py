@@ -162,6 +162,13 @@ class ViewpointManager:
         check(self.lib.fcvm_get_counters(self.h, ptr(out, i64p)))
         return out
 
+    def safety_check(self, xyz):
+        """viewpointSafetyCheck (viewpoint_manager.cpp:889-946) of n candidate positions -> uint8[n]."""
+        xyz = np.ascontiguousarray(xyz, dtype=np.float32).reshape(-1, 3)
+        ok = np.zeros(len(xyz), np.uint8)
+        check(self.lib.fcvm_safety_check(self.h, ptr(xyz, f32p), len(xyz), ptr(ok, u8p)))
+        return ok
+
     # ---- evaluator level ----------------------------------------------------------------------
     def evaluate(self, stage, pose5, restrict_rows=None, want_rows=True, out=None):
         """One evaluator pass over host poses -> (count[n], rows[n, words]); H2D + kernel + D2H.

@@ -123,6 +123,11 @@ int64_t fcvm_get_cover_state(fcvm_t* h, uint8_t* covered, int32_t* cover_contrib
  * reference's x-major order, 1 bit per voxel (LSB first), cap_bytes >= ceil(G/8). */
 int     fcvm_get_grid(fcvm_t* h, double* origin3, int32_t* voxel_num3, uint8_t* bits, int64_t cap_bytes);
 
+/* viewpointSafetyCheck (viewpoint_manager.cpp:889-914, with nearCheck :916-946) for n candidate positions
+ * (packed float triples, as pcl::PointXYZ holds them): ok[i] = 1 if the position is kept.  One kernel launch;
+ * counter [7] advances by the safety_check probes the reference would have made. */
+int     fcvm_safety_check(fcvm_t* h, const float* xyz, int64_t n, uint8_t* ok);
+
 /* Event log of every evaluator launch, in execution order, for mask-level parity:
  * enable before the calls to be traced.  Entry i has stage[i], vp_id[i] and a bitset row of
  * fcvm_trace_words() 32-bit words (bit j of the row = model point j visible). */

@@ -196,3 +196,35 @@ def test_lattice_aligned_viewpoints(small_plant, oracle_mod):
     assert clean > 100
     assert (gpu_trips > 0) == (capped > 0) or capped == 0
     print(f"lattice-aligned: {clean} clean viewpoints bit-exact, {capped} with capped rays (oracle), gpu cap trips {gpu_trips}")
+
+
+def test_safety_check_batch_matches_oracle(small_plant, oracle_mod):
+    """viewpointSafetyCheck on the device (k_safety): verdicts and the number of safety_check probes (early exit
+    included) against the oracle, for positions near, inside, far from and outside the map, with and without ground."""
+    for over in (dict(), dict(z_ground=1, ground_pos=-2.0), dict(safe_radius=1.3), dict(safe_radius=0.9)):
+        vm, orc, prm = _mk(small_plant, oracle_mod, **over)
+        rng = np.random.default_rng(17)
+        pts = small_plant["points"]
+        lo, hi = pts.min(0), pts.max(0)
+        q = np.concatenate([
+            small_plant["viewpoints"][:300, :3],                                   # 8 m off the surface
+            pts[rng.integers(0, len(pts), 200)] + rng.normal(0, 1.5, (200, 3)),    # close to the surface
+            pts[rng.integers(0, len(pts), 100)] + rng.normal(0, 3.5, (100, 3)),    # around safe_radius
+            rng.uniform(lo - 30, hi + 30, (200, 3)),                               # up to outside the map
+            np.array([[np.nan, 0, 0], [np.inf, 0, 0], [1e30, 1e30, 1e30]]),
+        ]).astype(np.float32)
+        c0, o0 = vm.counters()[7], orc.counters()[7]
+        ok = vm.safety_check(q)
+        ook = orc.safety_check(q)
+        assert np.array_equal(ok, ook)
+        assert vm.counters()[7] - c0 == orc.counters()[7] - o0 > 0
+        assert 0 < ok.sum() < len(ok)
+
+
+def test_device_grid_equals_host_build(small_plant, oracle_mod):
+    """initHCMap voxelisation on the device (k_voxelise) against the oracle's grid: origin, voxel counts, every bit."""
+    vm, orc, prm = _mk(small_plant, oracle_mod)
+    g_org, g_dims, g_bits = vm.grid()
+    o_org, o_dims, o_bits = orc.grid()
+    assert np.array_equal(g_org, o_org) and np.array_equal(g_dims, o_dims) and np.array_equal(g_bits, o_bits)
+    assert g_bits.any()
