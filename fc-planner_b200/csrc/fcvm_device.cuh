@@ -31,6 +31,7 @@ struct GridDesc {
   int nx, ny, nz;                    // map_voxel_num_
   int nbx, nby, nbz;                 // bricks per axis: ceil(n/4)
   int nbricks;                       // nbx * nby * nbz (< 2^31: the reference addresses voxels with int)
+  int guard_steps;                   // fast-path half-rays make at most this many steps; the allocation has guard words for them
   double res;                        // resolution_
   double offx, offy, offz;           // RayCaster::offset_ = 0.5 - origin/res   (raycast.cpp:344)
   double orgx, orgy, orgz;           // map_origin_

@@ -87,7 +87,9 @@ struct fcvm_handle {
 
   // map
   HostGrid grid;                               // geometry; the bricks live on the device (downloaded on demand for the parity tap)
-  DevBuf<unsigned long long> d_bricks;
+  DevBuf<unsigned long long> d_bricks;          // [guard | bricks | guard]; the guard words read 'occupied' (see occ_fast)
+  size_t brick_guard = 0;                       // guard words on each side
+  int guard_steps = 0;                          // longest half-ray (voxel steps) the fast path accepts
   // map cloud on the device + its uniform cell index (nearCheck), built by fcvm_map.cu
   DevBuf<float> d_map_xyz;
   DevBuf<float4> d_map_sorted;
@@ -185,7 +187,8 @@ static int ensure_device(fcvm_handle* h) {
 
 static void fill_grid_desc(const fcvm_handle* h, GridDesc& g) {
   const HostGrid& hg = h->grid;
-  g.bricks = h->d_bricks.p;
+  g.bricks = h->d_bricks.p + h->brick_guard;
+  g.guard_steps = h->guard_steps;
   g.nx = hg.dims[0]; g.ny = hg.dims[1]; g.nz = hg.dims[2];
   g.nbx = hg.ns[0]; g.nby = hg.ns[1]; g.nbz = hg.ns[2];
   g.nbricks = (int)hg.nbricks();
@@ -461,7 +464,7 @@ static int safety_batch(fcvm_handle* h, const std::vector<float>& xyz, int mode,
   SafetyArgs a;
   for (int c = 0; c < 3; ++c) { a.geom.org[c] = h->grid.origin[c]; a.geom.dims[c] = h->grid.dims[c]; a.geom.nb[c] = h->grid.ns[c]; }
   a.geom.res_inv = h->grid.res_inv;
-  a.bricks = h->d_bricks.p;
+  a.bricks = h->d_bricks.p + h->brick_guard;
   a.cells = h->cells;
   a.cell_start = h->d_cell_start.p;
   a.sorted = h->d_map_sorted.p;
@@ -1100,9 +1103,18 @@ int fcvm_set_map_cloud(fcvm_t* h, const float* xyz, int64_t n) {   // cpp:74-89
     MapGeom g;
     for (int c = 0; c < 3; ++c) { g.org[c] = h->grid.origin[c]; g.dims[c] = h->grid.dims[c]; g.nb[c] = h->grid.ns[c]; }
     g.res_inv = h->grid.res_inv;
-    CU(h->d_bricks.reserve(h->grid.nbricks()));
-    CU(cudaMemsetAsync(h->d_bricks.p, 0, h->grid.nbricks() * sizeof(unsigned long long), s));
-    CU(launch_voxelise(h->d_map_xyz.p, n, g, h->d_bricks.p, s));
+    // Guard bands: a fast-path half-ray makes at most guard_steps voxel steps from a voxel inside the map, so even a
+    // marcher that runs away (raycast.cpp has no termination guarantee) stays within guard_steps
+    // voxels of the map on every axis; its brick index then falls into [-guard, nbricks + guard), which is allocated
+    // and reads 'occupied'.  Longer rays (none pass the range test) take the literal, bounds-checked marcher.
+    h->guard_steps = 3 * ((int)std::ceil(std::max(h->prm.max_dist, h->prm.visible_range) / (2 * h->grid.res)) + 2);
+    const size_t G = (size_t)(h->guard_steps / 4 + 1);
+    h->brick_guard = G * ((size_t)h->grid.ns[1] * h->grid.ns[2] + h->grid.ns[2] + 1);
+    CU(h->d_bricks.reserve(h->grid.nbricks() + 2 * h->brick_guard));
+    CU(cudaMemsetAsync(h->d_bricks.p, 0xFF, h->brick_guard * sizeof(unsigned long long), s));
+    CU(cudaMemsetAsync(h->d_bricks.p + h->brick_guard, 0, h->grid.nbricks() * sizeof(unsigned long long), s));
+    CU(cudaMemsetAsync(h->d_bricks.p + h->brick_guard + h->grid.nbricks(), 0xFF, h->brick_guard * sizeof(unsigned long long), s));
+    CU(launch_voxelise(h->d_map_xyz.p, n, g, h->d_bricks.p + h->brick_guard, s));
     h->counters[5] += 2;
 
     // uniform cell index over the map cloud for nearCheck: cells well below the radius so that far cells are never visited
@@ -1252,7 +1264,7 @@ int fcvm_get_grid(fcvm_t* h, double* origin3, int32_t* voxel_num3, uint8_t* bits
   if (bits) {
     if (cap_bytes < (h->grid.voxels() + 7) / 8) return fail(FCVM_ECAP, "grid buffer too small");
     h->grid.bricks.resize(h->grid.nbricks());
-    CU(cudaMemcpy(h->grid.bricks.data(), h->d_bricks.p, h->grid.nbricks() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(h->grid.bricks.data(), h->d_bricks.p + h->brick_guard, h->grid.nbricks() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     h->grid.export_xmajor(bits);
     h->grid.bricks.clear();
     h->grid.bricks.shrink_to_fit();

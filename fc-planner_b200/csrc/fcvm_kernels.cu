@@ -57,6 +57,13 @@ __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarr
 // index of k_eval - queue slots, tile offsets, bitset words, brick indices - and count violations in
 // counter slot 5 instead of performing the access.  compute-sanitizer is closed on this GPU pool,
 // so this is the memory-safety evidence.  Release builds compile the checks away.
+#ifndef EVAL_BRICK_CHECK
+#ifdef FCVM_DEBUG_BOUNDS
+#define EVAL_BRICK_CHECK 1
+#else
+#define EVAL_BRICK_CHECK 0
+#endif
+#endif
 #ifdef FCVM_DEBUG_BOUNDS
 #define FCVM_CHECK(cond) ((cond) ? true : (a.counters ? (atomicAdd(a.counters + 5, 1ull), false) : false))
 #else
@@ -135,14 +142,20 @@ __device__ __forceinline__ void cont_load(const double* qd, const int* qi, int s
 // occCheck on the fast path.  No per-axis bounds test: the ray's extent was verified to lie inside the
 // map when it was prepared, and a sane marcher never leaves the box spanned by its end voxels.  The
 // reference marcher is not always sane (it can run away from a lattice-aligned start, see
-// tests/test_oracle_vs_ref.py), so the brick index is range-checked where a new brick is fetched:
-// a stray ray reads "occupied" instead of memory outside the grid, and is counted as a cap trip
-// when its two halves fail to meet.
+// tests/test_oracle_vs_ref.py).  A fast-path half-ray makes at most g.guard_steps steps, and the brick
+// array is allocated with guard words on both sides that cover every index reachable in that many
+// steps and read "occupied" (fcvm_set_map_cloud): a stray ray never reads outside the allocation and
+// is counted as a cap trip when its two halves fail to meet.  The index-checking debug build
+// (FCVM_DEBUG_BOUNDS) range-checks every fetch instead.
 __device__ __forceinline__ bool occ_fast(const GridDesc& g, int ix, int iy, int iz, int& ckey, unsigned long long& cword) {
   const int k = ((ix >> 2) * g.nby + (iy >> 2)) * g.nbz + (iz >> 2);
   if (k != ckey) {
     ckey = k;
+#if EVAL_BRICK_CHECK
     cword = (unsigned)k < (unsigned)g.nbricks ? __ldg(g.bricks + k) : ~0ull;
+#else
+    cword = __ldg(g.bricks + k);
+#endif
   }
   return ((cword >> brick_bit_index(ix, iy, iz)) & 1ull) == 0ull;
 }
@@ -182,7 +195,8 @@ __device__ __forceinline__ bool prepare_ray(const GridDesc& g, const FovConst& f
   // (the marcher never leaves the box spanned by its end voxels).
   const bool fast = inside(pix, piy, piz) && inside(mix, miy, miz) && inside(nix, niy, niz) &&
                     (mix - pix == mx - x0) && (miy - piy == my - y0) && (miz - piz == mz - z0) &&
-                    (mix - nix == mx - x1) && (miy - niy == my - y1) && (miz - niz == mz - z1);
+                    (mix - nix == mx - x1) && (miy - niy == my - y1) && (miz - niz == mz - z1) &&
+                    abs(mx - x0) + abs(my - y0) + abs(mz - z0) <= g.guard_steps && abs(mx - x1) + abs(my - y1) + abs(mz - z1) <= g.guard_steps;
   if (!fast) {
     slow_verdict = birc(g, vx, vy, vz, bx, by, bz, (flags & CONT_DISCARD) != 0, st) && (flags & CONT_INRANGE);
     return false;
