@@ -10,6 +10,7 @@ from .params import Camera, Params
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
+i8p = ctypes.POINTER(ctypes.c_int8)
 i32p = ctypes.POINTER(ctypes.c_int32)
 i64p = ctypes.POINTER(ctypes.c_int64)
 u8p = ctypes.POINTER(ctypes.c_uint8)
@@ -60,6 +61,13 @@ SYMBOLS = {
     "fcvm_host_fov_normals": (ctypes.c_int, [ctypes.POINTER(Params), f64, f64, f64p]),
     "fcvm_host_build_grid": (ctypes.c_int, [ctypes.POINTER(Params), f32p, i64, f64p, i32p, u8p, i64]),
     "fcvm_shard_range": (ctypes.c_int, [i64, i32, i32, i64p, i64p]),
+    "fcvm_grid_create": (vp, [i32, f64p, f64, i32p, i8p, i8p, i8p]),
+    "fcvm_grid_destroy": (None, [vp]),
+    "fcvm_grid_light_state": (ctypes.c_int, [vp, f64p, i64, f32p, i64, u8p, i32p, i32p]),
+    "fcvm_grid_safety_box": (ctypes.c_int, [vp, f32p, i64, f64, u8p]),
+    "fcvm_grid_line_of_sight": (ctypes.c_int, [vp, f64p, i64, u8p, f64p]),
+    "fcvm_grid_counters": (ctypes.c_int, [vp, i64p]),
+    "fcvm_grid_last_kernel_ms": (f64, [vp]),
     "fcvm_cov_create": (vp, [ctypes.POINTER(Params), ctypes.POINTER(Camera)]),
     "fcvm_cov_destroy": (None, [vp]),
     "fcvm_cov_set_cloud": (ctypes.c_int, [vp, f32p, i64]),

@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "_build", "libfcvm.so")
-SOURCES = ["fcvm_kernels.cu", "fcvm_host.cu", "fcvm_cov.cu", "fcvm_map.cu"]
+SOURCES = ["fcvm_kernels.cu", "fcvm_host.cu", "fcvm_cov.cu", "fcvm_map.cu", "fcvm_plan.cu"]
 DEPS = SOURCES + ["fcvm_device.cuh", "fcvm_kernels.h", "fcvm_geom.h", "fcvm_hostutil.h", os.path.join("..", "..", "include", "fcvm.h")]
 
 NVCC_FLAGS = [

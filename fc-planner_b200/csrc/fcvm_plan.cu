@@ -1,0 +1,359 @@
+// fcvm_plan.cu — three ray / probe loops of the planner that run on the planner's own SDFMap, batched on sm_100a
+// (outside the ViewpointManager boundary, and rank 4): kernels + C ABI (fcvm_grid_*).
+//
+//   hierarchical_coverage_planner/src/hcplanner.cpp:805-863   lightStateDet      -> k_light_state
+//   hierarchical_coverage_planner/src/hcplanner.cpp:658-692   candidate safety box -> k_safety_box
+//   hierarchical_coverage_planner/src/hcsolver.cpp:556-583    search_Path, straight-line part -> k_line_of_sight
+//
+// The planner's SDFMap holds three char buffers (sdf_map.h:217-227).  They are uploaded once and packed into the
+// bricked 1-bit layout of fcvm_device.cuh as the three planes these loops test:
+//   occ  = occupancy_buffer_hc_ == 1                              (SDFMap::occCheck, sdf_map.h:397-420)
+//   sblk = occupancy_buffer_hc_ == 1 || occupancy_buffer_internal_ == 1      (SDFMap::safety_check, :375-395)
+//   pblk = occupancy_inflate_buffer_hc_ == 1 || occupancy_buffer_internal_ == 1   (hcsolver.cpp:566)
+// Marchers: Marcher of fcvm_device.cuh (raycast.cpp restated, FP64, -fmad=false), literal and bounds-checked.
+// No CPU fallback.
+#include <cfloat>
+#include <cstring>
+
+#include "fcvm_hostutil.h"
+#include "fcvm_kernels.h"
+
+namespace fcvm {
+
+struct PlanPlanes {
+  GridDesc occ, sblk, pblk;     // same geometry, three brick arrays
+};
+
+// one thread per brick: 64 voxels of each buffer (x-major bytes, sdf_map.h:266-269) -> one word per plane
+__global__ void __launch_bounds__(256) k_pack_planes(const signed char* __restrict__ hc, const signed char* __restrict__ inflate,
+                                                     const signed char* __restrict__ internal, int nx, int ny, int nz, int nby, int nbz,
+                                                     long long nbricks, unsigned long long* __restrict__ occ,
+                                                     unsigned long long* __restrict__ sblk, unsigned long long* __restrict__ pblk) {
+  const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nbricks) return;
+  const int bz = (int)(b % nbz), by = (int)((b / nbz) % nby), bx = (int)(b / ((long long)nbz * nby));
+  unsigned long long wo = 0ull, ws = 0ull, wp = 0ull;
+  for (int dx = 0; dx < 4; ++dx)
+    for (int dy = 0; dy < 4; ++dy)
+      for (int dz = 0; dz < 4; ++dz) {
+        const int x = bx * 4 + dx, y = by * 4 + dy, z = bz * 4 + dz;
+        if (x >= nx || y >= ny || z >= nz) continue;
+        const long long a = ((long long)x * ny + y) * nz + z;
+        const bool h = hc && hc[a] == 1, f = inflate && inflate[a] == 1, t = internal && internal[a] == 1;
+        const unsigned long long bit = 1ull << brick_bit_index(x, y, z);
+        if (h) wo |= bit;
+        if (h || t) ws |= bit;
+        if (f || t) wp |= bit;
+      }
+  occ[b] = wo; sblk[b] = ws; pblk[b] = wp;
+}
+
+// lightStateDet (hcplanner.cpp:805-863), K = 1: nearest ROSA vertex with FLANN's L2_Simple<float> (lowest index on ties),
+// BiRC candidate -> vertex with the first biNextId discarded, every voxel of both half-rays tested with occCheck (no
+// early exit), `idxFwd` once more after the loop; det = the number of blocked voxels is odd.
+__global__ void __launch_bounds__(128) k_light_state(GridDesc g, const double* __restrict__ cand, long long n, const float* __restrict__ rosa,
+                                                     long long m, uint8_t* __restrict__ det, int* __restrict__ cross, int* __restrict__ nearest,
+                                                     unsigned long long* __restrict__ counters) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double ax = cand[3 * i], ay = cand[3 * i + 1], az = cand[3 * i + 2];
+  const float qx = (float)ax, qy = (float)ay, qz = (float)az;      // pcl::PointXYZ searchVP
+  int best = -1;
+  float bd = FLT_MAX;
+  for (long long v = 0; v < m; ++v) {
+    float result = 0.0f, diff;
+    diff = qx - __ldg(rosa + 3 * v); result += diff * diff;
+    diff = qy - __ldg(rosa + 3 * v + 1); result += diff * diff;
+    diff = qz - __ldg(rosa + 3 * v + 2); result += diff * diff;
+    if (result < bd) { bd = result; best = (int)v; }
+  }
+  int cc = 0;
+  unsigned long long looks = 0, trips = 0;
+  if (best >= 0) {
+    const double bx = (double)__ldg(rosa + 3 * best), by = (double)__ldg(rosa + 3 * best + 1), bz = (double)__ldg(rosa + 3 * best + 2);
+    const double res = g.res;
+    const int mx = (int)floor((0.5 * (ax + bx)) / res), my = (int)floor((0.5 * (ay + by)) / res), mz = (int)floor((0.5 * (az + bz)) / res);
+    Marcher p, q;
+    p.init(ax / res, ay / res, az / res, mx, my, mz, g);
+    q.init(bx / res, by / res, bz / res, mx, my, mz, g);
+    const int kp = p.manhattan(), kn = q.manhattan();
+    int budget = (kp > kn ? kp : kn) + 8;
+    BrickCache cp, cn;
+    cp.reset(); cn.reset();
+    int pix, piy, piz, nix, niy, niz;
+    bool more;
+#define FCVM_BI_NEXT(ret)                        \
+  {                                              \
+    pix = p.ix; piy = p.iy; piz = p.iz;          \
+    const bool pflag = !p.at_end();              \
+    if (pflag) p.step(g);                        \
+    nix = q.ix; niy = q.iy; niz = q.iz;          \
+    const bool nflag = !q.at_end();              \
+    if (nflag) q.step(g);                        \
+    ret = pflag || nflag;                        \
+  }
+    FCVM_BI_NEXT(more);
+    if (more) --budget;            // the discarded call counts against the step cap like any other (oracle: calls_)
+    for (;;) {
+      FCVM_BI_NEXT(more);
+      if (!more) break;
+      if (--budget < 0) { trips++; break; }
+      if (!occ_free(g, pix, piy, piz, cp)) cc++;
+      if (!occ_free(g, nix, niy, niz, cn)) cc++;
+      looks += 2;
+    }
+#undef FCVM_BI_NEXT
+    if (!occ_free(g, pix, piy, piz, cp)) cc++;
+    looks += 1;
+  }
+  det[i] = (best >= 0 && (cc % 2) != 0) ? 1 : 0;
+  if (cross) cross[i] = cc;
+  if (nearest) nearest[i] = best;
+  if (counters) { atomicAdd(counters + 0, looks); if (trips) atomicAdd(counters + 1, trips); }
+}
+
+// the candidate safety box (hcplanner.cpp:658-676).  `break` there leaves only the k loop and safe_flag is overwritten by
+// every probe, so the verdict is that of the last (i, j) column: all of its probes (stride 2 in k) free.
+__device__ __forceinline__ int box_steps(double v, double sr, double res) {
+  int cnt = 0;
+  for (int i = 0; v - sr + i * res < v + sr && cnt < 65536; i += 2) ++cnt;
+  return cnt;
+}
+__global__ void __launch_bounds__(128) k_safety_box(GridDesc g, double res_inv, const float* __restrict__ vp, long long n, double sr,
+                                                    uint8_t* __restrict__ ok, unsigned long long* __restrict__ counters) {
+  const long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= n) return;
+  const double x = (double)vp[3 * v], y = (double)vp[3 * v + 1], z = (double)vp[3 * v + 2];
+  const int ni = box_steps(x, sr, g.res), nj = box_steps(y, sr, g.res);
+  bool safe = true;
+  unsigned long long looks = 0;
+  if (ni > 0 && nj > 0) {
+    const double px = x - sr + (2 * (ni - 1)) * g.res, py = y - sr + (2 * (nj - 1)) * g.res;
+    const int ix = (int)floor((px - g.orgx) * res_inv), iy = (int)floor((py - g.orgy) * res_inv);
+    BrickCache c;
+    c.reset();
+    for (int k = 0, cnt = 0; z - sr + k * g.res < z + sr && cnt < 65536; k += 2, ++cnt) {
+      const int iz = (int)floor((z - sr + k * g.res - g.orgz) * res_inv);
+      looks++;
+      if (!occ_free(g, ix, iy, iz, c)) { safe = false; break; }
+    }
+  }
+  ok[v] = safe ? 1 : 0;
+  if (counters && looks) atomicAdd(counters + 0, looks);
+}
+
+// search_Path's straight-line test (hcsolver.cpp:556-583) for every ordered pair (i, j) of n positions
+__global__ void __launch_bounds__(128) k_line_of_sight(GridDesc g, const double* __restrict__ pts, long long n, uint8_t* __restrict__ safe,
+                                                       double* __restrict__ dist, unsigned long long* __restrict__ counters) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid = t < n * n;
+  unsigned long long looks = 0, trips = 0;
+  if (valid) {
+    const long long i = t / n, j = t % n;
+    const double ax = pts[3 * i], ay = pts[3 * i + 1], az = pts[3 * i + 2];
+    const double bx = pts[3 * j], by = pts[3 * j + 1], bz = pts[3 * j + 2];
+    const double res = g.res;
+    Marcher m;
+    m.init(ax / res, ay / res, az / res, (int)floor(bx / res), (int)floor(by / res), (int)floor(bz / res), g);
+    int budget = m.manhattan() + 8;
+    BrickCache c;
+    c.reset();
+    bool ok = true;
+    for (;;) {
+      const int ix = m.ix, iy = m.iy, iz = m.iz;     // nextId reports the voxel before stepping ...
+      if (m.at_end()) break;                          // ... and returns false at the end voxel (which is never tested)
+      if (--budget < 0) { trips++; ok = false; break; }
+      m.step(g);
+      looks++;
+      if (!occ_free(g, ix, iy, iz, c)) { ok = false; break; }   // blocked, or outside the map
+    }
+    safe[t] = ok ? 1 : 0;
+    if (dist) {
+      const double dx = ax - bx, dy = ay - by, dz = az - bz;
+      dist[t] = sqrt((dx * dx + dy * dy) + dz * dz);            // (p1 - p2).norm(), Eigen order
+    }
+  }
+  if (counters) {                                     // one atomic per warp
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { looks += __shfl_xor_sync(0xffffffffu, looks, o); trips += __shfl_xor_sync(0xffffffffu, trips, o); }
+    if ((threadIdx.x & 31) == 0) { if (looks) atomicAdd(counters + 0, looks); if (trips) atomicAdd(counters + 1, trips); }
+  }
+}
+
+}  // namespace fcvm
+
+using namespace fcvm;
+
+struct fcvm_grid_handle {
+  int device = 0;
+  double origin[3], res = 0;
+  int dims[3], nb[3];
+  long long nbricks = 0;
+  DevBuf<unsigned long long> d_occ, d_sblk, d_pblk;
+  DevBuf<double> d_in;
+  DevBuf<float> d_in_f, d_rosa;
+  DevBuf<uint8_t> d_u8;
+  DevBuf<int> d_i32a, d_i32b;
+  DevBuf<double> d_dist;
+  DevBuf<unsigned long long> d_counters;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  double last_kernel_ms = 0;
+  int64_t counters[3] = {0, 0, 0};    // lookups, cap trips, kernels launched
+};
+
+static void plan_desc(const fcvm_grid_handle* h, const unsigned long long* bricks, GridDesc& g) {
+  g.bricks = bricks;
+  g.nx = h->dims[0]; g.ny = h->dims[1]; g.nz = h->dims[2];
+  g.nbx = h->nb[0]; g.nby = h->nb[1]; g.nbz = h->nb[2];
+  g.nbricks = (int)h->nbricks;
+  g.guard_steps = 0;
+  g.res = h->res;
+  g.offx = 0.5 - h->origin[0] / h->res;      // RayCaster::setParams (raycast.cpp:341-345; hcplanner.cpp:89, hcsolver.cpp:40)
+  g.offy = 0.5 - h->origin[1] / h->res;
+  g.offz = 0.5 - h->origin[2] / h->res;
+  g.orgx = h->origin[0]; g.orgy = h->origin[1]; g.orgz = h->origin[2];
+}
+
+static int plan_finish(fcvm_grid_handle* h) {
+  unsigned long long c[2];
+  CU(cudaEventRecord(h->ev1, h->stream));
+  CU(cudaMemcpyAsync(c, h->d_counters.p, sizeof(c), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaMemsetAsync(h->d_counters.p, 0, sizeof(c), h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  float ms = 0.f;
+  CU(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+  h->last_kernel_ms = ms;
+  h->counters[0] += (int64_t)c[0];
+  h->counters[1] += (int64_t)c[1];
+  h->counters[2] += 1;
+  return FCVM_OK;
+}
+
+extern "C" {
+
+fcvm_grid_t* fcvm_grid_create(int32_t device, const double* origin3, double resolution, const int32_t* voxel_num3, const int8_t* occupancy_hc,
+                              const int8_t* occupancy_inflate, const int8_t* occupancy_internal) {
+  if (!origin3 || !voxel_num3 || !(resolution > 0)) { fail(FCVM_EINVAL, "bad grid geometry"); return nullptr; }
+  const long long G = (long long)voxel_num3[0] * voxel_num3[1] * voxel_num3[2];
+  if (voxel_num3[0] <= 0 || voxel_num3[1] <= 0 || voxel_num3[2] <= 0 || G >= (1ll << 31)) { fail(FCVM_EINVAL, "bad voxel counts"); return nullptr; }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    fail(FCVM_ENODEVICE, std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") + " (this library has no CPU fallback)");
+    return nullptr;
+  }
+  fcvm_grid_handle* h = new (std::nothrow) fcvm_grid_handle();
+  if (!h) { fail(FCVM_EINTERNAL, "out of memory"); return nullptr; }
+  h->device = device;
+  h->res = resolution;
+  for (int c = 0; c < 3; ++c) { h->origin[c] = origin3[c]; h->dims[c] = voxel_num3[c]; h->nb[c] = (voxel_num3[c] + 3) >> 2; }
+  h->nbricks = (long long)h->nb[0] * h->nb[1] * h->nb[2];
+  auto build = [&]() -> int {
+    CU(cudaSetDevice(device));
+    CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CU(cudaEventCreate(&h->ev0));
+    CU(cudaEventCreate(&h->ev1));
+    CU(h->d_counters.reserve(2));
+    CU(cudaMemset(h->d_counters.p, 0, 2 * sizeof(unsigned long long)));
+    CU(h->d_occ.reserve((size_t)h->nbricks));
+    CU(h->d_sblk.reserve((size_t)h->nbricks));
+    CU(h->d_pblk.reserve((size_t)h->nbricks));
+    DevBuf<signed char> b[3];
+    const int8_t* src[3] = {occupancy_hc, occupancy_inflate, occupancy_internal};
+    for (int k = 0; k < 3; ++k)
+      if (src[k]) {
+        CU(b[k].reserve((size_t)G));
+        CU(cudaMemcpyAsync(b[k].p, src[k], (size_t)G, cudaMemcpyHostToDevice, h->stream));
+      }
+    k_pack_planes<<<(unsigned)((h->nbricks + 255) / 256), 256, 0, h->stream>>>(b[0].p, b[1].p, b[2].p, h->dims[0], h->dims[1], h->dims[2], h->nb[1],
+                                                                                  h->nb[2], h->nbricks, h->d_occ.p, h->d_sblk.p, h->d_pblk.p);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(h->stream));
+    for (int k = 0; k < 3; ++k) b[k].free();
+    h->counters[2] += 1;
+    return FCVM_OK;
+  };
+  if (build() != FCVM_OK) { fcvm_grid_destroy(h); return nullptr; }
+  return h;
+}
+
+void fcvm_grid_destroy(fcvm_grid_t* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  h->d_occ.free(); h->d_sblk.free(); h->d_pblk.free(); h->d_in.free(); h->d_in_f.free(); h->d_rosa.free(); h->d_u8.free();
+  h->d_i32a.free(); h->d_i32b.free(); h->d_dist.free(); h->d_counters.free();
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+int fcvm_grid_light_state(fcvm_grid_t* h, const double* cand_xyz, int64_t n, const float* rosa_xyz, int64_t m, uint8_t* det, int32_t* cross,
+                          int32_t* nearest) {
+  if (!h || !cand_xyz || n <= 0 || !rosa_xyz || m < 0 || !det) return fail(FCVM_EINVAL, "bad arguments");
+  cudaStream_t s = h->stream;
+  CU(cudaSetDevice(h->device));
+  CU(h->d_in.reserve((size_t)3 * n));
+  CU(h->d_rosa.reserve((size_t)3 * std::max<int64_t>(m, 1)));
+  CU(h->d_u8.reserve((size_t)n));
+  CU(h->d_i32a.reserve((size_t)n));
+  CU(h->d_i32b.reserve((size_t)n));
+  CU(cudaMemcpyAsync(h->d_in.p, cand_xyz, (size_t)3 * n * sizeof(double), cudaMemcpyHostToDevice, s));
+  if (m > 0) CU(cudaMemcpyAsync(h->d_rosa.p, rosa_xyz, (size_t)3 * m * sizeof(float), cudaMemcpyHostToDevice, s));
+  GridDesc g;
+  plan_desc(h, h->d_occ.p, g);
+  CU(cudaEventRecord(h->ev0, s));
+  k_light_state<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(g, h->d_in.p, n, h->d_rosa.p, m, h->d_u8.p, h->d_i32a.p, h->d_i32b.p, h->d_counters.p);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(det, h->d_u8.p, (size_t)n, cudaMemcpyDeviceToHost, s));
+  if (cross) CU(cudaMemcpyAsync(cross, h->d_i32a.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, s));
+  if (nearest) CU(cudaMemcpyAsync(nearest, h->d_i32b.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, s));
+  return plan_finish(h);
+}
+
+int fcvm_grid_safety_box(fcvm_grid_t* h, const float* vp_xyz, int64_t n, double safe_radius, uint8_t* ok) {
+  if (!h || !vp_xyz || n <= 0 || !ok) return fail(FCVM_EINVAL, "bad arguments");
+  cudaStream_t s = h->stream;
+  CU(cudaSetDevice(h->device));
+  CU(h->d_in_f.reserve((size_t)3 * n));
+  CU(h->d_u8.reserve((size_t)n));
+  CU(cudaMemcpyAsync(h->d_in_f.p, vp_xyz, (size_t)3 * n * sizeof(float), cudaMemcpyHostToDevice, s));
+  GridDesc g;
+  plan_desc(h, h->d_sblk.p, g);
+  CU(cudaEventRecord(h->ev0, s));
+  k_safety_box<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(g, 1 / h->res, h->d_in_f.p, n, safe_radius, h->d_u8.p, h->d_counters.p);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(ok, h->d_u8.p, (size_t)n, cudaMemcpyDeviceToHost, s));
+  return plan_finish(h);
+}
+
+int fcvm_grid_line_of_sight(fcvm_grid_t* h, const double* p_xyz, int64_t n, uint8_t* safe_nxn, double* dist_nxn) {
+  if (!h || !p_xyz || n <= 0 || !safe_nxn) return fail(FCVM_EINVAL, "bad arguments");
+  if (n > 46340) return fail(FCVM_EINVAL, "too many positions for one pair matrix");
+  cudaStream_t s = h->stream;
+  CU(cudaSetDevice(h->device));
+  CU(h->d_in.reserve((size_t)3 * n));
+  CU(h->d_u8.reserve((size_t)n * n));
+  if (dist_nxn) CU(h->d_dist.reserve((size_t)n * n));
+  CU(cudaMemcpyAsync(h->d_in.p, p_xyz, (size_t)3 * n * sizeof(double), cudaMemcpyHostToDevice, s));
+  GridDesc g;
+  plan_desc(h, h->d_pblk.p, g);
+  CU(cudaEventRecord(h->ev0, s));
+  k_line_of_sight<<<(unsigned)((n * n + 127) / 128), 128, 0, s>>>(g, h->d_in.p, n, h->d_u8.p, dist_nxn ? h->d_dist.p : nullptr, h->d_counters.p);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(safe_nxn, h->d_u8.p, (size_t)n * n, cudaMemcpyDeviceToHost, s));
+  if (dist_nxn) CU(cudaMemcpyAsync(dist_nxn, h->d_dist.p, (size_t)n * n * sizeof(double), cudaMemcpyDeviceToHost, s));
+  return plan_finish(h);
+}
+
+int fcvm_grid_counters(fcvm_grid_t* h, int64_t* out3) {
+  if (!h || !out3) return fail(FCVM_EINVAL, "bad arguments");
+  for (int k = 0; k < 3; ++k) out3[k] = h->counters[k];
+  return FCVM_OK;
+}
+
+double fcvm_grid_last_kernel_ms(fcvm_grid_t* h) { return h ? h->last_kernel_ms : 0.0; }
+
+}  // extern "C"

@@ -242,6 +242,32 @@ double      fcvm_cov_last_kernel_ms(fcvm_cov_t* c);
 /* of which k_cov_scan (FOV + projection + z-buffer), the dominant kernel */
 double      fcvm_cov_last_scan_ms(fcvm_cov_t* c);
 
+/* --------------------------------------------------- planner-grid loops ---------------
+ * SURVEY.md 8(f) rank 2 (outside the manager) and rank 4: three ray / probe loops of the planner over ITS OWN SDFMap
+ * (the manager's private map has no inflate / internal marks), batched on the GPU.  No CPU fallback. */
+typedef struct fcvm_grid_handle fcvm_grid_t;
+
+/* The planner's SDFMap as initHCMap + InternalSpace / OuterCheck left it: map_origin_, resolution_, map_voxel_num_ and
+ * the three voxel buffers occupancy_buffer_hc_, occupancy_inflate_buffer_hc_, occupancy_buffer_internal_
+ * (sdf_map.h:217-227; x-major, sdf_map.h:266-269; any may be NULL = all zero).  Uploaded and bit-packed once. */
+fcvm_grid_t* fcvm_grid_create(int32_t device, const double* origin3, double resolution, const int32_t* voxel_num3, const int8_t* occupancy_hc,
+                              const int8_t* occupancy_inflate, const int8_t* occupancy_internal);
+void         fcvm_grid_destroy(fcvm_grid_t* g);
+/* lightStateDet (hcplanner.cpp:805-863) for n candidate viewpoints (FP64 triples) against the ROSA vertex cloud
+ * (m float triples): det[i] = 1 if the candidate is outside the structure (odd number of occupied voxels crossed on the
+ * way to its nearest vertex); cross[i], nearest[i] may be NULL.  `vpTest = vpCandi + 0.0 * res * normal` is vpCandi. */
+int          fcvm_grid_light_state(fcvm_grid_t* g, const double* cand_xyz, int64_t n, const float* rosa_xyz, int64_t m, uint8_t* det,
+                                   int32_t* cross, int32_t* nearest);
+/* the safety box around sampled viewpoints (hcplanner.cpp:658-676), n float triples (pcl::PointNormal positions) */
+int          fcvm_grid_safety_box(fcvm_grid_t* g, const float* vp_xyz, int64_t n, double safe_radius, uint8_t* ok);
+/* HCSolver::search_Path's straight-line test (hcsolver.cpp:556-583) for every ordered pair of n positions:
+ * safe[i * n + j] = 1 if the segment p_i -> p_j is free (then the path is {p_i, p_j} and its cost dist[i * n + j] =
+ * (p_i - p_j).norm()); 0 = the caller falls back to A* as the reference does.  dist may be NULL. */
+int          fcvm_grid_line_of_sight(fcvm_grid_t* g, const double* p_xyz, int64_t n, uint8_t* safe_nxn, double* dist_nxn);
+/* [0] voxel lookups / probes made [1] marches that hit the step cap (the reference would not terminate) [2] kernels launched */
+int          fcvm_grid_counters(fcvm_grid_t* g, int64_t* out3);
+double       fcvm_grid_last_kernel_ms(fcvm_grid_t* g);
+
 /* --------------------------------------------------- host-only helpers (CPU tests) --- */
 
 /* PerceptionUtils::init + setPose_PY (perception_utils.cpp:29-96): 4 world-frame inward normals

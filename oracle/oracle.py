@@ -24,7 +24,7 @@ def build(force=False):
     """Compile the oracle (and oracle/_ref when /root/reference exists) with the committed Makefile."""
     so = os.path.join(_HERE, "_build", "libfcvm_oracle.so")
     if force or not os.path.exists(so) or os.path.getmtime(so) < max(
-            os.path.getmtime(os.path.join(_HERE, f)) for f in ("fcvm_oracle.hpp", "fcvm_oracle_cov.hpp", "oracle_capi.cpp")):
+            os.path.getmtime(os.path.join(_HERE, f)) for f in ("fcvm_oracle.hpp", "fcvm_oracle_cov.hpp", "fcvm_oracle_plan.hpp", "oracle_capi.cpp")):
         subprocess.run(["make", "-C", _HERE, "all"], check=True, stdout=subprocess.DEVNULL)
     return so
 
@@ -50,6 +50,8 @@ def load(alt=False):
     lib.orc_cov_destroy.argtypes = [ctypes.c_void_p]
     lib.orc_cov_pinhole.restype = ctypes.c_int64
     lib.orc_cov_evaluate.restype = ctypes.c_int64
+    lib.orc_plan_create.restype = ctypes.c_void_p
+    lib.orc_plan_destroy.argtypes = [ctypes.c_void_p]
     lib.orc_intbound.restype = ctypes.c_double
     lib.orc_intbound.argtypes = [ctypes.c_double, ctypes.c_double]
     lib.orc_mod.restype = ctypes.c_double
@@ -512,3 +514,87 @@ class CoverageOracle:
             if total <= cap:
                 return rate.value, offsets, ids[:total], ever
             cap = int(total)
+
+
+# -- planner-grid loops (fcvm_oracle_plan.hpp; hcplanner.cpp:658-692, 805-863; hcsolver.cpp:556-583) ----------
+c_i8p = ctypes.POINTER(ctypes.c_int8)
+
+
+class PlanOracle:
+    """origin[3], resolution, voxel_num[3] + the three voxel buffers of the planner's SDFMap (x-major int8 arrays or None)."""
+
+    def __init__(self, origin, resolution, voxel_num, hc=None, inflate=None, internal=None):
+        self.lib = load()
+        self.origin = np.ascontiguousarray(origin, np.float64)
+        self.dims = np.ascontiguousarray(voxel_num, np.int32)
+        bufs = [None if b is None else np.ascontiguousarray(b, np.int8).ravel() for b in (hc, inflate, internal)]
+        self._bufs = bufs
+        self.h = ctypes.c_void_p(self.lib.orc_plan_create(_ptr(self.origin, c_f64p), ctypes.c_double(resolution), _ptr(self.dims, c_i32p),
+                                                          *[_ptr(b, c_i8p) for b in bufs]))
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.lib.orc_plan_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def lightStateDet(self, cand, rosa):
+        cand = np.ascontiguousarray(cand, np.float64).reshape(-1, 3); rosa = np.ascontiguousarray(rosa, np.float32).reshape(-1, 3)
+        n = len(cand)
+        det = np.zeros(n, np.uint8); cross = np.zeros(n, np.int32); near = np.zeros(n, np.int32)
+        self.lib.orc_plan_light_state(self.h, _ptr(cand, c_f64p), ctypes.c_int64(n), _ptr(rosa, c_f32p), ctypes.c_int64(len(rosa)), _ptr(det, c_u8p),
+                                      _ptr(cross, c_i32p), _ptr(near, c_i32p))
+        return det, cross, near
+
+    def safetyBox(self, vps, safe_radius):
+        vps = np.ascontiguousarray(vps, np.float32).reshape(-1, 3)
+        ok = np.zeros(len(vps), np.uint8)
+        self.lib.orc_plan_safety_box(self.h, _ptr(vps, c_f32p), ctypes.c_int64(len(vps)), ctypes.c_double(safe_radius), _ptr(ok, c_u8p))
+        return ok
+
+    def lineOfSight(self, pts, threads=1):
+        pts = np.ascontiguousarray(pts, np.float64).reshape(-1, 3)
+        n = len(pts)
+        safe = np.zeros((n, n), np.uint8); dist = np.zeros((n, n), np.float64)
+        self.lib.orc_plan_line_of_sight(self.h, _ptr(pts, c_f64p), ctypes.c_int64(n), _ptr(safe, c_u8p), _ptr(dist, c_f64p), ctypes.c_int32(threads))
+        return safe, dist
+
+    def counters(self):
+        out = np.zeros(2, np.int64)
+        self.lib.orc_plan_counters(self.h, _ptr(out, c_i64p))
+        return out
+
+
+class RefPlanGrid:
+    """The planner's call-site loops driving the REFERENCE's RayCaster (oracle/_ref/libfcvm_ref.so)."""
+
+    def __init__(self, origin, resolution, voxel_num, hc=None, inflate=None, internal=None):
+        self.lib = ref_load()
+        self.lib.ref_plan_grid_create.restype = ctypes.c_void_p
+        self.lib.ref_plan_grid_destroy.argtypes = [ctypes.c_void_p]
+        o = np.ascontiguousarray(origin, np.float64); d = np.ascontiguousarray(voxel_num, np.int32)
+        self._bufs = [None if b is None else np.ascontiguousarray(b, np.int8).ravel() for b in (hc, inflate, internal)]
+        self.h = ctypes.c_void_p(self.lib.ref_plan_grid_create(_ptr(o, c_f64p), ctypes.c_double(resolution), _ptr(d, c_i32p),
+                                                               *[_ptr(b, c_i8p) for b in self._bufs]))
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.lib.ref_plan_grid_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def light_state_cross(self, vp, vertex, max_calls=100000):
+        vp = np.ascontiguousarray(vp, np.float64); vertex = np.ascontiguousarray(vertex, np.float64)
+        cap = ctypes.c_int32(0)
+        c = self.lib.ref_light_state_cross(self.h, _ptr(vp, c_f64p), _ptr(vertex, c_f64p), ctypes.c_int64(max_calls), ctypes.byref(cap))
+        return int(c), bool(cap.value)
+
+    def straight_line(self, p1, p2, max_calls=100000):
+        p1 = np.ascontiguousarray(p1, np.float64); p2 = np.ascontiguousarray(p2, np.float64)
+        cap = ctypes.c_int32(0)
+        s = self.lib.ref_straight_line(self.h, _ptr(p1, c_f64p), _ptr(p2, c_f64p), ctypes.c_int64(max_calls), ctypes.byref(cap))
+        return bool(s), bool(cap.value)

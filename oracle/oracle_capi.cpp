@@ -3,6 +3,7 @@
 // load this library, as the checker.  See fcvm_oracle.hpp for the restatement and its citations.
 #include "fcvm_oracle.hpp"
 #include "fcvm_oracle_cov.hpp"
+#include "fcvm_oracle_plan.hpp"
 
 #include <atomic>
 #include <thread>
@@ -329,5 +330,65 @@ int orc_cov_image(orc_cov_handle* h, int32_t* wh, double* res2) {
   wh[0] = h->ce.xPixel; wh[1] = h->ce.yPixel; res2[0] = h->ce.xRes; res2[1] = h->ce.yRes;
   return 0;
 }
+
+// ---- planner-grid loops (fcvm_oracle_plan.hpp; hcplanner.cpp:658-692, 805-863; hcsolver.cpp:556-583) ----
+struct orc_plan_handle { PlanOps ops; };
+
+orc_plan_handle* orc_plan_create(const double* origin3, double res, const int32_t* dims3, const int8_t* hc, const int8_t* inflate, const int8_t* internal) {
+  orc_plan_handle* h = new orc_plan_handle();
+  const int d[3] = {dims3[0], dims3[1], dims3[2]};
+  h->ops.setGrid(origin3, res, d, hc, inflate, internal);
+  return h;
+}
+void orc_plan_destroy(orc_plan_handle* h) { delete h; }
+int orc_plan_light_state(orc_plan_handle* h, const double* cand, int64_t n, const float* rosa, int64_t m, uint8_t* det, int32_t* cross, int32_t* nearest) {
+  FloatCloudSearch tree;
+  tree.setInputCloud(std::vector<float>(rosa, rosa + 3 * m));
+  for (int64_t i = 0; i < n; ++i) {
+    int c = 0, id = -1;
+    const bool d = h->ops.lightStateDet(V3(cand[3 * i], cand[3 * i + 1], cand[3 * i + 2]), V3(0, 0, 1), tree, c, id);
+    det[i] = d ? 1 : 0;
+    if (cross) cross[i] = c;
+    if (nearest) nearest[i] = id;
+  }
+  return 0;
+}
+int orc_plan_safety_box(orc_plan_handle* h, const float* vp, int64_t n, double safe_radius, uint8_t* ok) {
+  for (int64_t i = 0; i < n; ++i) {
+    PointNormal p{vp[3 * i], vp[3 * i + 1], vp[3 * i + 2], 0, 0, 0};
+    ok[i] = h->ops.safetyBox(p, safe_radius) ? 1 : 0;
+  }
+  return 0;
+}
+// all ordered pairs (i, j): safe[i * n + j], dist[i * n + j]; `threads` std::threads over rows
+int orc_plan_line_of_sight(orc_plan_handle* h, const double* p, int64_t n, uint8_t* safe, double* dist, int32_t threads) {
+  if (threads < 1) threads = 1;
+  std::atomic<int64_t> next(0);
+  std::vector<PlanCounters> ctrs((size_t)threads);
+  auto work = [&](int t) {
+    PlanOps ops = h->ops;      // own RayCaster scratch; the grid copy is shared-nothing but read-only in use
+    ops.ctr = PlanCounters();
+    for (;;) {
+      const int64_t i = next.fetch_add(1);
+      if (i >= n) break;
+      for (int64_t j = 0; j < n; ++j) {
+        double d;
+        const bool s = ops.straightLine(V3(p[3 * i], p[3 * i + 1], p[3 * i + 2]), V3(p[3 * j], p[3 * j + 1], p[3 * j + 2]), d);
+        safe[i * n + j] = s ? 1 : 0;
+        if (dist) dist[i * n + j] = d;
+      }
+    }
+    ctrs[(size_t)t] = ops.ctr;
+  };
+  if (threads == 1) work(0);
+  else {
+    std::vector<std::thread> th;
+    for (int t = 0; t < threads; ++t) th.emplace_back(work, t);
+    for (auto& t : th) t.join();
+  }
+  for (auto& c : ctrs) { h->ops.ctr.lookups += c.lookups; h->ops.ctr.cap_trips += c.cap_trips; }
+  return 0;
+}
+int orc_plan_counters(orc_plan_handle* h, int64_t* out2) { out2[0] = h->ops.ctr.lookups; out2[1] = h->ops.ctr.cap_trips; return 0; }
 
 }  // extern "C"

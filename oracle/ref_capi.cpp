@@ -20,6 +20,7 @@
 #undef private
 
 #include "fcvm_oracle.hpp"
+#include "fcvm_oracle_plan.hpp"
 
 int signum(int x);   // raycast.cpp:26 defines this overload; raycast.h:29 only declares signum(double)
 
@@ -126,6 +127,59 @@ int64_t ref_biray_ids(double res, const double* origin3, const double* start3, c
   }
   return k;
 }
+
+// The planner's call-site loops (hcplanner.cpp:828-849 lightStateDet, hcsolver.cpp:562-576 search_Path) driving the
+// REFERENCE'S RayCaster; the grid is the oracle's PlanGrid, the nearest vertex is given.  max_calls bounds a marcher
+// that would not terminate (reported through *capped).
+int ref_light_state_cross(const orc::PlanGrid* g, const double* vp3, const double* vertex3, int64_t max_calls, int32_t* capped) {
+  RayCaster rc;
+  rc.setParams(g->map.resolution_, ev(g->map.map_origin_));
+  Eigen::Vector3i idxFwd, idxRev;
+  bool fwdFlag, revFlag;
+  auto occ = [&](const Eigen::Vector3i& i) { return g->map.occCheck(orc::V3i(i(0), i(1), i(2))); };
+  rc.biInput(Eigen::Vector3d(vp3[0], vp3[1], vp3[2]), Eigen::Vector3d(vertex3[0], vertex3[1], vertex3[2]));
+  rc.biNextId(idxFwd, idxRev);
+  int crossCount = 0;
+  int64_t calls = 0;
+  *capped = 0;
+  while (rc.biNextId(idxFwd, idxRev)) {
+    if (++calls > max_calls) { *capped = 1; break; }
+    fwdFlag = occ(idxFwd);
+    revFlag = occ(idxRev);
+    if (fwdFlag == false) crossCount++;
+    if (revFlag == false) crossCount++;
+  }
+  fwdFlag = occ(idxFwd);
+  if (fwdFlag == false) crossCount++;
+  return crossCount;
+}
+int ref_straight_line(const orc::PlanGrid* g, const double* p1, const double* p2, int64_t max_calls, int32_t* capped) {
+  RayCaster rc;
+  rc.setParams(g->map.resolution_, ev(g->map.map_origin_));
+  bool safe = true;
+  Eigen::Vector3i idx;
+  int64_t calls = 0;
+  *capped = 0;
+  rc.input(Eigen::Vector3d(p1[0], p1[1], p1[2]), Eigen::Vector3d(p2[0], p2[1], p2[2]));
+  while (rc.nextId(idx)) {
+    if (++calls > max_calls) { *capped = 1; safe = false; break; }
+    const orc::V3i id(idx(0), idx(1), idx(2));
+    bool blocked = !g->map.isInMap_hc(id);
+    if (!blocked) {
+      const size_t a = (size_t)g->map.toAddress_hc(id);
+      blocked = g->inflate[a] == 1 || g->map.occupancy_buffer_internal_[a] == 1;
+    }
+    if (blocked) { safe = false; break; }
+  }
+  return safe ? 1 : 0;
+}
+orc::PlanGrid* ref_plan_grid_create(const double* origin3, double res, const int32_t* dims3, const int8_t* hc, const int8_t* inflate, const int8_t* internal) {
+  orc::PlanGrid* g = new orc::PlanGrid();
+  const int d[3] = {dims3[0], dims3[1], dims3[2]};
+  g->set(origin3, res, d, hc, inflate, internal);
+  return g;
+}
+void ref_plan_grid_destroy(orc::PlanGrid* g) { delete g; }
 
 int ref_fov_normals(const orc::Params* p, double pitch, double yaw, double* out12) {
   set_params(*p);
