@@ -234,6 +234,63 @@ def coverage_leg(args, device, with_cpu):
     return out
 
 
+def planner_grid_leg(args, device, with_cpu):
+    """SURVEY.md 8(f) rank 4 / rank 2: HCSolver::search_Path's straight-line test for all ordered pairs of n positions
+    (hcsolver.cpp:556-583) and lightStateDet (hcplanner.cpp:805-863) on the MBS grid (hc = initHCMap of the shipped full
+    cloud, inflate = its 1-voxel dilation), next to the CPU oracle on all host threads / one thread."""
+    from fc_planner_b200 import launch_params
+    from fc_planner_b200.planner_grid import PlannerGrid
+    try:
+        z = np.load(os.path.join(ROOT, "tests", "golden", "mbs.npz"))
+    except Exception as e:
+        return {"unavailable": f"fixture not found: {e}"}
+    cloud = z["map_cloud"]
+    prm = launch_params("mbs")
+    res, infl = prm.resolution, prm.visible_range
+    mn, mx = cloud.min(0), cloud.max(0)
+    origin = mn.astype(np.float64) - 2 * infl
+    dims = np.ceil((4 * infl + mx.astype(np.float64) - mn) / res).astype(np.int32)
+    idx = np.floor((cloud.astype(np.float64) - origin) / res).astype(np.int64)
+    hc = np.zeros(tuple(dims), np.int8)
+    hc[idx[:, 0], idx[:, 1], idx[:, 2]] = 1
+    inflate = hc.copy()
+    for ax in range(3):
+        inflate = np.maximum(inflate, np.maximum(np.roll(inflate, 1, ax), np.roll(inflate, -1, ax)))
+    rng = np.random.default_rng(0)
+    n = args.los_points
+    P = np.concatenate([z["final_pose"][:, :3], rng.uniform(mn - 6.0, mx + 6.0, (max(0, n - len(z["final_pose"])), 3))])[:n]
+    pg = PlannerGrid(origin, res, dims, hc, inflate, None, device=device)
+    pg.lineOfSight(P)
+    best, kern = 1e9, 0.0
+    for _ in range(3):
+        t = time.perf_counter(); safe, dist = pg.lineOfSight(P); dt = time.perf_counter() - t
+        if dt < best:
+            best, kern = dt, pg.last_kernel_ms()
+    c0 = pg.counters(); pg.lineOfSight(P, want_dist=False); c = pg.counters() - c0
+    rosa = cloud[rng.integers(0, len(cloud), 400)]
+    cand = np.repeat(z["vps_pose"][:, :3], 8, axis=0) + rng.normal(0, 0.5, (8 * len(z["vps_pose"]), 3))
+    pg.lightStateDet(cand, rosa)
+    t = time.perf_counter(); det, cross, near = pg.lightStateDet(cand, rosa); ls_s = time.perf_counter() - t
+    out = {"workload": f"MBS grid {dims[0]}x{dims[1]}x{dims[2]} at {res} m; search_Path straight-line test for all {n}x{n} ordered pairs; "
+                       f"lightStateDet for {len(cand)} candidates x {len(rosa)} ROSA vertices",
+           "los_gpu_ms": 1e3 * best, "los_kernel_ms": kern, "los_pairs": int(n * n), "los_safe_pairs": int(safe.sum()), "los_voxel_lookups": int(c[0]),
+           "los_pairs_per_s": n * n / (kern * 1e-3), "light_state_gpu_ms": 1e3 * ls_s, "light_state_kernel_ms": pg.last_kernel_ms(),
+           "light_state_outside": int(det.sum()), "cap_trips": int(pg.counters()[1])}
+    if with_cpu:
+        from oracle import oracle
+        orc = oracle.PlanOracle(origin, res, dims, hc, inflate, None)
+        threads = host_cores()
+        m = min(n, 1024)
+        t = time.perf_counter(); o_safe, o_dist = orc.lineOfSight(P[:m], threads=threads); cpu_s = time.perf_counter() - t
+        t = time.perf_counter(); orc.lineOfSight(P[:min(m, 256)], threads=1); cpu1_s = time.perf_counter() - t
+        t = time.perf_counter(); o_det, o_cross, o_near = orc.lightStateDet(cand, rosa); cpu_ls = time.perf_counter() - t
+        out.update({"los_cpu_pairs_per_s": m * m / cpu_s, "los_cpu_cores": threads, "los_cpu_single_thread_pairs_per_s": min(m, 256) ** 2 / cpu1_s,
+                    "cpu_kind": "port", "los_identical_to_oracle": bool(np.array_equal(safe[:m, :m], o_safe) and np.array_equal(dist[:m, :m], o_dist)),
+                    "light_state_cpu_ms": 1e3 * cpu_ls, "light_state_identical_to_oracle": bool(np.array_equal(det, o_det) and np.array_equal(cross, o_cross)
+                                                                                               and np.array_equal(near, o_near))})
+    return out
+
+
 def run_reference(args, rank, world):
     """--impl reference: the reference's CPU implementation of the path (oracle port; the reference itself
     needs ROS/PCL/Eigen and cannot be built here) on the host cores, same metric and config."""
@@ -285,6 +342,8 @@ def main():
     ap.add_argument("--prune-views", type=int, default=4_000)
     ap.add_argument("--no-prune", action="store_true")
     ap.add_argument("--no-cov", action="store_true")
+    ap.add_argument("--no-plan", action="store_true")
+    ap.add_argument("--los-points", type=int, default=2048)
     ap.add_argument("--stage", type=int, default=1, choices=[1, 3, 4],
                     help="evaluator pass to time: 1 = getPose pass 1 (headline), 3 = gravitation pass, 4 = updateViewpointInfo (offset walk + BiRC)")
     args = ap.parse_args()
@@ -427,6 +486,8 @@ def main():
         line["pruning"] = prune
         if not args.no_cov:
             line["coverage_evaluation"] = coverage_leg(args, local_rank, with_cpu=not args.no_cpu and world == 1)
+        if not args.no_plan:
+            line["planner_grid"] = planner_grid_leg(args, local_rank, with_cpu=not args.no_cpu and world == 1)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
