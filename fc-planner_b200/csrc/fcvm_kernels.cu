@@ -408,12 +408,26 @@ __global__ void __launch_bounds__(kWarps * 32, EVAL_MIN_CTAS) k_eval(const __gri
     };
     load_rec();
     // whole-tile cull: squared distance from the viewpoint to the tile's bounding box.  Every point
-    // of a culled tile fails `dir.norm() > max_dist` in the reference, so skipping is exact.
+    // of a culled tile fails `dir.norm() > max_dist` in the reference, so skipping is exact ...
     {
       const double cx = fmax(fmax(aabb[0] - rec.px, rec.px - aabb[3]), 0.0);
       const double cy = fmax(fmax(aabb[1] - rec.py, rec.py - aabb[4]), 0.0);
       const double cz = fmax(fmax(aabb[2] - rec.pz, rec.pz - aabb[5]), 0.0);
-      if ((cx * cx + cy * cy) + cz * cz > fc.md2_hi * 1.000001) {
+      bool culled = (cx * cx + cy * cy) + cz * cz > fc.md2_hi * 1.000001;
+      if (!culled && STAGE != 2) {
+        // ... or the whole box lies behind one of the four FOV planes: the largest d.n over the box is negative by a
+        // margin far above rounding, so every point of the tile fails that plane's `dir.dot(n) >= 0` (exact skip)
+        const double lx = aabb[0] - rec.px, ly = aabb[1] - rec.py, lz = aabb[2] - rec.pz;
+        const double hx = aabb[3] - rec.px, hy = aabb[4] - rec.py, hz = aabb[5] - rec.pz;
+        const double margin = 1e-9 * ((fmax(fabs(lx), fabs(hx)) + fmax(fabs(ly), fabs(hy))) + fmax(fabs(lz), fabs(hz)) + 1.0);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const double best = (fmax(lx * rec.n[q][0], hx * rec.n[q][0]) + fmax(ly * rec.n[q][1], hy * rec.n[q][1])) +
+                              fmax(lz * rec.n[q][2], hz * rec.n[q][2]);
+          culled = culled || best < -margin;
+        }
+      }
+      if (culled) {
         if (STAGE != 2) npairs += (lane == 0) ? (unsigned long long)npts : 0ull;
         continue;
       }
