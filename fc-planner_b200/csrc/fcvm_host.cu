@@ -301,11 +301,12 @@ static int eval_batch(fcvm_handle* h, int stage, const VpRec* recs, int64_t n, c
   const int64_t lo = std::min(n, per_rank * h->rank), hi = std::min(n, per_rank * (h->rank + 1));
   h->timed = false;
   if (h->world > 1) CU(cudaMemsetAsync(d_rows.p, 0, (size_t)n_pad * W * sizeof(uint32_t), h->stream));
-  // Single GPU with rows wanted on the host: evaluate in up to 4 sub-batches and copy each finished
+  // Single GPU with rows wanted on the host: evaluate in sub-batches (FCVM_PIPE_SUBS of them) and copy each finished
   // one out on the copy stream while the next is being evaluated (the rows dominate the transfer).
   bool rows_streamed = false;
   if (rows_out && h->world == 1 && n >= 2 * kPipeMinRows) {
-    const int64_t sub = std::max<int64_t>(kPipeMinRows, (n + 3) / 4);
+    static const int pipe_subs = std::getenv("FCVM_PIPE_SUBS") ? std::max(1, atoi(std::getenv("FCVM_PIPE_SUBS"))) : 4;
+    const int64_t sub = std::max<int64_t>(kPipeMinRows, (n + pipe_subs - 1) / pipe_subs);
     size_t k = 0;
     for (int64_t s0 = 0; s0 < n; s0 += sub, ++k) {
       const int64_t sn = std::min(sub, n - s0);
@@ -551,10 +552,9 @@ static int get_pose_batch(fcvm_handle* h, const std::vector<D3>& pos, const std:
         const D3 cand{M[3 * j], M[3 * j + 1], M[3 * j + 2]};
         const D3 d = sub3(cand, vp);
         const D3 ray_dir = normalized3(d);
-        double pitch, yaw;
-        pitch_yaw(ray_dir, pitch, yaw);
+        // PitchYaw(ray_dir) (cpp:405-407): only the pitch is used here; the yaw (atan2) the reference also computes is dead
+        double pitch = std::asin(ray_dir.z / (norm3(ray_dir) + 1e-3));
         warp_angle(pitch);
-        warp_angle(yaw);
         avg_pitch += pitch;
         const double yaw_vec = std::min(std::max(dot3(fs[(size_t)i], ray_dir), -1.0), 1.0);
         double yawoff = std::acos(yaw_vec);

@@ -57,6 +57,9 @@ __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarr
 // index of k_eval - queue slots, tile offsets, bitset words, brick indices - and count violations in
 // counter slot 5 instead of performing the access.  compute-sanitizer is closed on this GPU pool,
 // so this is the memory-safety evidence.  Release builds compile the checks away.
+#ifndef EVAL_ASM_STEP
+#define EVAL_ASM_STEP 1
+#endif
 #ifndef EVAL_BRICK_CHECK
 #ifdef FCVM_DEBUG_BOUNDS
 #define EVAL_BRICK_CHECK 1
@@ -92,6 +95,35 @@ struct Side {
   // One conditional step: the branch ladder of biNextId (raycast.cpp:496-518: strict '<', z on ties
   // and NaN) evaluated as three predicates so that the updates are predicated, not branched.
   __device__ __forceinline__ void step_if(bool go) {
+#if EVAL_ASM_STEP
+    // Same ladder, written as predicated PTX: three ordered '<' compares (false on NaN, like the C++ operator), the
+    // axis predicates, then one predicated integer add and one predicated FP64 add (add.rn, never fused) per axis.
+    // The compiler's own rendering of the C++ below computes all three sums and selects (3 DADD + 6 FSEL + 3 SEL).
+    asm("{\n\t"
+        ".reg .pred g, xy, xz, yz, px, py, pz;\n\t"
+        "setp.ne.s32 g, %13, 0;\n\t"
+        "setp.lt.f64 xy, %4, %5;\n\t"
+        "setp.lt.f64 xz, %4, %6;\n\t"
+        "setp.lt.f64 yz, %5, %6;\n\t"
+        "and.pred px, xy, xz;\n\t"
+        "not.pred xy, xy;\n\t"
+        "and.pred py, xy, yz;\n\t"
+        "or.pred pz, px, py;\n\t"
+        "not.pred pz, pz;\n\t"
+        "and.pred px, px, g;\n\t"
+        "and.pred py, py, g;\n\t"
+        "and.pred pz, pz, g;\n\t"
+        "@px add.s32 %0, %0, %7;\n\t"
+        "@px add.rn.f64 %4, %4, %10;\n\t"
+        "@py add.s32 %1, %1, %8;\n\t"
+        "@py add.rn.f64 %5, %5, %11;\n\t"
+        "@pz add.s32 %2, %2, %9;\n\t"
+        "@pz add.rn.f64 %6, %6, %12;\n\t"
+        "@g add.s32 %3, %3, -1;\n\t"
+        "}"
+        : "+r"(ix), "+r"(iy), "+r"(iz), "+r"(rem), "+d"(tmx), "+d"(tmy), "+d"(tmz)
+        : "r"(sx), "r"(sy), "r"(sz), "d"(tdx), "d"(tdy), "d"(tdz), "r"((int)go));
+#else
     const bool xy = tmx < tmy, xz = tmx < tmz, yz = tmy < tmz;
     const bool selx = go && xy && xz;
     const bool sely = go && !xy && yz;
@@ -100,6 +132,7 @@ struct Side {
     if (sely) { iy += sy; tmy += tdy; }
     if (selz) { iz += sz; tmz += tdz; }
     rem -= go ? 1 : 0;
+#endif
   }
 };
 
