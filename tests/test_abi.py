@@ -107,6 +107,36 @@ def test_no_cpu_fallback_without_device(small_plant):
     assert e.value.code in (-2, -3)
 
 
+def test_widened_entry_points_have_no_cpu_fallback_either(small_plant):
+    """fcvm_cov_* and fcvm_grid_* (SURVEY.md 8f): creating a coverage handle is host-only, every evaluating call and the
+    grid upload need the device and say so."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    from fc_planner_b200 import _lib, launch_camera
+    from fc_planner_b200.coverage import CoverageEvaluator
+    from fc_planner_b200.planner_grid import PlannerGrid
+    ce = CoverageEvaluator(small_plant["params"], launch_camera("mbs"))
+    with pytest.raises(_lib.FcvmError) as e:
+        ce.setCloud(small_plant["points"])
+    assert e.value.code == -3 and "no CPU fallback" in str(e.value)
+    with pytest.raises(_lib.FcvmError) as e:
+        ce.PinHoleCamera(np.zeros((1, 5)))
+    assert e.value.code == -2                      # no cloud
+    with pytest.raises(_lib.FcvmError) as e:
+        PlannerGrid([0, 0, 0], 0.5, [8, 8, 8])
+    assert "no CPU fallback" in str(e.value)
+
+
+def test_camera_struct_layout_matches_header():
+    from fc_planner_b200 import Camera
+    src = open(os.path.join(ROOT, "include", "fcvm.h")).read()
+    body = re.search(r"typedef struct fcvm_camera \{(.*?)\} fcvm_camera;", src, flags=re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    names = [n.strip() for decl in body.split(";") if decl.strip() for n in decl.strip().split(None, 1)[1].split(",")]
+    assert names == [f for f, _ in Camera._fields_] and all(t is ctypes.c_double for _, t in Camera._fields_)
+
+
 def test_product_package_never_touches_the_oracle():
     """The oracle is test infrastructure: nothing under fc-planner_b200/ may import, link or open it."""
     pkg = os.path.join(ROOT, "fc-planner_b200")
