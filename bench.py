@@ -409,22 +409,37 @@ def main():
     pairs_step = int(c1[0] - c0[0])
 
     # ---------------- e2e: host buffers through the C ABI ---------------------------------------
-    # poses come from, and counts + bitset rows go to, page-locked host memory (fcvm_host_alloc);
-    # every step does the host pose -> FOV-normal conversion, H2D, the kernels and the full D2H.
+    # poses come from, and results go to, page-locked host memory (fcvm_host_alloc); every step does the host pose ->
+    # FOV-normal conversion, H2D, the kernels and the D2H of the result.  The headline call returns what the manager
+    # consumes from an evaluator pass - per-viewpoint counts + the visible sets as ascending index lists (the reference's
+    # `visible_structural_voxels`, viewpoint_manager.cpp:358-425); `e2e_rows` is the same pass returning the raw bitset
+    # rows (P / 8 bytes per viewpoint).
     from fc_planner_b200.manager import pinned_empty
     h_poses = pinned_empty(poses.shape, np.float64)
     h_poses[:] = poses
-    out = (pinned_empty((len(poses),), np.int32), pinned_empty((len(poses), words), np.uint32))
+    vis_cap = int(vm.evaluate(args.stage, h_poses, want_rows=False)[0].sum())
+    out_csr = (pinned_empty((len(poses),), np.int32), pinned_empty((len(poses) + 1,), np.int64), pinned_empty((vis_cap + 1024,), np.uint32))
     barrier()
     for _ in range(min(args.warmup, 3)):
-        vm.evaluate(args.stage, h_poses, out=out)
+        vm.evaluate_csr(args.stage, h_poses, out=out_csr)
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        cnt, rows = vm.evaluate(args.stage, h_poses, out=out)
+        cnt, offs, idx = vm.evaluate_csr(args.stage, h_poses, out=out_csr)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     e2e_visible = int(cnt.sum())
+    assert e2e_visible == len(idx) == int(offs[-1])
+    del out_csr
+    out = (pinned_empty((len(poses),), np.int32), pinned_empty((len(poses), words), np.uint32))
+    vm.evaluate(args.stage, h_poses, out=out)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cnt_r, rows = vm.evaluate(args.stage, h_poses, out=out)
+    torch.cuda.synchronize()
+    e2e_rows_s = time.perf_counter() - t0
+    assert int(cnt_r.sum()) == e2e_visible
 
     t = torch.tensor([dev_ms, e2e_s * 1e3, float(rays_step)], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -464,9 +479,13 @@ def main():
                        "l2": f"working set larger than L2: {V * words * 4 / 1e9:.2f} GB of bitset rows rewritten every step",
                        "parallelism": f"viewpoint shards x{world}, grid and points replicated, no data-path collective"},
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(V * 128), "d2h_bytes_per_step": int(V * 4 + V * words * 4),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(V * 128), "d2h_bytes_per_step": int(V * 4 + (V + 4) * 8 + e2e_visible * 4),
                     "ms_per_step": e2e_ms_max / args.steps, "visible_pairs_per_step_per_gpu": e2e_visible,
-                    "call": "fcvm_evaluate(E1, pinned host poses) -> pinned host counts + bitset rows; rows of a finished sub-batch copy out while the next is evaluated"},
+                    "call": f"fcvm_evaluate_csr(E{args.stage}, pinned host poses) -> pinned host counts + offsets + visible index lists; the lists of a "
+                            "finished sub-batch are compacted and copied out while the next is evaluated"},
+            "e2e_rows": {"value": rays_step / (e2e_rows_s / args.steps), "unit": UNIT, "ms_per_step": 1e3 * e2e_rows_s / args.steps,
+                         "d2h_bytes_per_step": int(V * 4 + V * words * 4), "note": "rank 0's own rate",
+                         "call": "fcvm_evaluate(...) -> counts + raw bitset rows"},
             "gpu_launches": 2 * args.steps,
             "rays_per_step_per_gpu": rays_step, "pair_tests_per_step_per_gpu": pairs_step, "voxel_lookups_per_step_per_gpu": lookups_step,
             "viewpoint_evals_per_s": V * world * args.steps / (dev_ms_max * 1e-3),

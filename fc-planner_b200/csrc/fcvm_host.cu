@@ -47,7 +47,14 @@ const char* last_error_cstr() { return g_err.c_str(); }
 
 struct Pose5 { double v[5]; };
 // visible sets of a batch as ascending index lists: row i = idx[offs[i] .. offs[i+1])
-struct CsrOut { std::vector<long long> offs; const uint32_t* idx = nullptr; };
+struct CsrOut {
+  std::vector<long long> offs;
+  const uint32_t* idx = nullptr;
+  // optional caller buffer (ideally page-locked, fcvm_host_alloc): the streamed path copies the index lists straight into it
+  uint32_t* user_idx = nullptr;
+  long long user_cap = 0;
+  bool in_user = false;      // the first min(total, user_cap) indices are in user_idx, nothing in idx
+};
 struct FinalVp { int vp_id; Pose5 pose; int vox_count; };
 struct TraceEv { int stage; int vp_id; Pose5 pose; std::vector<uint32_t> row; };
 struct PtNormal { float x, y, z, nx, ny, nz; };
@@ -304,7 +311,83 @@ static int eval_batch(fcvm_handle* h, int stage, const VpRec* recs, int64_t n, c
   // Single GPU with rows wanted on the host: evaluate in sub-batches (FCVM_PIPE_SUBS of them) and copy each finished
   // one out on the copy stream while the next is being evaluated (the rows dominate the transfer).
   bool rows_streamed = false;
-  if (rows_out && h->world == 1 && n >= 2 * kPipeMinRows) {
+  // Single GPU, visible sets wanted as CSR (what the manager consumes): evaluate in sub-batches; while sub-batch k + 1 is
+  // being evaluated, the rows of sub-batch k are counted, scanned, compacted to index lists and copied out on the copy
+  // stream.  The host only waits for the (tiny) offsets of a finished sub-batch, with the next kernel already queued.
+  bool csr_streamed = false;
+  if (csr && !rows_out && h->world == 1 && n >= 2 * kPipeMinRows) {
+    // two sub-batches: every extra launch costs ~2.5 ms of load-balance tail, the index lists are only ~4 B per visible ray
+    static const int pipe_subs = std::getenv("FCVM_PIPE_SUBS") ? std::max(1, atoi(std::getenv("FCVM_PIPE_SUBS"))) : 2;
+    const int64_t sub = std::max<int64_t>(kPipeMinRows, (n + pipe_subs - 1) / pipe_subs);
+    const size_t nsub = (size_t)((n + sub - 1) / sub);
+    CU(h->d_offsets.reserve((size_t)n + nsub));
+    CU(h->h_offsets.reserve((size_t)n + nsub));
+    while (h->pipe_ev.size() < 2 * nsub) {
+      cudaEvent_t e;
+      CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      h->pipe_ev.push_back(e);
+    }
+    size_t k = 0;
+    for (int64_t s0 = 0; s0 < n; s0 += sub, ++k) {      // everything of the evaluation side is queued up front
+      const int64_t sn = std::min(sub, n - s0);
+      rc = launch_stage(h, stage, h->d_recs.p + s0, sn, d_rows.p + s0 * W, d_restrict ? d_restrict + s0 * W : nullptr, h->stream, true);
+      if (rc) return rc;
+      CU(launch_popc_rows(d_rows.p + s0 * W, sn, W, h->d_count.p + s0, h->stream));
+      CU(launch_exscan(h->d_count.p + s0, sn, h->d_offsets.p + s0 + (int64_t)k, h->stream));
+      h->counters[5] += 2;
+      CU(cudaEventRecord(h->pipe_ev[2 * k], h->stream));
+    }
+    csr->offs.assign((size_t)n + 1, 0);
+    long long base = 0;
+    k = 0;
+    for (int64_t s0 = 0; s0 < n; s0 += sub, ++k) {
+      const int64_t sn = std::min(sub, n - s0);
+      long long* h_off = h->h_offsets.p + s0 + (int64_t)k;
+      CU(cudaStreamWaitEvent(h->copy_stream, h->pipe_ev[2 * k], 0));
+      CU(cudaMemcpyAsync(h_off, h->d_offsets.p + s0 + (int64_t)k, ((size_t)sn + 1) * sizeof(long long), cudaMemcpyDeviceToHost, h->copy_stream));
+      CU(cudaEventRecord(h->pipe_ev[2 * k + 1], h->copy_stream));
+      CU(cudaEventSynchronize(h->pipe_ev[2 * k + 1]));
+      const long long ct = h_off[sn];
+      for (int64_t i = 0; i < sn; ++i) csr->offs[(size_t)(s0 + i + 1)] = base + h_off[i + 1];
+      if (ct > 0) {
+        const size_t need = (size_t)(base + ct);
+        if (need > h->d_indices.cap || (!csr->user_idx && need > h->h_indices.cap)) {
+          // grow once, from the density seen so far (a later shortfall would have to move what is already there)
+          const size_t est = (size_t)((double)need * (double)n / (double)(s0 + sn) * 1.15) + 1024;
+          if (base == 0) {
+            CU(h->d_indices.reserve(est));
+            if (!csr->user_idx) CU(h->h_indices.reserve(est));
+          } else {
+            CU(cudaStreamSynchronize(h->copy_stream));
+            DevBuf<uint32_t> nd;
+            CU(nd.reserve(est));
+            h->d_indices.free();
+            h->d_indices = nd;
+            if (!csr->user_idx) {
+              PinBuf<uint32_t> nh;
+              CU(nh.reserve(est));
+              std::memcpy(nh.p, h->h_indices.p, (size_t)base * sizeof(uint32_t));
+              h->h_indices.free();
+              h->h_indices = nh;
+            }
+          }
+        }
+        CU(launch_compact_rows(d_rows.p + s0 * W, sn, W, h->d_offsets.p + s0 + (int64_t)k, h->d_indices.p + base, h->copy_stream));
+        h->counters[5] += 1;
+        if (csr->user_idx) {
+          const long long fit = std::min<long long>(ct, csr->user_cap - base);   // a caller buffer that is too small keeps a valid prefix
+          if (fit > 0)
+            CU(cudaMemcpyAsync(csr->user_idx + base, h->d_indices.p + base, (size_t)fit * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->copy_stream));
+        } else {
+          CU(cudaMemcpyAsync(h->h_indices.p + base, h->d_indices.p + base, (size_t)ct * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->copy_stream));
+        }
+      }
+      base += ct;
+    }
+    csr_streamed = true;
+    csr->in_user = csr->user_idx != nullptr;
+    h->timed = false;
+  } else if (rows_out && h->world == 1 && n >= 2 * kPipeMinRows) {
     static const int pipe_subs = std::getenv("FCVM_PIPE_SUBS") ? std::max(1, atoi(std::getenv("FCVM_PIPE_SUBS"))) : 4;
     const int64_t sub = std::max<int64_t>(kPipeMinRows, (n + pipe_subs - 1) / pipe_subs);
     size_t k = 0;
@@ -331,6 +414,16 @@ static int eval_batch(fcvm_handle* h, int stage, const VpRec* recs, int64_t n, c
     if (!h->gather) return fail(FCVM_EINVAL, "world > 1 but no all-gather callback set");
     if (h->gather(h->gather_user, d_rows.p, per_rank * W * (int64_t)sizeof(uint32_t), h->stream) != 0)
       return fail(FCVM_EINTERNAL, "all-gather callback failed");
+  }
+  if (csr_streamed) {
+    // the sub-batches already produced counts, offsets and index lists (see above)
+    if (rows_out) CU(cudaMemcpyAsync(rows_out, d_rows.p, (size_t)n * W * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+    if (count_out) CU(cudaMemcpyAsync(count_out, h->d_count.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    rc = fetch_counters(h);   // synchronises the stream
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(h->copy_stream));
+    csr->idx = h->h_indices.p;
+    return FCVM_OK;
   }
   CU(launch_popc_rows(d_rows.p, n, W, h->d_count.p, h->stream));
   h->counters[5] += 1;
@@ -1339,12 +1432,13 @@ int64_t fcvm_evaluate_csr(fcvm_t* h, int32_t stage, const double* pose5, int64_t
       h->cam.fill(h->h_recs.p[i], p[0], p[1], p[2], p[3], p[4]);
     });
     CsrOut csr;
+    if (indices && total < cap) { csr.user_idx = indices + total; csr.user_cap = cap - total; }
     rc = eval_batch(h, stage, h->h_recs.p, cn, restrict_rows ? restrict_rows + c0 * W : nullptr, nullptr, count ? count + c0 : nullptr,
                     h->d_rows1, false, &csr);
     if (rc) return rc;
     const long long ct = csr.offs[(size_t)cn];
     for (int64_t i = 0; i < cn; ++i) offsets[c0 + i + 1] = total + csr.offs[(size_t)i + 1];
-    if (indices && total < cap) std::memcpy(indices + total, csr.idx, (size_t)std::min<long long>(ct, cap - total) * sizeof(uint32_t));
+    if (indices && total < cap && !csr.in_user) std::memcpy(indices + total, csr.idx, (size_t)std::min<long long>(ct, cap - total) * sizeof(uint32_t));
     total += ct;
   }
   return total;

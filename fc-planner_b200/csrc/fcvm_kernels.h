@@ -22,7 +22,7 @@ namespace fcvm {
 #define EVAL_UNROLL 2         // march: biNextId calls per refill / suspend check
 #endif
 #ifndef EVAL_WAVES
-#define EVAL_WAVES 24         // CTA waves (over 148 SMs x EVAL_MIN_CTAS) the tiling aims at
+#define EVAL_WAVES 12         // CTA waves (over 148 SMs x EVAL_MIN_CTAS) the tiling aims at (3..96 measured: flat from 8 to 24, worse outside)
 #endif
 #ifndef EVAL_READYQ
 #define EVAL_READYQ 64        // ray continuations per warp in shared memory (140 B each)

@@ -187,13 +187,22 @@ class ViewpointManager:
         check(self.lib.fcvm_evaluate(self.h, stage, ptr(pose5, f64p), n, ptr(restrict_rows, u32p), ptr(count, i32p), ptr(rows, u32p)))
         return count, rows
 
-    def evaluate_csr(self, stage, pose5, restrict_rows=None, cap=None):
-        """Evaluator pass returning (count[n], offsets[n+1], indices[total]): the visible sets as CSR."""
+    def evaluate_csr(self, stage, pose5, restrict_rows=None, cap=None, out=None):
+        """Evaluator pass returning (count[n], offsets[n+1], indices[total]): the visible sets as CSR.
+        out = (count, offsets, indices) preallocated arrays (e.g. from pinned_empty: the index lists are then copied
+        straight from the device into `indices` while the next sub-batch is being evaluated)."""
         pose5 = np.ascontiguousarray(pose5, dtype=np.float64).reshape(-1, 5)
         n = len(pose5)
-        count = np.zeros(n, np.int32); offsets = np.zeros(n + 1, np.int64)
         if restrict_rows is not None:
             restrict_rows = np.ascontiguousarray(restrict_rows, dtype=np.uint32)
+        if out is not None:
+            count, offsets, indices = out
+            total = check(self.lib.fcvm_evaluate_csr(self.h, stage, ptr(pose5, f64p), n, ptr(restrict_rows, u32p), ptr(count, i32p),
+                                                     ptr(offsets, i64p), ptr(indices, u32p), len(indices)))
+            if total > len(indices):
+                raise ValueError(f"indices buffer too small: {total} visible pairs, room for {len(indices)}")
+            return count, offsets, indices[:total]
+        count = np.zeros(n, np.int32); offsets = np.zeros(n + 1, np.int64)
         cap = int(cap) if cap else max(1, 64 * n)
         while True:
             indices = np.empty(cap, np.uint32)

@@ -1,4 +1,5 @@
 timeout 2400 python -m pytest tests -m gpu -x -q 2>&1 | tail -5
-for st in 1 3; do python bench.py --stage $st --steps 3 --warmup 3 --no-prune --no-cov --no-plan --no-cpu 2>/dev/null | python -c "
-import json,sys
-d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('E$st', d['ms_per_step'], d['roofline']['kernel_ms'], d['e2e']['ms_per_step'], d['roofline']['frac'])"; done
+python bench.py --steps 3 --warmup 3 --no-prune --no-cov --no-plan --no-cpu > gpurun_out/b.json 2> gpurun_out/b.err; tail -3 gpurun_out/b.err; python -c "
+import json
+d=json.loads(open('gpurun_out/b.json').read().strip().splitlines()[-1]); print(d['ms_per_step'], d['e2e'], d['e2e_rows'])"
+FCVM_PROFILE=1 python profiles/fullscale_update.py 25000 2>&1 | tail -3
