@@ -124,7 +124,8 @@ def pruning_leg(args, device, with_cpu, world=1, rank=0):
     from fc_planner_b200 import launch_params, scenes
     from fc_planner_b200.manager import ViewpointManager
     pts, nrm, prims = scenes.make_plant(n_points=args.prune_points, scale=0.5, seed=0)
-    prm = launch_params("synthetic", seed=0, resolution=0.2, device=device)
+    # the ranks of one box share its cores: each rank reduces only its own shard of the viewpoints on its share of the threads
+    prm = launch_params("synthetic", seed=0, resolution=0.2, device=device, host_threads=max(1, host_cores() // max(1, world)))
     vps = scenes.plant_viewpoints(pts, nrm, prims, args.prune_views, prm.viewpoints_distance, seed=5)
 
     def run(m):

@@ -54,6 +54,9 @@ struct CsrOut {
   uint32_t* user_idx = nullptr;
   long long user_cap = 0;
   bool in_user = false;      // the first min(total, user_cap) indices are in user_idx, nothing in idx
+  // rows [lo, hi) only (hi < 0: all): a rank of a sharded run extracts the visible sets of its own viewpoints;
+  // offs then has hi - lo + 1 entries, row lo first
+  long long lo = 0, hi = -1;
 };
 struct FinalVp { int vp_id; Pose5 pose; int vox_count; };
 struct TraceEv { int stage; int vp_id; Pose5 pose; std::vector<uint32_t> row; };
@@ -106,6 +109,7 @@ struct fcvm_handle {
   CellGeom cells;
   int64_t n_map = 0;
   // batched safety checks
+  DevBuf<double> d_gather;
   DevBuf<float> d_cand;
   DevBuf<uint8_t> d_ok;
   DevBuf<unsigned long long> d_looks;
@@ -427,12 +431,14 @@ static int eval_batch(fcvm_handle* h, int stage, const VpRec* recs, int64_t n, c
   }
   CU(launch_popc_rows(d_rows.p, n, W, h->d_count.p, h->stream));
   h->counters[5] += 1;
+  const int64_t c_lo = csr ? std::max<long long>(0, csr->lo) : 0, c_hi = csr ? (csr->hi < 0 ? n : std::min<long long>(n, csr->hi)) : 0;
+  const int64_t c_n = std::max<int64_t>(0, c_hi - c_lo);
   if (csr) {
-    CU(h->d_offsets.reserve((size_t)n + 1));
-    CU(h->h_offsets.reserve((size_t)n + 1));
-    CU(launch_exscan(h->d_count.p, n, h->d_offsets.p, h->stream));
+    CU(h->d_offsets.reserve((size_t)c_n + 1));
+    CU(h->h_offsets.reserve((size_t)c_n + 1));
+    CU(launch_exscan(h->d_count.p + c_lo, c_n, h->d_offsets.p, h->stream));
     h->counters[5] += 1;
-    CU(cudaMemcpyAsync(h->h_offsets.p, h->d_offsets.p, ((size_t)n + 1) * sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(h->h_offsets.p, h->d_offsets.p, ((size_t)c_n + 1) * sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
   }
   if (rows_out && !rows_streamed) CU(cudaMemcpyAsync(rows_out, d_rows.p, (size_t)n * W * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
   if (count_out) CU(cudaMemcpyAsync(count_out, h->d_count.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
@@ -440,12 +446,12 @@ static int eval_batch(fcvm_handle* h, int stage, const VpRec* recs, int64_t n, c
   if (rc) return rc;
   if (rows_streamed) CU(cudaStreamSynchronize(h->copy_stream));
   if (csr) {
-    csr->offs.assign(h->h_offsets.p, h->h_offsets.p + n + 1);
-    const long long total = csr->offs[(size_t)n];
+    csr->offs.assign(h->h_offsets.p, h->h_offsets.p + c_n + 1);
+    const long long total = csr->offs[(size_t)c_n];
     CU(h->d_indices.reserve((size_t)std::max<long long>(total, 1)));
     CU(h->h_indices.reserve((size_t)std::max<long long>(total, 1)));
     if (total > 0) {
-      CU(launch_compact_rows(d_rows.p, n, W, h->d_offsets.p, h->d_indices.p, h->stream));
+      CU(launch_compact_rows(d_rows.p + c_lo * W, c_n, W, h->d_offsets.p, h->d_indices.p, h->stream));
       h->counters[5] += 1;
       CU(cudaMemcpyAsync(h->h_indices.p, h->d_indices.p, (size_t)total * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
       CU(cudaStreamSynchronize(h->stream));
@@ -583,6 +589,29 @@ static int safety_batch(fcvm_handle* h, const std::vector<float>& xyz, int mode,
   return FCVM_OK;
 }
 
+// Sharded runs: the per-viewpoint host reductions (libm over the visible rays) are the expensive host part, and the ranks
+// of one box share its cores.  Each rank reduces only the viewpoints of its own shard and the results (k doubles per
+// viewpoint) are exchanged with the same all-gather callback the bitset rows use.  vals holds n x k doubles; on return
+// every rank has all of them.  Every value is produced by exactly one rank with the same code, so the outcome is
+// bit-identical to the unsharded run.
+static void shard_of(const fcvm_handle* h, int64_t n, int64_t& lo, int64_t& hi) {
+  const int64_t per = (n + h->world - 1) / h->world;
+  lo = std::min(n, per * h->rank);
+  hi = std::min(n, per * (h->rank + 1));
+}
+static int gather_doubles(fcvm_handle* h, double* vals, int64_t n, int k) {
+  if (h->world <= 1 || n == 0) return FCVM_OK;
+  const int64_t per = (n + h->world - 1) / h->world, n_pad = per * h->world;
+  int64_t lo, hi;
+  shard_of(h, n, lo, hi);
+  CU(h->d_gather.reserve((size_t)n_pad * k));
+  if (hi > lo) CU(cudaMemcpyAsync(h->d_gather.p + lo * k, vals + lo * k, (size_t)(hi - lo) * k * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  if (h->gather(h->gather_user, h->d_gather.p, per * k * (int64_t)sizeof(double), h->stream) != 0) return fail(FCVM_EINTERNAL, "all-gather callback failed");
+  CU(cudaMemcpyAsync(vals, h->d_gather.p, (size_t)n * k * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return FCVM_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // getPose over a batch (viewpoint_manager.cpp:332-531).  ids[i] = viewpoint id of candidate i.
 // poses_out[i] receives the returned pose; ownership and vps_contri/voxcount are updated.
@@ -626,6 +655,8 @@ static int get_pose_batch(fcvm_handle* h, const std::vector<D3>& pos, const std:
 
     // ---- E1 ------------------------------------------------------------------------------
     CsrOut csr;
+    int64_t my_lo = 0, my_hi = cn;
+    if (h->world > 1) { shard_of(h, cn, my_lo, my_hi); csr.lo = my_lo; csr.hi = my_hi; }
     rc = eval_batch(h, FCVM_STAGE_E1, h->h_recs.p, cn, nullptr, h->trace_on ? h->h_rows.p : nullptr, h->h_count.p, h->d_rows1, false, &csr);
     if (rc) return rc;
     if (h->trace_on)
@@ -633,14 +664,16 @@ static int get_pose_batch(fcvm_handle* h, const std::vector<D3>& pos, const std:
 
     // ---- ordered pitch / yaw averages (cpp:398-447), libm on the host ---------------------
     std::vector<char> has_free((size_t)cn, 0);
+    std::vector<double> avg2((size_t)cn * 2, 0.0);      // (avg_pitch, avg_yaw) per viewpoint with free_num > 0
     const float* M = h->model.data();
     const double pu = h->pitch_upper * M_PI / 180.0, pl = h->pitch_lower * M_PI / 180.0;
-    parallel_for(cn, h->threads, [&](int64_t i) {
+    parallel_for(my_hi - my_lo, h->threads, [&](int64_t r) {
+      const int64_t i = my_lo + r;
       if (h->h_count.p[i] == 0) return;     // free_num == 0: pose stays (pos, init_py), no E2 (cpp:427-436)
       const D3 vp = pos[(size_t)(c0 + i)];
       double avg_pitch = 0.0, avg_yaw = 0.0;
       int free_num = 0;
-      for (long long k = csr.offs[(size_t)i]; k < csr.offs[(size_t)i + 1]; ++k) {
+      for (long long k = csr.offs[(size_t)r]; k < csr.offs[(size_t)r + 1]; ++k) {
         const size_t j = csr.idx[k];
         const D3 cand{M[3 * j], M[3 * j + 1], M[3 * j + 2]};
         const D3 d = sub3(cand, vp);
@@ -664,11 +697,19 @@ static int get_pose_batch(fcvm_handle* h, const std::vector<D3>& pos, const std:
       warp_angle(avg_yaw);
       if (avg_pitch > pu) avg_pitch = pu;
       if (avg_pitch < pl) avg_pitch = pl;
-      poses_out[(size_t)(c0 + i)].v[3] = avg_pitch;
-      poses_out[(size_t)(c0 + i)].v[4] = avg_yaw;
-      has_free[(size_t)i] = 1;
-      h->cam.fill(h->h_recs.p[i], vp.x, vp.y, vp.z, avg_pitch, avg_yaw);
+      avg2[(size_t)2 * i] = avg_pitch;
+      avg2[(size_t)2 * i + 1] = avg_yaw;
     });
+    rc = gather_doubles(h, avg2.data(), cn, 2);
+    if (rc) return rc;
+    for (int64_t i = 0; i < cn; ++i) {
+      if (h->h_count.p[i] == 0) continue;
+      const D3 vp = pos[(size_t)(c0 + i)];
+      poses_out[(size_t)(c0 + i)].v[3] = avg2[(size_t)2 * i];
+      poses_out[(size_t)(c0 + i)].v[4] = avg2[(size_t)2 * i + 1];
+      has_free[(size_t)i] = 1;
+      h->cam.fill(h->h_recs.p[i], vp.x, vp.y, vp.z, avg2[(size_t)2 * i], avg2[(size_t)2 * i + 1]);
+    }
 
     // ---- E2 on the E1 sets (cpp:457-498) ---------------------------------------------------
     // viewpoints with free_num == 0 have all-zero E1 rows, so they contribute nothing here
@@ -855,12 +896,16 @@ static int viewpoints_prune(fcvm_handle* h, const std::vector<Pose5>& vps_pose, 
         h->cam.fill(h->h_recs.p[i], gq.up.x, gq.up.y, gq.up.z, gq.upi, gq.uy);
       }
       CsrOut csr;
+      int64_t my_lo = 0, my_hi = cn;
+      if (h->world > 1) { shard_of(h, cn, my_lo, my_hi); csr.lo = my_lo; csr.hi = my_hi; }
       int rc = eval_batch(h, FCVM_STAGE_E3, h->h_recs.p, cn, nullptr, h->trace_on ? h->h_rows.p : nullptr, nullptr, h->d_rows1, false, &csr);
       if (rc) return rc;
-      parallel_for(cn, h->threads, [&](int64_t i) {
+      std::vector<double> upd((size_t)cn * 2, 0.0);
+      parallel_for(my_hi - my_lo, h->threads, [&](int64_t r) {
+        const int64_t i = my_lo + r;
         const Grav& gq = grav[(size_t)(c0 + i)];
         double avg_pitch = gq.upi, avg_yaw = gq.uy;
-        for (long long k = csr.offs[(size_t)i]; k < csr.offs[(size_t)i + 1]; ++k) {
+        for (long long k = csr.offs[(size_t)r]; k < csr.offs[(size_t)r + 1]; ++k) {
           const size_t j = csr.idx[k];
           const D3 cand{M[3 * j], M[3 * j + 1], M[3 * j + 2]};
           const D3 ray_dir = normalized3(sub3(cand, gq.up));
@@ -878,9 +923,16 @@ static int viewpoints_prune(fcvm_handle* h, const std::vector<Pose5>& vps_pose, 
         if (updated_pitch < pl) updated_pitch = pl;
         warp_angle(updated_pitch);
         warp_angle(updated_yaw);
-        slot_pose[(size_t)gq.slot].v[3] = updated_pitch;
-        slot_pose[(size_t)gq.slot].v[4] = updated_yaw;
+        upd[(size_t)2 * i] = updated_pitch;
+        upd[(size_t)2 * i + 1] = updated_yaw;
       });
+      rc = gather_doubles(h, upd.data(), cn, 2);
+      if (rc) return rc;
+      for (int64_t i = 0; i < cn; ++i) {
+        const Grav& gq = grav[(size_t)(c0 + i)];
+        slot_pose[(size_t)gq.slot].v[3] = upd[(size_t)2 * i];
+        slot_pose[(size_t)gq.slot].v[4] = upd[(size_t)2 * i + 1];
+      }
       if (h->trace_on)
         for (int64_t i = 0; i < cn; ++i) {
           const Grav& gq = grav[(size_t)(c0 + i)];
@@ -1140,7 +1192,7 @@ fcvm_t* fcvm_create(const fcvm_params* p) {
 void fcvm_destroy(fcvm_t* h) {
   if (!h) return;
   h->d_map_xyz.free(); h->d_map_sorted.free(); h->d_cell_start.free(); h->d_cell_count.free(); h->d_minmax.free();
-  h->d_cand.free(); h->d_ok.free(); h->d_looks.free();
+  h->d_cand.free(); h->d_ok.free(); h->d_looks.free(); h->d_gather.free();
   h->d_bricks.free(); h->d_points.free(); h->d_cover_contrib.free(); h->d_contrib_id.free(); h->d_voxcount.free();
   h->d_recs.free(); h->d_rows1.free(); h->d_rows2.free(); h->d_count.free(); h->d_sched.free(); h->d_counters.free();
   h->h_rows.free(); h->h_count.free(); h->h_recs.free(); h->d_offsets.free(); h->d_indices.free(); h->h_indices.free(); h->h_offsets.free();
