@@ -159,7 +159,7 @@ struct fcvm_handle {
   bool device_ok = false;
 
   // wall-clock split of the manager-level calls (FCVM_PROFILE=1 prints it after fcvm_update)
-  double t_eval = 0, t_own = 0, t_init = 0, t_update = 0, t_unc = 0;
+  double t_eval = 0, t_own = 0, t_init = 0, t_update = 0, t_unc = 0, t_sums = 0, t_chain = 0, t_safety = 0;
   // taps
   bool trace_on = false;
   std::vector<TraceEv> trace;
@@ -288,6 +288,15 @@ static int eval_batch(fcvm_handle* h, int stage, const VpRec* recs, int64_t n, c
   if (rc) return rc;
   if (n == 0) return FCVM_OK;
   Stopwatch sw(h->t_eval);
+  struct Verbose {     // FCVM_PROFILE=2: one line per evaluator batch
+    int stage; int64_t n; std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    ~Verbose() {
+      static const bool on = std::getenv("FCVM_PROFILE") && atoi(std::getenv("FCVM_PROFILE")) >= 2;
+      if (on) std::fprintf(stderr, "[fcvm]   eval_batch E%d n=%lld: %.2f ms\n", stage, (long long)n,
+                           std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+    }
+  } verbose{stage, n};
+  if (std::getenv("FCVM_PROFILE") && atoi(std::getenv("FCVM_PROFILE")) >= 3) { cudaStreamSynchronize(h->stream); }
   const int64_t W = h->W;
   // pad the batch to a multiple of the world size so that shards are equal (NCCL all-gather)
   const int64_t per_rank = (n + h->world - 1) / h->world;
@@ -341,6 +350,9 @@ static int eval_batch(fcvm_handle* h, int stage, const VpRec* recs, int64_t n, c
       h->counters[5] += 2;
       CU(cudaEventRecord(h->pipe_ev[2 * k], h->stream));
     }
+    static const bool vprof = std::getenv("FCVM_PROFILE") && atoi(std::getenv("FCVM_PROFILE")) >= 3;
+    auto tmark = [&](const char* what) { if (vprof) std::fprintf(stderr, "[fcvm]     %s at %.2f ms\n", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - verbose.t0).count()); };
+    tmark("kernels queued");
     csr->offs.assign((size_t)n + 1, 0);
     long long base = 0;
     k = 0;
@@ -352,6 +364,7 @@ static int eval_batch(fcvm_handle* h, int stage, const VpRec* recs, int64_t n, c
       CU(cudaEventRecord(h->pipe_ev[2 * k + 1], h->copy_stream));
       CU(cudaEventSynchronize(h->pipe_ev[2 * k + 1]));
       const long long ct = h_off[sn];
+      tmark("sub-batch offsets on host");
       for (int64_t i = 0; i < sn; ++i) csr->offs[(size_t)(s0 + i + 1)] = base + h_off[i + 1];
       if (ct > 0) {
         const size_t need = (size_t)(base + ct);
@@ -376,6 +389,7 @@ static int eval_batch(fcvm_handle* h, int stage, const VpRec* recs, int64_t n, c
             }
           }
         }
+        tmark("index buffers ready");
         CU(launch_compact_rows(d_rows.p + s0 * W, sn, W, h->d_offsets.p + s0 + (int64_t)k, h->d_indices.p + base, h->copy_stream));
         h->counters[5] += 1;
         if (csr->user_idx) {
@@ -425,8 +439,10 @@ static int eval_batch(fcvm_handle* h, int stage, const VpRec* recs, int64_t n, c
     if (count_out) CU(cudaMemcpyAsync(count_out, h->d_count.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     rc = fetch_counters(h);   // synchronises the stream
     if (rc) return rc;
+    if (std::getenv("FCVM_PROFILE") && atoi(std::getenv("FCVM_PROFILE")) >= 3) std::fprintf(stderr, "[fcvm]     main stream drained at %.2f ms\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - verbose.t0).count());
     CU(cudaStreamSynchronize(h->copy_stream));
     csr->idx = h->h_indices.p;
+    if (!csr->in_user) h->h_indices.note_use();
     return FCVM_OK;
   }
   CU(launch_popc_rows(d_rows.p, n, W, h->d_count.p, h->stream));
@@ -457,6 +473,7 @@ static int eval_batch(fcvm_handle* h, int stage, const VpRec* recs, int64_t n, c
       CU(cudaStreamSynchronize(h->stream));
     }
     csr->idx = h->h_indices.p;
+    h->h_indices.note_use();
   }
   if (h->timed) {
     float ms = 0.f;
@@ -551,6 +568,7 @@ static void for_each_bit(const uint32_t* row, int64_t words, F&& f) {
 // (ground test, lattice of safety_check probes with the reference's early exit, nearCheck with vox_num = 2), mode 1 =
 // nearCheck alone.  counters[7] advances by the number of safety_check probes the reference would have made.
 static int safety_batch(fcvm_handle* h, const std::vector<float>& xyz, int mode, std::vector<uint8_t>& ok) {
+  Stopwatch sw_safety(h->t_safety);
   const int64_t n = (int64_t)xyz.size() / 3;
   ok.assign((size_t)n, 0);
   if (n == 0) return FCVM_OK;
@@ -667,6 +685,7 @@ static int get_pose_batch(fcvm_handle* h, const std::vector<D3>& pos, const std:
     std::vector<double> avg2((size_t)cn * 2, 0.0);      // (avg_pitch, avg_yaw) per viewpoint with free_num > 0
     const float* M = h->model.data();
     const double pu = h->pitch_upper * M_PI / 180.0, pl = h->pitch_lower * M_PI / 180.0;
+    const auto t_sums0 = std::chrono::steady_clock::now();
     parallel_for(my_hi - my_lo, h->threads, [&](int64_t r) {
       const int64_t i = my_lo + r;
       if (h->h_count.p[i] == 0) return;     // free_num == 0: pose stays (pos, init_py), no E2 (cpp:427-436)
@@ -700,6 +719,7 @@ static int get_pose_batch(fcvm_handle* h, const std::vector<D3>& pos, const std:
       avg2[(size_t)2 * i] = avg_pitch;
       avg2[(size_t)2 * i + 1] = avg_yaw;
     });
+    h->t_sums += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_sums0).count();
     rc = gather_doubles(h, avg2.data(), cn, 2);
     if (rc) return rc;
     for (int64_t i = 0; i < cn; ++i) {
@@ -901,6 +921,7 @@ static int viewpoints_prune(fcvm_handle* h, const std::vector<Pose5>& vps_pose, 
       int rc = eval_batch(h, FCVM_STAGE_E3, h->h_recs.p, cn, nullptr, h->trace_on ? h->h_rows.p : nullptr, nullptr, h->d_rows1, false, &csr);
       if (rc) return rc;
       std::vector<double> upd((size_t)cn * 2, 0.0);
+      const auto t_sums0 = std::chrono::steady_clock::now();
       parallel_for(my_hi - my_lo, h->threads, [&](int64_t r) {
         const int64_t i = my_lo + r;
         const Grav& gq = grav[(size_t)(c0 + i)];
@@ -926,6 +947,7 @@ static int viewpoints_prune(fcvm_handle* h, const std::vector<Pose5>& vps_pose, 
         upd[(size_t)2 * i] = updated_pitch;
         upd[(size_t)2 * i + 1] = updated_yaw;
       });
+      h->t_sums += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_sums0).count();
       rc = gather_doubles(h, upd.data(), cn, 2);
       if (rc) return rc;
       for (int64_t i = 0; i < cn; ++i) {
@@ -1216,7 +1238,7 @@ int fcvm_reset(fcvm_t* h) {   // cpp:64-72
   h->trace.clear();
   for (int k = 0; k < FCVM_NCOUNTERS; ++k) h->counters[k] = 0;
   h->unc_calls = 0; h->sample_calls = 0;
-  h->t_eval = h->t_own = h->t_init = h->t_update = h->t_unc = 0;
+  h->t_eval = h->t_own = h->t_init = h->t_update = h->t_unc = h->t_sums = h->t_chain = h->t_safety = 0;
   if (h->device_ok && h->P > 0) return cover_reset(h);
   return FCVM_OK;
 }
@@ -1340,8 +1362,9 @@ int fcvm_update(fcvm_t* h) {   // cpp:143-330
   }
   if (std::getenv("FCVM_PROFILE"))
     std::fprintf(stderr, "[fcvm] setInitViewpoints %.1f ms, updateViewpoints %.1f ms; of which evaluator batches (H2D + kernels + D2H + sync) %.1f ms, "
-                 "ownership sweeps %.1f ms, uncovered-candidate generation %.1f ms; kernels launched %lld\n",
-                 h->t_init, h->t_update, h->t_eval, h->t_own, h->t_unc, (long long)h->counters[5]);
+                 "ownership sweeps %.1f ms, uncovered-candidate generation %.1f ms, host pitch / yaw sums %.1f ms, "
+                 "safety batches %.1f ms; kernels launched %lld\n",
+                 h->t_init, h->t_update, h->t_eval, h->t_own, h->t_unc, h->t_sums, h->t_safety, (long long)h->counters[5]);
   return rc;
 }
 
