@@ -1110,6 +1110,9 @@ static int update_impl(fcvm_handle* h) {
   std::vector<int> lib_slot((size_t)h->P, -1);
   {
     Stopwatch sw_unc(h->t_unc);
+    static const bool vprof = std::getenv("FCVM_PROFILE") && atoi(std::getenv("FCVM_PROFILE")) >= 3;
+    const auto t_unc0 = std::chrono::steady_clock::now();
+    auto tmark = [&](const char* what) { if (vprof) std::fprintf(stderr, "[fcvm]     unc: %s at %.2f ms\n", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_unc0).count()); };
     const int64_t n_unc = (int64_t)uncoveredID.size(), call0 = h->unc_calls;
     h->unc_calls += n_unc;
     for (int64_t k = 0; k < n_unc; ++k) lib_slot[(size_t)uncoveredID[(size_t)k]] = (int)k;
@@ -1121,17 +1124,21 @@ static int update_impl(fcvm_handle* h) {
       const D3 nd = it == h->pt_normal_pairs.end() ? D3{0, 0, 1} : it->second;
       const float nrm[3] = {(float)nd.x, (float)nd.y, (float)nd.z};
       unc_neigh_vps(h, &M[3 * p], nrm, &cand8[(size_t)8 * k], call0 + k);
+      uncVpsLib[(size_t)k].reserve(8);
       for (int c = 0; c < 8; ++c) {
         const PtNormal& u = cand8[(size_t)8 * k + c];
         q[(size_t)24 * k + 3 * c] = u.x; q[(size_t)24 * k + 3 * c + 1] = u.y; q[(size_t)24 * k + 3 * c + 2] = u.z;
       }
     });
+    tmark("candidates generated");
     std::vector<uint8_t> safe;
     rc = safety_batch(h, q, 0, safe);
     if (rc) return rc;
+    tmark("safety batch done");
     for (int64_t k = 0; k < n_unc; ++k)
       for (int c = 0; c < 8; ++c)
         if (safe[(size_t)8 * k + c]) uncVpsLib[(size_t)k].push_back(cand8[(size_t)8 * k + c]);
+    tmark("library filled");
   }
 
   int unc_iter = 0, last_unc_num = -1;
