@@ -6,13 +6,14 @@
 //   CameraModelProjection  :1196-1211      PinHoleCamera  :1128-1194      CoverageEvaluation  :1032-1126
 // and the path-coverage loop that calls PinHoleCamera (:250-271).
 //
-// PARITY UNPINNED for this row: hcplanner.cpp cannot be compiled here (it pulls in ROSA, HCSolver,
-// PCL, ROS), and unlike the viewpoint-manager path there is no small set of reference sources that
-// isolates these three functions.  The restatement is pinned by line-by-line correspondence and by
-// hand-derived known answers (tests/test_oracle_cov.py) only.  Third-party arithmetic assumed:
-// Eigen's 3x3 inverse = cofactors * (1 / det) with det = (c00*m00 + c10*m10) + c20*m20
-// (Eigen/src/LU/InverseImpl.h, compute_inverse<.., 3>, as recalled), and the SSE2 3-term reduction
-// order of fcvm_oracle.hpp for the matrix products.
+// PIN: hcplanner.cpp cannot be compiled here (it pulls in ROSA, HCSolver, PCL, ROS), but the reference ships the OUTPUT of
+// this very function: solution/Traj/CloudInfo{MBS,Pipe,Christ}.txt is `visible_group` of its own CoverageEvaluation run over
+// the poses printed in TrajInfo*.txt (hctraj.cpp:197-221).  tests/golden/make_cov_golden.py maps those points back to cloud
+// indices; this restatement reproduces 82 581 of 82 589 ids on MBS, 26 512 of 26 513 on pipe, 105 717 of 105 747 on Christ,
+// the residue being the 6-decimal rounding of the printed poses (tests/test_oracle_cov.py asserts >= 99.9 % per scene, plus
+// hand-derived known answers).  Third-party arithmetic assumed (not in this image): Eigen's 3x3 inverse =
+// cofactors * (1 / det) with det = (c00*m00 + c10*m10) + c20*m20 (Eigen/src/LU/InverseImpl.h, compute_inverse<.., 3>), and
+// the SSE2 3-term reduction order of fcvm_oracle.hpp for the matrix products.
 #pragma once
 
 #include <set>
