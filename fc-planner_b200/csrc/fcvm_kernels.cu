@@ -617,23 +617,38 @@ __global__ void __launch_bounds__(128) k_own_sweep(const uint32_t* __restrict__ 
   const bool inb = j < P;
   int contrib = inb ? cover_contrib[j] : 0;
   int owner = inb ? contrib_id[j] : -1;
-  for (int t = 0; t < nsched; ++t) {
-    const int4 s = __ldg(sched + t);          // x = row, y = vp id, z = contri
-    const uint32_t w = __ldg(rows + (long long)s.x * words + col);
-    if (w == 0u) continue;
-    const bool seen = inb && ((w >> lane) & 1u);
-    bool take = false;
-    if (seen) {
-      if (owner < 0) {
-        take = true;
-      } else if (s.z > contrib && owner >= last_vps_num) {
-        atomicSub(voxcount + owner, 1);
-        take = true;
-      }
-      if (take) { contrib = s.z; owner = s.y; }
+  // rows are consumed strictly in order, but their words are fetched eight at a time: the sweep is a chain of dependent
+  // L2 round trips otherwise (one warp-uniform 4-byte load per row)
+  constexpr int kAhead = 8;
+  for (int t0 = 0; t0 < nsched; t0 += kAhead) {
+    int4 sv[kAhead];
+    uint32_t wv[kAhead];
+#pragma unroll
+    for (int u = 0; u < kAhead; ++u) {
+      const int t = min(t0 + u, nsched - 1);
+      sv[u] = __ldg(sched + t);          // x = row, y = vp id, z = contri
+      wv[u] = __ldg(rows + (long long)sv[u].x * words + col);
     }
-    const unsigned m = __ballot_sync(0xffffffffu, take);
-    if (m != 0u && lane == 0) atomicAdd(voxcount + s.y, __popc(m));
+#pragma unroll
+    for (int u = 0; u < kAhead; ++u) {
+      if (t0 + u >= nsched) break;
+      const int4 s = sv[u];
+      const uint32_t w = wv[u];
+      if (w == 0u) continue;
+      const bool seen = inb && ((w >> lane) & 1u);
+      bool take = false;
+      if (seen) {
+        if (owner < 0) {
+          take = true;
+        } else if (s.z > contrib && owner >= last_vps_num) {
+          atomicSub(voxcount + owner, 1);
+          take = true;
+        }
+        if (take) { contrib = s.z; owner = s.y; }
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, take);
+      if (m != 0u && lane == 0) atomicAdd(voxcount + s.y, __popc(m));
+    }
   }
   if (inb) { cover_contrib[j] = contrib; contrib_id[j] = owner; }
 }
