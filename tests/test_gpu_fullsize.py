@@ -107,3 +107,28 @@ def test_ownership_sweep_properties(full):
     vox = vm.vps_voxcount()
     assert np.array_equal(vox[:len(poses)], np.bincount(owner[seen], minlength=len(poses)))
     assert vox.sum() == seen.sum()
+
+
+def test_csr_streamed_path_and_caller_buffers(full):
+    """fcvm_evaluate_csr on a batch large enough for the sub-batched path (index lists extracted and copied out while the
+    next sub-batch is evaluated): every list equals the bits of the row; preallocated page-locked output buffers receive
+    the lists directly; a buffer that is too small keeps a valid prefix and the call reports the full size."""
+    from fc_planner_b200.manager import pinned_empty
+    vm = full["vm"]
+    poses = np.concatenate([full["poses"]] * 3)               # 2304 rows: the sub-batched path needs >= 2 x 1024
+    n = len(poses)
+    assert n >= 2048
+    rows, cnt = np.concatenate([full["rows1"]] * 3), np.concatenate([full["cnt1"]] * 3)
+    total = int(cnt.sum())
+    c, offs, idx = vm.evaluate_csr(1, poses)
+    assert np.array_equal(c, cnt) and len(idx) == total and np.array_equal(np.diff(offs), cnt)
+    bits = np.unpackbits(rows.view(np.uint8), axis=1, bitorder="little")
+    r, j = np.nonzero(bits)                                   # row-major: ascending point index inside each row
+    assert np.array_equal(idx, j.astype(np.uint32))
+    out = (pinned_empty((n,), np.int32), pinned_empty((n + 1,), np.int64), pinned_empty((total + 5,), np.uint32))
+    c2, offs2, idx2 = vm.evaluate_csr(1, poses, out=out)
+    assert np.array_equal(c2, cnt) and np.array_equal(offs2, offs) and np.array_equal(idx2, idx)
+    small = (np.zeros(n, np.int32), np.zeros(n + 1, np.int64), np.full(total // 3, 0xFFFFFFFF, np.uint32))
+    with pytest.raises(ValueError):
+        vm.evaluate_csr(1, poses, out=small)
+    assert np.array_equal(small[2], idx[:total // 3]) and np.array_equal(small[1], offs)
