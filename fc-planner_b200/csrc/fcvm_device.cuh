@@ -29,7 +29,8 @@ namespace fcvm {
 struct GridDesc {
   const unsigned long long* bricks;  // [nbx*nby*nbz]
   int nx, ny, nz;                    // map_voxel_num_
-  int nbx, nby, nbz;                 // bricks per axis: ceil(n/4)
+  int nbx, nby, nbz;                 // bricks per axis: ceil(n/4), padded (pad_bricks)
+  int nly, nlz;                      // lines per axis in y and z: nby / 2, nbz / 4
   int nbricks;                       // nbx * nby * nbz (< 2^31: the reference addresses voxels with int)
   int guard_steps;                   // fast-path half-rays make at most this many steps; the allocation has guard words for them
   double res;                        // resolution_
@@ -37,8 +38,35 @@ struct GridDesc {
   double orgx, orgy, orgz;           // map_origin_
 };
 
+#ifndef FCVM_BRICK_LINES
+#define FCVM_BRICK_LINES 0      // measured: 88.2 ms per bench step with lines vs 84.0 ms flat (the extra index arithmetic costs more than the L1 hits return)
+#endif
+// Storage order of the bricks.  nby / nbz = bricks per axis, padded to a multiple of 2 (x, y) and 4 (z) (pad_bricks).
+// FCVM_BRICK_LINES: the 16 bricks of a 128-byte line form a 2 x 2 x 4 block of bricks (8 x 8 x 16 voxels), lines z-fastest,
+// so a ray stays inside one line for ~8-16 steps whatever its direction; flat (0): bricks z-fastest, a line is a
+// 4 x 4 x 64-voxel column that x- and y-going rays leave every 4 steps.
 __host__ __device__ __forceinline__ long long brick_word_index(int x, int y, int z, int nby, int nbz) {
+#if FCVM_BRICK_LINES
+  const long long line = ((long long)(x >> 3) * (nby >> 1) + (y >> 3)) * (nbz >> 2) + (z >> 4);
+  return (line << 4) | (((x >> 2) & 1) << 3) | (((y >> 2) & 1) << 2) | ((z >> 2) & 3);
+#else
   return ((long long)(x >> 2) * nby + (y >> 2)) * nbz + (z >> 2);
+#endif
+}
+__host__ __device__ __forceinline__ void pad_bricks(const int dims[3], int nb[3]) {
+  nb[0] = (((dims[0] + 3) >> 2) + 1) & ~1;
+  nb[1] = (((dims[1] + 3) >> 2) + 1) & ~1;
+  nb[2] = (((dims[2] + 3) >> 2) + 3) & ~3;
+}
+// guard words on each side of the brick array that cover every index reachable within `steps` voxel steps of the map
+__host__ __device__ __forceinline__ long long brick_guard_words(int steps, int nby, int nbz) {
+#if FCVM_BRICK_LINES
+  const long long G = steps / 8 + 1;
+  return 16 * G * ((long long)(nby >> 1) * (nbz >> 2) + (nbz >> 2) + 1);
+#else
+  const long long G = steps / 4 + 1;
+  return G * ((long long)nby * nbz + nbz + 1);
+#endif
 }
 __host__ __device__ __forceinline__ int brick_bit_index(int x, int y, int z) {
   return ((x & 3) << 4) | ((y & 3) << 2) | (z & 3);

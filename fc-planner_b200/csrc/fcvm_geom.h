@@ -132,7 +132,7 @@ struct HostGrid {
       origin[c] = mn[c] - 2 * inflate;              // sdf_map.cpp:151
       dims[c] = (int)std::ceil(size[c] / res);      // sdf_map.cpp:156-157
     }
-    for (int c = 0; c < 3; ++c) ns[c] = (dims[c] + 3) >> 2;
+    pad_bricks(dims, ns);
     bricks.clear();
     ready = true;
   }

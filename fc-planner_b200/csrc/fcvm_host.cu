@@ -202,6 +202,7 @@ static void fill_grid_desc(const fcvm_handle* h, GridDesc& g) {
   g.guard_steps = h->guard_steps;
   g.nx = hg.dims[0]; g.ny = hg.dims[1]; g.nz = hg.dims[2];
   g.nbx = hg.ns[0]; g.nby = hg.ns[1]; g.nbz = hg.ns[2];
+  g.nly = hg.ns[1] >> 1; g.nlz = hg.ns[2] >> 2;
   g.nbricks = (int)hg.nbricks();
   g.res = hg.res;
   // RayCaster::setParams (raycast.cpp:341-345): offset_ = half_ - origin / resolution_
@@ -1282,8 +1283,7 @@ int fcvm_set_map_cloud(fcvm_t* h, const float* xyz, int64_t n) {   // cpp:74-89
     // voxels of the map on every axis; its brick index then falls into [-guard, nbricks + guard), which is allocated
     // and reads 'occupied'.  Longer rays (none pass the range test) take the literal, bounds-checked marcher.
     h->guard_steps = 3 * ((int)std::ceil(std::max(h->prm.max_dist, h->prm.visible_range) / (2 * h->grid.res)) + 2);
-    const size_t G = (size_t)(h->guard_steps / 4 + 1);
-    h->brick_guard = G * ((size_t)h->grid.ns[1] * h->grid.ns[2] + h->grid.ns[2] + 1);
+    h->brick_guard = (size_t)brick_guard_words(h->guard_steps, h->grid.ns[1], h->grid.ns[2]);
     CU(h->d_bricks.reserve(h->grid.nbricks() + 2 * h->brick_guard));
     CU(cudaMemsetAsync(h->d_bricks.p, 0xFF, h->brick_guard * sizeof(unsigned long long), s));
     CU(cudaMemsetAsync(h->d_bricks.p + h->brick_guard, 0, h->grid.nbricks() * sizeof(unsigned long long), s));

@@ -181,7 +181,11 @@ __device__ __forceinline__ void cont_load(const double* qd, const int* qi, int s
 // is counted as a cap trip when its two halves fail to meet.  The index-checking debug build
 // (FCVM_DEBUG_BOUNDS) range-checks every fetch instead.
 __device__ __forceinline__ bool occ_fast(const GridDesc& g, int ix, int iy, int iz, int& ckey, unsigned long long& cword) {
+#if FCVM_BRICK_LINES
+  const int k = ((((ix >> 3) * g.nly + (iy >> 3)) * g.nlz + (iz >> 4)) << 4) | (((ix >> 2) & 1) << 3) | (((iy >> 2) & 1) << 2) | ((iz >> 2) & 3);
+#else
   const int k = ((ix >> 2) * g.nby + (iy >> 2)) * g.nbz + (iz >> 2);
+#endif
   if (k != ckey) {
     ckey = k;
 #if EVAL_BRICK_CHECK
@@ -350,12 +354,21 @@ __global__ void __launch_bounds__(kWarps * 32, EVAL_MIN_CTAS) k_eval(const __gri
       const QueueEntry qe = eq[en - cnt + lane];
       nrays++;
       bool verdict = false;
-      if (FCVM_CHECK(en - cnt + lane >= 0 && en - cnt + lane < kEntryQ && qe.pt < (uint32_t)npts && qe.vp < (uint32_t)a.V)) {
+#if defined(EVAL_EXP) && EVAL_EXP >= 2
+      if (qe.pt == 0xFFFFFFFFu)   // timing experiment: FOV phase only
+#else
+      if (FCVM_CHECK(en - cnt + lane >= 0 && en - cnt + lane < kEntryQ && qe.pt < (uint32_t)npts && qe.vp < (uint32_t)a.V))
+#endif
+      {
         queued = prepare_ray<STAGE>(g, fc, a.recs, qe.vp, qe.pt, tile[qe.pt], c, verdict, st);
         if (!queued && verdict) set_bit(qe.vp, qe.pt);
       }
     }
     en -= cnt;
+#if defined(EVAL_EXP) && EVAL_EXP >= 1
+    if (queued && c.p.rem == 123456789) set_bit(c.vp, c.pt);   // timing experiment: rays dropped after prepare
+    queued = false;
+#endif
     const unsigned m = __ballot_sync(0xffffffffu, queued);
     if (queued && FCVM_CHECK(rn + __popc(m & lt_mask) < kReadyQ)) cont_store(rqd, rqi, rn + __popc(m & lt_mask), c);
     rn += __popc(m);

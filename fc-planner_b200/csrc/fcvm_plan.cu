@@ -31,7 +31,8 @@ __global__ void __launch_bounds__(256) k_pack_planes(const signed char* __restri
                                                      unsigned long long* __restrict__ sblk, unsigned long long* __restrict__ pblk) {
   const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= nbricks) return;
-  const int bz = (int)(b % nbz), by = (int)((b / nbz) % nby), bx = (int)(b / ((long long)nbz * nby));
+  const int bz = (int)(b % nbz), by = (int)((b / nbz) % nby), bx = (int)(b / ((long long)nbz * nby));   // b enumerates brick coordinates
+  const long long dst = brick_word_index(bx * 4, by * 4, bz * 4, nby, nbz);                                   // ... stored in line order
   unsigned long long wo = 0ull, ws = 0ull, wp = 0ull;
   for (int dx = 0; dx < 4; ++dx)
     for (int dy = 0; dy < 4; ++dy)
@@ -45,7 +46,7 @@ __global__ void __launch_bounds__(256) k_pack_planes(const signed char* __restri
         if (h || t) ws |= bit;
         if (f || t) wp |= bit;
       }
-  occ[b] = wo; sblk[b] = ws; pblk[b] = wp;
+  occ[dst] = wo; sblk[dst] = ws; pblk[dst] = wp;
 }
 
 // lightStateDet (hcplanner.cpp:805-863), K = 1: nearest ROSA vertex with FLANN's L2_Simple<float> (lowest index on ties),
@@ -206,6 +207,7 @@ static void plan_desc(const fcvm_grid_handle* h, const unsigned long long* brick
   g.bricks = bricks;
   g.nx = h->dims[0]; g.ny = h->dims[1]; g.nz = h->dims[2];
   g.nbx = h->nb[0]; g.nby = h->nb[1]; g.nbz = h->nb[2];
+  g.nly = h->nb[1] >> 1; g.nlz = h->nb[2] >> 2;
   g.nbricks = (int)h->nbricks;
   g.guard_steps = 0;
   g.res = h->res;
@@ -247,7 +249,8 @@ fcvm_grid_t* fcvm_grid_create(int32_t device, const double* origin3, double reso
   if (!h) { fail(FCVM_EINTERNAL, "out of memory"); return nullptr; }
   h->device = device;
   h->res = resolution;
-  for (int c = 0; c < 3; ++c) { h->origin[c] = origin3[c]; h->dims[c] = voxel_num3[c]; h->nb[c] = (voxel_num3[c] + 3) >> 2; }
+  for (int c = 0; c < 3; ++c) { h->origin[c] = origin3[c]; h->dims[c] = voxel_num3[c]; }
+  pad_bricks(h->dims, h->nb);
   h->nbricks = (long long)h->nb[0] * h->nb[1] * h->nb[2];
   auto build = [&]() -> int {
     CU(cudaSetDevice(device));
