@@ -4,17 +4,22 @@
 // The reference evaluates one viewpoint at a time with a stateful ray caster.  Here each stage of
 // the call sequence becomes a few launches over ALL of the stage's viewpoints:
 //
+//   setMapPointCloud (cpp:74-89 + SDFMap::initHCMap)
+//       K_cloud_minmax -> host: grid geometry in FP64 -> K_voxelise; cell index of the map cloud (fcvm_map.cu)
 //   setInitViewpoints / round appends (getPose, cpp:332-531)
 //       host: PitchYaw(dir) -> FOV normals                (libm: host, same as the reference)
-//       K_E1 over the batch -> bitset rows                 (FOV + BiRC + range)
-//       host: ordered pitch / yaw sums over set bits       (asin / atan2 / acos: host)
+//       K_E1 over the batch -> bitset rows -> CSR          (FOV + BiRC + range; index lists copied out per sub-batch)
+//       host: ordered pitch / yaw sums over the visible rays (asin / acos: host; sharded over the ranks of a multi-GPU run)
 //       K_E2 restricted to the E1 rows -> rows, popc       (FOV' + offset walk + BiRC)
 //       K_own sweep in id order                            (ownership, cpp:500-528)
 //   viewpointsPrune (cpp:620-710)
-//       host: qualify, std::sort over the real unordered_map order, nearCheck / radius search,
-//             the sequential absorb flag chain and gravitation pulls (cpp:712-810)
+//       host: qualify, std::sort over the real unordered_map order; K_safety (nearCheck of every candidate); radius
+//             search; the sequential absorb flag chain and gravitation pulls (cpp:712-810); K_safety
+//             (viewpointSafetyCheck of the pulled positions)
 //       K_E3 over all gravitated viewpoints at once -> host ordered offset sums (cpp:817-886)
 //       K_E4 over the live viewpoints in unordered_map order -> popc -> K_own sweep
+//   uncovered-area rounds (cpp:206-330)
+//       host: 8 candidates per uncovered point (RNG + libm) -> K_safety over all of them -> getPose batch -> prune
 //
 // There is no CPU implementation of any K_* stage in this library: without a CUDA device every
 // evaluating call fails with FCVM_ENODEVICE.
