@@ -219,7 +219,6 @@ static void plan_desc(const fcvm_grid_handle* h, const unsigned long long* brick
 
 static int plan_finish(fcvm_grid_handle* h) {
   unsigned long long c[2];
-  CU(cudaEventRecord(h->ev1, h->stream));
   CU(cudaMemcpyAsync(c, h->d_counters.p, sizeof(c), cudaMemcpyDeviceToHost, h->stream));
   CU(cudaMemsetAsync(h->d_counters.p, 0, sizeof(c), h->stream));
   CU(cudaStreamSynchronize(h->stream));
@@ -310,6 +309,7 @@ int fcvm_grid_light_state(fcvm_grid_t* h, const double* cand_xyz, int64_t n, con
   CU(cudaEventRecord(h->ev0, s));
   k_light_state<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(g, h->d_in.p, n, h->d_rosa.p, m, h->d_u8.p, h->d_i32a.p, h->d_i32b.p, h->d_counters.p);
   CU(cudaGetLastError());
+  CU(cudaEventRecord(h->ev1, s));      // ev0 .. ev1 bracket the kernel alone
   CU(cudaMemcpyAsync(det, h->d_u8.p, (size_t)n, cudaMemcpyDeviceToHost, s));
   if (cross) CU(cudaMemcpyAsync(cross, h->d_i32a.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, s));
   if (nearest) CU(cudaMemcpyAsync(nearest, h->d_i32b.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, s));
@@ -328,6 +328,7 @@ int fcvm_grid_safety_box(fcvm_grid_t* h, const float* vp_xyz, int64_t n, double 
   CU(cudaEventRecord(h->ev0, s));
   k_safety_box<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(g, 1 / h->res, h->d_in_f.p, n, safe_radius, h->d_u8.p, h->d_counters.p);
   CU(cudaGetLastError());
+  CU(cudaEventRecord(h->ev1, s));      // ev0 .. ev1 bracket the kernel alone
   CU(cudaMemcpyAsync(ok, h->d_u8.p, (size_t)n, cudaMemcpyDeviceToHost, s));
   return plan_finish(h);
 }
@@ -346,6 +347,7 @@ int fcvm_grid_line_of_sight(fcvm_grid_t* h, const double* p_xyz, int64_t n, uint
   CU(cudaEventRecord(h->ev0, s));
   k_line_of_sight<<<(unsigned)((n * n + 127) / 128), 128, 0, s>>>(g, h->d_in.p, n, h->d_u8.p, dist_nxn ? h->d_dist.p : nullptr, h->d_counters.p);
   CU(cudaGetLastError());
+  CU(cudaEventRecord(h->ev1, s));      // ev0 .. ev1 bracket the kernel alone
   CU(cudaMemcpyAsync(safe_nxn, h->d_u8.p, (size_t)n * n, cudaMemcpyDeviceToHost, s));
   if (dist_nxn) CU(cudaMemcpyAsync(dist_nxn, h->d_dist.p, (size_t)n * n * sizeof(double), cudaMemcpyDeviceToHost, s));
   return plan_finish(h);
