@@ -139,7 +139,7 @@ int     fcvm_trace_get(fcvm_t* h, int64_t i, int32_t* stage, int32_t* vp_id, dou
 /* counters accumulated since create/reset (all evaluators):
  * [0] pair tests (insideFOV calls)   [1] rays (BiRC invocations)   [2] voxel lookups
  * [3] offset-walk lookups            [4] step-cap trips (must be 0) [5] kernels launched
- * [6] viewpoint evaluations          [7] safety_check lookups (host) */
+ * [6] viewpoint evaluations          [7] safety_check probes of viewpointSafetyCheck (counted on the device, k_safety) */
 #define FCVM_NCOUNTERS 8
 int     fcvm_get_counters(fcvm_t* h, int64_t* out8);
 
@@ -158,7 +158,9 @@ int fcvm_evaluate(fcvm_t* h, int32_t stage, const double* pose5, int64_t n,
                   const uint32_t* restrict_rows, int32_t* count, uint32_t* rows);
 
 /* The same pass with the visible sets returned as ascending index lists (CSR): offsets[n+1] and at most
- * cap indices; returns the total number of visible pairs (> cap: call again with a larger buffer).
+ * cap indices; returns the total number of visible pairs (> cap: `indices` holds the first cap of them; call again with
+ * a larger buffer).  Large batches are evaluated in sub-batches whose lists are extracted and copied straight into
+ * `indices` while the next sub-batch runs; give it page-locked memory (fcvm_host_alloc) for full PCIe rate.
  * This is the form the per-viewpoint host reductions of getPose / updatePoseGravitation consume
  * (viewpoint_manager.cpp:398-425, 856-875): 4 bytes per visible ray instead of P/8 bytes per pose. */
 int64_t fcvm_evaluate_csr(fcvm_t* h, int32_t stage, const double* pose5, int64_t n, const uint32_t* restrict_rows,
@@ -198,8 +200,9 @@ int64_t fcvm_debug_bounds_violations(fcvm_t* h);
 
 /* Shard assignment: this handle evaluates only viewpoints [lo, hi) of every batch given to
  * fcvm_set_init_viewpoints / the prune stages; rows of the other shards are supplied through the
- * exchange callback below (torch.distributed NCCL all-gather in fc-planner_b200/distributed.py).
- * world = 1 disables sharding. */
+ * exchange callback below (torch.distributed NCCL all-gather in fc-planner_b200/distributed.py).  The same callback
+ * exchanges the per-viewpoint host reductions (two doubles per viewpoint), which every rank computes for its own shard
+ * only.  world = 1 disables sharding. */
 typedef int (*fcvm_allgather_fn)(void* user, void* buf_dev, int64_t bytes_per_rank, void* stream);
 int fcvm_set_shard(fcvm_t* h, int32_t rank, int32_t world, fcvm_allgather_fn fn, void* user);
 
