@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""bench.py — visibility rays/s of the candidate-viewpoint x surface-point evaluator pass.
+"""bench.py — visibility rays/s of the candidate-viewpoint x surface-point evaluator pass, plus the legs `pruning`
+(viewpoint-pruning wall time, BASELINE.json's second metric), `coverage_evaluation` and `planner_grid`.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
@@ -12,8 +13,9 @@ FOV + range test of every (viewpoint, point) pair, a bidirectional voxel ray cas
 that passes, coverage bitsets and per-viewpoint counts out.  A ray = one BiRC invocation.
 
   value  rays/s with poses, points and grid resident in HBM (bitset rows stay on the device)
-  e2e    rays/s through the C ABI call fcvm_evaluate() with HOST buffers: host pose -> FOV normals,
-         H2D, kernels, D2H of the per-viewpoint counts and of the coverage bitsets
+  e2e    rays/s through the C ABI call fcvm_evaluate_csr() with HOST (page-locked) buffers: host pose -> FOV normals,
+         H2D, kernels, extraction of the visible sets as index lists, D2H of the per-viewpoint counts, offsets and lists
+         (what the manager consumes from a pass); e2e_rows: the same pass returning the raw coverage bitsets
   roofline  k_eval alone: algorithmic bytes / CUDA-event time / measured HBM peak
   cpu_baseline  the CPU oracle (port of the reference) on a bounded sample of the same batch
 """
