@@ -60,6 +60,9 @@ __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarr
 #ifndef EVAL_ASM_STEP
 #define EVAL_ASM_STEP 1
 #endif
+#ifndef EVAL_STAGED_FOV
+#define EVAL_STAGED_FOV 1
+#endif
 #ifndef EVAL_BRICK_CHECK
 #ifdef FCVM_DEBUG_BOUNDS
 #define EVAL_BRICK_CHECK 1
@@ -488,11 +491,57 @@ __global__ void __launch_bounds__(kWarps * 32, EVAL_MIN_CTAS) k_eval(const __gri
         valid = valid && ((rw >> lane) & 1u);
       }
       bool pass = false;
+#if EVAL_STAGED_FOV
+      // inside_fov (fcvm_device.cuh) unrolled into stages with warp-wide early outs: most groups of 32 consecutive
+      // points are entirely out of range or entirely behind one FOV plane, and then the remaining dot products are
+      // never computed.  A lane is dropped only where inside_fov would return false on either of its paths
+      // (n2 > md2_hi; s[q] < -plane_eps), so the verdicts are unchanged.
+      {
+        double dx = 0.0, dy = 0.0, dz = 0.0, n2 = 0.0;
+        bool alive = valid;
+        if (valid) {
+          const float4 pt = tile[i];
+          dx = (double)pt.x - rec.px; dy = (double)pt.y - rec.py; dz = (double)pt.z - rec.pz;
+          n2 = (dx * dx + dy * dy) + dz * dz;
+          alive = !(n2 > fc.md2_hi);
+          npairs++;
+        }
+        if (!__any_sync(0xffffffffu, alive)) continue;
+        bool exact = !(n2 < fc.md2_lo);
+        bool dead_group = false;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const double sq = (dx * rec.n[q][0] + dy * rec.n[q][1]) + dz * rec.n[q][2];
+          exact |= fabs(sq) <= fc.plane_eps;
+          alive = alive && !(sq < -fc.plane_eps);
+          if (!__any_sync(0xffffffffu, alive)) { dead_group = true; break; }
+        }
+        if (dead_group) continue;
+        if (alive) {
+          if (!exact) {
+            pass = true;                      // all four s[q] > plane_eps and the range is clear of its band
+          } else {
+            // literal path (perception_utils.cpp:115-124)
+            const double nrm = sqrt(n2);
+            pass = !(nrm > fc.max_dist);
+            if (pass) {
+              if (n2 > 0.0) { dx = dx / nrm; dy = dy / nrm; dz = dz / nrm; }
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const double d = (dx * rec.n[q][0] + dy * rec.n[q][1]) + dz * rec.n[q][2];
+                if (d < 0.0) pass = false;
+              }
+            }
+          }
+        }
+      }
+#else
       if (valid) {
         const float4 pt = tile[i];
         pass = inside_fov(rec, fc, (double)pt.x, (double)pt.y, (double)pt.z);
         npairs++;
       }
+#endif
       const unsigned m = __ballot_sync(0xffffffffu, pass);
       if (m == 0u) continue;
       if (pass) {
