@@ -100,3 +100,65 @@ def test_pinhole_golden_and_threads(oracle_mod):
     full = ce.pinhole(z["poses"], threads=4)
     assert zlib.crc32(full[1].tobytes()) == int(z["pin_ids_crc"]) and np.array_equal(np.packbits(full[2], bitorder="little"), z["covered"])
     assert np.array_equal(full[3], z["counters"])
+
+
+def test_literal_python_restatement_of_the_loops(oracle_mod):
+    """A second, literal restatement of hcplanner.cpp:1032-1126 in plain Python (dict image tables, the reference's own
+    insideFOV from oracle/_ref where it is built, `math` for libm) against the C++ oracle on small random scenes with a
+    coarse image, so that pixel contention, displacement and the cross-pose cover_state all occur."""
+    import math
+    from fc_planner_b200 import Camera
+    prm = launch_params("mbs")
+    cam = Camera(fx=417.0467, fy=461.0951, cx=12.0, cy=9.0, fov_h=prm.fov_h, fov_w=prm.fov_w)
+    fov = oracle_mod.ref_inside_fov if oracle_mod.ref_available() else oracle_mod.inside_fov
+    rng = np.random.default_rng(3)
+    cloud = rng.uniform(-5, 5, (400, 3)).astype(np.float32)
+    poses = np.concatenate([rng.uniform(-7, 7, (25, 3)), rng.uniform(-0.8, 0.8, (25, 1)), rng.uniform(-math.pi, math.pi, (25, 1))], axis=1)
+    poses = np.concatenate([poses, poses[:10]])                  # revisits: the cover_state carried across poses matters
+
+    def inv3(m):                                                 # Eigen 3x3 inverse: cofactors * (1 / det)
+        cof = lambda i, j: m[(i + 1) % 3][(j + 1) % 3] * m[(i + 2) % 3][(j + 2) % 3] - m[(i + 1) % 3][(j + 2) % 3] * m[(i + 2) % 3][(j + 1) % 3]
+        c0, c1, c2 = cof(0, 0), cof(1, 0), cof(2, 0)
+        inv = 1.0 / ((c0 * m[0][0] + c1 * m[1][0]) + c2 * m[2][0])
+        return [[c0 * inv, c1 * inv, c2 * inv], [cof(0, 1) * inv, cof(1, 1) * inv, cof(2, 1) * inv], [cof(0, 2) * inv, cof(1, 2) * inv, cof(2, 2) * inv]]
+
+    xPixel, yPixel = 2 * int(cam.cx), 2 * int(cam.cy)
+    xRange = cam.fx * math.tan(0.5 * cam.fov_w * math.pi / 180.0) / 1000.0
+    yRange = cam.fy * math.tan(0.5 * cam.fov_h * math.pi / 180.0) / 1000.0
+    xRes, yRes = 2 * xRange / xPixel, 2 * yRange / yPixel
+    cover_state = [False] * len(cloud)
+    groups, all_visible = [], set()
+    for vp in poses:
+        state, point, dist_t = {}, {}, {}
+        inside = fov(prm, vp, cloud.astype(np.float64))
+        Ry = [[math.cos(vp[4]), -math.sin(vp[4]), 0.0], [math.sin(vp[4]), math.cos(vp[4]), 0.0], [0.0, 0.0, 1.0]]
+        Rp = [[math.cos(vp[3]), 0.0, -math.sin(vp[3])], [0.0, 1.0, 0.0], [math.sin(vp[3]), 0.0, math.cos(vp[3])]]
+        A, B = inv3(Rp), inv3(Ry)
+        M = [[(A[i][0] * B[0][j] + A[i][1] * B[1][j]) + A[i][2] * B[2][j] for j in range(3)] for i in range(3)]
+        for i, p in enumerate(cloud):
+            if not inside[i]:
+                continue
+            d = [float(p[0]) - vp[0], float(p[1]) - vp[1], float(p[2]) - vp[2]]
+            camDist = math.sqrt((d[0] * d[0] + d[1] * d[1]) + d[2] * d[2])
+            pc = [(M[r][0] * d[0] + M[r][1] * d[1]) + M[r][2] * d[2] for r in range(3)]
+            xID = math.floor((cam.fx * pc[1] / (1000.0 * pc[0]) - (-xRange)) / xRes)
+            yID = math.floor((cam.fy * pc[2] / (1000.0 * pc[0]) - (-yRange)) / yRes)
+            if xID < 0 or yID < 0 or xID >= xPixel or yID >= yPixel:
+                continue
+            if (xID, yID) not in state:
+                state[(xID, yID)] = 1.0; point[(xID, yID)] = i; dist_t[(xID, yID)] = camDist
+            elif camDist < dist_t[(xID, yID)]:
+                cover_state[point[(xID, yID)]] = False
+                point[(xID, yID)] = i; dist_t[(xID, yID)] = camDist
+        visSet = sorted(set(point.values()))
+        groups.append([v for v in visSet if not cover_state[v]])
+        for v in visSet:
+            cover_state[v] = True
+        all_visible.update(visSet)
+    ce = oracle_mod.CoverageOracle(prm, cam)
+    ce.setCloud(cloud)
+    rate, offs, ids, ever = ce.CoverageEvaluation(poses)
+    assert rate == len(all_visible) / len(cloud)
+    assert [ids[offs[k]:offs[k + 1]].tolist() for k in range(len(poses))] == groups
+    assert sorted(np.flatnonzero(ever).tolist()) == sorted(all_visible)
+    assert sum(len(g) for g in groups) > len(all_visible) > 50            # re-pushed points exist: displacement un-covers
