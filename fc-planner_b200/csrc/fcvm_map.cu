@@ -108,13 +108,13 @@ __global__ void __launch_bounds__(256) k_safety(const __grid_constant__ SafetyAr
     if (ok) {
       const int nx = lattice_steps(vx, a.sr, a.res, a.safe_voxel), ny = lattice_steps(vy, a.sr, a.res, a.safe_voxel),
                 nz = lattice_steps(vz, a.sr, a.res, a.safe_voxel);
-      const int total = nx * ny * nz;
+      const long long total = (long long)nx * ny * nz;      // up to 4096^3: 64-bit
       looks = (unsigned long long)total;
-      for (int base = 0; base < total; base += 32) {
-        const int t = base + lane;
+      for (long long base = 0; base < total; base += 32) {
+        const long long t = base + lane;
         bool bad = false;
         if (t < total) {
-          const int k = t % nz, j = (t / nz) % ny, i = t / (nz * ny);
+          const int k = (int)(t % nz), j = (int)((t / nz) % ny), i = (int)(t / ((long long)nz * ny));
           bad = !safety_probe(a, vx - a.sr + (i * a.safe_voxel) * a.res, vy - a.sr + (j * a.safe_voxel) * a.res, vz - a.sr + (k * a.safe_voxel) * a.res);
         }
         const unsigned m = __ballot_sync(0xffffffffu, bad);
