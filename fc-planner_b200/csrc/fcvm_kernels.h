@@ -16,7 +16,7 @@ namespace fcvm {
 #define EVAL_MIN_CTAS 2       // resident CTAs per SM the register allocation is tuned for
 #endif
 #ifndef EVAL_KEEP
-#define EVAL_KEEP 24          // march: suspend back to the FOV phase when fewer lanes than this are busy and the queue is empty
+#define EVAL_KEEP 28          // march: suspend back to the FOV phase when fewer lanes than this are busy and the queue is empty
 #endif
 #ifndef EVAL_UNROLL
 #define EVAL_UNROLL 2         // march: biNextId calls per refill / suspend check
