@@ -20,7 +20,9 @@ f64p = ctypes.POINTER(ctypes.c_double)
 vp = ctypes.c_void_p
 i32, i64, f64 = ctypes.c_int32, ctypes.c_int64, ctypes.c_double
 
-ALLGATHER_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p)
+# fcvm_comm_fn: (user, op, buf_dev, n, stream) -> int
+COMM_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p)
+COMM_ALLGATHER, COMM_ALLREDUCE_MAX = 0, 1
 
 # name -> (restype, argtypes): every symbol include/fcvm.h declares
 SYMBOLS = {
@@ -57,7 +59,11 @@ SYMBOLS = {
     "fcvm_host_free": (None, [vp]),
     "fcvm_last_kernel_ms": (f64, [vp]),
     "fcvm_debug_bounds_violations": (i64, [vp]),
-    "fcvm_set_shard": (ctypes.c_int, [vp, i32, i32, ALLGATHER_FN, vp]),
+    "fcvm_set_shard": (ctypes.c_int, [vp, i32, i32, COMM_FN, vp]),
+    "fcvm_nccl_unique_id": (ctypes.c_int, [u8p]),
+    "fcvm_set_shard_nccl": (ctypes.c_int, [vp, u8p, i32, i32]),
+    "fcvm_comm_stats": (ctypes.c_int, [vp, i64p]),
+    "fcvm_get_timers": (ctypes.c_int, [vp, f64p]),
     "fcvm_host_fov_normals": (ctypes.c_int, [ctypes.POINTER(Params), f64, f64, f64p]),
     "fcvm_host_build_grid": (ctypes.c_int, [ctypes.POINTER(Params), f32p, i64, f64p, i32p, u8p, i64]),
     "fcvm_shard_range": (ctypes.c_int, [i64, i32, i32, i64p, i64p]),

@@ -13,8 +13,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "_build", "libfcvm.so")
-SOURCES = ["fcvm_kernels.cu", "fcvm_host.cu", "fcvm_cov.cu", "fcvm_map.cu", "fcvm_plan.cu"]
-DEPS = SOURCES + ["fcvm_device.cuh", "fcvm_kernels.h", "fcvm_geom.h", "fcvm_hostutil.h", os.path.join("..", "..", "include", "fcvm.h")]
+SOURCES = ["fcvm_kernels.cu", "fcvm_host.cu", "fcvm_cov.cu", "fcvm_map.cu", "fcvm_plan.cu", "fcvm_pose.cu", "fcvm_comm.cu"]
+DEPS = SOURCES + ["fcvm_device.cuh", "fcvm_kernels.h", "fcvm_geom.h", "fcvm_hostutil.h", "fcvm_ddmath.h", "fcvm_ddmath_tables.h", "fcvm_comm.h", os.path.join("..", "..", "include", "fcvm.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",

@@ -37,12 +37,14 @@
 namespace fcvm {
 namespace ddm {
 
-#if defined(__CUDA_ARCH__)
+static const double kTableHost[FCVM_DD_TABLE_ROWS * 4] = {FCVM_DD_TABLE_INIT};
+#if defined(__CUDACC__)
 static __device__ const double kTable[FCVM_DD_TABLE_ROWS * 4] = {FCVM_DD_TABLE_INIT};
+#endif
+#if defined(__CUDA_ARCH__)
 #define FCVM_DD_TBL(i) __ldg(&kTable[i])
 #define FCVM_DD_FMA(a, b, c) __fma_rn((a), (b), (c))
 #else
-static const double kTableHost[FCVM_DD_TABLE_ROWS * 4] = {FCVM_DD_TABLE_INIT};
 #define FCVM_DD_TBL(i) kTableHost[i]
 #define FCVM_DD_FMA(a, b, c) __builtin_fma((a), (b), (c))
 #endif

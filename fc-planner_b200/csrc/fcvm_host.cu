@@ -28,6 +28,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <map>
+#include <memory>
 #include <random>
 #include <string>
 #include <thread>
@@ -37,6 +38,7 @@
 #include <cuda_runtime.h>
 
 #include "../../include/fcvm.h"
+#include "fcvm_comm.h"
 #include "fcvm_geom.h"
 #include "fcvm_hostutil.h"
 #include "fcvm_kernels.h"
@@ -96,6 +98,7 @@ struct fcvm_handle {
   double pitch_upper, pitch_lower, fov_base;
   Camera cam;
   int threads = 1;
+  bool host_sums = false, own_sweep = false;   // A/B switches, taken from the environment when the handle is created
 
   // TaskState (viewpoint_manager.h:102-125)
   bool map_flag = false, model_flag = false, viewpoints_flag = false, normal_flag = false;
@@ -155,16 +158,42 @@ struct fcvm_handle {
   PinBuf<int> h_count;
   PinBuf<VpRec> h_recs;
   int64_t resident_n = 0;
+  int64_t resident_W = 0;
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;          // D2H of finished sub-batches while the next one is evaluated
+  cudaStream_t aux_stream = nullptr;           // pose-sum pipeline of a finished E1 sub-batch while the next one is evaluated (high priority)
   std::vector<cudaEvent_t> pipe_ev;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   double last_kernel_ms = 0.0;
   bool timed = false;
   bool device_ok = false;
+  // device time per evaluator stage: event pairs recorded around every k_eval launch, read after the next stream sync
+  struct StageEv { cudaEvent_t a, b; int stage; };
+  std::vector<StageEv> stage_ev_pending, stage_ev_free;
+  double stage_ms[4] = {0, 0, 0, 0};
 
-  // wall-clock split of the manager-level calls (FCVM_PROFILE=1 prints it after fcvm_update)
-  double t_eval = 0, t_own = 0, t_init = 0, t_update = 0, t_unc = 0, t_sums = 0, t_chain = 0, t_safety = 0;
+  // ownership as a per-point arg-max (k_own_best / k_own_apply)
+  DevBuf<unsigned long long> d_best;
+  DevBuf<int> d_ids;
+  // pitch / yaw sums of getPose on the device (fcvm_pose.cu)
+  DevBuf<PoseAux> d_aux;
+  PinBuf<PoseAux> h_aux;
+  AsyncBuf<double> d_valp, d_valy, d_argp, d_argy;     // stream-ordered: they grow while the next E1 sub-batch is running
+  AsyncBuf<unsigned long long> d_keyp, d_keyy;
+  AsyncBuf<uint32_t> d_pidx;
+  DevBuf<double> d_sums;
+  DevBuf<unsigned long long> d_nflag;
+  PinBuf<double> h_sums;
+  PinBuf<unsigned long long> h_nflag;
+  static constexpr int kRing = 4;                      // page-locked staging ring for the flagged arguments / their libm values
+  static constexpr size_t kPiece = 1u << 20;           // doubles per slot (8 MB)
+  PinBuf<double> h_ring[kRing];
+  cudaEvent_t ring_d2h[kRing] = {nullptr, nullptr, nullptr, nullptr}, ring_h2d[kRing] = {nullptr, nullptr, nullptr, nullptr};
+  std::unique_ptr<WorkerPool> pool;
+  int64_t pose_rays = 0, pose_flagged = 0;     // rays summed on the device / of which sent to the host's libm
+
+  // wall-clock split of the manager-level calls (FCVM_PROFILE=1 prints it after fcvm_update; fcvm_get_timers)
+  double t_eval = 0, t_own = 0, t_init = 0, t_update = 0, t_unc = 0, t_sums = 0, t_chain = 0, t_safety = 0, t_pose = 0, t_comm = 0;
   // taps
   bool trace_on = false;
   std::vector<TraceEv> trace;
@@ -174,8 +203,10 @@ struct fcvm_handle {
 
   // sharding
   int rank = 0, world = 1;
-  fcvm_allgather_fn gather = nullptr;
-  void* gather_user = nullptr;
+  fcvm_comm_fn comm = nullptr;
+  void* comm_user = nullptr;
+  NcclComm* nccl = nullptr;                    // owned when set by fcvm_set_shard_nccl
+  int64_t comm_stats[4] = {0, 0, 0, 0};        // all-gathers, bytes gathered, all-reduces, bytes reduced
 };
 
 namespace fcvm {
@@ -183,8 +214,13 @@ namespace fcvm {
 // ------------------------------------------------------------------------------------------------
 // device bring-up (lazy: creating a handle and the host-only helpers work without a GPU)
 // ------------------------------------------------------------------------------------------------
+// Every public entry that touches CUDA passes through here first: the handle's device becomes the calling thread's
+// current device (a process may hold handles on several devices, driven from several threads).
 static int ensure_device(fcvm_handle* h) {
-  if (h->device_ok) return FCVM_OK;
+  if (h->device_ok) {
+    CU(cudaSetDevice(h->prm.device));
+    return FCVM_OK;
+  }
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0)
@@ -193,6 +229,18 @@ static int ensure_device(fcvm_handle* h) {
   CU(cudaSetDevice(h->prm.device));
   CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   CU(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+  {
+    int lo_pri = 0, hi_pri = 0;
+    CU(cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri));
+    CU(cudaStreamCreateWithPriority(&h->aux_stream, cudaStreamNonBlocking, hi_pri));
+  }
+  {
+    // the stream-ordered allocator keeps what the pose-sum pipeline frees (default: returned to the OS at the next sync)
+    cudaMemPool_t pool;
+    CU(cudaDeviceGetDefaultMemPool(&pool, h->prm.device));
+    uint64_t keep = ~0ull;
+    CU(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+  }
   CU(cudaEventCreate(&h->ev0));
   CU(cudaEventCreate(&h->ev1));
   CU(h->d_counters.reserve(8));
@@ -258,7 +306,14 @@ static int launch_stage(fcvm_handle* h, int stage, const VpRec* d_recs, int64_t 
   a.counters = count_stats ? h->d_counters.p : nullptr;
   CU(cudaMemsetAsync(d_rows, 0, (size_t)n * h->W * sizeof(uint32_t), s));
   CU(cudaEventRecord(h->ev0, s));      // ev0..ev1 bracket the visibility kernel alone (roofline timing)
+  fcvm_handle::StageEv se{nullptr, nullptr, stage};
+  if (count_stats) {                   // per-stage device time of the manager-level calls (fcvm_get_timers)
+    if (!h->stage_ev_free.empty()) { se = h->stage_ev_free.back(); h->stage_ev_free.pop_back(); se.stage = stage; }
+    else { CU(cudaEventCreate(&se.a)); CU(cudaEventCreate(&se.b)); }
+    CU(cudaEventRecord(se.a, s));
+  }
   CU(launch_eval(stage, a, s));
+  if (count_stats) { CU(cudaEventRecord(se.b, s)); h->stage_ev_pending.push_back(se); }
   CU(cudaEventRecord(h->ev1, s));
   h->timed = true;
   h->counters[5] += 1;
@@ -273,6 +328,24 @@ static int fetch_counters(fcvm_handle* h) {
   CU(cudaStreamSynchronize(h->stream));
   for (int k = 0; k < 5; ++k) h->counters[k] += (int64_t)c[k];
   h->bounds_violations += (int64_t)c[5];   // only FCVM_DEBUG_BOUNDS builds ever write slot 5
+  for (auto& se : h->stage_ev_pending) {
+    float ms = 0.f;
+    if (cudaEventQuery(se.b) == cudaSuccess && cudaEventElapsedTime(&ms, se.a, se.b) == cudaSuccess) h->stage_ms[se.stage - 1] += ms;
+    else (void)cudaGetLastError();       // launched on a caller's stream that has not finished: not accounted
+    h->stage_ev_free.push_back(se);
+  }
+  h->stage_ev_pending.clear();
+  return FCVM_OK;
+}
+
+// one collective on the handle's stream (fcvm_comm.h); n = bytes per rank (all-gather) or int64 elements (all-reduce)
+static int do_comm(fcvm_handle* h, int32_t op, void* buf_dev, int64_t n) {
+  Stopwatch sw(h->t_comm);
+  if (!h->comm) return fail(FCVM_EINVAL, "world > 1 but no collectives set (fcvm_set_shard / fcvm_set_shard_nccl)");
+  if (h->comm(h->comm_user, op, buf_dev, n, h->stream) != 0) return fail(FCVM_EINTERNAL, std::string("collective failed: ") + last_error_cstr());
+  if (op == FCVM_COMM_ALLGATHER) { h->comm_stats[0] += 1; h->comm_stats[1] += n * h->world; }
+  else { h->comm_stats[2] += 1; h->comm_stats[3] += n * 8; }
+  if (env().profile >= 2) CU(cudaStreamSynchronize(h->stream));    // attribute the wait to the collective, not to whoever syncs next
   return FCVM_OK;
 }
 
@@ -288,8 +361,10 @@ static int64_t chunk_rows(const fcvm_handle* h, int64_t n) {
 // Evaluate `stage` for recs (host) [0..n): upload, launch, optional exchange across ranks, download
 // rows into rows_out (n x W, host) and/or counts.  d_rows_keep: leave rows on the device in this
 // buffer (must hold n x W words).
+// gather_rows (sharded runs only): true = every rank ends up with all rows and counts (the evaluator-level API); false = rows
+// and counts of the other ranks' blocks stay zero (the manager: nothing it does needs foreign rows, see ownership()).
 static int eval_batch(fcvm_handle* h, int stage, const VpRec* recs, int64_t n, const uint32_t* restrict_host, uint32_t* rows_out,
-                      int* count_out, DevBuf<uint32_t>& d_rows, bool restrict_resident = false, CsrOut* csr = nullptr) {
+                      int* count_out, DevBuf<uint32_t>& d_rows, bool restrict_resident = false, CsrOut* csr = nullptr, bool gather_rows = true) {
   int rc = ensure_device(h);
   if (rc) return rc;
   if (n == 0) return FCVM_OK;
@@ -297,12 +372,11 @@ static int eval_batch(fcvm_handle* h, int stage, const VpRec* recs, int64_t n, c
   struct Verbose {     // FCVM_PROFILE=2: one line per evaluator batch
     int stage; int64_t n; std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
     ~Verbose() {
-      static const bool on = std::getenv("FCVM_PROFILE") && atoi(std::getenv("FCVM_PROFILE")) >= 2;
-      if (on) std::fprintf(stderr, "[fcvm]   eval_batch E%d n=%lld: %.2f ms\n", stage, (long long)n,
+      if (env().profile >= 2) std::fprintf(stderr, "[fcvm]   eval_batch E%d n=%lld: %.2f ms\n", stage, (long long)n,
                            std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
     }
   } verbose{stage, n};
-  if (std::getenv("FCVM_PROFILE") && atoi(std::getenv("FCVM_PROFILE")) >= 3) { cudaStreamSynchronize(h->stream); }
+  if (env().profile >= 3) { cudaStreamSynchronize(h->stream); }
   const int64_t W = h->W;
   // pad the batch to a multiple of the world size so that shards are equal (NCCL all-gather)
   const int64_t per_rank = (n + h->world - 1) / h->world;
@@ -326,7 +400,8 @@ static int eval_batch(fcvm_handle* h, int stage, const VpRec* recs, int64_t n, c
   }
   const int64_t lo = std::min(n, per_rank * h->rank), hi = std::min(n, per_rank * (h->rank + 1));
   h->timed = false;
-  if (h->world > 1) CU(cudaMemsetAsync(d_rows.p, 0, (size_t)n_pad * W * sizeof(uint32_t), h->stream));
+  const bool sharded = h->world > 1;
+  if (sharded && gather_rows) CU(cudaMemsetAsync(d_rows.p, 0, (size_t)n_pad * W * sizeof(uint32_t), h->stream));
   // Single GPU with rows wanted on the host: evaluate in sub-batches (FCVM_PIPE_SUBS of them) and copy each finished
   // one out on the copy stream while the next is being evaluated (the rows dominate the transfer).
   bool rows_streamed = false;
@@ -336,7 +411,7 @@ static int eval_batch(fcvm_handle* h, int stage, const VpRec* recs, int64_t n, c
   bool csr_streamed = false;
   if (csr && !rows_out && h->world == 1 && n >= 2 * kPipeMinRows) {
     // two sub-batches: every extra launch costs ~2.5 ms of load-balance tail, the index lists are only ~4 B per visible ray
-    static const int pipe_subs = std::getenv("FCVM_PIPE_SUBS") ? std::max(1, atoi(std::getenv("FCVM_PIPE_SUBS"))) : 2;
+    const int pipe_subs = env().pipe_subs ? env().pipe_subs : 2;
     const int64_t sub = std::max<int64_t>(kPipeMinRows, (n + pipe_subs - 1) / pipe_subs);
     const size_t nsub = (size_t)((n + sub - 1) / sub);
     CU(h->d_offsets.reserve((size_t)n + nsub));
@@ -356,7 +431,7 @@ static int eval_batch(fcvm_handle* h, int stage, const VpRec* recs, int64_t n, c
       h->counters[5] += 2;
       CU(cudaEventRecord(h->pipe_ev[2 * k], h->stream));
     }
-    static const bool vprof = std::getenv("FCVM_PROFILE") && atoi(std::getenv("FCVM_PROFILE")) >= 3;
+    const bool vprof = env().profile >= 3;
     auto tmark = [&](const char* what) { if (vprof) std::fprintf(stderr, "[fcvm]     %s at %.2f ms\n", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - verbose.t0).count()); };
     tmark("kernels queued");
     csr->offs.assign((size_t)n + 1, 0);
@@ -384,14 +459,12 @@ static int eval_batch(fcvm_handle* h, int stage, const VpRec* recs, int64_t n, c
             CU(cudaStreamSynchronize(h->copy_stream));
             DevBuf<uint32_t> nd;
             CU(nd.reserve(est));
-            h->d_indices.free();
-            h->d_indices = nd;
+            h->d_indices = std::move(nd);
             if (!csr->user_idx) {
               PinBuf<uint32_t> nh;
               CU(nh.reserve(est));
               std::memcpy(nh.p, h->h_indices.p, (size_t)base * sizeof(uint32_t));
-              h->h_indices.free();
-              h->h_indices = nh;
+              h->h_indices = std::move(nh);
             }
           }
         }
@@ -412,7 +485,7 @@ static int eval_batch(fcvm_handle* h, int stage, const VpRec* recs, int64_t n, c
     csr->in_user = csr->user_idx != nullptr;
     h->timed = false;
   } else if (rows_out && h->world == 1 && n >= 2 * kPipeMinRows) {
-    static const int pipe_subs = std::getenv("FCVM_PIPE_SUBS") ? std::max(1, atoi(std::getenv("FCVM_PIPE_SUBS"))) : 4;
+    const int pipe_subs = env().pipe_subs ? env().pipe_subs : 4;
     const int64_t sub = std::max<int64_t>(kPipeMinRows, (n + pipe_subs - 1) / pipe_subs);
     size_t k = 0;
     for (int64_t s0 = 0; s0 < n; s0 += sub, ++k) {
@@ -434,10 +507,9 @@ static int eval_batch(fcvm_handle* h, int stage, const VpRec* recs, int64_t n, c
     rc = launch_stage(h, stage, h->d_recs.p + lo, hi - lo, d_rows.p + lo * W, d_restrict ? d_restrict + lo * W : nullptr, h->stream, true);
     if (rc) return rc;
   }
-  if (h->world > 1) {
-    if (!h->gather) return fail(FCVM_EINVAL, "world > 1 but no all-gather callback set");
-    if (h->gather(h->gather_user, d_rows.p, per_rank * W * (int64_t)sizeof(uint32_t), h->stream) != 0)
-      return fail(FCVM_EINTERNAL, "all-gather callback failed");
+  if (sharded && gather_rows) {
+    rc = do_comm(h, FCVM_COMM_ALLGATHER, d_rows.p, per_rank * W * (int64_t)sizeof(uint32_t));
+    if (rc) return rc;
   }
   if (csr_streamed) {
     // the sub-batches already produced counts, offsets and index lists (see above)
@@ -445,13 +517,19 @@ static int eval_batch(fcvm_handle* h, int stage, const VpRec* recs, int64_t n, c
     if (count_out) CU(cudaMemcpyAsync(count_out, h->d_count.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     rc = fetch_counters(h);   // synchronises the stream
     if (rc) return rc;
-    if (std::getenv("FCVM_PROFILE") && atoi(std::getenv("FCVM_PROFILE")) >= 3) std::fprintf(stderr, "[fcvm]     main stream drained at %.2f ms\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - verbose.t0).count());
+    if (env().profile >= 3) std::fprintf(stderr, "[fcvm]     main stream drained at %.2f ms\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - verbose.t0).count());
     CU(cudaStreamSynchronize(h->copy_stream));
     csr->idx = h->h_indices.p;
     if (!csr->in_user) h->h_indices.note_use();
     return FCVM_OK;
   }
-  CU(launch_popc_rows(d_rows.p, n, W, h->d_count.p, h->stream));
+  if (sharded && !gather_rows) {
+    // only this rank's block was evaluated: the other rows of the buffer are stale, their counts read 0
+    CU(cudaMemsetAsync(h->d_count.p, 0, (size_t)n_pad * sizeof(int), h->stream));
+    CU(launch_popc_rows(d_rows.p + lo * W, hi - lo, W, h->d_count.p + lo, h->stream));
+  } else {
+    CU(launch_popc_rows(d_rows.p, n, W, h->d_count.p, h->stream));
+  }
   h->counters[5] += 1;
   const int64_t c_lo = csr ? std::max<long long>(0, csr->lo) : 0, c_hi = csr ? (csr->hi < 0 ? n : std::min<long long>(n, csr->hi)) : 0;
   const int64_t c_n = std::max<int64_t>(0, c_hi - c_lo);
@@ -489,27 +567,77 @@ static int eval_batch(fcvm_handle* h, int stage, const VpRec* recs, int64_t n, c
   return FCVM_OK;
 }
 
-// Ownership sweep over rows resident in d_rows (n rows), processed in `order` (row indices), rows
-// standing for viewpoint ids vp_ids[row] with popcounts count[row].
-static int own_sweep(fcvm_handle* h, const DevBuf<uint32_t>& d_rows, const std::vector<int>& order, const std::vector<int>& vp_ids,
-                     const int* count) {
+// The ownership rule (viewpoint_manager.cpp:500-528, 589-617) for one stage: rows [0, n) of d_rows stand for viewpoint ids
+// vp_ids[row]; `order` lists the row indices in processing order.  Of the rows, [lo, hi) are resident on this GPU with their
+// popcounts in d_count[lo..hi) (a single GPU holds them all).  Default: per-point arg-max (k_own_best over the local rows,
+// one all-reduce MAX of the P keys when sharded, k_own_apply); FCVM_OWN_SWEEP=1 on a single GPU: the ordered row sweep.
+// count_host (n ints) receives every row's contribute_voxel_num.
+static int ownership(fcvm_handle* h, const DevBuf<uint32_t>& d_rows, int64_t n, int64_t lo, int64_t hi, const std::vector<int>& order,
+                     const std::vector<int>& vp_ids, int* count_host) {
   Stopwatch sw(h->t_own);
-  std::vector<int4> sched;
+  if (n <= 0) return FCVM_OK;
+  int rc;
+  const int64_t per = (n + h->world - 1) / h->world, n_pad = per * h->world;
+  if (h->world > 1) {
+    // every rank needs every row's contribute_voxel_num (vps_contri, the keys' decode): 4 bytes per viewpoint
+    rc = do_comm(h, FCVM_COMM_ALLGATHER, h->d_count.p, per * (int64_t)sizeof(int));
+    if (rc) return rc;
+  }
+  (void)n_pad;
+  CU(cudaMemcpyAsync(count_host, h->d_count.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
   int max_id = -1;
-  for (int r : order) {
-    if (count[r] <= 0) continue;     // `if (contribute_voxel_num > 0)` cpp:500 / `== 0 return` cpp:586
-    sched.push_back(make_int4(r, vp_ids[(size_t)r], count[r], 0));
-    h->vps_contri[(size_t)vp_ids[(size_t)r]] = count[r];
+  bool any = false;
+  for (size_t t = 0; t < order.size(); ++t) {
+    const int r = order[t];
+    if (count_host[r] <= 0) continue;     // `if (contribute_voxel_num > 0)` cpp:500 / `== 0 return` cpp:586
+    any = true;
+    h->vps_contri[(size_t)vp_ids[(size_t)r]] = count_host[r];
     max_id = std::max(max_id, vp_ids[(size_t)r]);
   }
-  if (sched.empty()) return FCVM_OK;
+  if (!any) return FCVM_OK;
   if ((size_t)max_id >= h->voxcount_n) return fail(FCVM_EINTERNAL, "vps_voxcount shorter than a viewpoint id");
-  CU(h->d_sched.reserve(sched.size()));
-  CU(cudaMemcpyAsync(h->d_sched.p, sched.data(), sched.size() * sizeof(int4), cudaMemcpyHostToDevice, h->stream));
-  CU(launch_own_sweep(d_rows.p, h->W, h->d_sched.p, (int)sched.size(), h->last_vps_num, h->P, h->d_cover_contrib.p, h->d_contrib_id.p,
-                      h->d_voxcount.p, h->stream));
+
+  if (h->own_sweep && h->world == 1) {
+    std::vector<int4> sched;
+    for (int r : order)
+      if (count_host[r] > 0) sched.push_back(make_int4(r, vp_ids[(size_t)r], count_host[r], 0));
+    CU(h->d_sched.reserve(sched.size()));
+    CU(cudaMemcpyAsync(h->d_sched.p, sched.data(), sched.size() * sizeof(int4), cudaMemcpyHostToDevice, h->stream));
+    CU(launch_own_sweep(d_rows.p, h->W, h->d_sched.p, (int)sched.size(), h->last_vps_num, h->P, h->d_cover_contrib.p, h->d_contrib_id.p,
+                        h->d_voxcount.p, h->stream));
+    h->counters[5] += 1;
+    CU(cudaStreamSynchronize(h->stream));
+    return FCVM_OK;
+  }
+
+  // id_at_pos[t] = viewpoint id of the t-th row in processing order; the local rows with a positive count, sorted by
+  // key = (contri, ~position) descending, are what k_own_best walks
+  std::vector<int> id_at_pos(order.size());
+  std::vector<int4> sched;
+  for (size_t t = 0; t < order.size(); ++t) {
+    const int r = order[t];
+    id_at_pos[t] = vp_ids[(size_t)r];
+    if (r >= lo && r < hi && count_host[r] > 0) sched.push_back(make_int4(r, count_host[r], (int)~(uint32_t)t, 0));
+  }
+  std::sort(sched.begin(), sched.end(), [](const int4& a, const int4& b) {
+    return a.y != b.y ? a.y > b.y : (uint32_t)a.z > (uint32_t)b.z;
+  });
+  CU(h->d_ids.reserve(id_at_pos.size()));
+  CU(cudaMemcpyAsync(h->d_ids.p, id_at_pos.data(), id_at_pos.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  CU(h->d_sched.reserve(std::max<size_t>(sched.size(), 1)));
+  if (!sched.empty()) CU(cudaMemcpyAsync(h->d_sched.p, sched.data(), sched.size() * sizeof(int4), cudaMemcpyHostToDevice, h->stream));
+  CU(h->d_best.reserve((size_t)h->P));
+  CU(cudaMemsetAsync(h->d_best.p, 0, (size_t)h->P * sizeof(unsigned long long), h->stream));
+  CU(launch_own_best(d_rows.p, h->W, h->d_sched.p, (int)sched.size(), h->P, h->d_best.p, h->stream));
   h->counters[5] += 1;
-  CU(cudaStreamSynchronize(h->stream));
+  if (h->world > 1) {
+    rc = do_comm(h, FCVM_COMM_ALLREDUCE_MAX, h->d_best.p, h->P);     // keys are < 2^63: a signed MAX orders them like the unsigned one
+    if (rc) return rc;
+  }
+  CU(launch_own_apply(h->d_best.p, h->d_ids.p, h->last_vps_num, h->P, h->d_cover_contrib.p, h->d_contrib_id.p, h->d_voxcount.p, h->stream));
+  h->counters[5] += 1;
+  CU(cudaStreamSynchronize(h->stream));      // the host vectors above must outlive the copies
   return FCVM_OK;
 }
 
@@ -520,8 +648,7 @@ static int voxcount_resize(fcvm_handle* h, size_t n) {   // grow with zeros, kee
     DevBuf<int> nb;
     CU(nb.reserve(std::max(n, h->d_voxcount.cap * 2)));
     if (h->voxcount_n) CU(cudaMemcpy(nb.p, h->d_voxcount.p, h->voxcount_n * sizeof(int), cudaMemcpyDeviceToDevice));
-    h->d_voxcount.free();
-    h->d_voxcount = nb;
+    h->d_voxcount = std::move(nb);
   }
   CU(cudaMemset(h->d_voxcount.p + h->voxcount_n, 0, (n - h->voxcount_n) * sizeof(int)));
   h->voxcount_n = n;
@@ -630,7 +757,10 @@ static int gather_doubles(fcvm_handle* h, double* vals, int64_t n, int k) {
   shard_of(h, n, lo, hi);
   CU(h->d_gather.reserve((size_t)n_pad * k));
   if (hi > lo) CU(cudaMemcpyAsync(h->d_gather.p + lo * k, vals + lo * k, (size_t)(hi - lo) * k * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-  if (h->gather(h->gather_user, h->d_gather.p, per * k * (int64_t)sizeof(double), h->stream) != 0) return fail(FCVM_EINTERNAL, "all-gather callback failed");
+  {
+    int rc = do_comm(h, FCVM_COMM_ALLGATHER, h->d_gather.p, per * k * (int64_t)sizeof(double));
+    if (rc) return rc;
+  }
   CU(cudaMemcpyAsync(vals, h->d_gather.p, (size_t)n * k * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
   return FCVM_OK;
@@ -640,111 +770,324 @@ static int gather_doubles(fcvm_handle* h, double* vals, int64_t n, int k) {
 // getPose over a batch (viewpoint_manager.cpp:332-531).  ids[i] = viewpoint id of candidate i.
 // poses_out[i] receives the returned pose; ownership and vps_contri/voxcount are updated.
 // ------------------------------------------------------------------------------------------------
+// rows of the last stage -> host (trace tap only); a sharded run first gathers the other ranks' blocks
+static int fetch_rows_for_trace(fcvm_handle* h, DevBuf<uint32_t>& d_rows, int64_t n) {
+  const int64_t W = h->W;
+  if (h->world > 1) {
+    const int64_t per = (n + h->world - 1) / h->world;
+    int rc = do_comm(h, FCVM_COMM_ALLGATHER, d_rows.p, per * W * (int64_t)sizeof(uint32_t));
+    if (rc) return rc;
+  }
+  CU(h->h_rows.reserve((size_t)n * W));
+  CU(cudaMemcpyAsync(h->h_rows.p, d_rows.p, (size_t)n * W * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return FCVM_OK;
+}
+
+// per-viewpoint inputs of the pose sums (cpp:341-345): position, fov_sample_ray, fov_yaw_ray
+struct PoseSeed { D3 vp, fs, fy; double init_yaw; };
+
+// cpp:438-447: the averages of one viewpoint from its two ordered sums
+static inline void finish_average(const fcvm_handle* h, double sum_pitch, double sum_yaw, long long free_num, double init_yaw, double& out_pitch, double& out_yaw) {
+  const double pu = h->pitch_upper * M_PI / 180.0, pl = h->pitch_lower * M_PI / 180.0;
+  double avg_pitch = sum_pitch / free_num;
+  double avg_yaw = sum_yaw / free_num;
+  avg_yaw = init_yaw + avg_yaw;
+  warp_angle(avg_pitch);
+  warp_angle(avg_yaw);
+  if (avg_pitch > pu) avg_pitch = pu;
+  if (avg_pitch < pl) avg_pitch = pl;
+  out_pitch = avg_pitch;
+  out_yaw = avg_yaw;
+}
+
+// the reference's loop body (cpp:398-421) for one viewpoint over its visible index list, all on the host (FCVM_HOST_SUMS=1)
+static inline void host_pose_sums(const float* M, const PoseSeed& sd, const uint32_t* idx, long long cnt, double& sum_pitch, double& sum_yaw) {
+  double avg_pitch = 0.0, avg_yaw = 0.0;
+  for (long long k = 0; k < cnt; ++k) {
+    const size_t j = idx[k];
+    const D3 cand{M[3 * j], M[3 * j + 1], M[3 * j + 2]};
+    const D3 d = sub3(cand, sd.vp);
+    const D3 ray_dir = normalized3(d);
+    // PitchYaw(ray_dir) (cpp:405-407): only the pitch is used here; the yaw (atan2) the reference also computes is dead
+    double pitch = std::asin(ray_dir.z / (norm3(ray_dir) + 1e-3));
+    warp_angle(pitch);
+    avg_pitch += pitch;
+    const double yaw_vec = std::min(std::max(dot3(sd.fs, ray_dir), -1.0), 1.0);
+    double yawoff = std::acos(yaw_vec);
+    // ray_dir_yaw.cross(fov_yaw_ray)[2] with the UNnormalised ray_dir_yaw (cpp:399-401, A.9)
+    if (d.x * sd.fy.y - d.y * sd.fy.x < 0) yawoff = -yawoff;
+    avg_yaw += yawoff;
+  }
+  sum_pitch = avg_pitch;
+  sum_yaw = avg_yaw;
+}
+
+// E1 over rows [lo, hi) of a chunk (records and PoseAux already on the device) in sub-batches, each followed - on the
+// high-priority aux stream, while the next sub-batch is being evaluated - by the device pose-sum pipeline:
+//   rows -> popc -> offsets -> index lists -> k_pose_terms -> flagged arguments D2H -> glibc asin / acos on the host ->
+//   H2D -> k_pose_patch -> k_pose_sum -> two sums per viewpoint D2H.
+// free_num[i] / sums[2 i], sums[2 i + 1] are filled for i in [lo, hi).
+static int e1_with_pose_sums(fcvm_handle* h, int64_t lo, int64_t hi, const std::vector<PoseSeed>& seed, std::vector<long long>& free_num,
+                             std::vector<double>& sums) {
+  const int64_t W = h->W, ln = hi - lo;
+  if (ln <= 0) return FCVM_OK;
+  int rc;
+  const int want = env().pipe_subs ? env().pipe_subs : (int)std::min<int64_t>(8, std::max<int64_t>(1, ln / 6144));
+  const int64_t sub = std::max<int64_t>(std::min<int64_t>(kPipeMinRows, ln), (ln + want - 1) / want);
+  const size_t nsub = (size_t)((ln + sub - 1) / sub);
+  CU(h->d_offsets.reserve((size_t)ln + nsub));
+  CU(h->h_offsets.reserve((size_t)ln + nsub));
+  CU(h->d_sums.reserve((size_t)2 * ln));
+  CU(h->h_sums.reserve((size_t)2 * ln));
+  CU(h->d_nflag.reserve(2));
+  CU(h->h_nflag.reserve(2));
+  while (h->pipe_ev.size() < nsub + 1) {
+    cudaEvent_t e;
+    CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    h->pipe_ev.push_back(e);
+  }
+  // everything of the evaluation side is queued up front on the main stream
+  size_t k = 0;
+  for (int64_t s0 = 0; s0 < ln; s0 += sub, ++k) {
+    const int64_t sn = std::min(sub, ln - s0), r0 = lo + s0;
+    rc = launch_stage(h, FCVM_STAGE_E1, h->d_recs.p + r0, sn, h->d_rows1.p + r0 * W, nullptr, h->stream, true);
+    if (rc) return rc;
+    CU(launch_popc_rows(h->d_rows1.p + r0 * W, sn, W, h->d_count.p + r0, h->stream));
+    CU(launch_exscan(h->d_count.p + r0, sn, h->d_offsets.p + s0 + (int64_t)k, h->stream));
+    h->counters[5] += 2;
+    CU(cudaEventRecord(h->pipe_ev[k], h->stream));
+  }
+  const float* M = h->model.data();
+  cudaStream_t ax = h->aux_stream;
+  k = 0;
+  for (int64_t s0 = 0; s0 < ln; s0 += sub, ++k) {
+    const int64_t sn = std::min(sub, ln - s0), r0 = lo + s0;
+    long long* h_off = h->h_offsets.p + s0 + (int64_t)k;
+    const long long* d_off = h->d_offsets.p + s0 + (int64_t)k;
+    CU(cudaStreamWaitEvent(ax, h->pipe_ev[k], 0));
+    CU(cudaMemcpyAsync(h_off, d_off, ((size_t)sn + 1) * sizeof(long long), cudaMemcpyDeviceToHost, ax));
+    CU(cudaStreamSynchronize(ax));                               // E1 of this sub-batch is done; the next one is already running
+    Stopwatch sw(h->t_pose);
+    const long long total = h_off[sn];
+    for (int64_t i = 0; i < sn; ++i) free_num[(size_t)(r0 + i)] = h_off[i + 1] - h_off[i];
+    if (total == 0) continue;
+    const auto t_sub0 = std::chrono::steady_clock::now();
+    auto mark = [&](const char* what) {
+      if (env().profile >= 3)
+        std::fprintf(stderr, "[fcvm]     pose sums, sub-batch %zu (%lld rows, %lld rays): %s at %.2f ms\n", k, (long long)sn, total, what,
+                     std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_sub0).count());
+    };
+    CU(h->d_pidx.reserve((size_t)total, ax));
+    CU(launch_compact_rows(h->d_rows1.p + r0 * W, sn, W, d_off, h->d_pidx.p, ax));
+    h->counters[5] += 1;
+    if (h->host_sums) {
+      // round-1 path, kept for A/B timing and as the cross-check of the device pipeline: index lists to the host, libm on every ray
+      CU(h->h_indices.reserve((size_t)total));
+      CU(cudaMemcpyAsync(h->h_indices.p, h->d_pidx.p, (size_t)total * sizeof(uint32_t), cudaMemcpyDeviceToHost, ax));
+      CU(cudaStreamSynchronize(ax));
+      h->h_indices.note_use();
+      Stopwatch sw2(h->t_sums);
+      parallel_for(sn, h->threads, [&](int64_t i) {
+        const long long cnt = h_off[i + 1] - h_off[i];
+        if (cnt > 0) host_pose_sums(M, seed[(size_t)(r0 + i)], h->h_indices.p + h_off[i], cnt, sums[(size_t)2 * (r0 + i)], sums[(size_t)2 * (r0 + i) + 1]);
+      });
+      continue;
+    }
+    CU(h->d_valp.reserve((size_t)total, ax));
+    CU(h->d_valy.reserve((size_t)total, ax));
+    unsigned long long cap = (unsigned long long)total / 5 + 4096;       // ~12.5 % of the rays are flagged per function
+    unsigned long long np = 0, ny = 0;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+      CU(h->d_keyp.reserve((size_t)cap, ax)); CU(h->d_argp.reserve((size_t)cap, ax));
+      CU(h->d_keyy.reserve((size_t)cap, ax)); CU(h->d_argy.reserve((size_t)cap, ax));
+      cap = std::min<unsigned long long>(std::min(h->d_keyp.cap, h->d_argp.cap), std::min(h->d_keyy.cap, h->d_argy.cap));
+      CU(cudaMemsetAsync(h->d_nflag.p, 0, 2 * sizeof(unsigned long long), ax));
+      CU(launch_pose_terms(h->d_points.p, h->d_aux.p + r0, d_off, h->d_pidx.p, (int)sn, h->d_valp.p, h->d_valy.p, h->d_keyp.p, h->d_argp.p,
+                           h->d_keyy.p, h->d_argy.p, h->d_nflag.p, cap, ax));
+      h->counters[5] += 1;
+      CU(cudaMemcpyAsync(h->h_nflag.p, h->d_nflag.p, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ax));
+      CU(cudaStreamSynchronize(ax));
+      np = h->h_nflag.p[0]; ny = h->h_nflag.p[1];
+      if (np <= cap && ny <= cap) break;
+      if (attempt == 1) return fail(FCVM_EINTERNAL, "flagged-ray list overflow");
+      cap = std::max(np, ny);                                             // an unusual batch (e.g. many coincident points): redo with room for all
+    }
+    mark("terms done");
+    h->pose_rays += total;
+    h->pose_flagged += (int64_t)(np + ny);
+    if (np + ny > 0) {
+      // The reference's own libm on exactly the arguments whose correctly rounded value glibc might not return.  Pieces of
+      // kPiece arguments travel through a ring of page-locked slots: D2H of piece i + 1 (aux stream) and H2D of piece i - 1
+      // (copy stream) run while the worker pool evaluates piece i; the values replace the arguments in place on the device.
+      constexpr int R = fcvm_handle::kRing;
+      const size_t PIECE = fcvm_handle::kPiece;
+      if (!h->pool) h->pool.reset(new WorkerPool(h->threads));
+      for (int q = 0; q < R; ++q) {
+        CU(h->h_ring[q].reserve(std::min<size_t>(PIECE, (size_t)std::max(np, ny))));
+        if (!h->ring_d2h[q]) { CU(cudaEventCreateWithFlags(&h->ring_d2h[q], cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&h->ring_h2d[q], cudaEventDisableTiming)); }
+      }
+      struct Piece { int which; size_t off, cnt; };
+      std::vector<Piece> pieces;
+      for (size_t o = 0; o < (size_t)np; o += PIECE) pieces.push_back(Piece{0, o, std::min(PIECE, (size_t)np - o)});
+      for (size_t o = 0; o < (size_t)ny; o += PIECE) pieces.push_back(Piece{1, o, std::min(PIECE, (size_t)ny - o)});
+      std::vector<char> slot_used(R, 0);
+      auto process = [&](size_t i) -> int {
+        const Piece& pc = pieces[i];
+        const int q = (int)(i % R);
+        CU(cudaEventSynchronize(h->ring_d2h[q]));
+        double* g = h->h_ring[q].p;
+        {
+          Stopwatch sw2(h->t_sums);
+          const int64_t nb = ((int64_t)pc.cnt + 2047) / 2048;
+          if (pc.which == 0)
+            h->pool->run(nb, 1, [&](int64_t b) { const size_t e = std::min(pc.cnt, (size_t)(b + 1) * 2048); for (size_t j = (size_t)b * 2048; j < e; ++j) g[j] = std::asin(g[j]); });
+          else
+            h->pool->run(nb, 1, [&](int64_t b) { const size_t e = std::min(pc.cnt, (size_t)(b + 1) * 2048); for (size_t j = (size_t)b * 2048; j < e; ++j) g[j] = std::acos(g[j]); });
+        }
+        double* dst = (pc.which == 0 ? h->d_argp.p : h->d_argy.p) + pc.off;
+        CU(cudaMemcpyAsync(dst, g, pc.cnt * sizeof(double), cudaMemcpyHostToDevice, h->copy_stream));
+        CU(cudaEventRecord(h->ring_h2d[q], h->copy_stream));
+        return FCVM_OK;
+      };
+      for (size_t i = 0; i < pieces.size(); ++i) {
+        const Piece& pc = pieces[i];
+        const int q = (int)(i % R);
+        if (slot_used[q]) CU(cudaEventSynchronize(h->ring_h2d[q]));       // the slot's previous values have left
+        slot_used[q] = 1;
+        const double* src = (pc.which == 0 ? h->d_argp.p : h->d_argy.p) + pc.off;
+        CU(cudaMemcpyAsync(h->h_ring[q].p, src, pc.cnt * sizeof(double), cudaMemcpyDeviceToHost, ax));
+        CU(cudaEventRecord(h->ring_d2h[q], ax));
+        if (i >= 1) { rc = process(i - 1); if (rc) return rc; }
+      }
+      rc = process(pieces.size() - 1);
+      if (rc) return rc;
+      for (int q = 0; q < R; ++q)
+        if (slot_used[q]) CU(cudaStreamWaitEvent(ax, h->ring_h2d[q], 0));
+      mark("libm values on their way back");
+      CU(launch_pose_patch(h->d_keyp.p, h->d_argp.p, (long long)np, h->d_keyy.p, h->d_argy.p, (long long)ny, h->d_valp.p, h->d_valy.p, ax));
+      h->counters[5] += 1;
+    }
+    CU(launch_pose_sum(d_off, (int)sn, h->d_valp.p, h->d_valy.p, h->d_sums.p + 2 * s0, ax));
+    h->counters[5] += 1;
+    CU(cudaMemcpyAsync(h->h_sums.p + 2 * s0, h->d_sums.p + 2 * s0, (size_t)2 * sn * sizeof(double), cudaMemcpyDeviceToHost, ax));
+    CU(cudaStreamSynchronize(ax));
+    mark("sums on the host");
+    for (int64_t i = 0; i < sn; ++i) { sums[(size_t)2 * (r0 + i)] = h->h_sums.p[2 * (s0 + i)]; sums[(size_t)2 * (r0 + i) + 1] = h->h_sums.p[2 * (s0 + i) + 1]; }
+  }
+  return FCVM_OK;
+}
+
 static int get_pose_batch(fcvm_handle* h, const std::vector<D3>& pos, const std::vector<D3>& dir, int first_id, std::vector<Pose5>& poses_out) {
   const int64_t n = (int64_t)pos.size();
   poses_out.assign((size_t)n, Pose5());
   if (n == 0) return FCVM_OK;
-  const int64_t W = h->W, P = h->P;
-  const double vr = h->prm.visible_range;
+  const int64_t W = h->W;
   int rc;
   for (int64_t c0 = 0; c0 < n; c0 += chunk_rows(h, n)) {
     const int64_t cn = std::min(chunk_rows(h, n), n - c0);
-    std::vector<D3> fs((size_t)cn), fy((size_t)cn);
-    std::vector<double> ip((size_t)cn), iy((size_t)cn);
+    std::vector<PoseSeed> seed((size_t)cn);
+    std::vector<double> ip((size_t)cn);
     CU(h->h_recs.reserve((size_t)cn));
-    if (h->trace_on) CU(h->h_rows.reserve((size_t)cn * W));
+    CU(h->h_aux.reserve((size_t)cn));
     CU(h->h_count.reserve((size_t)cn));
-    for (int64_t i = 0; i < cn; ++i) {
+    parallel_for(cn, h->threads, [&](int64_t i) {
       // fov_sample_ray = dir.normalized(); fov_yaw_ray = (x, y, 0).normalized(); init_py = PitchYaw
-      fs[(size_t)i] = normalized3(dir[(size_t)(c0 + i)]);
-      fy[(size_t)i] = normalized3(D3{fs[(size_t)i].x, fs[(size_t)i].y, 0.0});
-      pitch_yaw(fs[(size_t)i], ip[(size_t)i], iy[(size_t)i]);
-      const D3& p = pos[(size_t)(c0 + i)];
-      h->cam.fill(h->h_recs.p[i], p.x, p.y, p.z, ip[(size_t)i], iy[(size_t)i]);
-      poses_out[(size_t)(c0 + i)] = Pose5{{p.x, p.y, p.z, ip[(size_t)i], iy[(size_t)i]}};
-    }
+      PoseSeed& sd = seed[(size_t)i];
+      sd.vp = pos[(size_t)(c0 + i)];
+      sd.fs = normalized3(dir[(size_t)(c0 + i)]);
+      sd.fy = normalized3(D3{sd.fs.x, sd.fs.y, 0.0});
+      pitch_yaw(sd.fs, ip[(size_t)i], sd.init_yaw);
+      h->cam.fill(h->h_recs.p[i], sd.vp.x, sd.vp.y, sd.vp.z, ip[(size_t)i], sd.init_yaw);
+      h->h_aux.p[i] = PoseAux{sd.vp.x, sd.vp.y, sd.vp.z, sd.fs.x, sd.fs.y, sd.fs.z, sd.fy.x, sd.fy.y};
+      poses_out[(size_t)(c0 + i)] = Pose5{{sd.vp.x, sd.vp.y, sd.vp.z, ip[(size_t)i], sd.init_yaw}};
+    });
     std::vector<int> ids((size_t)cn), order((size_t)cn);
     for (int64_t i = 0; i < cn; ++i) { ids[(size_t)i] = first_id + (int)(c0 + i); order[(size_t)i] = (int)i; }
+    int64_t lo = 0, hi = cn;
+    if (h->world > 1) shard_of(h, cn, lo, hi);
 
     if (!h->prm.pose_update) {
       // getPose with pose_update == false delegates to updateViewpointInfo (cpp:347-353): E4 + ownership
-      rc = eval_batch(h, FCVM_STAGE_E4, h->h_recs.p, cn, nullptr, h->trace_on ? h->h_rows.p : nullptr, h->h_count.p, h->d_rows1);
+      rc = eval_batch(h, FCVM_STAGE_E4, h->h_recs.p, cn, nullptr, nullptr, nullptr, h->d_rows1, false, nullptr, false);
       if (rc) return rc;
-      if (h->trace_on)
+      if (h->trace_on) {
+        rc = fetch_rows_for_trace(h, h->d_rows1, cn);
+        if (rc) return rc;
         for (int64_t i = 0; i < cn; ++i) record(h, 4, ids[(size_t)i], poses_out[(size_t)(c0 + i)], h->h_rows.p + i * W);
-      rc = own_sweep(h, h->d_rows1, order, ids, h->h_count.p);
+      }
+      rc = ownership(h, h->d_rows1, cn, lo, hi, order, ids, h->h_count.p);
       if (rc) return rc;
       continue;
     }
 
-    // ---- E1 ------------------------------------------------------------------------------
-    CsrOut csr;
-    int64_t my_lo = 0, my_hi = cn;
-    if (h->world > 1) { shard_of(h, cn, my_lo, my_hi); csr.lo = my_lo; csr.hi = my_hi; }
-    rc = eval_batch(h, FCVM_STAGE_E1, h->h_recs.p, cn, nullptr, h->trace_on ? h->h_rows.p : nullptr, h->h_count.p, h->d_rows1, false, &csr);
-    if (rc) return rc;
-    if (h->trace_on)
+    // ---- E1 + the ordered pitch / yaw sums (cpp:355-447) ------------------------------------
+    const int64_t per = (cn + h->world - 1) / h->world, cn_pad = per * h->world;
+    {
+      Stopwatch sw(h->t_eval);
+      CU(h->d_recs.reserve((size_t)cn_pad));
+      CU(h->d_aux.reserve((size_t)cn_pad));
+      CU(h->d_rows1.reserve((size_t)cn_pad * W));
+      CU(h->d_rows2.reserve((size_t)cn_pad * W));
+      CU(h->d_count.reserve((size_t)cn_pad));
+      CU(cudaMemcpyAsync(h->d_recs.p, h->h_recs.p, (size_t)cn * sizeof(VpRec), cudaMemcpyHostToDevice, h->stream));
+      CU(cudaMemcpyAsync(h->d_aux.p, h->h_aux.p, (size_t)cn * sizeof(PoseAux), cudaMemcpyHostToDevice, h->stream));
+    }
+    std::vector<long long> free_num((size_t)cn, 0);
+    std::vector<double> sums((size_t)2 * cn, 0.0);
+    {
+      Stopwatch sw(h->t_eval);
+      rc = e1_with_pose_sums(h, lo, hi, seed, free_num, sums);
+      if (rc) return rc;
+      rc = fetch_counters(h);      // synchronises the main stream
+      if (rc) return rc;
+    }
+    if (h->trace_on) {
+      rc = fetch_rows_for_trace(h, h->d_rows1, cn);
+      if (rc) return rc;
       for (int64_t i = 0; i < cn; ++i) record(h, 1, ids[(size_t)i], poses_out[(size_t)(c0 + i)], h->h_rows.p + i * W);
-
-    // ---- ordered pitch / yaw averages (cpp:398-447), libm on the host ---------------------
-    std::vector<char> has_free((size_t)cn, 0);
-    std::vector<double> avg2((size_t)cn * 2, 0.0);      // (avg_pitch, avg_yaw) per viewpoint with free_num > 0
-    const float* M = h->model.data();
-    const double pu = h->pitch_upper * M_PI / 180.0, pl = h->pitch_lower * M_PI / 180.0;
-    const auto t_sums0 = std::chrono::steady_clock::now();
-    parallel_for(my_hi - my_lo, h->threads, [&](int64_t r) {
-      const int64_t i = my_lo + r;
-      if (h->h_count.p[i] == 0) return;     // free_num == 0: pose stays (pos, init_py), no E2 (cpp:427-436)
-      const D3 vp = pos[(size_t)(c0 + i)];
-      double avg_pitch = 0.0, avg_yaw = 0.0;
-      int free_num = 0;
-      for (long long k = csr.offs[(size_t)r]; k < csr.offs[(size_t)r + 1]; ++k) {
-        const size_t j = csr.idx[k];
-        const D3 cand{M[3 * j], M[3 * j + 1], M[3 * j + 2]};
-        const D3 d = sub3(cand, vp);
-        const D3 ray_dir = normalized3(d);
-        // PitchYaw(ray_dir) (cpp:405-407): only the pitch is used here; the yaw (atan2) the reference also computes is dead
-        double pitch = std::asin(ray_dir.z / (norm3(ray_dir) + 1e-3));
-        warp_angle(pitch);
-        avg_pitch += pitch;
-        const double yaw_vec = std::min(std::max(dot3(fs[(size_t)i], ray_dir), -1.0), 1.0);
-        double yawoff = std::acos(yaw_vec);
-        // ray_dir_yaw.cross(fov_yaw_ray)[2] with the UNnormalised ray_dir_yaw (cpp:399-401, A.9)
-        if (d.x * fy[(size_t)i].y - d.y * fy[(size_t)i].x < 0) yawoff = -yawoff;
-        avg_yaw += yawoff;
-        free_num++;
-      }
-      (void)vr; (void)P;
-      avg_pitch = avg_pitch / free_num;
-      avg_yaw = avg_yaw / free_num;
-      avg_yaw = iy[(size_t)i] + avg_yaw;
-      warp_angle(avg_pitch);
-      warp_angle(avg_yaw);
-      if (avg_pitch > pu) avg_pitch = pu;
-      if (avg_pitch < pl) avg_pitch = pl;
-      avg2[(size_t)2 * i] = avg_pitch;
-      avg2[(size_t)2 * i + 1] = avg_yaw;
-    });
-    h->t_sums += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_sums0).count();
-    rc = gather_doubles(h, avg2.data(), cn, 2);
+    }
+    // averaged poses (cpp:427-447); (pitch, yaw, free_num) of every viewpoint reach every rank
+    std::vector<double> avg3((size_t)cn * 3, 0.0);
+    for (int64_t i = lo; i < hi; ++i) {
+      if (free_num[(size_t)i] == 0) continue;     // free_num == 0: pose stays (pos, init_py), no E2, no ownership (cpp:427-436)
+      finish_average(h, sums[(size_t)2 * i], sums[(size_t)2 * i + 1], free_num[(size_t)i], seed[(size_t)i].init_yaw, avg3[(size_t)3 * i], avg3[(size_t)3 * i + 1]);
+      avg3[(size_t)3 * i + 2] = (double)free_num[(size_t)i];
+    }
+    rc = gather_doubles(h, avg3.data(), cn, 3);
     if (rc) return rc;
+    std::vector<char> has_free((size_t)cn, 0);
     for (int64_t i = 0; i < cn; ++i) {
-      if (h->h_count.p[i] == 0) continue;
-      const D3 vp = pos[(size_t)(c0 + i)];
-      poses_out[(size_t)(c0 + i)].v[3] = avg2[(size_t)2 * i];
-      poses_out[(size_t)(c0 + i)].v[4] = avg2[(size_t)2 * i + 1];
+      if (avg3[(size_t)3 * i + 2] == 0.0) continue;
+      const D3& vp = seed[(size_t)i].vp;
+      poses_out[(size_t)(c0 + i)].v[3] = avg3[(size_t)3 * i];
+      poses_out[(size_t)(c0 + i)].v[4] = avg3[(size_t)3 * i + 1];
       has_free[(size_t)i] = 1;
-      h->cam.fill(h->h_recs.p[i], vp.x, vp.y, vp.z, avg2[(size_t)2 * i], avg2[(size_t)2 * i + 1]);
+      h->cam.fill(h->h_recs.p[i], vp.x, vp.y, vp.z, avg3[(size_t)3 * i], avg3[(size_t)3 * i + 1]);
     }
 
     // ---- E2 on the E1 sets (cpp:457-498) ---------------------------------------------------
     // viewpoints with free_num == 0 have all-zero E1 rows, so they contribute nothing here
-    rc = eval_batch(h, FCVM_STAGE_E2, h->h_recs.p, cn, nullptr, h->trace_on ? h->h_rows.p : nullptr, h->h_count.p, h->d_rows2, true);
-    if (rc) return rc;
-    if (h->trace_on)
+    {
+      Stopwatch sw(h->t_eval);
+      CU(cudaMemcpyAsync(h->d_recs.p, h->h_recs.p, (size_t)cn * sizeof(VpRec), cudaMemcpyHostToDevice, h->stream));
+      if (h->world > 1) CU(cudaMemsetAsync(h->d_count.p, 0, (size_t)cn_pad * sizeof(int), h->stream));
+      if (hi > lo) {
+        rc = launch_stage(h, FCVM_STAGE_E2, h->d_recs.p + lo, hi - lo, h->d_rows2.p + lo * W, h->d_rows1.p + lo * W, h->stream, true);
+        if (rc) return rc;
+        CU(launch_popc_rows(h->d_rows2.p + lo * W, hi - lo, W, h->d_count.p + lo, h->stream));
+        h->counters[5] += 1;
+      }
+      rc = fetch_counters(h);
+      if (rc) return rc;
+    }
+    if (h->trace_on) {
+      rc = fetch_rows_for_trace(h, h->d_rows2, cn);
+      if (rc) return rc;
       for (int64_t i = 0; i < cn; ++i)
         if (has_free[(size_t)i]) record(h, 2, ids[(size_t)i], poses_out[(size_t)(c0 + i)], h->h_rows.p + i * W);
-    rc = own_sweep(h, h->d_rows2, order, ids, h->h_count.p);
+    }
+    rc = ownership(h, h->d_rows2, cn, lo, hi, order, ids, h->h_count.p);
     if (rc) return rc;
   }
   return FCVM_OK;
@@ -759,7 +1102,6 @@ static int update_info_batch(fcvm_handle* h, const std::vector<int>& ids, const 
     const int64_t cn = std::min(chunk_rows(h, n), n - c0);
     CU(h->h_recs.reserve((size_t)cn));
     CU(h->h_count.reserve((size_t)cn));
-    if (h->trace_on) CU(h->h_rows.reserve((size_t)cn * W));
     std::vector<int> cid((size_t)cn), order((size_t)cn);
     for (int64_t i = 0; i < cn; ++i) {
       const Pose5& p = poses[(size_t)(c0 + i)];
@@ -767,11 +1109,16 @@ static int update_info_batch(fcvm_handle* h, const std::vector<int>& ids, const 
       cid[(size_t)i] = ids[(size_t)(c0 + i)];
       order[(size_t)i] = (int)i;
     }
-    rc = eval_batch(h, FCVM_STAGE_E4, h->h_recs.p, cn, nullptr, h->trace_on ? h->h_rows.p : nullptr, h->h_count.p, h->d_rows1);
+    rc = eval_batch(h, FCVM_STAGE_E4, h->h_recs.p, cn, nullptr, nullptr, nullptr, h->d_rows1, false, nullptr, false);
     if (rc) return rc;
-    if (h->trace_on)
+    if (h->trace_on) {
+      rc = fetch_rows_for_trace(h, h->d_rows1, cn);
+      if (rc) return rc;
       for (int64_t i = 0; i < cn; ++i) record(h, 4, cid[(size_t)i], poses[(size_t)(c0 + i)], h->h_rows.p + i * W);
-    rc = own_sweep(h, h->d_rows1, order, cid, h->h_count.p);
+    }
+    int64_t lo = 0, hi = cn;
+    if (h->world > 1) shard_of(h, cn, lo, hi);
+    rc = ownership(h, h->d_rows1, cn, lo, hi, order, cid, h->h_count.p);
     if (rc) return rc;
   }
   return FCVM_OK;
@@ -783,6 +1130,11 @@ static int update_info_batch(fcvm_handle* h, const std::vector<int>& ids, const 
 // ------------------------------------------------------------------------------------------------
 static int viewpoints_prune(fcvm_handle* h, const std::vector<Pose5>& vps_pose, const std::vector<int>& sub_voxcount) {
   const fcvm_params& prm = h->prm;
+  const auto t_prune0 = std::chrono::steady_clock::now();
+  auto pmark = [&](const char* what) {
+    if (env().profile >= 2)
+      std::fprintf(stderr, "[fcvm]   viewpointsPrune: %s at %.2f ms\n", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_prune0).count());
+  };
   auto& inverse_idx = h->inverse_idx;
   auto& idx_slot = h->idx_slot;
   auto& idx_ctrl_voxels = h->idx_ctrl_voxels;
@@ -821,6 +1173,7 @@ static int viewpoints_prune(fcvm_handle* h, const std::vector<Pose5>& vps_pose, 
   const double pitch_bound = 0.3 * prm.fov_h * M_PI / 180.0;
   const double yaw_bound = 0.3 * prm.fov_w * M_PI / 180.0;
 
+  pmark("candidates collected, sorted, indexed");
   // nearCheck of every candidate's own position (cpp:678-682): the poses read here are never modified before their
   // own turn in the chain below, so the checks are independent and run as one device batch
   std::vector<uint8_t> near_ok;
@@ -829,6 +1182,7 @@ static int viewpoints_prune(fcvm_handle* h, const std::vector<Pose5>& vps_pose, 
     if (rc) return rc;
   }
 
+  pmark("nearCheck batch done");
   struct Grav { int slot; D3 up; double upi, uy; };
   std::vector<Grav> grav;
   std::vector<int> neigh;
@@ -893,6 +1247,7 @@ static int viewpoints_prune(fcvm_handle* h, const std::vector<Pose5>& vps_pose, 
     }
   }
 
+  pmark("flag chain done");
   if (!pulled.empty()) {
     std::vector<float> q;
     q.reserve(3 * pulled.size());
@@ -907,6 +1262,7 @@ static int viewpoints_prune(fcvm_handle* h, const std::vector<Pose5>& vps_pose, 
     }
   }
 
+  pmark("pulled positions checked");
   // ---- E3 for every gravitated viewpoint in one batch (cpp:817-886) ---------------------------
   if (!grav.empty()) {
     const int64_t W = h->W;
@@ -916,7 +1272,6 @@ static int viewpoints_prune(fcvm_handle* h, const std::vector<Pose5>& vps_pose, 
     for (int64_t c0 = 0; c0 < n; c0 += chunk_rows(h, n)) {
       const int64_t cn = std::min(chunk_rows(h, n), n - c0);
       CU(h->h_recs.reserve((size_t)cn));
-      if (h->trace_on) CU(h->h_rows.reserve((size_t)cn * W));
       for (int64_t i = 0; i < cn; ++i) {
         const Grav& gq = grav[(size_t)(c0 + i)];
         h->cam.fill(h->h_recs.p[i], gq.up.x, gq.up.y, gq.up.z, gq.upi, gq.uy);
@@ -924,8 +1279,12 @@ static int viewpoints_prune(fcvm_handle* h, const std::vector<Pose5>& vps_pose, 
       CsrOut csr;
       int64_t my_lo = 0, my_hi = cn;
       if (h->world > 1) { shard_of(h, cn, my_lo, my_hi); csr.lo = my_lo; csr.hi = my_hi; }
-      int rc = eval_batch(h, FCVM_STAGE_E3, h->h_recs.p, cn, nullptr, h->trace_on ? h->h_rows.p : nullptr, nullptr, h->d_rows1, false, &csr);
+      int rc = eval_batch(h, FCVM_STAGE_E3, h->h_recs.p, cn, nullptr, nullptr, nullptr, h->d_rows1, false, &csr, false);
       if (rc) return rc;
+      if (h->trace_on) {
+        rc = fetch_rows_for_trace(h, h->d_rows1, cn);
+        if (rc) return rc;
+      }
       std::vector<double> upd((size_t)cn * 2, 0.0);
       const auto t_sums0 = std::chrono::steady_clock::now();
       parallel_for(my_hi - my_lo, h->threads, [&](int64_t r) {
@@ -974,8 +1333,10 @@ static int viewpoints_prune(fcvm_handle* h, const std::vector<Pose5>& vps_pose, 
   std::vector<Pose5> poses;
   for (auto& kv : idx_slot)
     if (live[(size_t)kv.second]) { ids.push_back(kv.first); poses.push_back(slot_pose[(size_t)kv.second]); }
+  pmark("E3 done");
   int rc = update_info_batch(h, ids, poses);
   if (rc) return rc;
+  pmark("E4 + ownership done");
   rc = voxcount_download(h, h->vps_voxcount);
   if (rc) return rc;
   for (auto& kv : idx_slot)       // cpp:699-709
@@ -1116,14 +1477,16 @@ static int update_impl(fcvm_handle* h) {
   std::vector<int> lib_slot((size_t)h->P, -1);
   {
     Stopwatch sw_unc(h->t_unc);
-    static const bool vprof = std::getenv("FCVM_PROFILE") && atoi(std::getenv("FCVM_PROFILE")) >= 3;
+    const bool vprof = env().profile >= 3;
     const auto t_unc0 = std::chrono::steady_clock::now();
     auto tmark = [&](const char* what) { if (vprof) std::fprintf(stderr, "[fcvm]     unc: %s at %.2f ms\n", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_unc0).count()); };
+    tmark("start");
     const int64_t n_unc = (int64_t)uncoveredID.size(), call0 = h->unc_calls;
     h->unc_calls += n_unc;
     for (int64_t k = 0; k < n_unc; ++k) lib_slot[(size_t)uncoveredID[(size_t)k]] = (int)k;
     std::vector<PtNormal> cand8((size_t)8 * n_unc);
     std::vector<float> q((size_t)24 * n_unc);
+    tmark("buffers ready");
     parallel_for(n_unc, h->threads, [&](int64_t k) {
       const int p = uncoveredID[(size_t)k];
       auto it = h->pt_normal_pairs.find(D3{M[3 * p], M[3 * p + 1], M[3 * p + 2]});
@@ -1179,7 +1542,7 @@ static int update_impl(fcvm_handle* h) {
     }
     std::vector<Pose5> pose_set_unc;
     rc = get_pose_batch(h, pos, dir, oriVpNum, pose_set_unc);
-    if (rc) { snap_contrib.free(); snap_id.free(); return rc; }
+    if (rc) return rc;      // the snapshots are released by their destructors
     h->vps_pose.insert(h->vps_pose.end(), pose_set_unc.begin(), pose_set_unc.end());
 
     // restore MCI, swap the voxcounts (cpp:304-309)
@@ -1221,11 +1584,26 @@ fcvm_t* fcvm_create(const fcvm_params* p) {
   h->cam.init(*p);
   int t = p->host_threads > 0 ? p->host_threads : (int)std::thread::hardware_concurrency();
   h->threads = std::max(1, std::min(t, 64));
+  const EnvSettings e = env_now();
+  h->host_sums = e.host_sums;
+  h->own_sweep = e.own_sweep;
   return h;
 }
 
 void fcvm_destroy(fcvm_t* h) {
   if (!h) return;
+  if (h->device_ok) {
+    cudaSetDevice(h->prm.device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->aux_stream) cudaStreamSynchronize(h->aux_stream);
+    if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
+  }
+  if (h->nccl) { nccl_comm_destroy(h->nccl); h->nccl = nullptr; }
+  for (auto& se : h->stage_ev_pending) { cudaEventDestroy(se.a); cudaEventDestroy(se.b); }
+  for (auto& se : h->stage_ev_free) { cudaEventDestroy(se.a); cudaEventDestroy(se.b); }
+  for (int q = 0; q < fcvm_handle::kRing; ++q) { if (h->ring_d2h[q]) cudaEventDestroy(h->ring_d2h[q]); if (h->ring_h2d[q]) cudaEventDestroy(h->ring_h2d[q]); }
+  h->pool.reset();
+  if (h->aux_stream) cudaStreamDestroy(h->aux_stream);
   h->d_map_xyz.free(); h->d_map_sorted.free(); h->d_cell_start.free(); h->d_cell_count.free(); h->d_minmax.free();
   h->d_cand.free(); h->d_ok.free(); h->d_looks.free(); h->d_gather.free();
   h->d_bricks.free(); h->d_points.free(); h->d_cover_contrib.free(); h->d_contrib_id.free(); h->d_voxcount.free();
@@ -1251,8 +1629,15 @@ int fcvm_reset(fcvm_t* h) {   // cpp:64-72
   h->trace.clear();
   for (int k = 0; k < FCVM_NCOUNTERS; ++k) h->counters[k] = 0;
   h->unc_calls = 0; h->sample_calls = 0;
-  h->t_eval = h->t_own = h->t_init = h->t_update = h->t_unc = h->t_sums = h->t_chain = h->t_safety = 0;
-  if (h->device_ok && h->P > 0) return cover_reset(h);
+  h->t_eval = h->t_own = h->t_init = h->t_update = h->t_unc = h->t_sums = h->t_chain = h->t_safety = h->t_pose = h->t_comm = 0;
+  for (int k = 0; k < 4; ++k) { h->stage_ms[k] = 0; h->comm_stats[k] = 0; }
+  h->pose_rays = h->pose_flagged = 0;
+  h->resident_n = 0;
+  if (h->device_ok && h->P > 0) {
+    int rc = ensure_device(h);
+    if (rc) return rc;
+    return cover_reset(h);
+  }
   return FCVM_OK;
 }
 
@@ -1320,7 +1705,7 @@ int fcvm_set_map_cloud(fcvm_t* h, const float* xyz, int64_t n) {   // cpp:74-89
     CU(cudaStreamSynchronize(s));
     h->n_map = n;
   }
-  if (std::getenv("FCVM_PROFILE"))
+  if (env().profile)
     std::fprintf(stderr, "[fcvm] setMapPointCloud: device bring-up %.1f ms, upload + grid + cell index on the device %.1f ms\n", t_dev, t_grid);
   h->map_flag = true;
   return FCVM_OK;
@@ -1332,6 +1717,7 @@ int fcvm_set_model(fcvm_t* h, const float* xyz, int64_t n) {   // cpp:91-108
   if (rc) return rc;
   h->model.assign(xyz, xyz + 3 * n);
   const bool grown = n != h->P;
+  h->resident_n = 0;          // a staged batch was sized for the previous model (row stride W)
   h->P = n;
   h->W = ((n + 31) / 32 + 3) / 4 * 4;
   // one extra tile of slack so the TMA bulk copy of the last tile never needs a tail case
@@ -1372,11 +1758,13 @@ int fcvm_update(fcvm_t* h) {   // cpp:143-330
     Stopwatch sw(h->t_update);
     rc = update_impl(h);
   }
-  if (std::getenv("FCVM_PROFILE"))
-    std::fprintf(stderr, "[fcvm] setInitViewpoints %.1f ms, updateViewpoints %.1f ms; of which evaluator batches (H2D + kernels + D2H + sync) %.1f ms, "
-                 "ownership sweeps %.1f ms, uncovered-candidate generation %.1f ms, host pitch / yaw sums %.1f ms, "
-                 "safety batches %.1f ms; kernels launched %lld\n",
-                 h->t_init, h->t_update, h->t_eval, h->t_own, h->t_unc, h->t_sums, h->t_safety, (long long)h->counters[5]);
+  if (env().profile)
+    std::fprintf(stderr, "[fcvm] rank %d/%d: setInitViewpoints %.1f ms, updateViewpoints %.1f ms; of which evaluator batches (H2D + kernels + D2H + sync, "
+                 "incl. the pose-sum pipeline) %.1f ms, ownership %.1f ms, uncovered-candidate generation %.1f ms, host libm of the pose sums %.1f ms, "
+                 "pose-sum pipeline %.1f ms, safety batches %.1f ms, collectives (enqueue) %.1f ms; device time E1 %.1f E2 %.1f E3 %.1f E4 %.1f ms; "
+                 "rays summed on the device %lld, of which flagged for the host's libm %lld; kernels launched %lld\n",
+                 h->rank, h->world, h->t_init, h->t_update, h->t_eval, h->t_own, h->t_unc, h->t_sums, h->t_pose, h->t_safety, h->t_comm, h->stage_ms[0],
+                 h->stage_ms[1], h->stage_ms[2], h->stage_ms[3], (long long)h->pose_rays, (long long)h->pose_flagged, (long long)h->counters[5]);
   return rc;
 }
 
@@ -1395,6 +1783,7 @@ int64_t fcvm_get_uncovered(fcvm_t* h, float* xyz, int64_t cap) {   // cpp:1138-1
   if (!h) return fail(FCVM_EINVAL, "null handle");
   if (!h->device_ok || h->P == 0) return 0;
   std::vector<int> cid((size_t)h->P);
+  if (ensure_device(h)) return FCVM_ECUDA;
   if (cudaMemcpy(cid.data(), h->d_contrib_id.p, (size_t)h->P * sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess)
     return fail(FCVM_ECUDA, "download of contrib_id failed");
   int64_t n = 0;
@@ -1414,7 +1803,12 @@ int64_t fcvm_get_vps_pose(fcvm_t* h, double* pose5, int64_t cap_rows) {
 }
 int64_t fcvm_get_vps_voxcount(fcvm_t* h, int32_t* out, int64_t cap) {
   if (!h) return fail(FCVM_EINVAL, "null handle");
-  if (h->device_ok) { int rc = voxcount_download(h, h->vps_voxcount); if (rc) return rc; }
+  if (h->device_ok) {
+    int rc = ensure_device(h);
+    if (rc) return rc;
+    rc = voxcount_download(h, h->vps_voxcount);
+    if (rc) return rc;
+  }
   for (int64_t i = 0; i < (int64_t)h->vps_voxcount.size() && i < cap; ++i) out[i] = h->vps_voxcount[(size_t)i];
   return (int64_t)h->vps_voxcount.size();
 }
@@ -1426,6 +1820,7 @@ int64_t fcvm_get_vps_contri(fcvm_t* h, int32_t* out, int64_t cap) {
 int64_t fcvm_get_cover_state(fcvm_t* h, uint8_t* covered, int32_t* cover_contrib, int32_t* contrib_id, int64_t cap) {
   if (!h) return fail(FCVM_EINVAL, "null handle");
   if (!h->device_ok || h->P == 0 || cap <= 0) return h->P;
+  if (ensure_device(h)) return FCVM_ECUDA;
   std::vector<int> cc((size_t)h->P), ci((size_t)h->P);
   if (cudaMemcpy(cc.data(), h->d_cover_contrib.p, (size_t)h->P * sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess ||
       cudaMemcpy(ci.data(), h->d_contrib_id.p, (size_t)h->P * sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess)
@@ -1443,6 +1838,8 @@ int fcvm_get_grid(fcvm_t* h, double* origin3, int32_t* voxel_num3, uint8_t* bits
   for (int c = 0; c < 3; ++c) { if (origin3) origin3[c] = h->grid.origin[c]; if (voxel_num3) voxel_num3[c] = h->grid.dims[c]; }
   if (bits) {
     if (cap_bytes < (h->grid.voxels() + 7) / 8) return fail(FCVM_ECAP, "grid buffer too small");
+    int rc = ensure_device(h);
+    if (rc) return rc;
     h->grid.bricks.resize(h->grid.nbricks());
     CU(cudaMemcpy(h->grid.bricks.data(), h->d_bricks.p + h->brick_guard, h->grid.nbricks() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     h->grid.export_xmajor(bits);
@@ -1455,6 +1852,10 @@ int fcvm_get_grid(fcvm_t* h, double* origin3, int32_t* voxel_num3, uint8_t* bits
 int fcvm_safety_check(fcvm_t* h, const float* xyz, int64_t n, uint8_t* ok) {
   if (!h || !xyz || n <= 0 || !ok) return fail(FCVM_EINVAL, "bad arguments");
   if (!h->map_flag) return fail(FCVM_ENOTREADY, "safety check needs the map");
+  {
+    int rc = ensure_device(h);
+    if (rc) return rc;
+  }
   std::vector<float> q(xyz, xyz + 3 * n);
   std::vector<uint8_t> out;
   int rc = safety_batch(h, q, 0, out);
@@ -1544,14 +1945,17 @@ int fcvm_stage_poses(fcvm_t* h, const double* pose5, int64_t n) {
   CU(cudaMemcpyAsync(h->d_recs.p, h->h_recs.p, (size_t)n * sizeof(VpRec), cudaMemcpyHostToDevice, h->stream));
   CU(cudaStreamSynchronize(h->stream));
   h->resident_n = n;
+  h->resident_W = h->W;
   return FCVM_OK;
 }
 
 int fcvm_evaluate_resident(fcvm_t* h, int32_t stage, void* stream, int32_t sync, int64_t* rays_out) {
   if (!h || stage < 1 || stage > 4 || stage == FCVM_STAGE_E2) return fail(FCVM_EINVAL, "bad stage (E2 needs restrict rows: use fcvm_evaluate)");
-  if (h->resident_n <= 0) return fail(FCVM_ENOTREADY, "no resident batch: call fcvm_stage_poses first");
+  if (h->resident_n <= 0 || h->resident_W != h->W) return fail(FCVM_ENOTREADY, "no resident batch: call fcvm_stage_poses first (after setModel)");
+  int rc = ensure_device(h);
+  if (rc) return rc;
   cudaStream_t s = stream ? (cudaStream_t)stream : h->stream;
-  int rc = launch_stage(h, stage, h->d_recs.p, h->resident_n, h->d_rows1.p, nullptr, s, sync != 0);
+  rc = launch_stage(h, stage, h->d_recs.p, h->resident_n, h->d_rows1.p, nullptr, s, sync != 0);
   if (rc) return rc;
   CU(launch_popc_rows(h->d_rows1.p, h->resident_n, h->W, h->d_count.p, s));
   h->counters[5] += 1;
@@ -1580,14 +1984,24 @@ int fcvm_resident_buffers(fcvm_t* h, void** rows_dev, void** count_dev, int64_t*
 
 int fcvm_own_resident(fcvm_t* h, const int32_t* vp_ids, const int32_t* order, int64_t n) {
   if (!h || !vp_ids || n <= 0 || n > h->resident_n) return fail(FCVM_EINVAL, "bad arguments");
+  int rc = ensure_device(h);
+  if (rc) return rc;
+  if (h->world > 1) return fail(FCVM_EINVAL, "fcvm_own_resident works on an unsharded resident batch");
   std::vector<int> cnt((size_t)n), ids(vp_ids, vp_ids + n), ord((size_t)n);
-  CU(cudaMemcpy(cnt.data(), h->d_count.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost));
+  std::vector<char> seen((size_t)n, 0);
   int max_id = 0;
-  for (int64_t i = 0; i < n; ++i) { ord[(size_t)i] = order ? order[i] : (int)i; max_id = std::max(max_id, ids[(size_t)i]); }
-  int rc = voxcount_resize(h, std::max(h->voxcount_n, (size_t)max_id + 1));
+  for (int64_t i = 0; i < n; ++i) {
+    const int r = order ? order[i] : (int)i;
+    if (r < 0 || r >= n || seen[(size_t)r]) return fail(FCVM_EINVAL, "order must be a permutation of the row indices 0..n-1");
+    if (ids[(size_t)i] < 0) return fail(FCVM_EINVAL, "negative viewpoint id");
+    seen[(size_t)r] = 1;
+    ord[(size_t)i] = r;
+    max_id = std::max(max_id, ids[(size_t)i]);
+  }
+  rc = voxcount_resize(h, std::max(h->voxcount_n, (size_t)max_id + 1));
   if (rc) return rc;
   if (h->vps_contri.size() < (size_t)max_id + 1) h->vps_contri.resize((size_t)max_id + 1, 0);
-  return own_sweep(h, h->d_rows1, ord, ids, cnt.data());
+  return ownership(h, h->d_rows1, n, 0, n, ord, ids, cnt.data());
 }
 
 double fcvm_last_kernel_ms(fcvm_t* h) { return h ? h->last_kernel_ms : 0.0; }
@@ -1601,10 +2015,45 @@ int64_t fcvm_debug_bounds_violations(fcvm_t* h) {
 #endif
 }
 
-int fcvm_set_shard(fcvm_t* h, int32_t rank, int32_t world, fcvm_allgather_fn fn, void* user) {
+int fcvm_set_shard(fcvm_t* h, int32_t rank, int32_t world, fcvm_comm_fn fn, void* user) {
   if (!h || world < 1 || rank < 0 || rank >= world) return fail(FCVM_EINVAL, "bad shard");
-  if (world > 1 && !fn) return fail(FCVM_EINVAL, "world > 1 needs an all-gather callback");
-  h->rank = rank; h->world = world; h->gather = fn; h->gather_user = user;
+  if (world > 1 && !fn) return fail(FCVM_EINVAL, "world > 1 needs the collectives callback");
+  if (h->nccl) { nccl_comm_destroy(h->nccl); h->nccl = nullptr; }
+  h->rank = rank; h->world = world; h->comm = world > 1 ? fn : nullptr; h->comm_user = user;
+  return FCVM_OK;
+}
+
+int fcvm_nccl_unique_id(uint8_t* id128) {
+  if (!id128) return fail(FCVM_EINVAL, "null");
+  return nccl_unique_id(id128);
+}
+
+int fcvm_set_shard_nccl(fcvm_t* h, const uint8_t* id128, int32_t rank, int32_t world) {
+  if (!h || !id128 || world < 1 || rank < 0 || rank >= world) return fail(FCVM_EINVAL, "bad shard");
+  int rc = ensure_device(h);          // the communicator binds to the handle's device
+  if (rc) return rc;
+  if (h->nccl) { nccl_comm_destroy(h->nccl); h->nccl = nullptr; }
+  h->rank = 0; h->world = 1; h->comm = nullptr; h->comm_user = nullptr;
+  if (world == 1) return FCVM_OK;
+  NcclComm* c = nullptr;
+  rc = nccl_comm_create(id128, rank, world, &c);
+  if (rc) return rc;
+  h->nccl = c;
+  h->rank = rank; h->world = world; h->comm = nccl_comm_call; h->comm_user = c;
+  return FCVM_OK;
+}
+
+int fcvm_comm_stats(fcvm_t* h, int64_t* out4) {
+  if (!h || !out4) return fail(FCVM_EINVAL, "null");
+  for (int k = 0; k < 4; ++k) out4[k] = h->comm_stats[k];
+  return FCVM_OK;
+}
+
+int fcvm_get_timers(fcvm_t* h, double* out) {
+  if (!h || !out) return fail(FCVM_EINVAL, "null");
+  const double v[FCVM_NTIMERS] = {h->t_init, h->t_update, h->t_eval, h->t_own, h->t_unc, h->t_sums, h->t_safety, h->t_pose, h->t_comm,
+                                  h->stage_ms[0], h->stage_ms[1], h->stage_ms[2], h->stage_ms[3]};
+  for (int k = 0; k < FCVM_NTIMERS; ++k) out[k] = v[k];
   return FCVM_OK;
 }
 

@@ -5,6 +5,9 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <cstdint>
 #include <cstdlib>
 #include <string>
@@ -28,6 +31,27 @@ const char* last_error_cstr();
                         std::string(#call) + ": " + cudaGetErrorString(e__));                             \
   } while (0)
 
+// Environment switches (they select profiling output and A/B variants; none changes results).  env() is read once per
+// process; a handle takes its own copy of the A/B switches when it is created (EnvSettings::now()), so one process can
+// hold handles of both variants - tests/test_gpu_pose_sums.py compares them.
+struct EnvSettings {
+  int profile = 0;          // FCVM_PROFILE: 1 = wall-clock split after fcvm_update, 2 = one line per evaluator batch, 3 = + marks
+  int pipe_subs = 0;        // FCVM_PIPE_SUBS: sub-batches of the streamed evaluator paths (0 = default per path)
+  bool host_sums = false;   // FCVM_HOST_SUMS=1: pitch / yaw sums of getPose entirely on the host (the round-1 path; A/B and cross-check)
+  bool own_sweep = false;   // FCVM_OWN_SWEEP=1: ownership by the ordered row sweep instead of the per-point arg-max (single GPU only)
+  EnvSettings() {
+    if (const char* e = std::getenv("FCVM_PROFILE")) profile = atoi(e);
+    if (const char* e = std::getenv("FCVM_PIPE_SUBS")) pipe_subs = std::max(1, atoi(e));
+    if (const char* e = std::getenv("FCVM_HOST_SUMS")) host_sums = atoi(e) != 0;
+    if (const char* e = std::getenv("FCVM_OWN_SWEEP")) own_sweep = atoi(e) != 0;
+  }
+};
+inline EnvSettings env_now() { return EnvSettings(); }
+inline const EnvSettings& env() {
+  static const EnvSettings e;
+  return e;
+}
+
 template <class F>
 static void parallel_for(int64_t n, int threads, F&& f) {
   if (threads <= 1 || n < 2 * threads) {
@@ -47,6 +71,77 @@ static void parallel_for(int64_t n, int threads, F&& f) {
   for (auto& t : th) t.join();
 }
 
+// A small persistent worker pool: run(n, f) calls f(i) for i in [0, n) on the pool's threads and the caller's, in blocks
+// handed out by an atomic counter.  parallel_for above spawns its threads per call (~0.3 ms for 16), which is too much for
+// the ~1 ms pieces of the pose-sum pipeline.
+class WorkerPool {
+ public:
+  explicit WorkerPool(int threads) {
+    for (int t = 1; t < threads; ++t) workers_.emplace_back([this] { loop(); });
+  }
+  ~WorkerPool() {
+    {
+      std::lock_guard<std::mutex> g(m_);
+      stop_ = true;
+    }
+    cv_.notify_all();
+    for (auto& t : workers_) t.join();
+  }
+  template <class F>
+  void run(int64_t n, int64_t block, F&& f) {
+    if (n <= 0) return;
+    if (workers_.empty() || n <= block) {
+      for (int64_t i = 0; i < n; ++i) f(i);
+      return;
+    }
+    std::function<void(int64_t)> fn = std::ref(f);
+    {
+      std::lock_guard<std::mutex> g(m_);
+      fn_ = &fn; n_ = n; block_ = block; next_.store(0); active_ = (int)workers_.size(); ++epoch_;
+    }
+    cv_.notify_all();
+    work();
+    std::unique_lock<std::mutex> g(m_);
+    done_.wait(g, [this] { return active_ == 0; });
+    fn_ = nullptr;
+  }
+
+ private:
+  void work() {
+    for (;;) {
+      const int64_t i0 = next_.fetch_add(block_);
+      if (i0 >= n_) break;
+      const int64_t e = std::min(n_, i0 + block_);
+      for (int64_t i = i0; i < e; ++i) (*fn_)(i);
+    }
+  }
+  void loop() {
+    uint64_t seen = 0;
+    for (;;) {
+      {
+        std::unique_lock<std::mutex> g(m_);
+        cv_.wait(g, [&] { return stop_ || epoch_ != seen; });
+        if (stop_) return;
+        seen = epoch_;
+      }
+      work();
+      {
+        std::lock_guard<std::mutex> g(m_);
+        if (--active_ == 0) done_.notify_one();
+      }
+    }
+  }
+  std::vector<std::thread> workers_;
+  std::mutex m_;
+  std::condition_variable cv_, done_;
+  const std::function<void(int64_t)>* fn_ = nullptr;
+  int64_t n_ = 0, block_ = 1;
+  std::atomic<int64_t> next_{0};
+  int active_ = 0;
+  uint64_t epoch_ = 0;
+  bool stop_ = false;
+};
+
 struct Stopwatch {
   double& acc;
   std::chrono::steady_clock::time_point t0;
@@ -54,10 +149,21 @@ struct Stopwatch {
   ~Stopwatch() { acc += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); }
 };
 
+// Device buffer that only grows.  Owns its allocation (freed by the destructor on the device that was current when it
+// was made: every public entry point selects the handle's device first); movable, not copyable.
 template <class T>
 struct DevBuf {
   T* p = nullptr;
   size_t cap = 0;
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  DevBuf(DevBuf&& o) noexcept : p(o.p), cap(o.cap) { o.p = nullptr; o.cap = 0; }
+  DevBuf& operator=(DevBuf&& o) noexcept {
+    if (this != &o) { free(); p = o.p; cap = o.cap; o.p = nullptr; o.cap = 0; }
+    return *this;
+  }
+  ~DevBuf() { free(); }
   cudaError_t reserve(size_t n) {
     if (n <= cap) return cudaSuccess;
     if (p) cudaFree(p);
@@ -68,6 +174,29 @@ struct DevBuf {
   }
   void free() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
+// Device buffer from the stream-ordered allocator: growing it neither waits for, nor stalls, work on other streams
+// (cudaFree is device-synchronising, cudaFreeAsync is not), which the pose-sum pipeline relies on while the next
+// evaluator sub-batch is running.  Grows with 25 % slack.  The device's default pool keeps what is freed (its release
+// threshold is raised in ensure_device).
+template <class T>
+struct AsyncBuf {
+  T* p = nullptr;
+  size_t cap = 0;
+  AsyncBuf() = default;
+  AsyncBuf(const AsyncBuf&) = delete;
+  AsyncBuf& operator=(const AsyncBuf&) = delete;
+  ~AsyncBuf() { if (p) cudaFree(p); }
+  cudaError_t reserve(size_t n, cudaStream_t s) {
+    if (n <= cap) return cudaSuccess;
+    if (p) { cudaError_t e = cudaFreeAsync(p, s); if (e != cudaSuccess) return e; }
+    p = nullptr; cap = 0;
+    const size_t want = n + n / 4 + 1024;
+    cudaError_t e = cudaMallocAsync((void**)&p, want * sizeof(T), s);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+};
+
 // Host staging buffer for D2H / H2D copies.  Page-locking costs ~0.4 ms per MB on the B200 boxes (600 MB: 240 ms, measured,
 // profiles/pin_cost.py) against 23 ms saved per 600 MB copied, so a large buffer starts pageable and is page-locked in place
 // (cudaHostRegister) only once it has been used a few times; small buffers are page-locked at once.
@@ -77,6 +206,19 @@ struct PinBuf {
   size_t cap = 0;
   bool pinned = false, registered = false;
   int uses = 0;
+  PinBuf() = default;
+  PinBuf(const PinBuf&) = delete;
+  PinBuf& operator=(const PinBuf&) = delete;
+  PinBuf(PinBuf&& o) noexcept : p(o.p), cap(o.cap), pinned(o.pinned), registered(o.registered), uses(o.uses) { o.p = nullptr; o.cap = 0; o.pinned = o.registered = false; o.uses = 0; }
+  PinBuf& operator=(PinBuf&& o) noexcept {
+    if (this != &o) {
+      free();
+      p = o.p; cap = o.cap; pinned = o.pinned; registered = o.registered; uses = o.uses;
+      o.p = nullptr; o.cap = 0; o.pinned = o.registered = false; o.uses = 0;
+    }
+    return *this;
+  }
+  ~PinBuf() { free(); }
   static constexpr size_t kPinAtOnceBytes = 8u << 20;
   static constexpr int kPinAfterUses = 3;
   cudaError_t reserve(size_t n) {

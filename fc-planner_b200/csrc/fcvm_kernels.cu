@@ -16,6 +16,8 @@
 // continuation immediately, so the divergent phase keeps its lanes busy although ray lengths vary
 // by two orders of magnitude.  Visible bits are OR-ed into the viewpoint's bitset row in HBM.
 // No tensor cores: nothing here is a contraction.
+#include <atomic>
+
 #include "fcvm_device.cuh"
 #include "fcvm_kernels.h"
 
@@ -716,15 +718,86 @@ __global__ void __launch_bounds__(128) k_own_sweep(const uint32_t* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------
+// Ownership as a per-point arg-max, the form that shards over GPUs.
+// The rule of viewpoint_manager.cpp:500-528 / 589-617 applied to a whole stage is order-dependent only through ties:
+// after all rows of the stage, point j belongs to the seer with the largest contribute_voxel_num, the earliest in
+// processing order among equals - provided it beats (strictly) what j had before the stage, and j was not locked
+// (owner id < last_vps_num).  Intermediate take-overs cancel in vps_voxcount (+1 then -1).  So:
+//   k_own_best   key[j] = max over the rows a GPU holds of (contri << 32 | ~position-in-order), 0 = no seer
+//   (N GPUs: one all-reduce MAX over the P keys - 8 MB at P = 10^6 - instead of gathering V x P / 8 bytes of rows)
+//   k_own_apply  decode the winner, apply the rule once per point, +1 / -1 the two viewpoints' counts.
+// ------------------------------------------------------------------------------------------
+// sched[t] = {row, key_hi = contri, key_lo = ~position} for the local rows with contri > 0, sorted by key DESCENDING: the
+// first row that sees a point is its local winner, so a thread only has to remember which of its 32 points are taken.
+// The thread IS a 32-point word column: consecutive lanes read consecutive words of a row (128-byte coalesced loads,
+// every row word read exactly once), stores happen once per point.
+__global__ void __launch_bounds__(256) k_own_best(const uint32_t* __restrict__ rows, long long words, const int4* __restrict__ sched, int nsched,
+                                                  long long P, unsigned long long* __restrict__ best) {
+  const long long col = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (col * 32 >= P) return;
+  uint32_t taken = 0u;
+  constexpr int kAhead = 8;
+  for (int t0 = 0; t0 < nsched; t0 += kAhead) {
+    int4 sv[kAhead];
+    uint32_t wv[kAhead];
+#pragma unroll
+    for (int u = 0; u < kAhead; ++u) {
+      sv[u] = __ldg(sched + min(t0 + u, nsched - 1));
+      wv[u] = __ldg(rows + (long long)sv[u].x * words + col);
+    }
+#pragma unroll
+    for (int u = 0; u < kAhead; ++u) {
+      if (t0 + u >= nsched) break;
+      uint32_t w = wv[u] & ~taken;
+      if (w == 0u) continue;
+      taken |= w;
+      const unsigned long long key = ((unsigned long long)(uint32_t)sv[u].y << 32) | (unsigned long long)(uint32_t)sv[u].z;
+      while (w) {
+        const int bit = __ffs(w) - 1;
+        w &= w - 1;
+        const long long j = col * 32 + bit;
+        if (j < P) best[j] = key;
+      }
+    }
+    if (taken == 0xffffffffu) break;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_own_apply(const unsigned long long* __restrict__ best, const int* __restrict__ id_at_pos, int last_vps_num,
+                                                   long long P, int* __restrict__ cover_contrib, int* __restrict__ contrib_id, int* __restrict__ voxcount) {
+  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= P) return;
+  const unsigned long long key = best[j];
+  if (key == 0ull) return;
+  const int c = (int)(key >> 32);
+  const int vp = __ldg(id_at_pos + (uint32_t)(~(uint32_t)key));
+  const int owner = contrib_id[j];
+  if (owner < 0) {
+    atomicAdd(voxcount + vp, 1);
+  } else if (c > cover_contrib[j] && owner >= last_vps_num) {
+    atomicSub(voxcount + owner, 1);
+    atomicAdd(voxcount + vp, 1);
+  } else {
+    return;
+  }
+  cover_contrib[j] = c;
+  contrib_id[j] = vp;
+}
+
+// ------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------
 template <int STAGE>
 static cudaError_t launch_eval_t(const EvalArgs& a, dim3 grid, size_t smem, cudaStream_t s) {
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(k_eval<STAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)eval_smem_bytes(EVAL_MAX_TILE));
+  // the opt-in to > 48 KB of dynamic shared memory is a per-device function attribute: remember it per device ordinal
+  static std::atomic<bool> attr_done[64];
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev < 0 || dev >= 64 || !attr_done[dev].load(std::memory_order_acquire)) {
+    e = cudaFuncSetAttribute(k_eval<STAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)eval_smem_bytes(EVAL_MAX_TILE));
     if (e != cudaSuccess) return e;
-    attr_done = true;
+    if (dev >= 0 && dev < 64) attr_done[dev].store(true, std::memory_order_release);
   }
   k_eval<STAGE><<<grid, kWarps * 32, smem, s>>>(a);
   return cudaGetLastError();
@@ -776,6 +849,20 @@ cudaError_t launch_own_sweep(const uint32_t* rows, long long words, const int4* 
   const long long cols = (P + 31) / 32;
   const int wpb = 4;
   k_own_sweep<<<(unsigned)((cols + wpb - 1) / wpb), wpb * 32, 0, s>>>(rows, words, sched, nsched, last_vps_num, P, cover_contrib, contrib_id, voxcount);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_own_best(const uint32_t* rows, long long words, const int4* sched, int nsched, long long P, unsigned long long* best, cudaStream_t s) {
+  if (nsched <= 0 || P <= 0) return cudaSuccess;
+  const long long cols = (P + 31) / 32;
+  k_own_best<<<(unsigned)((cols + 255) / 256), 256, 0, s>>>(rows, words, sched, nsched, P, best);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_own_apply(const unsigned long long* best, const int* id_at_pos, int last_vps_num, long long P, int* cover_contrib, int* contrib_id,
+                             int* voxcount, cudaStream_t s) {
+  if (P <= 0) return cudaSuccess;
+  k_own_apply<<<(unsigned)((P + 255) / 256), 256, 0, s>>>(best, id_at_pos, last_vps_num, P, cover_contrib, contrib_id, voxcount);
   return cudaGetLastError();
 }
 

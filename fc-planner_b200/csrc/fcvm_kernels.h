@@ -54,7 +54,25 @@ cudaError_t launch_compact_rows(const uint32_t* rows, long long n, long long wor
 // sched[t] = {row index, viewpoint id, contribute_voxel_num, 0} in processing order, rows with 0 omitted
 cudaError_t launch_own_sweep(const uint32_t* rows, long long words, const int4* sched, int nsched, int last_vps_num, long long P,
                              int* cover_contrib, int* contrib_id, int* voxcount, cudaStream_t s);
+// the same rule as a per-point arg-max (shards over GPUs): best[P] (zeroed by the caller) = largest key over the rows listed in
+// sched[t] = {row, contri, ~position in processing order, 0}, which must be sorted by (contri, ~position) descending; then one
+// apply pass decodes the winners (id_at_pos[position] = viewpoint id)
+cudaError_t launch_own_best(const uint32_t* rows, long long words, const int4* sched, int nsched, long long P, unsigned long long* best, cudaStream_t s);
+cudaError_t launch_own_apply(const unsigned long long* best, const int* id_at_pos, int last_vps_num, long long P, int* cover_contrib, int* contrib_id,
+                             int* voxcount, cudaStream_t s);
 
+// ---- pitch / yaw sums of getPose on the device (fcvm_pose.cu) -------------------------------------
+struct PoseAux {            // per viewpoint: position, fov_sample_ray = dir.normalized(), (x, y) of fov_yaw_ray (cpp:341-345)
+  double vx, vy, vz, fsx, fsy, fsz, fyx, fyy;
+};
+// offsets[nrows + 1] / indices: the visible sets of the rows as ascending index lists; val_*: one double per ray;
+// key_* / arg_*: compact lists of the rays whose asin (p) / acos (y) must come from the host's libm, nflag[2] their counts
+cudaError_t launch_pose_terms(const float4* points, const PoseAux* aux, const long long* offsets, const uint32_t* indices, int nrows, double* val_p,
+                              double* val_y, unsigned long long* key_p, double* arg_p, unsigned long long* key_y, double* arg_y,
+                              unsigned long long* nflag, unsigned long long cap, cudaStream_t s);
+cudaError_t launch_pose_patch(const unsigned long long* key_p, const double* g_p, long long np, const unsigned long long* key_y, const double* g_y,
+                              long long ny, double* val_p, double* val_y, cudaStream_t s);
+cudaError_t launch_pose_sum(const long long* offsets, int nrows, const double* val_p, const double* val_y, double* sums, cudaStream_t s);
 
 // ---- map side (fcvm_map.cu) --------------------------------------------------------------------
 struct MapGeom {            // SDFMap geometry as initHCMap derives it (sdf_map.cpp:144-157)

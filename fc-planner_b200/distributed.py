@@ -1,13 +1,13 @@
-"""Viewpoint sharding across the GPUs of one box: one process per GPU, the occupancy
-grid and the model cloud replicated on every GPU, each rank evaluating a contiguous block of every
-viewpoint batch, and ONE exchange per evaluator stage — an all-gather of the coverage bitset rows —
-after which every rank holds all rows and runs the (cheap, order-sensitive) host logic and the
-ownership sweep redundantly, so the result is bit-identical to the single-GPU run.
+"""Viewpoint sharding across the GPUs of one box: one process per GPU, the occupancy grid and the model
+cloud replicated on every GPU, each rank evaluating a contiguous block of every viewpoint batch.  Bitset rows stay on the
+GPU that produced them; per stage the ranks exchange the per-viewpoint results of their blocks (all-gather, a few bytes
+per viewpoint) and run the ownership rule as one all-reduce MAX over per-point keys (8 bytes per model point), after which
+every rank applies the same winners to its replica of the cover state - bit-identical to the single-GPU run.
 
-`torch.distributed` is plumbing only: the C library calls back into `Exchange.__call__` with the
-device buffer that holds `world` equal slices (this rank's slice already filled) and the CUDA
-stream its kernels run on; the all-gather is enqueued behind them on that stream (NCCL over
-NVLink / NVSwitch).  With the `gloo` backend (CPU tests) the same callback gathers a host buffer.
+`torch.distributed` is plumbing only.  Default (`attach`): the C library drives NCCL itself over NVLink / NVSwitch
+(`fcvm_set_shard_nccl`); torch merely broadcasts the 128-byte ncclUniqueId.  `attach(..., native=False)` routes the two
+collectives through torch.distributed instead (`Exchange`, the `fcvm_comm_fn` callback of include/fcvm.h) - the form any
+other communication backend would plug into.  With the `gloo` backend (CPU tests) the callback works on host buffers.
 """
 import ctypes
 
@@ -15,39 +15,57 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
+from ._lib import COMM_ALLGATHER, COMM_ALLREDUCE_MAX
+
 
 class _DevBuf:
-    """A raw device pointer as a `__cuda_array_interface__` object (uint8, 1-D)."""
+    """A raw device pointer as a `__cuda_array_interface__` object (1-D)."""
 
-    def __init__(self, ptr, nbytes):
-        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False), "version": 3, "strides": None}
+    def __init__(self, ptr, n, typestr="|u1"):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": typestr, "data": (int(ptr), False), "version": 3, "strides": None}
 
 
 def shard_bounds(n, rank, world):
-    """Contiguous shard [lo, hi) of n items: equal blocks of ceil(n / world) — the layout an
+    """Contiguous shard [lo, hi) of n items: equal blocks of ceil(n / world) - the layout an
     all-gather of equal slices needs (include/fcvm.h: fcvm_shard_range)."""
     per = (n + world - 1) // world
     return min(n, per * rank), min(n, per * (rank + 1))
 
 
-class Exchange:
-    """All-gather callback for `fcvm_set_shard` (fcvm_allgather_fn in include/fcvm.h)."""
+def ownership_key(contrib, pos):
+    """The per-point key of the arg-max ownership exchange: larger contribute_voxel_num wins, the earlier position in
+    processing order among equals (k_own_best in fcvm_kernels.cu); 0 = no seer.  Fits a signed 64-bit MAX."""
+    return (int(contrib) << 32) | (~int(pos) & 0xFFFFFFFF)
 
-    def __init__(self, group=None):
+
+def decode_ownership_key(key):
+    return int(key) >> 32, (~int(key)) & 0xFFFFFFFF
+
+
+class Exchange:
+    """`fcvm_comm_fn` over torch.distributed: op 0 = in-place all-gather of `world` equal byte slices, op 1 = in-place
+    all-reduce MAX over int64 values."""
+
+    def __init__(self, group=None, host_buffers=None):
         self.group = group
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
         self.on_device = dist.get_backend(group) == "nccl"
+        # host_buffers=True: the pointers handed to the callback are host memory (the gloo CPU tests call it directly)
+        self.host_buffers = (not self.on_device) if host_buffers is None else host_buffers
         self.calls = 0
         self.bytes = 0
+        self.reduces = 0
+
+    def _stream(self, stream):
+        return torch.cuda.ExternalStream(stream) if stream else torch.cuda.current_stream()
 
     def gather(self, buf_ptr, bytes_per_rank, stream):
         total = bytes_per_rank * self.world
         if self.on_device:
             whole = torch.as_tensor(_DevBuf(buf_ptr, total), device=torch.device("cuda", torch.cuda.current_device()))
             mine = whole[self.rank * bytes_per_rank:(self.rank + 1) * bytes_per_rank]
-            ext = torch.cuda.ExternalStream(stream) if stream else torch.cuda.current_stream()
-            with torch.cuda.stream(ext):
+            with torch.cuda.stream(self._stream(stream)):
                 dist.all_gather_into_tensor(whole, mine, group=self.group)   # in place: slice r of the output is rank r's input
         else:
             host = np.ctypeslib.as_array(ctypes.cast(buf_ptr, ctypes.POINTER(ctypes.c_uint8)), shape=(total,))
@@ -61,19 +79,56 @@ class Exchange:
         self.bytes += total
         return 0
 
-    def __call__(self, user, buf, bytes_per_rank, stream):
+    def reduce_max(self, buf_ptr, count, stream):
+        if self.on_device:
+            t = torch.as_tensor(_DevBuf(buf_ptr, count, "<i8"), device=torch.device("cuda", torch.cuda.current_device()))
+            with torch.cuda.stream(self._stream(stream)):
+                dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+        else:
+            host = np.ctypeslib.as_array(ctypes.cast(buf_ptr, ctypes.POINTER(ctypes.c_int64)), shape=(count,))
+            t = torch.from_numpy(host)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+        self.reduces += 1
+        return 0
+
+    def __call__(self, user, op, buf, n, stream):
         try:
-            return self.gather(buf, bytes_per_rank, stream)
-        except Exception as e:   # never raise through the C ABI
+            if op == COMM_ALLGATHER:
+                return self.gather(buf, n, stream)
+            if op == COMM_ALLREDUCE_MAX:
+                return self.reduce_max(buf, n, stream)
+            return -1
+        except Exception:   # never raise through the C ABI
             import traceback
             traceback.print_exc()
             return -1
 
 
-def attach(manager, group=None):
-    """Shard `manager` (a fc_planner_b200.manager.ViewpointManager) over the ranks of `group`."""
-    ex = Exchange(group)
-    manager.set_shard(ex.rank, ex.world, ex if ex.world > 1 else None)
+def broadcast_unique_id(group=None):
+    """ncclUniqueId made on rank 0 of `group` by the library, broadcast with whatever backend the group has."""
+    from .manager import nccl_unique_id
+    rank = dist.get_rank(group)
+    payload = [nccl_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(payload, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    return payload[0]
+
+
+def attach(manager, group=None, native=True):
+    """Shard `manager` (a fc_planner_b200.manager.ViewpointManager) over the ranks of `group`.
+    native=True: the library's own NCCL communicator (one per handle).  native=False: collectives through torch.distributed;
+    the library always passes DEVICE pointers, so that needs the nccl backend."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    if world == 1:
+        manager.set_shard(0, 1, None)
+        return None
+    if native:
+        manager.set_shard_nccl(broadcast_unique_id(group), rank, world)
+        return None
+    ex = Exchange(group, host_buffers=False)
+    if not ex.on_device:
+        raise RuntimeError("fcvm hands device pointers to the collectives callback: attach(native=False) needs the nccl backend "
+                           f"(got {dist.get_backend(group)}); use attach(native=True) or a CUDA-aware backend")
+    manager.set_shard(ex.rank, ex.world, ex)
     manager._exchange = ex
     return ex
 

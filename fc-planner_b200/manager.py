@@ -238,10 +238,32 @@ class ViewpointManager:
     def last_kernel_ms(self):
         return float(self.lib.fcvm_last_kernel_ms(self.h))
 
-    def set_shard(self, rank, world, gather_cb=None):
-        cb = _lib.ALLGATHER_FN(gather_cb) if gather_cb is not None else ctypes.cast(None, _lib.ALLGATHER_FN)
+    def set_shard(self, rank, world, comm_cb=None):
+        """Caller-supplied collectives: comm_cb(user, op, buf_dev, n, stream) -> 0 (include/fcvm.h: fcvm_comm_fn)."""
+        cb = _lib.COMM_FN(comm_cb) if comm_cb is not None else ctypes.cast(None, _lib.COMM_FN)
         self._keep.append(cb)
         check(self.lib.fcvm_set_shard(self.h, rank, world, cb, None))
+
+    def set_shard_nccl(self, unique_id, rank, world):
+        """The library drives NCCL itself; unique_id = the 128 bytes fcvm_nccl_unique_id() produced on one rank."""
+        uid = np.frombuffer(bytes(unique_id), dtype=np.uint8).copy()
+        assert uid.size == 128
+        check(self.lib.fcvm_set_shard_nccl(self.h, ptr(uid, u8p), rank, world))
+
+    def comm_stats(self):
+        """(all-gathers, bytes gathered, all-reduces, bytes reduced) issued by this handle since create / reset."""
+        out = np.zeros(4, np.int64)
+        check(self.lib.fcvm_comm_stats(self.h, ptr(out, i64p)))
+        return out
+
+    TIMER_NAMES = ("setInitViewpoints", "updateViewpoints", "evaluator_batches", "ownership", "uncovered_candidates", "host_libm",
+                   "safety_batches", "pose_sum_pipeline", "collectives_enqueue", "k_eval_E1", "k_eval_E2", "k_eval_E3", "k_eval_E4")
+
+    def timers(self):
+        """Wall-clock split of the manager-level calls since create / reset, ms (fcvm_get_timers)."""
+        out = np.zeros(13, np.float64)
+        check(self.lib.fcvm_get_timers(self.h, ptr(out, f64p)))
+        return dict(zip(self.TIMER_NAMES, (float(x) for x in out)))
 
 
 class _Pinned:
@@ -290,6 +312,13 @@ def host_build_grid(params, xyz, with_bits=True):
         bits = np.zeros((g + 7) // 8, np.uint8)
         check(_lib.load().fcvm_host_build_grid(ctypes.byref(params), ptr(xyz, f32p), len(xyz), None, None, ptr(bits, u8p), len(bits)))
     return origin, dims, bits
+
+
+def nccl_unique_id():
+    """128 bytes of a fresh ncclUniqueId (fcvm_nccl_unique_id): make it on one rank, hand it to the others."""
+    out = np.zeros(128, np.uint8)
+    check(_lib.load().fcvm_nccl_unique_id(ptr(out, u8p)))
+    return out.tobytes()
 
 
 def shard_range(n, rank, world):

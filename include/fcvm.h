@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define FCVM_ABI_VERSION 1
+#define FCVM_ABI_VERSION 2
 
 /* error codes */
 #define FCVM_OK          0
@@ -196,15 +196,41 @@ double fcvm_last_kernel_ms(fcvm_t* h);
  * returns the number of violations seen since create; a release build returns -1. */
 int64_t fcvm_debug_bounds_violations(fcvm_t* h);
 
-/* --------------------------------------------------- multi-GPU (one process per GPU) - */
+/* --------------------------------------------------- multi-GPU ----------------------- */
 
-/* Shard assignment: this handle evaluates only viewpoints [lo, hi) of every batch given to
- * fcvm_set_init_viewpoints / the prune stages; rows of the other shards are supplied through the
- * exchange callback below (torch.distributed NCCL all-gather in fc-planner_b200/distributed.py).  The same callback
- * exchanges the per-viewpoint host reductions (two doubles per viewpoint), which every rank computes for its own shard
- * only.  world = 1 disables sharding. */
-typedef int (*fcvm_allgather_fn)(void* user, void* buf_dev, int64_t bytes_per_rank, void* stream);
-int fcvm_set_shard(fcvm_t* h, int32_t rank, int32_t world, fcvm_allgather_fn fn, void* user);
+/* Viewpoint sharding over the GPUs of one box (north_star (4)).  Every handle of a group is given the SAME
+ * inputs through the SAME call sequence; the occupancy grid and the model cloud are replicated, and of every viewpoint
+ * batch (setInitViewpoints, the E3 / E4 batches of viewpointsPrune, the round appends) a handle evaluates only the
+ * contiguous block fcvm_shard_range(n, rank, world).  Bitset rows never leave the GPU that produced them.  Per stage the
+ * ranks exchange
+ *   - the per-viewpoint results of their blocks (visible counts: 4 B, averaged pitch / yaw: 24 B per viewpoint): all-gather;
+ *   - the ownership rule (viewpoint_manager.cpp:500-528, 589-617) as ONE all-reduce MAX over per-point keys
+ *     (contribute_voxel_num << 32 | ~position in processing order; 8 B per model point),
+ * after which every rank applies the same winners to its replica of the cover state.  Every value is produced by exactly
+ * one rank with the same code, so all ranks end with results bit-identical to the single-GPU run.
+ *
+ * fcvm_set_shard_nccl: the library drives NCCL itself (libnccl.so.2 is dlopen'ed; collectives are enqueued on the handle's
+ * stream).  id128 = an ncclUniqueId made by fcvm_nccl_unique_id on one rank and handed to the others by any means (the
+ * caller's launcher, a file, MPI, torch.distributed ...).  Works for one process per GPU and for one thread per GPU in a
+ * single process (each handle on its own device, each driven by its own thread: the call blocks until all ranks joined).
+ * fcvm_set_shard: the caller supplies the collectives instead (any backend that can run them on device memory). */
+#define FCVM_COMM_ALLGATHER      0   /* buf_dev = world equal slices of n BYTES, slice `rank` filled; in place */
+#define FCVM_COMM_ALLREDUCE_MAX  1   /* buf_dev = n int64 values; element-wise MAX over the ranks, in place */
+typedef int (*fcvm_comm_fn)(void* user, int32_t op, void* buf_dev, int64_t n, void* stream);
+int fcvm_set_shard(fcvm_t* h, int32_t rank, int32_t world, fcvm_comm_fn fn, void* user);
+int fcvm_nccl_unique_id(uint8_t* id128);
+int fcvm_set_shard_nccl(fcvm_t* h, const uint8_t* id128, int32_t rank, int32_t world);
+/* collectives issued by this handle since create / reset: out4 = { all-gathers, bytes gathered (all slices),
+ * all-reduces, bytes reduced } */
+int fcvm_comm_stats(fcvm_t* h, int64_t* out4);
+
+/* Wall-clock split of the manager-level calls since create / reset, in milliseconds (the timers FCVM_PROFILE=1 prints):
+ * out[0] setInitViewpoints  [1] updateViewpoints  [2] evaluator batches (H2D + kernels + D2H + sync)  [3] ownership
+ * [4] uncovered-candidate generation  [5] host libm on flagged / all rays of the pose sums  [6] safety batches
+ * [7] device pose-sum pipeline (terms + patch + sum, incl. its copies)  [8] collectives (host-side wait included)
+ * [9] E1 kernels  [10] E2 kernels  [11] E3 kernels  [12] E4 kernels (device time, CUDA events) */
+#define FCVM_NTIMERS 13
+int fcvm_get_timers(fcvm_t* h, double* out13);
 
 /* --------------------------------------------------- pin-hole coverage evaluation -------
  * the brute-force loop that follows the viewpoint path in a real run -

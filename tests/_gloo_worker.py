@@ -22,12 +22,22 @@ def main():
     ex = fd.Exchange()
     assert ex.rank == rank and ex.world == world and not ex.on_device
 
+    from fc_planner_b200._lib import COMM_ALLGATHER, COMM_ALLREDUCE_MAX
     # 1. the callback on a host buffer: slice r must come from rank r
     B = 1000
     buf = np.zeros(world * B, np.uint8)
     buf[rank * B:(rank + 1) * B] = rank + 1
-    assert ex(None, buf.ctypes.data, B, None) == 0
+    assert ex(None, COMM_ALLGATHER, buf.ctypes.data, B, None) == 0
     assert all((buf[r * B:(r + 1) * B] == r + 1).all() for r in range(world))
+    assert ex(None, 7, buf.ctypes.data, B, None) == -1          # unknown op: refused, not raised
+    # attach() refuses a backend that cannot take the device pointers the library hands out
+    class _M:
+        def set_shard(self, *a): raise AssertionError("must not be reached")
+    try:
+        fd.attach(_M(), native=False)
+        raise SystemExit("attach(native=False) accepted gloo")
+    except RuntimeError as e:
+        assert "nccl" in str(e)
 
     # 2. sharded evaluator pass == unsharded pass (an odd batch size exercises the padding)
     pts, nrm, prims = scenes.make_plant(n_points=2500, scale=0.3, seed=2)
@@ -45,10 +55,35 @@ def main():
     if hi > lo:
         _, mine, _ = orc.evaluate(1, poses[lo:hi])
         rows[lo:hi] = mine
-    assert ex(None, rows.ctypes.data, per * W * 4, None) == 0
-    _, full, _ = orc.evaluate(1, poses)
+    assert ex(None, COMM_ALLGATHER, rows.ctypes.data, per * W * 4, None) == 0
+    ocnt, full, _ = orc.evaluate(1, poses)
     assert np.array_equal(rows[:n], full) and not rows[n:].any()
     assert full.any()
+
+    # 2b. the sharded ownership exchange: every rank reduces ITS rows to one key per point
+    # (contribute_voxel_num << 32 | ~position), one all-reduce MAX, and the winners must be exactly those of the
+    # reference's ordered rule (viewpoint_manager.cpp:500-528) run over all rows on one process.
+    P = len(pts)
+    bits = np.unpackbits(full.view(np.uint8), axis=1, bitorder="little")[:, :P].astype(bool)      # [n, P]
+    keys = np.zeros(P, np.int64)
+    for r in range(lo, hi):
+        if ocnt[r] > 0:
+            k = fd.ownership_key(ocnt[r], r)
+            keys[bits[r]] = np.maximum(keys[bits[r]], k)
+    assert ex(None, COMM_ALLREDUCE_MAX, keys.ctypes.data, P, None) == 0
+    owner = np.full(P, -1, np.int64); contrib = np.zeros(P, np.int64)
+    for r in range(n):                                     # the ordered rule, all rows, processing order = row order
+        if ocnt[r] <= 0:
+            continue
+        take = bits[r] & ((owner < 0) | (ocnt[r] > contrib))
+        owner[take] = r; contrib[take] = ocnt[r]
+    for j in range(P):
+        if keys[j] == 0:
+            assert owner[j] == -1
+        else:
+            c, pos = fd.decode_ownership_key(keys[j])
+            assert (c, pos) == (contrib[j], owner[j]), (j, c, pos, contrib[j], owner[j])
+    assert (keys > 0).any() and keys.max() < 2 ** 63
 
     # 3. timing / throughput reductions used by bench.py
     assert fd.max_over_ranks([float(rank), 5.0 - rank]) == [float(world - 1), 5.0]

@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def _declared_symbols():
     src = open(os.path.join(ROOT, "include", "fcvm.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(fcvm_[a-z0-9_]+)\s*\(", src)) - {"fcvm_allgather_fn"})
+    return sorted(set(re.findall(r"\b(fcvm_[a-z0-9_]+)\s*\(", src)) - {"fcvm_comm_fn"})
 
 
 def test_library_exports_every_declared_symbol():
@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, n), f"libfcvm.so does not export {n}"
         assert n in _lib.SYMBOLS, f"ctypes mirror lacks {n}"
     assert set(_lib.SYMBOLS) <= set(names)
-    assert lib.fcvm_abi_version() == 1
+    assert lib.fcvm_abi_version() == 2
 
 
 def test_params_struct_layout_matches_header():

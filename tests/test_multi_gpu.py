@@ -16,15 +16,16 @@ def _ngpu():
     return torch.cuda.device_count() if torch.cuda.is_available() else 0
 
 
+@pytest.mark.parametrize("comm", ["native", "torch"])
 @pytest.mark.parametrize("world", [2, 4, 8])
-def test_sharded_update_matches_oracle(world, oracle_mod):
+def test_sharded_update_matches_oracle(world, comm, oracle_mod):
     if _ngpu() < world:
         pytest.skip(f"needs {world} GPUs")
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
-           "--master-port", str(port), os.path.join(HERE, "_nccl_worker.py")]
+           "--master-port", str(port), os.path.join(HERE, "_nccl_worker.py"), comm]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-4000:]
     for k in range(world):
