@@ -144,33 +144,27 @@ def pruning_leg(args, device, with_cpu, world=1, rank=0):
     # the selected set - of a handle depends on its history, and the oracle below is a fresh handle too.
     vm = ViewpointManager(prm)
     if world > 1:
-        # viewpoints sharded over the ranks, grid + model replicated, one NCCL all-gather of the bitset
-        # rows per evaluator stage; every rank obtains the same result (fc-planner_b200/distributed.py)
+        # viewpoints sharded over the ranks, grid + model replicated; per stage an all-gather of the per-viewpoint results
+        # and one all-reduce MAX of the ownership keys (native NCCL inside the library); every rank obtains the same result
         from fc_planner_b200 import distributed as fd
-        ex = fd.attach(vm)
+        fd.attach(vm)
     first_s = run(vm)                         # includes every device allocation of the handle
     gi, gp, gx = vm.final_arrays()
     c = vm.counters()
     n_unc = int(len(vm.getUncoveredModelCloud()))
     gpu_s = min(run(vm), run(vm))
+    st = vm.comm_stats()
     if world > 1:
-        import hashlib
-        import torch
-        import torch.distributed as dist
         gpu_s, first_s = fd.max_over_ranks([gpu_s, first_s], device="cuda")     # wall time: max over ranks
-        # every rank must have selected the same set: compare a digest of (ids, poses, vox counts)
-        dig = int.from_bytes(hashlib.sha256(gi.tobytes() + gp.tobytes() + gx.tobytes()).digest()[:7], "little")
-        t = torch.tensor([dig], dtype=torch.int64, device="cuda")
-        lo, hi = t.clone(), t.clone()
-        dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
-        ranks_agree = bool(int(lo) == int(hi))
+        ranks_agree = ranks_agree_on(gi, gp, gx)
     out = {"workload": f"synthetic plant scale 0.5: P={len(pts)} points, {len(vps)} initial candidate viewpoints, 0.2 m grid, "
                        f"max_iter_num={prm.max_iter_num}; setInitViewpoints + updateViewpoints",
            "gpu_ms": 1e3 * gpu_s, "gpu_ms_first_call": 1e3 * first_s, "final_viewpoints": int(len(gi)), "uncovered_points": n_unc,
            "rays": int(c[1]), "kernel_launches": int(c[5]), "n_gpus": world,
            "scaling": "strong (one fixed problem sharded over the ranks; latency-bound at this size)"}
     if world > 1:
-        out.update({"ranks_agree": ranks_agree, "allgathers_per_run": ex.calls // 3, "allgather_mb_per_run": ex.bytes / 3 / 1e6})
+        out.update({"ranks_agree": ranks_agree, "allgathers_per_run": int(st[0]), "allgather_mb_per_run": st[1] / 1e6,
+                    "allreduces_per_run": int(st[2]), "allreduce_mb_per_run": st[3] / 1e6})
     if with_cpu and rank == 0:
         from oracle import oracle
         orc = oracle.Oracle(prm)
@@ -178,6 +172,113 @@ def pruning_leg(args, device, with_cpu, world=1, rank=0):
         oi, op, ox = orc.getUpdatedViewpoints()
         out.update({"cpu_ms": 1e3 * cpu_s, "cpu_cores": 1, "cpu_kind": "port", "speedup": cpu_s / gpu_s,
                     "selected_set_identical": bool(np.array_equal(gi, oi) and np.array_equal(gp, op) and np.array_equal(gx, ox))})
+    return out
+
+
+def ranks_agree_on(*arrays):
+    """Every rank must hold the same result: a digest of the arrays, MIN and MAX over the ranks compared."""
+    import hashlib
+    import torch
+    import torch.distributed as dist
+    dig = int.from_bytes(hashlib.sha256(b"".join(np.ascontiguousarray(a).tobytes() for a in arrays)).digest()[:7], "little")
+    t = torch.tensor([dig], dtype=torch.int64, device="cuda")
+    lo, hi = t.clone(), t.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    return bool(int(lo) == int(hi))
+
+
+def pruning_full_leg(args, device, world=1, rank=0):
+    """BASELINE.json configs[4] in full through the public call sequence: P = 10^6 surface points x 200 000 initial candidate
+    viewpoints on a 0.1 m grid, setInitViewpoints + updateViewpoints (hcplanner.cpp:709-716), STRONG scaling: the same
+    problem at every N, viewpoints sharded over the ranks.  Reported with the library's own phase split (fcvm_get_timers,
+    rank 0's view) and the bytes the collectives moved.  The CPU oracle would need days here; parity at this size is
+    covered by size-independent properties (tests/test_gpu_fullsize.py) and by `ranks_agree`."""
+    from fc_planner_b200 import launch_params, scenes
+    from fc_planner_b200.manager import ViewpointManager
+    pts, nrm, prims = scenes.make_plant(n_points=args.points, scale=args.scale, seed=0)
+    prm = launch_params("synthetic", seed=0, resolution=args.resolution, device=device, host_threads=max(1, host_cores() // max(1, world)))
+    vps = scenes.plant_viewpoints(pts, nrm, prims, args.full_views, prm.viewpoints_distance, seed=100)
+    vm = ViewpointManager(prm)
+    if world > 1:
+        import torch.distributed as dist
+        from fc_planner_b200 import distributed as fd
+        fd.attach(vm)
+    nd = pts.astype(np.float64)
+
+    def run():
+        vm.reset(); vm.setMapPointCloud(pts); vm.setModel(pts); vm.setNormals(nd, nrm)
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter(); vm.setInitViewpoints(vps); t1 = time.perf_counter()
+        rc = vm.updateViewpoints(); t2 = time.perf_counter()
+        assert rc == 0
+        return t1 - t0, t2 - t1
+
+    first = run()                                   # device allocations, page-locking, NCCL channel set-up
+    init_s, upd_s = run()
+    tm, st, c = vm.timers(), vm.comm_stats(), vm.counters()
+    gi, gp, gx = vm.final_arrays()
+    cov, con, cid = vm.cover_state()
+    vox = vm.vps_voxcount()
+    agree = True
+    if world > 1:
+        init_s, upd_s, f0, f1 = fd.max_over_ranks([init_s, upd_s, first[0], first[1]], device="cuda")
+        first = (f0, f1)
+        agree = ranks_agree_on(gi, gp, gx, cid)
+    out = {"workload": f"BASELINE configs[4]: synthetic plant seed 0, P={len(pts)} points x {len(vps)} initial candidate viewpoints, {args.resolution} m grid, "
+                       f"max_iter_num={prm.max_iter_num}; setInitViewpoints + updateViewpoints",
+           "n_gpus": world, "scaling": "strong", "seconds": init_s + upd_s, "setInitViewpoints_s": init_s, "updateViewpoints_s": upd_s,
+           "first_call_seconds": first[0] + first[1], "final_viewpoints": int(len(gi)), "uncovered_points": int((cid < 0).sum()),
+           "candidates_total": int(len(vm.vps_pose())), "rays_this_rank": int(c[1]), "cap_trips": int(c[4]), "kernel_launches_this_rank": int(c[5]),
+           "host_threads_per_rank": prm.host_threads, "ranks_agree": agree,
+           "owned_points_equal_sum_of_counts": bool(int(cov.sum()) == int(vox.sum())), "final_counts_positive": bool((gx > 0).all()),
+           "phase_ms_rank0": {k: round(v, 2) for k, v in tm.items()},
+           "collectives": {"allgathers": int(st[0]), "allgather_mb": st[1] / 1e6, "allreduces": int(st[2]), "allreduce_mb": st[3] / 1e6}}
+    vm.close()
+    return out
+
+
+def golden_sharded_leg(device, world=1, rank=0):
+    """BASELINE.json configs[2] (Christ the Redeemer) and configs[3] (the Pacifico substitute: pipe with 4x the candidate
+    density) through the manager sharded over this run's ranks, against the committed fixtures of the CPU oracle
+    (tests/golden/*.npz, themselves checked against the reference's own viewpoint_manager.cpp compiled here)."""
+    from fc_planner_b200 import launch_params
+    from fc_planner_b200.manager import ViewpointManager
+    out = {}
+    for scene in ("christ", "pipe4x"):
+        try:
+            z = np.load(os.path.join(ROOT, "tests", "golden", f"{scene}.npz"))
+        except Exception as e:
+            out[scene] = {"unavailable": f"fixture not found: {e}"}
+            continue
+        prm = launch_params({"pipe4x": "pipe"}.get(scene, scene), seed=int(z["seed"]), device=device)
+        vm = ViewpointManager(prm)
+        if world > 1:
+            from fc_planner_b200 import distributed as fd
+            fd.attach(vm)
+
+        def run():
+            vm.reset(); vm.setMapPointCloud(z["map_cloud"]); vm.setModel(z["model"]); vm.setNormals(z["model"].astype(np.float64), z["normals"])
+            t = time.perf_counter(); rc = vm.updateViewpoints(); dt = time.perf_counter() - t
+            assert rc == 0
+            return dt
+        first = run()
+        ids, pose, vox = vm.final_arrays()
+        cov, con, cid = vm.cover_state()
+        ok = bool(np.array_equal(ids, z["final_ids"]) and np.array_equal(pose, z["final_pose"]) and np.array_equal(vox, z["final_vox"])
+                  and np.array_equal(vm.vps_pose(), z["vps_pose"]) and np.array_equal(cid, z["contrib_id"]) and np.array_equal(con, z["cover_contrib"])
+                  and np.array_equal(vm.getUncoveredModelCloud(), z["uncovered"]))
+        warm = min(run(), run())
+        if world > 1:
+            import torch
+            import torch.distributed as dist
+            t = torch.tensor([1 if ok else 0], dtype=torch.int64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            ok = bool(int(t))
+            warm, first = fd.max_over_ranks([warm, first], device="cuda")
+        out[scene] = {"matches_golden": ok, "n_gpus": world, "P": int(len(z["model"])), "candidates": int(len(z["vps_pose"])), "final_viewpoints": int(len(ids)),
+                      "updateViewpoints_ms": 1e3 * warm, "first_call_ms": 1e3 * first}
+        vm.close()
     return out
 
 
@@ -344,6 +445,9 @@ def main():
     ap.add_argument("--prune-points", type=int, default=40_000)
     ap.add_argument("--prune-views", type=int, default=4_000)
     ap.add_argument("--no-prune", action="store_true")
+    ap.add_argument("--full-views", type=int, default=200_000, help="initial candidate viewpoints of the pruning_full leg (configs[4]: 200 000 in total)")
+    ap.add_argument("--no-full", action="store_true")
+    ap.add_argument("--no-golden", action="store_true")
     ap.add_argument("--no-cov", action="store_true")
     ap.add_argument("--no-plan", action="store_true")
     ap.add_argument("--los-points", type=int, default=2048)
@@ -453,7 +557,9 @@ def main():
         dev_ms_max, e2e_ms_max, rays_total = dev_ms, e2e_s * 1e3, float(rays_step)
 
     # second metric (collective when world > 1: every rank takes part)
-    prune = None if args.no_prune else pruning_leg(args, local_rank, with_cpu=not args.no_cpu and world == 1, world=world, rank=rank)
+    prune = None if args.no_prune else pruning_leg(args, local_rank, with_cpu=not args.no_cpu, world=world, rank=rank)
+    prune_full = None if args.no_full else pruning_full_leg(args, local_rank, world=world, rank=rank)
+    golden = None if args.no_golden else golden_sharded_leg(local_rank, world=world, rank=rank)
 
     if rank == 0:
         P, V = len(pts), len(poses)
@@ -506,6 +612,8 @@ def main():
             rate1, n1, dt1, _, _ = cpu_oracle_rate(pts, nrm, prm, poses[:max(8, n // max(threads, 1))], args.cpu_seconds / 3, 1, args.stage)
             line["cpu_baseline"]["single_thread_value"] = rate1
         line["pruning"] = prune
+        line["pruning_full"] = prune_full
+        line["golden_sharded"] = golden
         if not args.no_cov:
             line["coverage_evaluation"] = coverage_leg(args, local_rank, with_cpu=not args.no_cpu and world == 1)
         if not args.no_plan:

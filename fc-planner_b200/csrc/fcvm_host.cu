@@ -1183,32 +1183,60 @@ static int viewpoints_prune(fcvm_handle* h, const std::vector<Pose5>& vps_pose, 
   }
 
   pmark("nearCheck batch done");
+  // Tables that stand in for the reference's per-neighbour map look-ups inside the chain (cpp:733-745): the slot of an id,
+  // the ctrl-voxel count of a slot, and - because inverse_idx_ is keyed by the float position, so coincident candidates
+  // collapse to the LAST inserted id - the slot the reference actually reaches from cloud point s.
+  // The radius searches (cpp:685) read only the original float cloud, so they are independent of the chain's state and run
+  // up front on all host threads, for exactly the candidates that can reach them (count > 1 and nearCheck passed).
+  const int nslot = (int)slot_id.size();
+  const int id0 = h->last_vps_num;
+  std::vector<int> slot_of_id(vps_pose.size() - (size_t)id0, -1), slot_vox((size_t)nslot), canon((size_t)nslot);
+  for (int sl = 0; sl < nslot; ++sl) { slot_of_id[(size_t)(slot_id[(size_t)sl] - id0)] = sl; slot_vox[(size_t)sl] = sub_voxcount[(size_t)slot_id[(size_t)sl]]; }
+  constexpr int kBlock = 512;
+  const int nblk = (nslot + kBlock - 1) / kBlock;
+  std::vector<std::vector<int>> arena((size_t)nblk);
+  std::vector<int64_t> nb_off((size_t)nslot, 0);
+  std::vector<int> nb_cnt((size_t)nslot, -1);
+  if (!h->pool) h->pool.reset(new WorkerPool(h->threads));
+  h->pool->run(nblk, 1, [&](int64_t bk) {
+    std::vector<int> found;
+    std::vector<int>& ar = arena[(size_t)bk];
+    for (int sl = (int)bk * kBlock; sl < std::min(nslot, ((int)bk + 1) * kBlock); ++sl) {
+      const float* q = &vp_cloud[3 * (size_t)sl];
+      canon[(size_t)sl] = slot_of_id[(size_t)(inverse_idx.find(D3{q[0], q[1], q[2]})->second - id0)];
+      if (!(slot_vox[(size_t)sl] > 1 && near_ok[(size_t)sl])) continue;
+      vps_tree.radius_search(q, bubble_radius, found);
+      nb_off[(size_t)sl] = (int64_t)ar.size();
+      nb_cnt[(size_t)sl] = (int)found.size();
+      ar.insert(ar.end(), found.begin(), found.end());
+    }
+  });
+  pmark("neighbour lists ready");
+
   struct Grav { int slot; D3 up; double upi, uy; };
   std::vector<Grav> grav;
-  std::vector<int> neigh;
   struct Pulled { int slot; D3 up; D3 cur; };
   std::vector<Pulled> pulled;                 // positions whose viewpointSafetyCheck (cpp:805-810) is resolved after the chain
+  std::vector<int> updated;                   // slots absorbed by the current candidate
   for (const auto& pr : ctrlVector) {
     const int c = pr.first;
-    const int cs = idx_slot.find(c)->second;
+    const int cs = slot_of_id[(size_t)(c - id0)];
     const Pose5 cur_pose = slot_pose[(size_t)cs];
     const D3 cur_position{cur_pose.v[0], cur_pose.v[1], cur_pose.v[2]};
-    const int cur_vox = idx_ctrl_voxels.find(c)->second;
+    const int cur_vox = slot_vox[(size_t)cs];
     if (!(cur_vox > 1 && near_ok[(size_t)cs])) { live[(size_t)cs] = 0; continue; }     // nearCheck(cur_position, cur_vox)
-    const float q[3] = {(float)cur_pose.v[0], (float)cur_pose.v[1], (float)cur_pose.v[2]};
-    vps_tree.radius_search(q, bubble_radius, neigh);
-    if (!(live[(size_t)cs] && (int)neigh.size() > 1)) continue;
+    const int* neigh = arena[(size_t)(cs / kBlock)].data() + nb_off[(size_t)cs];      // radiusSearch result, (distance, index)-sorted
+    const int n_neigh = nb_cnt[(size_t)cs];
+    if (!(live[(size_t)cs] && n_neigh > 1)) continue;
 
     // ---- updatePoseGravitation, host part (cpp:714-810) -----------------------------------
     query[(size_t)cs] = 1;
     const double cur_pitch = cur_pose.v[3], cur_yaw = cur_pose.v[4];
-    std::vector<int> updated;   // slots
-    for (int id_ : neigh) {
-      const D3 key{vp_cloud[3 * (size_t)id_], vp_cloud[3 * (size_t)id_ + 1], vp_cloud[3 * (size_t)id_ + 2]};
-      const int index_finder = inverse_idx.find(key)->second;
-      const int ms = idx_slot.find(index_finder)->second;
+    updated.clear();
+    for (int e = 0; e < n_neigh; ++e) {
+      const int ms = canon[(size_t)neigh[e]];
       const Pose5& inner_pose = slot_pose[(size_t)ms];
-      const int inner_vox = idx_ctrl_voxels.find(index_finder)->second;
+      const int inner_vox = slot_vox[(size_t)ms];
       if (inner_vox > cur_vox) continue;
       double diff_yaw = std::fabs(cur_pose.v[4] - inner_pose.v[4]);
       warp_angle(diff_yaw);
@@ -1223,7 +1251,7 @@ static int viewpoints_prune(fcvm_handle* h, const std::vector<Pose5>& vps_pose, 
     D3 up = cur_position;
     double upi = cur_pitch, uy = cur_yaw;
     for (int ms : updated) {
-      const double grav_factor = (double)idx_ctrl_voxels.find(slot_id[(size_t)ms])->second / (double)cur_vox;
+      const double grav_factor = (double)slot_vox[(size_t)ms] / (double)cur_vox;
       const Pose5& o = slot_pose[(size_t)ms];
       const D3 pull{grav_factor * (o.v[0] - cur_position.x), grav_factor * (o.v[1] - cur_position.y), grav_factor * (o.v[2] - cur_position.z)};
       up = D3{up.x + pull.x, up.y + pull.y, up.z + pull.z};
