@@ -106,15 +106,28 @@ def host_cores():
         return os.cpu_count() or 1
 
 
-def cpu_oracle_rate(pts, nrm, prm, poses, seconds, threads, stage=1):
-    """Time the CPU oracle's E1 pass on a bounded prefix of the batch.  Returns (rays/s, sample, counters)."""
+def cpu_evaluator(prm, pts, kind):
+    """kind 'reference': the reference's own RayCaster / PerceptionUtils (raycast.cpp, perception_utils.cpp compiled from
+    /root/reference into oracle/_ref, driven by viewpoint_manager.cpp's loops); 'port': the oracle's restatement."""
     from oracle import oracle
-    orc = oracle.Oracle(prm)
+    orc = oracle.RefEvaluator(prm) if kind == "reference" else oracle.Oracle(prm)
     orc.setMapPointCloud(pts); orc.setModel(pts)
+    return orc
+
+
+def cpu_kind():
+    from oracle import oracle
+    return "reference" if oracle.ref_available() else "port"
+
+
+def cpu_oracle_rate(pts, nrm, prm, poses, seconds, threads, stage=1, kind="port", orc=None):
+    """Time the CPU implementation's evaluator pass on a bounded prefix of the batch.  Returns (rays/s, sample, s, counters, counts)."""
+    orc = orc or cpu_evaluator(prm, pts, kind)
     n0 = min(len(poses), max(threads, 4))
     t = time.perf_counter(); _, _, c = orc.evaluate(stage, poses[:n0], threads=threads); dt = time.perf_counter() - t
     n = int(min(len(poses), max(n0, n0 * seconds / max(dt, 1e-3))))
     t = time.perf_counter(); cnt, rows, c = orc.evaluate(stage, poses[:n], threads=threads); dt = time.perf_counter() - t
+    del rows
     return c[1] / dt, n, dt, c, cnt
 
 
@@ -396,15 +409,17 @@ def planner_grid_leg(args, device, with_cpu):
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the reference's CPU implementation of the path (oracle port; the reference itself
-    needs ROS/PCL/Eigen and cannot be built here) on the host cores, same metric and config."""
+    """--impl reference: the reference's CPU implementation of the path on all host cores, same metric and config.
+    The reference's own raycast.cpp + perception_utils.cpp, compiled from /root/reference into oracle/_ref and driven by the
+    loops of viewpoint_manager.cpp:358-425 ('kind': 'reference'), when that library travelled with the repo; the oracle's
+    restatement ('port') otherwise.  The reference is single-threaded on this path; here its viewpoints are handed out to
+    every host thread."""
     if rank != 0:
         return
     pts, nrm, prm, poses = build_scene(args, 0)
-    from oracle import oracle
     threads = host_cores()
-    orc = oracle.Oracle(prm)
-    orc.setMapPointCloud(pts); orc.setModel(pts)
+    kind = cpu_kind()
+    orc = cpu_evaluator(prm, pts, kind)
     # size one step so that warmup + steps end within a few minutes
     n0 = max(threads, 4)
     t = time.perf_counter(); orc.evaluate(args.stage, poses[:n0], threads=threads); dt0 = time.perf_counter() - t
@@ -422,7 +437,7 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic", "config": {"workload": workload_name(args), "l2": "n/a (CPU)"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind,
                          "sample": f"first {n} of {len(poses)} viewpoints x all {len(pts)} points per step"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -448,6 +463,7 @@ def main():
     ap.add_argument("--full-views", type=int, default=200_000, help="initial candidate viewpoints of the pruning_full leg (configs[4]: 200 000 in total)")
     ap.add_argument("--no-full", action="store_true")
     ap.add_argument("--no-golden", action="store_true")
+    ap.add_argument("--no-stages", action="store_true", help="skip the E2 / E3 / E4 kernel timings")
     ap.add_argument("--no-cov", action="store_true")
     ap.add_argument("--no-plan", action="store_true")
     ap.add_argument("--los-points", type=int, default=2048)
@@ -514,6 +530,19 @@ def main():
     c1 = vm.counters()
     lookups_step = int(c1[2] - c0[2])        # only the synchronising launch accumulates counters
     pairs_step = int(c1[0] - c0[0])
+    # the other three evaluators on the same resident batch, kernel alone (E2 re-tests the E1 sets): what updateViewpoints spends
+    # its kernel time in besides E1
+    other_stages = {}
+    if args.stage == 1 and not args.no_stages:
+        for st in (2, 3, 4):
+            if st == 2:
+                vm.evaluate_resident(1, stream=stream, sync=True)
+            vm.evaluate_resident(st, stream=stream, sync=True)            # warm
+            ca = vm.counters()
+            r = vm.evaluate_resident(st, stream=stream, sync=True)
+            cb = vm.counters() - ca
+            other_stages[f"E{st}"] = {"kernel_ms": vm.last_kernel_ms(), "rays": int(r), "voxel_lookups": int(cb[2]), "pair_tests": int(cb[0])}
+        vm.evaluate_resident(1, stream=stream, sync=True)
 
     # ---------------- e2e: host buffers through the C ABI ---------------------------------------
     # poses come from, and results go to, page-locked host memory (fcvm_host_alloc); every step does the host pose ->
@@ -598,19 +627,29 @@ def main():
             "gpu_launches": 2 * args.steps,
             "rays_per_step_per_gpu": rays_step, "pair_tests_per_step_per_gpu": pairs_step, "voxel_lookups_per_step_per_gpu": lookups_step,
             "viewpoint_evals_per_s": V * world * args.steps / (dev_ms_max * 1e-3),
+            "other_evaluators_rank0": other_stages,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "kernel": f"k_eval<E{args.stage}>", "kernel_ms": kernel_ms, "algorithmic_bytes": b_alg, "peak_source": peak_src},
         }
         if not args.no_cpu and world == 1:      # the CPU baseline is timed on rank 0 at N = 1 only
             threads = host_cores()
-            rate, n, dt, c, ocnt = cpu_oracle_rate(pts, nrm, prm, poses, args.cpu_seconds, threads, args.stage)
-            # the kernel's lookup / ray counters must equal the oracle's on the same viewpoints
+            kind = cpu_kind()
+            orc = cpu_evaluator(prm, pts, kind)
+            rate, n, dt, c, ocnt = cpu_oracle_rate(pts, nrm, prm, poses, args.cpu_seconds, threads, args.stage, kind, orc)
+            # the kernel's per-viewpoint visible counts and its ray / look-up counters must equal the CPU implementation's
+            g0 = vm.counters()
             vm2_cnt, _ = vm.evaluate(args.stage, poses[:n], want_rows=False)
-            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+            g1 = vm.counters() - g0
+            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": kind,
                                     "sample": f"first {n} of {V} viewpoints x all {P} points, {dt:.1f} s, {threads} threads",
-                                    "counts_match_gpu": bool(np.array_equal(vm2_cnt, ocnt))}   # per-viewpoint visible counts, GPU vs oracle
-            rate1, n1, dt1, _, _ = cpu_oracle_rate(pts, nrm, prm, poses[:max(8, n // max(threads, 1))], args.cpu_seconds / 3, 1, args.stage)
+                                    "counts_match_gpu": bool(np.array_equal(vm2_cnt, ocnt)),
+                                    "rays_and_lookups_match_gpu": bool(int(g1[1]) == int(c[1]) and int(g1[2]) == int(c[2]))}
+            rate1, n1, dt1, _, _ = cpu_oracle_rate(pts, nrm, prm, poses[:max(8, n // max(threads, 1))], args.cpu_seconds / 3, 1, args.stage, kind, orc)
             line["cpu_baseline"]["single_thread_value"] = rate1
+            del orc
+            if kind == "reference":      # the oracle's restatement beside the reference's own code, same sample size
+                ratep, npp, dtp, _, _ = cpu_oracle_rate(pts, nrm, prm, poses[:n], args.cpu_seconds / 2, threads, args.stage, "port")
+                line["cpu_baseline"]["port_value"] = ratep
         line["pruning"] = prune
         line["pruning_full"] = prune_full
         line["golden_sharded"] = golden

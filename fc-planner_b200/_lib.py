@@ -72,6 +72,11 @@ SYMBOLS = {
     "fcvm_grid_light_state": (ctypes.c_int, [vp, f64p, i64, f32p, i64, u8p, i32p, i32p]),
     "fcvm_grid_safety_box": (ctypes.c_int, [vp, f32p, i64, f64, u8p]),
     "fcvm_grid_line_of_sight": (ctypes.c_int, [vp, f64p, i64, u8p, f64p]),
+    "fcvm_grid_set_occ": (ctypes.c_int, [vp, f32p, i64]),
+    "fcvm_grid_internal_space": (ctypes.c_int, [vp, f32p, i64p, i64, f64p, i32, f64, f64]),
+    "fcvm_grid_outer_check": (ctypes.c_int, [vp, f64p, i64, f64]),
+    "fcvm_grid_get_buffers": (ctypes.c_int, [vp, i8p, i8p, i8p]),
+    "fcvm_grid_oob_writes": (i64, [vp]),
     "fcvm_grid_counters": (ctypes.c_int, [vp, i64p]),
     "fcvm_grid_last_kernel_ms": (f64, [vp]),
     "fcvm_cov_create": (vp, [ctypes.POINTER(Params), ctypes.POINTER(Camera)]),

@@ -33,6 +33,11 @@ struct GridDesc {
   int nly, nlz;                      // lines per axis in y and z: nby / 2, nbz / 4
   int nbricks;                       // nbx * nby * nbz (< 2^31: the reference addresses voxels with int)
   int guard_steps;                   // fast-path half-rays make at most this many steps; the allocation has guard words for them
+  // summed-area table over 8 x 8 x 8-voxel cells (2 x 2 x 2 bricks): sat[(x * sat_ny + y) * sat_nz + z] = number of
+  // non-empty cells with coordinates < (x, y, z).  Eight loads tell whether a box of voxels is entirely free; k_eval uses
+  // it to certify the viewpoint-side half-ray, which then needs no marching (nullptr = feature off).
+  const int* sat;
+  int sat_ny, sat_nz;                // (nby / 2 + 1), (nbz / 2 + 1)
   double res;                        // resolution_
   double offx, offy, offz;           // RayCaster::offset_ = 0.5 - origin/res   (raycast.cpp:344)
   double orgx, orgy, orgz;           // map_origin_
@@ -70,6 +75,15 @@ __host__ __device__ __forceinline__ long long brick_guard_words(int steps, int n
 }
 __host__ __device__ __forceinline__ int brick_bit_index(int x, int y, int z) {
   return ((x & 3) << 4) | ((y & 3) << 2) | (z & 3);
+}
+
+// number of non-empty 8^3-voxel cells in the inclusive cell box [lo, hi] (coordinates already >> 3)
+__device__ __forceinline__ int sat_box_count(const GridDesc& g, int x0, int y0, int z0, int x1, int y1, int z1) {
+  const int* s = g.sat;
+  const long long ny = g.sat_ny, nz = g.sat_nz;
+  x1 += 1; y1 += 1; z1 += 1;
+  auto at = [&](int x, int y, int z) { return __ldg(s + ((long long)x * ny + y) * nz + z); };
+  return ((at(x1, y1, z1) - at(x0, y1, z1)) - (at(x1, y0, z1) - at(x0, y0, z1))) - ((at(x1, y1, z0) - at(x0, y1, z0)) - (at(x1, y0, z0) - at(x0, y0, z0)));
 }
 
 // One-entry register cache of the last brick a ray touched.

@@ -106,6 +106,8 @@ struct fcvm_handle {
   // map
   HostGrid grid;                               // geometry; the bricks live on the device (downloaded on demand for the parity tap)
   DevBuf<unsigned long long> d_bricks;          // [guard | bricks | guard]; the guard words read 'occupied' (see occ_fast)
+  DevBuf<int> d_sat;                            // summed-area table over 8^3-voxel cells (GridDesc::sat)
+  bool use_sat = true;                          // FCVM_NO_PFREE=1 switches the half-ray certificate off (A/B)
   size_t brick_guard = 0;                       // guard words on each side
   int guard_steps = 0;                          // longest half-ray (voxel steps) the fast path accepts
   // map cloud on the device + its uniform cell index (nearCheck), built by fcvm_map.cu
@@ -159,6 +161,7 @@ struct fcvm_handle {
   PinBuf<VpRec> h_recs;
   int64_t resident_n = 0;
   int64_t resident_W = 0;
+  bool resident_e1 = false;                    // the first rows buffer holds the E1 rows of the resident batch
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;          // D2H of finished sub-batches while the next one is evaluated
   cudaStream_t aux_stream = nullptr;           // pose-sum pipeline of a finished E1 sub-batch while the next one is evaluated (high priority)
@@ -253,6 +256,8 @@ static void fill_grid_desc(const fcvm_handle* h, GridDesc& g) {
   const HostGrid& hg = h->grid;
   g.bricks = h->d_bricks.p + h->brick_guard;
   g.guard_steps = h->guard_steps;
+  g.sat = h->use_sat ? h->d_sat.p : nullptr;
+  g.sat_ny = hg.ns[1] / 2 + 1; g.sat_nz = hg.ns[2] / 2 + 1;
   g.nx = hg.dims[0]; g.ny = hg.dims[1]; g.nz = hg.dims[2];
   g.nbx = hg.ns[0]; g.nby = hg.ns[1]; g.nbz = hg.ns[2];
   g.nly = hg.ns[1] >> 1; g.nlz = hg.ns[2] >> 2;
@@ -319,6 +324,11 @@ static int launch_stage(fcvm_handle* h, int stage, const VpRec* d_recs, int64_t 
   h->counters[5] += 1;
   h->counters[6] += n;
   return FCVM_OK;
+}
+
+static int safety_batch(fcvm_handle* h, const float* xyz, int64_t n, int mode, std::vector<uint8_t>& ok);
+static inline int safety_batch(fcvm_handle* h, const std::vector<float>& xyz, int mode, std::vector<uint8_t>& ok) {
+  return safety_batch(h, xyz.data(), (int64_t)xyz.size() / 3, mode, ok);
 }
 
 static int fetch_counters(fcvm_handle* h) {
@@ -542,22 +552,32 @@ static int eval_batch(fcvm_handle* h, int stage, const VpRec* recs, int64_t n, c
   }
   if (rows_out && !rows_streamed) CU(cudaMemcpyAsync(rows_out, d_rows.p, (size_t)n * W * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
   if (count_out) CU(cudaMemcpyAsync(count_out, h->d_count.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  auto vmark = [&](const char* what) {
+    if (env().profile >= 3)
+      std::fprintf(stderr, "[fcvm]     E%d n=%lld: %s at %.2f ms\n", stage, (long long)n, what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - verbose.t0).count());
+  };
+  vmark("queued");
   rc = fetch_counters(h);   // synchronises the stream
   if (rc) return rc;
+  vmark("kernels done");
   if (rows_streamed) CU(cudaStreamSynchronize(h->copy_stream));
   if (csr) {
     csr->offs.assign(h->h_offsets.p, h->h_offsets.p + c_n + 1);
     const long long total = csr->offs[(size_t)c_n];
     CU(h->d_indices.reserve((size_t)std::max<long long>(total, 1)));
+    vmark("device index buffer ready");
     CU(h->h_indices.reserve((size_t)std::max<long long>(total, 1)));
+    vmark("host index buffer ready");
     if (total > 0) {
       CU(launch_compact_rows(d_rows.p + c_lo * W, c_n, W, h->d_offsets.p, h->d_indices.p, h->stream));
       h->counters[5] += 1;
       CU(cudaMemcpyAsync(h->h_indices.p, h->d_indices.p, (size_t)total * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
       CU(cudaStreamSynchronize(h->stream));
     }
+    vmark("index lists on the host");
     csr->idx = h->h_indices.p;
     h->h_indices.note_use();
+    vmark("note_use");
   }
   if (h->timed) {
     float ms = 0.f;
@@ -700,9 +720,8 @@ static void for_each_bit(const uint32_t* row, int64_t words, F&& f) {
 // Both run on the device for whole batches of candidate positions (k_safety, fcvm_map.cu): mode 0 = viewpointSafetyCheck
 // (ground test, lattice of safety_check probes with the reference's early exit, nearCheck with vox_num = 2), mode 1 =
 // nearCheck alone.  counters[7] advances by the number of safety_check probes the reference would have made.
-static int safety_batch(fcvm_handle* h, const std::vector<float>& xyz, int mode, std::vector<uint8_t>& ok) {
+static int safety_batch(fcvm_handle* h, const float* xyz, int64_t n, int mode, std::vector<uint8_t>& ok) {
   Stopwatch sw_safety(h->t_safety);
-  const int64_t n = (int64_t)xyz.size() / 3;
   ok.assign((size_t)n, 0);
   if (n == 0) return FCVM_OK;
   const fcvm_params& p = h->prm;
@@ -710,7 +729,7 @@ static int safety_batch(fcvm_handle* h, const std::vector<float>& xyz, int mode,
   CU(h->d_ok.reserve((size_t)n));
   CU(h->d_looks.reserve(1));
   cudaStream_t s = h->stream;
-  CU(cudaMemcpyAsync(h->d_cand.p, xyz.data(), (size_t)3 * n * sizeof(float), cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync(h->d_cand.p, xyz, (size_t)3 * n * sizeof(float), cudaMemcpyHostToDevice, s));
   CU(cudaMemsetAsync(h->d_looks.p, 0, sizeof(unsigned long long), s));
   SafetyArgs a;
   for (int c = 0; c < 3; ++c) { a.geom.org[c] = h->grid.origin[c]; a.geom.dims[c] = h->grid.dims[c]; a.geom.nb[c] = h->grid.ns[c]; }
@@ -750,21 +769,26 @@ static void shard_of(const fcvm_handle* h, int64_t n, int64_t& lo, int64_t& hi) 
   lo = std::min(n, per * h->rank);
   hi = std::min(n, per * (h->rank + 1));
 }
-static int gather_doubles(fcvm_handle* h, double* vals, int64_t n, int k) {
+// vals = n records of `bytes` each, of which this rank has filled its own block [lo, hi); on return every rank has all
+static int gather_records(fcvm_handle* h, void* vals, int64_t n, int64_t bytes) {
   if (h->world <= 1 || n == 0) return FCVM_OK;
   const int64_t per = (n + h->world - 1) / h->world, n_pad = per * h->world;
   int64_t lo, hi;
   shard_of(h, n, lo, hi);
-  CU(h->d_gather.reserve((size_t)n_pad * k));
-  if (hi > lo) CU(cudaMemcpyAsync(h->d_gather.p + lo * k, vals + lo * k, (size_t)(hi - lo) * k * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  const size_t words = (size_t)((n_pad * bytes + 7) / 8);
+  CU(h->d_gather.reserve(words));
+  char* dev = reinterpret_cast<char*>(h->d_gather.p);
+  char* host = static_cast<char*>(vals);
+  if (hi > lo) CU(cudaMemcpyAsync(dev + lo * bytes, host + lo * bytes, (size_t)((hi - lo) * bytes), cudaMemcpyHostToDevice, h->stream));
   {
-    int rc = do_comm(h, FCVM_COMM_ALLGATHER, h->d_gather.p, per * k * (int64_t)sizeof(double));
+    int rc = do_comm(h, FCVM_COMM_ALLGATHER, dev, per * bytes);
     if (rc) return rc;
   }
-  CU(cudaMemcpyAsync(vals, h->d_gather.p, (size_t)n * k * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaMemcpyAsync(host, dev, (size_t)(n * bytes), cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
   return FCVM_OK;
 }
+static int gather_doubles(fcvm_handle* h, double* vals, int64_t n, int k) { return gather_records(h, vals, n, (int64_t)k * (int64_t)sizeof(double)); }
 
 // ------------------------------------------------------------------------------------------------
 // getPose over a batch (viewpoint_manager.cpp:332-531).  ids[i] = viewpoint id of candidate i.
@@ -1408,14 +1432,15 @@ static void unc_neigh_vps(const fcvm_handle* h, const float pt[3], const float n
   }
 }
 
-// stand-in for pcl::RandomSample (cpp:249-255): selection sampling driven by minstd_rand0(seed + phi + call#)
-static std::vector<PtNormal> random_sample(fcvm_handle* h, const std::vector<PtNormal>& in, int sample) {
+// stand-in for pcl::RandomSample (cpp:249-255): selection sampling driven by minstd_rand0(seed + phi + call#).
+// Returns the (ascending) positions chosen out of a pool of `pool_size` elements; the pool itself need not exist.
+static std::vector<size_t> random_sample_positions(fcvm_handle* h, size_t pool_size, int sample) {
   std::minstd_rand0 g((std::minstd_rand0::result_type)(h->prm.seed + 0x9e3779b9ull + (uint64_t)h->sample_calls++));
-  std::vector<PtNormal> out;
-  size_t N = in.size(), n = (size_t)sample, index = 0;
-  while (n > 0 && index < in.size()) {
+  std::vector<size_t> out;
+  size_t N = pool_size, n = (size_t)sample, index = 0;
+  while (n > 0 && index < pool_size) {
     const float U = (float)((double)g() / 2147483646.0);
-    if ((float)N * U <= (float)n) { out.push_back(in[index]); --n; }
+    if ((float)N * U <= (float)n) { out.push_back(index); --n; }
     ++index; --N;
   }
   return out;
@@ -1498,10 +1523,15 @@ static int update_impl(fcvm_handle* h) {
   rc = uncovered(uncoveredID);
   if (rc) return rc;
 
-  // cpp:206-221: candidate library for the uncovered points
-  // The points are independent (candidate q of the c-th call draws from engines seeded seed + 8c + k), so
-  // the library is built by all host threads; slot k belongs to uncoveredID[k] of this first list.
-  std::vector<std::vector<PtNormal>> uncVpsLib(uncoveredID.size());
+  // cpp:206-221: candidate library for the uncovered points.
+  // The points are independent (candidate q of the c-th call draws from engines seeded seed + 8c + k): the library is one
+  // flat array of 8 candidates + 8 safety verdicts per uncovered point, built by all host threads (RNG + libm) and one
+  // k_safety launch; a sharded run builds only its block of the points and all-gathers the records (200 B per point).
+  struct LibRec { PtNormal c[8]; uint8_t safe[8]; };
+  static_assert(sizeof(LibRec) == 200, "LibRec is exchanged between ranks as raw bytes");
+  const int64_t n_lib = (int64_t)uncoveredID.size();
+  const int64_t lib_per = (n_lib + h->world - 1) / h->world;
+  std::unique_ptr<LibRec[]> lib(new LibRec[(size_t)std::max<int64_t>(1, lib_per * h->world)]);     // not value-initialised: 60 MB at 300 000 points
   std::vector<int> lib_slot((size_t)h->P, -1);
   {
     Stopwatch sw_unc(h->t_unc);
@@ -1509,42 +1539,62 @@ static int update_impl(fcvm_handle* h) {
     const auto t_unc0 = std::chrono::steady_clock::now();
     auto tmark = [&](const char* what) { if (vprof) std::fprintf(stderr, "[fcvm]     unc: %s at %.2f ms\n", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_unc0).count()); };
     tmark("start");
-    const int64_t n_unc = (int64_t)uncoveredID.size(), call0 = h->unc_calls;
-    h->unc_calls += n_unc;
-    for (int64_t k = 0; k < n_unc; ++k) lib_slot[(size_t)uncoveredID[(size_t)k]] = (int)k;
-    std::vector<PtNormal> cand8((size_t)8 * n_unc);
-    std::vector<float> q((size_t)24 * n_unc);
+    const int64_t call0 = h->unc_calls;
+    h->unc_calls += n_lib;
+    for (int64_t k = 0; k < n_lib; ++k) lib_slot[(size_t)uncoveredID[(size_t)k]] = (int)k;
+    int64_t lo = 0, hi = n_lib;
+    if (h->world > 1) shard_of(h, n_lib, lo, hi);
+    std::unique_ptr<float[]> q(new float[(size_t)std::max<int64_t>(1, 24 * (hi - lo))]);
+    if (!h->pool) h->pool.reset(new WorkerPool(h->threads));
     tmark("buffers ready");
-    parallel_for(n_unc, h->threads, [&](int64_t k) {
+    h->pool->run(hi - lo, 64, [&](int64_t r) {
+      const int64_t k = lo + r;
       const int p = uncoveredID[(size_t)k];
       auto it = h->pt_normal_pairs.find(D3{M[3 * p], M[3 * p + 1], M[3 * p + 2]});
       const D3 nd = it == h->pt_normal_pairs.end() ? D3{0, 0, 1} : it->second;
       const float nrm[3] = {(float)nd.x, (float)nd.y, (float)nd.z};
-      unc_neigh_vps(h, &M[3 * p], nrm, &cand8[(size_t)8 * k], call0 + k);
-      uncVpsLib[(size_t)k].reserve(8);
-      for (int c = 0; c < 8; ++c) {
-        const PtNormal& u = cand8[(size_t)8 * k + c];
-        q[(size_t)24 * k + 3 * c] = u.x; q[(size_t)24 * k + 3 * c + 1] = u.y; q[(size_t)24 * k + 3 * c + 2] = u.z;
-      }
+      LibRec& rec = lib[(size_t)k];
+      unc_neigh_vps(h, &M[3 * p], nrm, rec.c, call0 + k);
+      for (int c = 0; c < 8; ++c) { q[(size_t)24 * r + 3 * c] = rec.c[c].x; q[(size_t)24 * r + 3 * c + 1] = rec.c[c].y; q[(size_t)24 * r + 3 * c + 2] = rec.c[c].z; }
     });
     tmark("candidates generated");
     std::vector<uint8_t> safe;
-    rc = safety_batch(h, q, 0, safe);
+    rc = safety_batch(h, q.get(), 8 * (hi - lo), 0, safe);
     if (rc) return rc;
     tmark("safety batch done");
-    for (int64_t k = 0; k < n_unc; ++k)
-      for (int c = 0; c < 8; ++c)
-        if (safe[(size_t)8 * k + c]) uncVpsLib[(size_t)k].push_back(cand8[(size_t)8 * k + c]);
-    tmark("library filled");
+    for (int64_t r = 0; r < hi - lo; ++r) std::memcpy(lib[(size_t)(lo + r)].safe, &safe[(size_t)8 * r], 8);
+    rc = gather_records(h, lib.get(), n_lib, (int64_t)sizeof(LibRec));
+    if (rc) return rc;
+    tmark("library complete");
   }
 
   int unc_iter = 0, last_unc_num = -1;
   while ((int)uncoveredID.size() > 0 && unc_iter < prm.max_iter_num && last_unc_num != (int)uncoveredID.size()) {
     last_unc_num = (int)uncoveredID.size();
+    // pool = the safe candidates of the still-uncovered points, in point order (cpp:240-247); at most 100 of them are drawn
+    // (cpp:249-255).  The pool is only counted and walked, never materialised.
     std::vector<PtNormal> cand;
-    for (int p : uncoveredID)
-      for (auto& u : uncVpsLib[(size_t)lib_slot[(size_t)p]]) cand.push_back(u);
-    if ((int)cand.size() > 100) cand = random_sample(h, cand, 100);
+    {
+      size_t pool_size = 0;
+      for (int p : uncoveredID) {
+        const uint8_t* sf = lib[(size_t)lib_slot[(size_t)p]].safe;
+        for (int c = 0; c < 8; ++c) pool_size += sf[c] ? 1 : 0;
+      }
+      std::vector<size_t> pick;
+      const bool all = pool_size <= 100;
+      if (!all) pick = random_sample_positions(h, pool_size, 100);
+      size_t pos = 0, next = 0;
+      for (int p : uncoveredID) {
+        if (!all && next >= pick.size()) break;
+        const LibRec& rec = lib[(size_t)lib_slot[(size_t)p]];
+        for (int c = 0; c < 8; ++c) {
+          if (!rec.safe[c]) continue;
+          if (all) cand.push_back(rec.c[c]);
+          else if (next < pick.size() && pick[next] == pos) { cand.push_back(rec.c[c]); ++next; }
+          ++pos;
+        }
+      }
+    }
 
     // snapshot of MCI (cpp:272-274)
     DevBuf<int> snap_contrib, snap_id;
@@ -1615,6 +1665,7 @@ fcvm_t* fcvm_create(const fcvm_params* p) {
   const EnvSettings e = env_now();
   h->host_sums = e.host_sums;
   h->own_sweep = e.own_sweep;
+  h->use_sat = !e.no_pfree;
   return h;
 }
 
@@ -1707,7 +1758,10 @@ int fcvm_set_map_cloud(fcvm_t* h, const float* xyz, int64_t n) {   // cpp:74-89
     CU(cudaMemsetAsync(h->d_bricks.p + h->brick_guard, 0, h->grid.nbricks() * sizeof(unsigned long long), s));
     CU(cudaMemsetAsync(h->d_bricks.p + h->brick_guard + h->grid.nbricks(), 0xFF, h->brick_guard * sizeof(unsigned long long), s));
     CU(launch_voxelise(h->d_map_xyz.p, n, g, h->d_bricks.p + h->brick_guard, s));
-    h->counters[5] += 2;
+    CU(launch_mark_padding(h->d_bricks.p + h->brick_guard, h->grid.dims, h->grid.ns, s));
+    CU(h->d_sat.reserve((size_t)(h->grid.ns[0] / 2 + 1) * (h->grid.ns[1] / 2 + 1) * (h->grid.ns[2] / 2 + 1)));
+    CU(launch_build_sat(h->d_bricks.p + h->brick_guard, h->grid.ns, h->d_sat.p, s));
+    h->counters[5] += 7;
 
     // uniform cell index over the map cloud for nearCheck: cells well below the radius so that far cells are never visited
     Stopwatch sw2(t_index);
@@ -1974,18 +2028,29 @@ int fcvm_stage_poses(fcvm_t* h, const double* pose5, int64_t n) {
   CU(cudaStreamSynchronize(h->stream));
   h->resident_n = n;
   h->resident_W = h->W;
+  h->resident_e1 = false;
   return FCVM_OK;
 }
 
 int fcvm_evaluate_resident(fcvm_t* h, int32_t stage, void* stream, int32_t sync, int64_t* rays_out) {
-  if (!h || stage < 1 || stage > 4 || stage == FCVM_STAGE_E2) return fail(FCVM_EINVAL, "bad stage (E2 needs restrict rows: use fcvm_evaluate)");
+  if (!h || stage < 1 || stage > 4) return fail(FCVM_EINVAL, "bad stage");
   if (h->resident_n <= 0 || h->resident_W != h->W) return fail(FCVM_ENOTREADY, "no resident batch: call fcvm_stage_poses first (after setModel)");
+  if (stage == FCVM_STAGE_E2 && !h->resident_e1) return fail(FCVM_ENOTREADY, "E2 re-tests the visible sets of an E1 pass over the same resident batch: run stage 1 first");
   int rc = ensure_device(h);
   if (rc) return rc;
   cudaStream_t s = stream ? (cudaStream_t)stream : h->stream;
-  rc = launch_stage(h, stage, h->d_recs.p, h->resident_n, h->d_rows1.p, nullptr, s, sync != 0);
-  if (rc) return rc;
-  CU(launch_popc_rows(h->d_rows1.p, h->resident_n, h->W, h->d_count.p, s));
+  if (stage == FCVM_STAGE_E2) {
+    // the E1 rows stay in the first rows buffer; E2's rows (and counts) go to the second one
+    CU(h->d_rows2.reserve((size_t)h->resident_n * h->W));
+    rc = launch_stage(h, stage, h->d_recs.p, h->resident_n, h->d_rows2.p, h->d_rows1.p, s, sync != 0);
+    if (rc) return rc;
+    CU(launch_popc_rows(h->d_rows2.p, h->resident_n, h->W, h->d_count.p, s));
+  } else {
+    rc = launch_stage(h, stage, h->d_recs.p, h->resident_n, h->d_rows1.p, nullptr, s, sync != 0);
+    if (rc) return rc;
+    CU(launch_popc_rows(h->d_rows1.p, h->resident_n, h->W, h->d_count.p, s));
+    h->resident_e1 = stage == FCVM_STAGE_E1;
+  }
   h->counters[5] += 1;
   if (sync) {
     CU(cudaStreamSynchronize(s));

@@ -39,11 +39,13 @@ struct EnvSettings {
   int pipe_subs = 0;        // FCVM_PIPE_SUBS: sub-batches of the streamed evaluator paths (0 = default per path)
   bool host_sums = false;   // FCVM_HOST_SUMS=1: pitch / yaw sums of getPose entirely on the host (the round-1 path; A/B and cross-check)
   bool own_sweep = false;   // FCVM_OWN_SWEEP=1: ownership by the ordered row sweep instead of the per-point arg-max (single GPU only)
+  bool no_pfree = false;    // FCVM_NO_PFREE=1: k_eval marches the viewpoint-side half-ray even where the summed-area table certifies it free
   EnvSettings() {
     if (const char* e = std::getenv("FCVM_PROFILE")) profile = atoi(e);
     if (const char* e = std::getenv("FCVM_PIPE_SUBS")) pipe_subs = std::max(1, atoi(e));
     if (const char* e = std::getenv("FCVM_HOST_SUMS")) host_sums = atoi(e) != 0;
     if (const char* e = std::getenv("FCVM_OWN_SWEEP")) own_sweep = atoi(e) != 0;
+    if (const char* e = std::getenv("FCVM_NO_PFREE")) no_pfree = atoi(e) != 0;
   }
 };
 inline EnvSettings env_now() { return EnvSettings(); }

@@ -143,6 +143,8 @@ struct Side {
 
 #define CONT_DISCARD 1      // prepare only: the call sites make one biNextId call and discard it
 #define CONT_INRANGE 2      // E1: ray_length <= visible_range (ANDed into the verdict)
+#define CONT_PFREE 4        // every voxel the viewpoint-side half-ray can visit is free (summed-area-table certificate): that
+                            // side is not marched; p.ix/iy/iz hold the midpoint voxel, p.rem its remaining biNextId calls
 
 struct Cont {
   Side p, n;
@@ -246,11 +248,32 @@ __device__ __forceinline__ bool prepare_ray(const GridDesc& g, const FovConst& f
   c.vp = v; c.pt = pti; c.flags = flags;
   {
     const int dx = mx - x0, dy = my - y0, dz = mz - z0;
-    c.p.ix = pix; c.p.iy = piy; c.p.iz = piz;
+    // Certificate for the viewpoint-side half-ray.  A marcher whose start is strictly inside its voxel on every moving axis
+    // makes exactly |dx| + |dy| + |dz| steps and never leaves the box spanned by its start and midpoint voxels (all its
+    // boundary crossings have t < 1 by a margin no rounding can bridge; the reference's runaway cases start ON a lattice
+    // plane).  If the summed-area table says that box holds no occupied voxel, every occCheck of this
+    // side returns true whatever the exact voxel sequence is, so the side is not marched at all: its biNextId calls and
+    // occCheck look-ups are only counted.
+    bool pfree = false;
+    if (g.sat != nullptr) {
+      const double fx = sxf - floor(sxf), fy = syf - floor(syf), fz = szf - floor(szf);
+      const bool interior = (dx == 0 || (fx > 1e-9 && fx < 1.0 - 1e-9)) && (dy == 0 || (fy > 1e-9 && fy < 1.0 - 1e-9)) &&
+                            (dz == 0 || (fz > 1e-9 && fz < 1.0 - 1e-9));
+      if (interior)
+        pfree = sat_box_count(g, min(pix, mix) >> 3, min(piy, miy) >> 3, min(piz, miz) >> 3, max(pix, mix) >> 3, max(piy, miy) >> 3, max(piz, miz) >> 3) == 0;
+    }
     c.p.rem = abs(dx) + abs(dy) + abs(dz);
-    c.p.sx = d_signum(dx); c.p.sy = d_signum(dy); c.p.sz = d_signum(dz);
-    c.p.tmx = d_intbound(sxf, (double)dx); c.p.tmy = d_intbound(syf, (double)dy); c.p.tmz = d_intbound(szf, (double)dz);
-    c.p.tdx = ((double)c.p.sx) / (double)dx; c.p.tdy = ((double)c.p.sy) / (double)dy; c.p.tdz = ((double)c.p.sz) / (double)dz;
+    if (pfree) {
+      c.flags |= CONT_PFREE;
+      c.p.ix = mix; c.p.iy = miy; c.p.iz = miz;
+      c.p.sx = c.p.sy = c.p.sz = 0;
+      c.p.tmx = c.p.tmy = c.p.tmz = 0.0; c.p.tdx = c.p.tdy = c.p.tdz = 0.0;
+    } else {
+      c.p.ix = pix; c.p.iy = piy; c.p.iz = piz;
+      c.p.sx = d_signum(dx); c.p.sy = d_signum(dy); c.p.sz = d_signum(dz);
+      c.p.tmx = d_intbound(sxf, (double)dx); c.p.tmy = d_intbound(syf, (double)dy); c.p.tmz = d_intbound(szf, (double)dz);
+      c.p.tdx = ((double)c.p.sx) / (double)dx; c.p.tdy = ((double)c.p.sy) / (double)dy; c.p.tdz = ((double)c.p.sz) / (double)dz;
+    }
   }
   {
     const int dx = mx - x1, dy = my - y1, dz = mz - z1;
@@ -263,7 +286,8 @@ __device__ __forceinline__ bool prepare_ray(const GridDesc& g, const FovConst& f
   if (flags & CONT_DISCARD) {
     // `raycaster_->biNextId(idx, idx_rev);` before the loop (cpp:387, 483, 845): both sides advance
     // one voxel (if they can), the reported voxels are not looked at
-    c.p.step_if(c.p.rem > 0);
+    if (c.flags & CONT_PFREE) c.p.rem -= c.p.rem > 0 ? 1 : 0;
+    else c.p.step_if(c.p.rem > 0);
     c.n.step_if(c.n.rem > 0);
     c.flags &= ~CONT_DISCARD;
   }
@@ -419,18 +443,34 @@ __global__ void __launch_bounds__(kWarps * 32, EVAL_MIN_CTAS) k_eval(const __gri
           // ---- one biNextId call and the loop body that follows it.  The call reports the voxels
           // BEFORE it steps, so they are looked up first and both sides advance afterwards.
           const bool pflag = c.p.rem > 0, nflag = c.n.rem > 0;
+          const bool pfree = (c.flags & CONT_PFREE) != 0;
           if (!(pflag || nflag)) {
             // the call returned false: visible_flag = occCheck(idx); visible_flag_rev keeps its last (true) value
-            const bool f = occ_fast(g, c.p.ix, c.p.iy, c.p.iz, pkey, pword);
+            bool f = true;                                              // certified side: the midpoint voxel lies in the free box
+            if (!pfree) f = occ_fast(g, c.p.ix, c.p.iy, c.p.iz, pkey, pword);
             st.lookups += 1;
-            if (c.p.ix != c.n.ix || c.p.iy != c.n.iy || c.p.iz != c.n.iz) st.trips++;   // both sides must have met in the midpoint voxel
-            if (f && (c.flags & CONT_INRANGE)) set_bit(c.vp, c.pt);
+            // Both sides must have met in the midpoint voxel.  If they have not, the reference's marcher never reports
+            // "at end": it walks on until an occCheck fails (an occupied voxel, or the map's edge), so the pair is NOT
+            // visible there; counted as a cap trip (0 on every scene and test so far).
+            const bool met = c.p.ix == c.n.ix && c.p.iy == c.n.iy && c.p.iz == c.n.iz;
+            if (!met) st.trips++;
+            if (met && f && (c.flags & CONT_INRANGE)) set_bit(c.vp, c.pt);
             active = false;
+          } else if (pfree && !nflag) {
+            // the target side already waits in the midpoint voxel (free: it lies in the certified box) and the viewpoint
+            // side is certified: the remaining calls each look at two free voxels
+            st.lookups += 2u * (unsigned)c.p.rem;
+            c.p.rem = 0;
           } else {
-            const bool f = occ_fast(g, c.p.ix, c.p.iy, c.p.iz, pkey, pword);
+            bool f = true;
+            if (!pfree) {
+              f = occ_fast(g, c.p.ix, c.p.iy, c.p.iz, pkey, pword);
+              c.p.step_if(pflag);
+            } else {
+              c.p.rem -= pflag ? 1 : 0;
+            }
             const bool r = occ_fast(g, c.n.ix, c.n.iy, c.n.iz, nkey, nword);
             st.lookups += 2;
-            c.p.step_if(pflag);
             c.n.step_if(nflag);
             if (!f || !r) {
               st.lookups += 1;                        // the re-check after the break (same voxel, same answer)

@@ -55,6 +55,48 @@ __global__ void __launch_bounds__(256) k_voxelise(const float* __restrict__ xyz,
   atomicOr(bricks + brick_word_index(x, y, z, g.nb[1], g.nb[2]), 1ull << brick_bit_index(x, y, z));
 }
 
+// ---- the voxels of the padded brick array that lie outside the map read 'occupied', like occCheck outside the map
+// (sdf_map.h:397-420 returns false there): a fast-path ray that strays beyond the last voxel stops where the reference's would
+__global__ void __launch_bounds__(256) k_mark_padding(unsigned long long* __restrict__ bricks, int nx, int ny, int nz, int nbx, int nby, int nbz) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)nbx * nby * nbz) return;
+  const int bz = (int)(i % nbz), by = (int)((i / nbz) % nby), bx = (int)(i / ((long long)nbz * nby));
+  if (4 * bx + 3 < nx && 4 * by + 3 < ny && 4 * bz + 3 < nz) return;       // interior brick
+  unsigned long long m = 0ull;
+  for (int x = 0; x < 4; ++x)
+    for (int y = 0; y < 4; ++y)
+      for (int z = 0; z < 4; ++z)
+        if (4 * bx + x >= nx || 4 * by + y >= ny || 4 * bz + z >= nz) m |= 1ull << brick_bit_index(x, y, z);
+  bricks[i] |= m;
+}
+
+// ---- summed-area table of "cell has an occupied voxel" over 2 x 2 x 2-brick cells (GridDesc::sat) ------------------
+// flags into sat[(x + 1, y + 1, z + 1)] (the table is zeroed first), then one inclusive prefix pass per axis.
+__global__ void __launch_bounds__(256) k_sat_flags(const unsigned long long* __restrict__ bricks, int nby, int nbz, int cx, int cy, int cz, int* __restrict__ sat) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)cx * cy * cz) return;
+  const int z = (int)(i % cz), y = (int)((i / cz) % cy), x = (int)(i / ((long long)cz * cy));
+  unsigned long long any = 0ull;
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < 2; ++b)
+#pragma unroll
+      for (int c = 0; c < 2; ++c) any |= __ldg(bricks + ((long long)(2 * x + a) * nby + (2 * y + b)) * nbz + (2 * z + c));
+  sat[((long long)(x + 1) * (cy + 1) + (y + 1)) * (cz + 1) + (z + 1)] = any ? 1 : 0;
+}
+// axis 0 / 1 / 2 = prefix along x / y / z; one thread per line of the other two axes
+__global__ void __launch_bounds__(256) k_sat_scan(int* __restrict__ sat, int nx, int ny, int nz, int axis) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long base, stride;
+  int len;
+  if (axis == 2) { if (i >= (long long)nx * ny) return; base = i * nz; stride = 1; len = nz; }
+  else if (axis == 1) { if (i >= (long long)nx * nz) return; base = (i / nz) * (long long)ny * nz + (i % nz); stride = nz; len = ny; }
+  else { if (i >= (long long)ny * nz) return; base = i; stride = (long long)ny * nz; len = nx; }
+  int run = 0;
+  for (int k = 0; k < len; ++k) { run += sat[base + k * stride]; sat[base + k * stride] = run; }
+}
+
 // ---- cell index: count, (exclusive scan by k_exscan), fill ---------------------------------------------------------
 __device__ __forceinline__ int cell_coord(const CellGeom& cg, double v, int c) {
   const int k = (int)floor((v - (double)cg.mn[c]) / cg.cell);
@@ -187,6 +229,24 @@ cudaError_t launch_voxelise(const float* xyz, long long n, const MapGeom& g, uns
   k_voxelise<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(xyz, n, g, bricks);
   return cudaGetLastError();
 }
+cudaError_t launch_mark_padding(unsigned long long* bricks, const int dims[3], const int nb[3], cudaStream_t s) {
+  const long long n = (long long)nb[0] * nb[1] * nb[2];
+  k_mark_padding<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(bricks, dims[0], dims[1], dims[2], nb[0], nb[1], nb[2]);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_build_sat(const unsigned long long* bricks, const int nb[3], int* sat, cudaStream_t s) {
+  const int cx = nb[0] / 2, cy = nb[1] / 2, cz = nb[2] / 2;
+  const long long n = (long long)(cx + 1) * (cy + 1) * (cz + 1);
+  cudaError_t e = cudaMemsetAsync(sat, 0, (size_t)n * sizeof(int), s);
+  if (e != cudaSuccess) return e;
+  k_sat_flags<<<(unsigned)(((long long)cx * cy * cz + 255) / 256), 256, 0, s>>>(bricks, nb[1], nb[2], cx, cy, cz, sat);
+  k_sat_scan<<<(unsigned)(((long long)(cx + 1) * (cy + 1) + 255) / 256), 256, 0, s>>>(sat, cx + 1, cy + 1, cz + 1, 2);
+  k_sat_scan<<<(unsigned)(((long long)(cx + 1) * (cz + 1) + 255) / 256), 256, 0, s>>>(sat, cx + 1, cy + 1, cz + 1, 1);
+  k_sat_scan<<<(unsigned)(((long long)(cy + 1) * (cz + 1) + 255) / 256), 256, 0, s>>>(sat, cx + 1, cy + 1, cz + 1, 0);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_cell_count(const float* xyz, long long n, const CellGeom& cg, int* count, cudaStream_t s) {
   k_cell_count<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(xyz, n, cg, count);
   return cudaGetLastError();

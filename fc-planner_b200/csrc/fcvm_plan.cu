@@ -11,6 +11,14 @@
 //   sblk = occupancy_buffer_hc_ == 1 || occupancy_buffer_internal_ == 1      (SDFMap::safety_check, :375-395)
 //   pblk = occupancy_inflate_buffer_hc_ == 1 || occupancy_buffer_internal_ == 1   (hcsolver.cpp:566)
 // Marchers: Marcher of fcvm_device.cuh (raycast.cpp restated, FP64, -fmad=false), literal and bounds-checked.
+//
+// The buffers themselves can also be BUILT on the device, from an empty grid:
+//   plan_env/src/sdf_map.cpp:440-455   SDFMap::SetOcc (and the marking loop of initHCMap, :178-187)  -> k_grid_mark_points
+//   plan_env/src/sdf_map.cpp:263-395   SDFMap::InternalSpace  -> k_grid_mark_points (hc + inflate dilation), k_internal_cut,
+//                                      k_internal_remain (rays from the segment's projection points, marking `internal`)
+//   plan_env/src/sdf_map.cpp:457-473   SDFMap::OuterCheck     -> k_outer_check (clears `internal` along outward rays)
+// Every write of those loops is "set to 1" (or "clear if 1"), so all rays of a call are independent: one thread per ray,
+// atomicOr / atomicAnd on the bricked bit planes.
 // No CPU fallback.
 #include <cfloat>
 #include <cstring>
@@ -24,29 +32,178 @@ struct PlanPlanes {
   GridDesc occ, sblk, pblk;     // same geometry, three brick arrays
 };
 
-// one thread per brick: 64 voxels of each buffer (x-major bytes, sdf_map.h:266-269) -> one word per plane
+// one thread per brick: 64 voxels of each buffer (x-major bytes, sdf_map.h:266-269) -> one word per raw plane
 __global__ void __launch_bounds__(256) k_pack_planes(const signed char* __restrict__ hc, const signed char* __restrict__ inflate,
                                                      const signed char* __restrict__ internal, int nx, int ny, int nz, int nby, int nbz,
-                                                     long long nbricks, unsigned long long* __restrict__ occ,
-                                                     unsigned long long* __restrict__ sblk, unsigned long long* __restrict__ pblk) {
+                                                     long long nbricks, unsigned long long* __restrict__ p_hc,
+                                                     unsigned long long* __restrict__ p_inf, unsigned long long* __restrict__ p_int) {
   const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= nbricks) return;
   const int bz = (int)(b % nbz), by = (int)((b / nbz) % nby), bx = (int)(b / ((long long)nbz * nby));   // b enumerates brick coordinates
   const long long dst = brick_word_index(bx * 4, by * 4, bz * 4, nby, nbz);                                   // ... stored in line order
-  unsigned long long wo = 0ull, ws = 0ull, wp = 0ull;
+  unsigned long long wo = 0ull, wf = 0ull, wt = 0ull;
   for (int dx = 0; dx < 4; ++dx)
     for (int dy = 0; dy < 4; ++dy)
       for (int dz = 0; dz < 4; ++dz) {
         const int x = bx * 4 + dx, y = by * 4 + dy, z = bz * 4 + dz;
         if (x >= nx || y >= ny || z >= nz) continue;
         const long long a = ((long long)x * ny + y) * nz + z;
-        const bool h = hc && hc[a] == 1, f = inflate && inflate[a] == 1, t = internal && internal[a] == 1;
         const unsigned long long bit = 1ull << brick_bit_index(x, y, z);
-        if (h) wo |= bit;
-        if (h || t) ws |= bit;
-        if (f || t) wp |= bit;
+        if (hc && hc[a] == 1) wo |= bit;
+        if (inflate && inflate[a] == 1) wf |= bit;
+        if (internal && internal[a] == 1) wt |= bit;
       }
-  occ[dst] = wo; sblk[dst] = ws; pblk[dst] = wp;
+  p_hc[dst] = wo; p_inf[dst] = wf; p_int[dst] = wt;
+}
+// the planes the three loops test: sblk = hc | internal (safety_check), pblk = inflate | internal (search_Path); occ = hc itself
+__global__ void __launch_bounds__(256) k_derive_planes(const unsigned long long* __restrict__ p_hc, const unsigned long long* __restrict__ p_inf,
+                                                       const unsigned long long* __restrict__ p_int, long long nbricks,
+                                                       unsigned long long* __restrict__ sblk, unsigned long long* __restrict__ pblk) {
+  const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nbricks) return;
+  const unsigned long long t = p_int[b];
+  sblk[b] = p_hc[b] | t;
+  pblk[b] = p_inf[b] | t;
+}
+// raw planes -> the reference's x-major char buffers (parity tap)
+__global__ void __launch_bounds__(256) k_unpack_plane(const unsigned long long* __restrict__ plane, int nx, int ny, int nz, int nby, int nbz,
+                                                      signed char* __restrict__ out) {
+  const long long a = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= (long long)nx * ny * nz) return;
+  const int z = (int)(a % nz), y = (int)((a / nz) % ny), x = (int)(a / ((long long)nz * ny));
+  out[a] = (signed char)((plane[brick_word_index(x, y, z, nby, nbz)] >> brick_bit_index(x, y, z)) & 1ull);
+}
+
+struct PlaneGeom {          // SDFMap geometry for posToIndex_hc / isInMap_hc (sdf_map.h:234-237, 367-373)
+  double org[3], res_inv;
+  int dims[3], nby, nbz;
+};
+__device__ __forceinline__ bool plane_in_map(const PlaneGeom& g, int x, int y, int z) {
+  return (unsigned)x < (unsigned)g.dims[0] && (unsigned)y < (unsigned)g.dims[1] && (unsigned)z < (unsigned)g.dims[2];
+}
+__device__ __forceinline__ void plane_set(unsigned long long* plane, const PlaneGeom& g, int x, int y, int z) {
+  atomicOr(plane + brick_word_index(x, y, z, g.nby, g.nbz), 1ull << brick_bit_index(x, y, z));
+}
+
+// SetOcc (sdf_map.cpp:440-455; dilate < 0) or the first loop of InternalSpace (:282-297; dilate = inflateVoxel >= 0): the voxel of
+// every point is marked in hc (and inflate), and inflate additionally in the (2 dilate + 1)^3 cube around it.  Writes outside
+// the map (undefined behaviour in the reference, which does not test) are skipped and counted in counters[2].
+__global__ void __launch_bounds__(256) k_grid_mark_points(PlaneGeom g, const float* __restrict__ xyz, long long n, int dilate,
+                                                          unsigned long long* __restrict__ p_hc, unsigned long long* __restrict__ p_inf,
+                                                          unsigned long long* __restrict__ counters) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int x = (int)floor(((double)xyz[3 * i] - g.org[0]) * g.res_inv);
+  const int y = (int)floor(((double)xyz[3 * i + 1] - g.org[1]) * g.res_inv);
+  const int z = (int)floor(((double)xyz[3 * i + 2] - g.org[2]) * g.res_inv);
+  unsigned long long oob = 0;
+  if (plane_in_map(g, x, y, z)) {
+    plane_set(p_hc, g, x, y, z);
+    if (dilate >= 0) plane_set(p_inf, g, x, y, z);
+  } else if (dilate >= 0) {
+    oob++;
+  }
+  for (int a = -dilate; a <= dilate; ++a)
+    for (int b = -dilate; b <= dilate; ++b)
+      for (int c = -dilate; c <= dilate; ++c) {
+        if (a == 0 && b == 0 && c == 0) continue;
+        if (plane_in_map(g, x + a, y + b, z + c)) plane_set(p_inf, g, x + a, y + b, z + c);
+        else oob++;
+      }
+  if (oob) atomicAdd(counters + 2, oob);
+}
+
+// `internal_cast_->input(a, b); nextId(idx); while (nextId(idx)) buffer[idx] = ...` (sdf_map.cpp:332-337, 379-384, 465-471): the
+// voxels strictly between the first and the last one of the one-directional march a -> b.  SET: mark; !SET: clear.
+template <bool SET>
+__device__ __forceinline__ void cast_mark(const GridDesc& g, const PlaneGeom& pg, double ax, double ay, double az, double bx, double by, double bz,
+                                          unsigned long long* __restrict__ plane, unsigned long long& looks, unsigned long long& trips, unsigned long long& oob) {
+  const double res = g.res;
+  Marcher m;
+  m.init(ax / res, ay / res, az / res, (int)floor(bx / res), (int)floor(by / res), (int)floor(bz / res), g);
+  if (m.at_end()) return;
+  int budget = m.manhattan() + 8;
+  m.step(g);                                    // the discarded first nextId
+  --budget;
+  for (;;) {
+    const int ix = m.ix, iy = m.iy, iz = m.iz;  // nextId reports the voxel before stepping and returns false at the end voxel
+    if (m.at_end()) break;
+    if (--budget < 0) { trips++; break; }
+    m.step(g);
+    looks++;
+    if (plane_in_map(pg, ix, iy, iz)) {
+      const unsigned long long bit = 1ull << brick_bit_index(ix, iy, iz);
+      if (SET) atomicOr(plane + brick_word_index(ix, iy, iz, pg.nby, pg.nbz), bit);
+      else atomicAnd(plane + brick_word_index(ix, iy, iz, pg.nby, pg.nbz), ~bit);
+    } else {
+      oob++;
+    }
+  }
+}
+__device__ __forceinline__ void plan_flush(unsigned long long* counters, unsigned long long looks, unsigned long long trips, unsigned long long oob) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    looks += __shfl_xor_sync(0xffffffffu, looks, o); trips += __shfl_xor_sync(0xffffffffu, trips, o); oob += __shfl_xor_sync(0xffffffffu, oob, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (looks) atomicAdd(counters + 0, looks);
+    if (trips) atomicAdd(counters + 1, trips);
+    if (oob) atomicAdd(counters + 2, oob);
+  }
+}
+
+// InternalSpace, cutting-plane part (sdf_map.cpp:315-341) of ONE segment: thread = (cloud point i, projection point k); the
+// point lies in k's cutting plane when |(pt - proj_k) . seg_dir| <= thickness (points_in_plane, :475-491); then the ray
+// proj_k -> pt marks `internal` and the point counts as visited.
+__global__ void __launch_bounds__(128) k_internal_cut(GridDesc g, PlaneGeom pg, const float* __restrict__ cloud, long long n, const double* __restrict__ proj,
+                                                      int K, double dirx, double diry, double dirz, double thickness, unsigned long long* __restrict__ p_int,
+                                                      unsigned char* __restrict__ visited, unsigned long long* __restrict__ counters) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long looks = 0, trips = 0, oob = 0;
+  if (t < n * K) {
+    const long long i = t / K;
+    const int k = (int)(t % K);
+    const double px = (double)cloud[3 * i], py = (double)cloud[3 * i + 1], pz = (double)cloud[3 * i + 2];
+    const double qx = proj[3 * k], qy = proj[3 * k + 1], qz = proj[3 * k + 2];
+    const double d = ((px - qx) * dirx + (py - qy) * diry) + (pz - qz) * dirz;        // Eigen 3-term order
+    if (fabs(d) <= thickness) {
+      visited[i] = 1;
+      cast_mark<true>(g, pg, qx, qy, qz, px, py, pz, p_int, looks, trips, oob);
+    }
+  }
+  plan_flush(counters, looks, trips, oob);
+}
+// InternalSpace, the points no plane caught (sdf_map.cpp:343-384): ray from the nearest projection point (first minimum, strict <,
+// starting from 100000)
+__global__ void __launch_bounds__(128) k_internal_remain(GridDesc g, PlaneGeom pg, const float* __restrict__ cloud, long long n, const double* __restrict__ proj,
+                                                         int K, const unsigned char* __restrict__ visited, unsigned long long* __restrict__ p_int,
+                                                         unsigned long long* __restrict__ counters) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long looks = 0, trips = 0, oob = 0;
+  if (i < n && !visited[i]) {
+    const double px = (double)cloud[3 * i], py = (double)cloud[3 * i + 1], pz = (double)cloud[3 * i + 2];
+    double dist_min = 100000.0;
+    int id = -1;
+    for (int k = 0; k < K; ++k) {
+      const double dx = proj[3 * k] - px, dy = proj[3 * k + 1] - py, dz = proj[3 * k + 2] - pz;
+      const double dist = sqrt((dx * dx + dy * dy) + dz * dz);
+      if (dist < dist_min) { dist_min = dist; id = k; }
+    }
+    if (id >= 0) cast_mark<true>(g, pg, proj[3 * id], proj[3 * id + 1], proj[3 * id + 2], px, py, pz, p_int, looks, trips, oob);
+  }
+  plan_flush(counters, looks, trips, oob);
+}
+// OuterCheck (sdf_map.cpp:457-473): start = o.head(3), end = start + checkScale * o.tail(3)
+__global__ void __launch_bounds__(128) k_outer_check(GridDesc g, PlaneGeom pg, const double* __restrict__ outers, long long n, double check_scale,
+                                                     unsigned long long* __restrict__ p_int, unsigned long long* __restrict__ counters) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long looks = 0, trips = 0, oob = 0;
+  if (i < n) {
+    const double sx = outers[6 * i], sy = outers[6 * i + 1], sz = outers[6 * i + 2];
+    cast_mark<false>(g, pg, sx, sy, sz, sx + check_scale * outers[6 * i + 3], sy + check_scale * outers[6 * i + 4], sz + check_scale * outers[6 * i + 5], p_int,
+                     looks, trips, oob);
+  }
+  plan_flush(counters, looks, trips, oob);
 }
 
 // lightStateDet (hcplanner.cpp:805-863), K = 1: nearest ROSA vertex with FLANN's L2_Simple<float> (lowest index on ties),
@@ -190,7 +347,9 @@ struct fcvm_grid_handle {
   double origin[3], res = 0;
   int dims[3], nb[3];
   long long nbricks = 0;
-  DevBuf<unsigned long long> d_occ, d_sblk, d_pblk;
+  DevBuf<unsigned long long> d_occ, d_inf, d_int;     // raw planes: occupancy_buffer_hc_ (= occ), occupancy_inflate_buffer_hc_, occupancy_buffer_internal_
+  DevBuf<unsigned long long> d_sblk, d_pblk;          // derived planes, refreshed after every change of the raw ones
+  DevBuf<unsigned char> d_visited;
   DevBuf<double> d_in;
   DevBuf<float> d_in_f, d_rosa;
   DevBuf<uint8_t> d_u8;
@@ -201,6 +360,7 @@ struct fcvm_grid_handle {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   double last_kernel_ms = 0;
   int64_t counters[3] = {0, 0, 0};    // lookups, cap trips, kernels launched
+  int64_t oob_writes = 0;             // voxel writes of SetOcc / InternalSpace / OuterCheck that fell outside the map (skipped)
 };
 
 static void plan_desc(const fcvm_grid_handle* h, const unsigned long long* bricks, GridDesc& g) {
@@ -210,6 +370,7 @@ static void plan_desc(const fcvm_grid_handle* h, const unsigned long long* brick
   g.nly = h->nb[1] >> 1; g.nlz = h->nb[2] >> 2;
   g.nbricks = (int)h->nbricks;
   g.guard_steps = 0;
+  g.sat = nullptr; g.sat_ny = g.sat_nz = 0;
   g.res = h->res;
   g.offx = 0.5 - h->origin[0] / h->res;      // RayCaster::setParams (raycast.cpp:341-345; hcplanner.cpp:89, hcsolver.cpp:40)
   g.offy = 0.5 - h->origin[1] / h->res;
@@ -217,8 +378,19 @@ static void plan_desc(const fcvm_grid_handle* h, const unsigned long long* brick
   g.orgx = h->origin[0]; g.orgy = h->origin[1]; g.orgz = h->origin[2];
 }
 
+static void plane_geom(const fcvm_grid_handle* h, PlaneGeom& g) {
+  for (int c = 0; c < 3; ++c) { g.org[c] = h->origin[c]; g.dims[c] = h->dims[c]; }
+  g.res_inv = 1 / h->res;
+  g.nby = h->nb[1]; g.nbz = h->nb[2];
+}
+static int plan_derive(fcvm_grid_handle* h) {
+  k_derive_planes<<<(unsigned)((h->nbricks + 255) / 256), 256, 0, h->stream>>>(h->d_occ.p, h->d_inf.p, h->d_int.p, h->nbricks, h->d_sblk.p, h->d_pblk.p);
+  CU(cudaGetLastError());
+  return FCVM_OK;
+}
+
 static int plan_finish(fcvm_grid_handle* h) {
-  unsigned long long c[2];
+  unsigned long long c[3];
   CU(cudaMemcpyAsync(c, h->d_counters.p, sizeof(c), cudaMemcpyDeviceToHost, h->stream));
   CU(cudaMemsetAsync(h->d_counters.p, 0, sizeof(c), h->stream));
   CU(cudaStreamSynchronize(h->stream));
@@ -227,6 +399,7 @@ static int plan_finish(fcvm_grid_handle* h) {
   h->last_kernel_ms = ms;
   h->counters[0] += (int64_t)c[0];
   h->counters[1] += (int64_t)c[1];
+  h->oob_writes += (int64_t)c[2];
   h->counters[2] += 1;
   return FCVM_OK;
 }
@@ -256,9 +429,11 @@ fcvm_grid_t* fcvm_grid_create(int32_t device, const double* origin3, double reso
     CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     CU(cudaEventCreate(&h->ev0));
     CU(cudaEventCreate(&h->ev1));
-    CU(h->d_counters.reserve(2));
-    CU(cudaMemset(h->d_counters.p, 0, 2 * sizeof(unsigned long long)));
+    CU(h->d_counters.reserve(3));
+    CU(cudaMemset(h->d_counters.p, 0, 3 * sizeof(unsigned long long)));
     CU(h->d_occ.reserve((size_t)h->nbricks));
+    CU(h->d_inf.reserve((size_t)h->nbricks));
+    CU(h->d_int.reserve((size_t)h->nbricks));
     CU(h->d_sblk.reserve((size_t)h->nbricks));
     CU(h->d_pblk.reserve((size_t)h->nbricks));
     DevBuf<signed char> b[3];
@@ -269,8 +444,9 @@ fcvm_grid_t* fcvm_grid_create(int32_t device, const double* origin3, double reso
         CU(cudaMemcpyAsync(b[k].p, src[k], (size_t)G, cudaMemcpyHostToDevice, h->stream));
       }
     k_pack_planes<<<(unsigned)((h->nbricks + 255) / 256), 256, 0, h->stream>>>(b[0].p, b[1].p, b[2].p, h->dims[0], h->dims[1], h->dims[2], h->nb[1],
-                                                                                  h->nb[2], h->nbricks, h->d_occ.p, h->d_sblk.p, h->d_pblk.p);
+                                                                                  h->nb[2], h->nbricks, h->d_occ.p, h->d_inf.p, h->d_int.p);
     CU(cudaGetLastError());
+    if (plan_derive(h) != FCVM_OK) return FCVM_ECUDA;
     CU(cudaStreamSynchronize(h->stream));
     for (int k = 0; k < 3; ++k) b[k].free();
     h->counters[2] += 1;
@@ -284,7 +460,7 @@ void fcvm_grid_destroy(fcvm_grid_t* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
-  h->d_occ.free(); h->d_sblk.free(); h->d_pblk.free(); h->d_in.free(); h->d_in_f.free(); h->d_rosa.free(); h->d_u8.free();
+  h->d_occ.free(); h->d_inf.free(); h->d_int.free(); h->d_sblk.free(); h->d_pblk.free(); h->d_visited.free(); h->d_in.free(); h->d_in_f.free(); h->d_rosa.free(); h->d_u8.free();
   h->d_i32a.free(); h->d_i32b.free(); h->d_dist.free(); h->d_counters.free();
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
@@ -352,6 +528,121 @@ int fcvm_grid_line_of_sight(fcvm_grid_t* h, const double* p_xyz, int64_t n, uint
   if (dist_nxn) CU(cudaMemcpyAsync(dist_nxn, h->d_dist.p, (size_t)n * n * sizeof(double), cudaMemcpyDeviceToHost, s));
   return plan_finish(h);
 }
+
+int fcvm_grid_set_occ(fcvm_grid_t* h, const float* xyz, int64_t n) {
+  if (!h || !xyz || n <= 0) return fail(FCVM_EINVAL, "bad arguments");
+  cudaStream_t s = h->stream;
+  CU(cudaSetDevice(h->device));
+  CU(h->d_in_f.reserve((size_t)3 * n));
+  CU(cudaMemcpyAsync(h->d_in_f.p, xyz, (size_t)3 * n * sizeof(float), cudaMemcpyHostToDevice, s));
+  PlaneGeom pg;
+  plane_geom(h, pg);
+  CU(cudaEventRecord(h->ev0, s));
+  k_grid_mark_points<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(pg, h->d_in_f.p, n, -1, h->d_occ.p, h->d_inf.p, h->d_counters.p);
+  CU(cudaGetLastError());
+  CU(cudaEventRecord(h->ev1, s));
+  int rc = plan_derive(h);
+  if (rc) return rc;
+  return plan_finish(h);
+}
+
+int fcvm_grid_internal_space(fcvm_grid_t* h, const float* seg_xyz, const int64_t* seg_offsets, int64_t nseg, const double* seg_ends6, int32_t inflate_num,
+                             double proj_interval, double thickness) {
+  if (!h || !seg_xyz || !seg_offsets || nseg <= 0 || !seg_ends6 || inflate_num < 0 || !(proj_interval > 0)) return fail(FCVM_EINVAL, "bad arguments");
+  cudaStream_t s = h->stream;
+  CU(cudaSetDevice(h->device));
+  const int64_t n_all = seg_offsets[nseg];
+  if (n_all <= 0) return fail(FCVM_EINVAL, "empty segment clouds");
+  CU(h->d_in_f.reserve((size_t)3 * n_all));
+  CU(h->d_visited.reserve((size_t)n_all));
+  CU(cudaMemcpyAsync(h->d_in_f.p, seg_xyz, (size_t)3 * n_all * sizeof(float), cudaMemcpyHostToDevice, s));
+  CU(cudaMemsetAsync(h->d_visited.p, 0, (size_t)n_all, s));
+  PlaneGeom pg;
+  plane_geom(h, pg);
+  GridDesc g;
+  plan_desc(h, h->d_int.p, g);
+  CU(cudaEventRecord(h->ev0, s));
+  // first loop of every segment (:282-297): one launch over all points
+  k_grid_mark_points<<<(unsigned)((n_all + 255) / 256), 256, 0, s>>>(pg, h->d_in_f.p, n_all, inflate_num, h->d_occ.p, h->d_inf.p, h->d_counters.p);
+  CU(cudaGetLastError());
+  // projection points of every segment (:318-324), on the host in the reference's arithmetic: seg_start + (interval * i) * seg_dir
+  std::vector<double> proj;
+  std::vector<int64_t> proj_off((size_t)nseg + 1, 0);
+  std::vector<double> dirs((size_t)3 * nseg);
+  for (int64_t sg = 0; sg < nseg; ++sg) {
+    const double* e = seg_ends6 + 6 * sg;
+    const double dx = e[3] - e[0], dy = e[4] - e[1], dz = e[5] - e[2];
+    const double z = (dx * dx + dy * dy) + dz * dz;
+    const double len = std::sqrt(z);
+    double ux = dx, uy = dy, uz = dz;
+    if (z > 0.0) { ux = dx / len; uy = dy / len; uz = dz / len; }           // normalized()
+    dirs[3 * sg] = ux; dirs[3 * sg + 1] = uy; dirs[3 * sg + 2] = uz;
+    for (int i = 0; proj_interval * i < len; ++i) {
+      const double t = proj_interval * i;
+      proj.push_back(e[0] + t * ux); proj.push_back(e[1] + t * uy); proj.push_back(e[2] + t * uz);
+    }
+    proj.push_back(e[3]); proj.push_back(e[4]); proj.push_back(e[5]);
+    proj_off[(size_t)sg + 1] = (int64_t)proj.size() / 3;
+  }
+  CU(h->d_in.reserve(proj.size()));
+  CU(cudaMemcpyAsync(h->d_in.p, proj.data(), proj.size() * sizeof(double), cudaMemcpyHostToDevice, s));
+  for (int64_t sg = 0; sg < nseg; ++sg) {
+    const int64_t p0 = seg_offsets[sg], np = seg_offsets[sg + 1] - p0;
+    const int K = (int)(proj_off[(size_t)sg + 1] - proj_off[(size_t)sg]);
+    if (np <= 0 || K <= 0) continue;
+    const double* dproj = h->d_in.p + 3 * proj_off[(size_t)sg];
+    k_internal_cut<<<(unsigned)((np * K + 127) / 128), 128, 0, s>>>(g, pg, h->d_in_f.p + 3 * p0, np, dproj, K, dirs[3 * sg], dirs[3 * sg + 1], dirs[3 * sg + 2],
+                                                                      thickness, h->d_int.p, h->d_visited.p + p0, h->d_counters.p);
+    CU(cudaGetLastError());
+    k_internal_remain<<<(unsigned)((np + 127) / 128), 128, 0, s>>>(g, pg, h->d_in_f.p + 3 * p0, np, dproj, K, h->d_visited.p + p0, h->d_int.p, h->d_counters.p);
+    CU(cudaGetLastError());
+    h->counters[2] += 2;
+  }
+  CU(cudaEventRecord(h->ev1, s));
+  int rc = plan_derive(h);
+  if (rc) return rc;
+  return plan_finish(h);      // synchronises: `proj` must outlive its copy
+}
+
+int fcvm_grid_outer_check(fcvm_grid_t* h, const double* outers6, int64_t n, double check_scale) {
+  if (!h || !outers6 || n <= 0) return fail(FCVM_EINVAL, "bad arguments");
+  cudaStream_t s = h->stream;
+  CU(cudaSetDevice(h->device));
+  CU(h->d_in.reserve((size_t)6 * n));
+  CU(cudaMemcpyAsync(h->d_in.p, outers6, (size_t)6 * n * sizeof(double), cudaMemcpyHostToDevice, s));
+  PlaneGeom pg;
+  plane_geom(h, pg);
+  GridDesc g;
+  plan_desc(h, h->d_int.p, g);
+  CU(cudaEventRecord(h->ev0, s));
+  k_outer_check<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(g, pg, h->d_in.p, n, check_scale, h->d_int.p, h->d_counters.p);
+  CU(cudaGetLastError());
+  CU(cudaEventRecord(h->ev1, s));
+  int rc = plan_derive(h);
+  if (rc) return rc;
+  return plan_finish(h);
+}
+
+int fcvm_grid_get_buffers(fcvm_grid_t* h, int8_t* hc, int8_t* inflate, int8_t* internal) {
+  if (!h) return fail(FCVM_EINVAL, "null handle");
+  cudaStream_t s = h->stream;
+  CU(cudaSetDevice(h->device));
+  const long long G = (long long)h->dims[0] * h->dims[1] * h->dims[2];
+  DevBuf<signed char> tmp;
+  CU(tmp.reserve((size_t)G));
+  int8_t* dst[3] = {hc, inflate, internal};
+  const unsigned long long* src[3] = {h->d_occ.p, h->d_inf.p, h->d_int.p};
+  for (int k = 0; k < 3; ++k) {
+    if (!dst[k]) continue;
+    k_unpack_plane<<<(unsigned)((G + 255) / 256), 256, 0, s>>>(src[k], h->dims[0], h->dims[1], h->dims[2], h->nb[1], h->nb[2], tmp.p);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(dst[k], tmp.p, (size_t)G, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+  }
+  return FCVM_OK;
+}
+
+int64_t fcvm_grid_oob_writes(fcvm_grid_t* h) { return h ? h->oob_writes : 0; }
 
 int fcvm_grid_counters(fcvm_grid_t* h, int64_t* out3) {
   if (!h || !out3) return fail(FCVM_EINVAL, "bad arguments");

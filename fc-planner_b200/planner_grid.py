@@ -1,6 +1,7 @@
 """Host-side mirror of three loops of the planner that run on its own SDFMap, over the C ABI (`fcvm_grid_*`):
 `hierarchical_coverage_planner::lightStateDet` (hcplanner.cpp:805-863), the candidate safety box (:658-676) and the
-straight-line test of `HCSolver::search_Path` (hcsolver.cpp:556-583), each for whole batches.  CUDA only."""
+straight-line test of `HCSolver::search_Path` (hcsolver.cpp:556-583), each for whole batches - and of the SDFMap calls that
+build that map's buffers (`SetOcc`, `InternalSpace`, `OuterCheck`, plan_env/src/sdf_map.cpp:263-473), same names.  CUDA only."""
 import ctypes
 
 import numpy as np
@@ -19,6 +20,7 @@ class PlannerGrid:
         for b in bufs:
             if b is not None and b.size != int(d[0]) * int(d[1]) * int(d[2]):
                 raise ValueError("voxel buffer size does not match voxel_num")
+        self.dims = d
         self.h = ctypes.c_void_p(self.lib.fcvm_grid_create(device, ptr(o, f64p), float(resolution), ptr(d, i32p), *[ptr(b, i8p) for b in bufs]))
         if not self.h:
             raise _lib.FcvmError(-1, self.lib.fcvm_last_error().decode())
@@ -56,6 +58,37 @@ class PlannerGrid:
         dist = np.zeros((n, n), np.float64) if want_dist else None
         check(self.lib.fcvm_grid_line_of_sight(self.h, ptr(p, f64p), n, ptr(safe, u8p), ptr(dist, f64p)))
         return safe, dist
+
+    # ---- building the buffers on the device (start from PlannerGrid(origin, res, voxel_num): all three zero) ----
+    def SetOcc(self, cloud):
+        """SDFMap::SetOcc (sdf_map.cpp:440-455) / initHCMap's marking loop (:178-187)."""
+        c = np.ascontiguousarray(cloud, np.float32).reshape(-1, 3)
+        check(self.lib.fcvm_grid_set_occ(self.h, ptr(c, f32p), len(c)))
+
+    def InternalSpace(self, seg_clouds, seg_ends, inflate_num, proj_interval, thickness):
+        """SDFMap::InternalSpace (sdf_map.cpp:263-395).  seg_clouds: the per-segment clouds (list of float32 [n_s, 3]);
+        seg_ends[s] = (start xyz, end xyz) of the segment's two skeleton vertices."""
+        xyz = np.ascontiguousarray(np.concatenate(seg_clouds), np.float32)
+        offs = np.concatenate([[0], np.cumsum([len(c) for c in seg_clouds])]).astype(np.int64)
+        ends = np.ascontiguousarray(seg_ends, np.float64).reshape(-1, 6)
+        assert len(ends) == len(seg_clouds)
+        check(self.lib.fcvm_grid_internal_space(self.h, ptr(xyz, f32p), ptr(offs, i64p), len(seg_clouds), ptr(ends, f64p), int(inflate_num),
+                                                float(proj_interval), float(thickness)))
+
+    def OuterCheck(self, outers, check_scale):
+        """SDFMap::OuterCheck (sdf_map.cpp:457-473): outers = n x (position, direction)."""
+        o = np.ascontiguousarray(outers, np.float64).reshape(-1, 6)
+        check(self.lib.fcvm_grid_outer_check(self.h, ptr(o, f64p), len(o), float(check_scale)))
+
+    def buffers(self):
+        """(occupancy_buffer_hc_, occupancy_inflate_buffer_hc_, occupancy_buffer_internal_) as x-major int8 arrays."""
+        G = int(np.prod(self.dims.astype(np.int64)))
+        out = [np.zeros(G, np.int8) for _ in range(3)]
+        check(self.lib.fcvm_grid_get_buffers(self.h, *[ptr(b, i8p) for b in out]))
+        return tuple(out)
+
+    def oob_writes(self):
+        return int(self.lib.fcvm_grid_oob_writes(self.h))
 
     def counters(self):
         out = np.zeros(3, np.int64)

@@ -12,6 +12,12 @@
 //            getUncoveredModelCloud
 // Error convention as the reference: void methods, ROS_ERROR + return on bad input; nothing throws.
 // A missing CUDA device is reported the same way — the library has no CPU fallback.
+//
+// Multi-GPU switch: the launch parameter `fcvm/gpus` (default 1).  With N > 1 the manager holds N library handles, one per
+// CUDA device fcvm/device .. fcvm/device + N - 1, joined by the library's own NCCL communicator (fcvm_set_shard_nccl), and
+// every public call is made on all of them at once, one host thread per handle: each GPU evaluates its block of every
+// viewpoint batch, all end with the same (bit-identical) state, results are read from the first.  The planner's code does
+// not change.
 #ifndef _VIEWPOINT_MANAGER_H_
 #define _VIEWPOINT_MANAGER_H_
 
@@ -25,6 +31,7 @@
 #include <map>
 #include <memory>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "fcvm.h"
@@ -69,7 +76,7 @@ namespace predrecon
   {
   public:
     ViewpointManager() : h_(nullptr) {}
-    ~ViewpointManager() { fcvm_destroy(h_); }
+    ~ViewpointManager() { destroy_all(); }
     ViewpointManager(const ViewpointManager &) = delete;
     ViewpointManager &operator=(const ViewpointManager &) = delete;
 
@@ -79,7 +86,7 @@ namespace predrecon
     {
       fcvm_params p = fcvm_params();
       std::string attitude;
-      bool zflag = false, pose_update = false;
+      bool zflag = false, pose_update = true;
       nh.param("viewpoint_manager/visible_range", p.visible_range, -1.0);
       nh.param("viewpoint_manager/viewpoints_distance", p.viewpoints_distance, -1.0);
       nh.param("viewpoint_manager/fov_h", p.fov_h, -1.0);
@@ -91,43 +98,59 @@ namespace predrecon
       nh.param("viewpoint_manager/safeHeight", p.safe_height, -1.0);
       nh.param("viewpoint_manager/safe_radius", p.safe_radius, -1.0);
       nh.param("viewpoint_manager/attitude_type", attitude, std::string("null"));
-      nh.param("viewpoint_manager/max_iter_num", p.max_iter_num, -1);
-      nh.param("viewpoint_manager/pose_update", pose_update, false);
+      nh.param("viewpoint_manager/max_iter_num", p.max_iter_num, 0);            // reference default (cpp:46)
+      nh.param("viewpoint_manager/pose_update", pose_update, true);         // reference default (cpp:47)
       nh.param("perception_utils/top_angle", p.top_angle, -1.0);
       nh.param("perception_utils/left_angle", p.left_angle, -1.0);
       nh.param("perception_utils/right_angle", p.right_angle, -1.0);
       nh.param("perception_utils/max_dist", p.max_dist, -1.0);
       nh.param("perception_utils/vis_dist", p.vis_dist, -1.0);
       nh.param("hcmap/resolution", p.resolution, -1.0);
-      int seed = 0, device = 0, threads = 0;
+      int seed = 0, device = 0, threads = 0, gpus = 1;
       nh.param("fcvm/seed", seed, 0);             // replaces the reference's wall-clock seeds (cpp:962-977, 249-255)
       nh.param("fcvm/device", device, 0);
       nh.param("fcvm/host_threads", threads, 0);
+      nh.param("fcvm/gpus", gpus, 1);
       p.z_ground = zflag ? 1 : 0;
       p.pose_update = pose_update ? 1 : 0;
       p.attitude = attitude == "yaw" ? FCVM_ATTITUDE_YAW : (attitude == "all" ? FCVM_ATTITUDE_ALL : FCVM_ATTITUDE_OTHER);
       p.seed = (uint64_t)seed;
-      p.device = device;
       p.host_threads = threads;
-      fcvm_destroy(h_);
-      h_ = fcvm_create(&p);
-      if (!h_) ROS_ERROR("[ViewpointManager] %s", fcvm_last_error());
+      destroy_all();
+      if (gpus < 1) gpus = 1;
+      if (gpus > 1 && threads <= 0)               // the handles of one process share its cores
+        p.host_threads = (int)(std::thread::hardware_concurrency() / (unsigned)gpus > 0 ? std::thread::hardware_concurrency() / (unsigned)gpus : 1);
+      for (int k = 0; k < gpus; ++k)
+      {
+        p.device = device + k;
+        fcvm_t *h = fcvm_create(&p);
+        if (!h) { ROS_ERROR("[ViewpointManager] %s", fcvm_last_error()); destroy_all(); return; }
+        hs_.push_back(h);
+      }
+      h_ = hs_[0];
+      if (gpus > 1)
+      {
+        uint8_t id[128];
+        if (fcvm_nccl_unique_id(id) != FCVM_OK) { ROS_ERROR("[ViewpointManager] %s", fcvm_last_error()); destroy_all(); return; }
+        const int n = gpus;
+        if (all([&](int k, fcvm_t *h) { return fcvm_set_shard_nccl(h, id, k, n); }) != FCVM_OK) destroy_all();
+      }
     }
 
-    void reset() { ok(fcvm_reset(h_)); }
+    void reset() { all([](int, fcvm_t *h) { return fcvm_reset(h); }); }
 
     void setModel(pcl::PointCloud<pcl::PointXYZ>::Ptr input_model)
     {
       std::vector<float> xyz;
       pack(*input_model, xyz);
-      ok(fcvm_set_model(h_, xyz.data(), (int64_t)(xyz.size() / 3)));
+      all([&](int, fcvm_t *h) { return fcvm_set_model(h, xyz.data(), (int64_t)(xyz.size() / 3)); });
     }
 
     void setMapPointCloud(pcl::PointCloud<pcl::PointXYZ>::Ptr input_map)
     {
       std::vector<float> xyz;
       pack(*input_map, xyz);
-      ok(fcvm_set_map_cloud(h_, xyz.data(), (int64_t)(xyz.size() / 3)));
+      all([&](int, fcvm_t *h) { return fcvm_set_map_cloud(h, xyz.data(), (int64_t)(xyz.size() / 3)); });
     }
 
     void setNormals(std::map<Eigen::Vector3d, Eigen::Vector3d, Vector3dCompare0> &pt_normal_pairs)
@@ -141,7 +164,7 @@ namespace predrecon
           k.push_back(kv.first(i));
           v.push_back(kv.second(i));
         }
-      ok(fcvm_set_normals(h_, k.data(), v.data(), (int64_t)pt_normal_pairs.size()));
+      all([&](int, fcvm_t *h) { return fcvm_set_normals(h, k.data(), v.data(), (int64_t)pt_normal_pairs.size()); });
     }
 
     void setInitViewpoints(pcl::PointCloud<pcl::PointNormal>::Ptr input_normal_vps)
@@ -153,10 +176,10 @@ namespace predrecon
         const float r[6] = {q.x, q.y, q.z, q.normal_x, q.normal_y, q.normal_z};
         rows.insert(rows.end(), r, r + 6);
       }
-      ok(fcvm_set_init_viewpoints(h_, rows.data(), (int64_t)(rows.size() / 6)));
+      all([&](int, fcvm_t *h) { return fcvm_set_init_viewpoints(h, rows.data(), (int64_t)(rows.size() / 6)); });
     }
 
-    void updateViewpoints() { ok(fcvm_update(h_)); }
+    void updateViewpoints() { all([](int, fcvm_t *h) { return fcvm_update(h); }); }
 
     void getUpdatedViewpoints(std::vector<SingleViewpoint> &viewpoints)
     {
@@ -202,11 +225,31 @@ namespace predrecon
         xyz.push_back(q.x); xyz.push_back(q.y); xyz.push_back(q.z);
       }
     }
-    void ok(int rc)
+    // f(rank, handle) on every handle at once (one thread per extra handle: the sharded calls are collective); the first
+    // failure is logged like the reference logs bad input, and its code returned
+    template <class F>
+    int all(F f)
     {
-      if (rc != FCVM_OK) ROS_ERROR("[ViewpointManager] %s (code %d)", h_ ? fcvm_last_error() : "init() was not called", rc);
+      if (hs_.empty()) { ROS_ERROR("[ViewpointManager] init() was not called (code %d)", FCVM_ENOTREADY); return FCVM_ENOTREADY; }
+      std::vector<int> rc(hs_.size(), FCVM_OK);
+      std::vector<std::string> msg(hs_.size());
+      auto run = [&](size_t k) { rc[k] = f((int)k, hs_[k]); if (rc[k] != FCVM_OK) msg[k] = fcvm_last_error(); };
+      std::vector<std::thread> th;
+      for (size_t k = 1; k < hs_.size(); ++k) th.emplace_back(run, k);
+      run(0);
+      for (auto &t : th) t.join();
+      for (size_t k = 0; k < hs_.size(); ++k)
+        if (rc[k] != FCVM_OK) { ROS_ERROR("[ViewpointManager] %s (code %d)", msg[k].c_str(), rc[k]); return rc[k]; }
+      return FCVM_OK;
     }
-    fcvm_t *h_;
+    void destroy_all()
+    {
+      for (fcvm_t *h : hs_) fcvm_destroy(h);
+      hs_.clear();
+      h_ = nullptr;
+    }
+    fcvm_t *h_;                    // hs_[0]: where results are read from
+    std::vector<fcvm_t *> hs_;     // one handle per GPU
   };
 } // namespace predrecon
 

@@ -64,7 +64,7 @@ typedef struct fcvm_params {
   double ground_pos;           /* viewpoint_manager/GroundPos                                */
   double safe_height;          /* viewpoint_manager/safeHeight                               */
   double safe_radius;          /* viewpoint_manager/safe_radius                              */
-  double top_angle, left_angle, right_angle; /* perception_utils/*, radians                 */
+  double top_angle, left_angle, right_angle; /* perception_utils/..., radians               */
   double max_dist;             /* perception_utils/max_dist                                  */
   double vis_dist;             /* perception_utils/vis_dist (visualisation only; unused)     */
   double resolution;           /* hcmap/resolution                                           */
@@ -170,7 +170,8 @@ int64_t fcvm_evaluate_csr(fcvm_t* h, int32_t stage, const double* pose5, int64_t
  * bitset rows and counts on the device.  fcvm_stage_poses copies/derives the per-pose device
  * record (position + 4 world-frame FOV normals) once; fcvm_evaluate_resident can then be
  * launched repeatedly on `stream` (a cudaStream_t passed as void*, NULL = the handle's stream).
- * rays_out (host, may be NULL) is only read back when sync != 0. */
+ * rays_out (host, may be NULL) is only read back when sync != 0.  Stage 2 re-tests the visible sets the most recent stage-1 pass
+ * over the same resident batch left on the device (same poses; its rows go to a second buffer, the E1 rows stay). */
 int fcvm_stage_poses(fcvm_t* h, const double* pose5, int64_t n);
 int fcvm_evaluate_resident(fcvm_t* h, int32_t stage, void* stream, int32_t sync, int64_t* rays_out);
 /* device pointers of the resident batch: rows (n x words uint32), counts (n int32) */
@@ -293,6 +294,24 @@ int          fcvm_grid_safety_box(fcvm_grid_t* g, const float* vp_xyz, int64_t n
  * safe[i * n + j] = 1 if the segment p_i -> p_j is free (then the path is {p_i, p_j} and its cost dist[i * n + j] =
  * (p_i - p_j).norm()); 0 = the caller falls back to A* as the reference does.  dist may be NULL. */
 int          fcvm_grid_line_of_sight(fcvm_grid_t* g, const double* p_xyz, int64_t n, uint8_t* safe_nxn, double* dist_nxn);
+/* The buffers can also be built on the device (pass NULL for all three to fcvm_grid_create = the zeroed buffers of
+ * SDFMap::initHCMap, sdf_map.cpp:159-172):
+ * fcvm_grid_set_occ         SDFMap::SetOcc (sdf_map.cpp:440-455) / the marking loop of initHCMap (:178-187): hc = 1 at the voxel of
+ *                           every point that lies in the map.
+ * fcvm_grid_internal_space  SDFMap::InternalSpace (sdf_map.cpp:263-395) for all skeleton segments at once: seg_xyz = the points of
+ *                           the segment clouds concatenated (segment s = points seg_offsets[s] .. seg_offsets[s+1]), seg_ends6[6 s ..] =
+ *                           vertices.row(segments[id][0]) and vertices.row(segments[id][1]); inflate_num, proj_interval, thickness =
+ *                           hcmap/{inflateVoxel, interval, plane_thickness} (sdf_map.cpp:129-133).
+ * fcvm_grid_outer_check     SDFMap::OuterCheck (sdf_map.cpp:457-473): outers6 = n x (position, direction), check_scale = hcmap/checkScale.
+ * fcvm_grid_get_buffers     the three buffers back in the reference's x-major char layout (any pointer may be NULL).
+ * The reference writes voxels outside the map unchecked (undefined behaviour); those writes are skipped and counted
+ * (fcvm_grid_oob_writes). */
+int          fcvm_grid_set_occ(fcvm_grid_t* g, const float* xyz, int64_t n);
+int          fcvm_grid_internal_space(fcvm_grid_t* g, const float* seg_xyz, const int64_t* seg_offsets, int64_t nseg, const double* seg_ends6,
+                                      int32_t inflate_num, double proj_interval, double thickness);
+int          fcvm_grid_outer_check(fcvm_grid_t* g, const double* outers6, int64_t n, double check_scale);
+int          fcvm_grid_get_buffers(fcvm_grid_t* g, int8_t* hc, int8_t* inflate, int8_t* internal);
+int64_t      fcvm_grid_oob_writes(fcvm_grid_t* g);
 /* [0] voxel lookups / probes made [1] marches that hit the step cap (the reference would not terminate) [2] kernels launched */
 int          fcvm_grid_counters(fcvm_grid_t* g, int64_t* out3);
 double       fcvm_grid_last_kernel_ms(fcvm_grid_t* g);

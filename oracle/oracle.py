@@ -327,15 +327,15 @@ class RefEvaluator:
         self.P = len(xyz)
         self.lib.ref_set_model(self.h, _ptr(xyz, c_f32p), ctypes.c_int64(len(xyz)))
 
-    def evaluate(self, stage, pose5, restrict_rows=None):
+    def evaluate(self, stage, pose5, restrict_rows=None, threads=1, want_rows=True):
         pose5 = np.ascontiguousarray(pose5, dtype=np.float64).reshape(-1, 5)
         n = len(pose5)
         words = (self.P + 31) // 32
-        count = np.zeros(n, np.int32); rows = np.zeros((n, words), np.uint32); ctr = np.zeros(4, np.int64)
+        count = np.zeros(n, np.int32); rows = np.zeros((n, words), np.uint32) if want_rows else None; ctr = np.zeros(4, np.int64)
         if restrict_rows is not None:
             restrict_rows = np.ascontiguousarray(restrict_rows, dtype=np.uint32)
-        rc = self.lib.ref_evaluate(self.h, ctypes.c_int32(stage), _ptr(pose5, c_f64p), ctypes.c_int64(n), _ptr(restrict_rows, c_u32p),
-                                   _ptr(count, c_i32p), _ptr(rows, c_u32p), _ptr(ctr, c_i64p))
+        rc = self.lib.ref_evaluate_mt(self.h, ctypes.c_int32(stage), _ptr(pose5, c_f64p), ctypes.c_int64(n), _ptr(restrict_rows, c_u32p),
+                                      _ptr(count, c_i32p), _ptr(rows, c_u32p), _ptr(ctr, c_i64p), ctypes.c_int32(threads))
         if rc != 0:
             raise RuntimeError(f"ref_evaluate failed: {rc}")
         return count, rows, ctr
@@ -566,6 +566,33 @@ class PlanOracle:
         self.lib.orc_plan_counters(self.h, _ptr(out, c_i64p))
         return out
 
+    # ---- SDFMap::SetOcc / InternalSpace / OuterCheck (sdf_map.cpp:263-473) on the three buffers
+    def setOcc(self, xyz):
+        xyz = np.ascontiguousarray(xyz, np.float32).reshape(-1, 3)
+        self.lib.orc_plan_set_occ(self.h, _ptr(xyz, c_f32p), ctypes.c_int64(len(xyz)))
+
+    def InternalSpace(self, seg_clouds, seg_ends, inflate_num, proj_interval, thickness):
+        """seg_clouds: list of float32 [n_s, 3]; seg_ends: [nseg, 6] = (start xyz, end xyz) of each skeleton segment."""
+        xyz = np.ascontiguousarray(np.concatenate(seg_clouds) if len(seg_clouds) else np.zeros((0, 3)), np.float32)
+        offs = np.concatenate([[0], np.cumsum([len(c) for c in seg_clouds])]).astype(np.int64)
+        ends = np.ascontiguousarray(seg_ends, np.float64).reshape(-1, 6)
+        self.lib.orc_plan_internal_space(self.h, _ptr(xyz, c_f32p), _ptr(offs, c_i64p), ctypes.c_int64(len(seg_clouds)), _ptr(ends, c_f64p),
+                                         ctypes.c_int32(inflate_num), ctypes.c_double(proj_interval), ctypes.c_double(thickness))
+
+    def OuterCheck(self, outers, check_scale):
+        o = np.ascontiguousarray(outers, np.float64).reshape(-1, 6)
+        self.lib.orc_plan_outer_check(self.h, _ptr(o, c_f64p), ctypes.c_int64(len(o)), ctypes.c_double(check_scale))
+
+    def buffers(self):
+        G = int(np.prod(self.dims.astype(np.int64)))
+        hc = np.zeros(G, np.int8); inf = np.zeros(G, np.int8); internal = np.zeros(G, np.int8)
+        self.lib.orc_plan_get_buffers(self.h, _ptr(hc, c_i8p), _ptr(inf, c_i8p), _ptr(internal, c_i8p))
+        return hc, inf, internal
+
+    def oob_writes(self):
+        self.lib.orc_plan_oob_writes.restype = ctypes.c_int64
+        return int(self.lib.orc_plan_oob_writes(self.h))
+
 
 class RefPlanGrid:
     """The planner's call-site loops driving the REFERENCE's RayCaster (oracle/_ref/libfcvm_ref.so)."""
@@ -592,6 +619,15 @@ class RefPlanGrid:
         cap = ctypes.c_int32(0)
         c = self.lib.ref_light_state_cross(self.h, _ptr(vp, c_f64p), _ptr(vertex, c_f64p), ctypes.c_int64(max_calls), ctypes.byref(cap))
         return int(c), bool(cap.value)
+
+    def cast_marks(self, a, b, cap=4096, max_calls=100000):
+        """voxels the InternalSpace / OuterCheck marking loop touches for the ray a -> b -> ([k, 3] map indices, capped?)"""
+        a = np.ascontiguousarray(a, np.float64); b = np.ascontiguousarray(b, np.float64)
+        out = np.zeros((cap, 3), np.int32)
+        c = ctypes.c_int32(0)
+        self.lib.ref_cast_marks.restype = ctypes.c_int64
+        k = self.lib.ref_cast_marks(self.h, _ptr(a, c_f64p), _ptr(b, c_f64p), _ptr(out, c_i32p), ctypes.c_int64(cap), ctypes.c_int64(max_calls), ctypes.byref(c))
+        return out[:min(int(k), cap)].copy(), bool(c.value)
 
     def straight_line(self, p1, p2, max_calls=100000):
         p1 = np.ascontiguousarray(p1, np.float64); p2 = np.ascontiguousarray(p2, np.float64)

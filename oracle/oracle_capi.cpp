@@ -389,6 +389,26 @@ int orc_plan_line_of_sight(orc_plan_handle* h, const double* p, int64_t n, uint8
   for (auto& c : ctrs) { h->ops.ctr.lookups += c.lookups; h->ops.ctr.cap_trips += c.cap_trips; }
   return 0;
 }
+// SDFMap::SetOcc / InternalSpace / OuterCheck (sdf_map.cpp:263-473) on the handle's three buffers
+int orc_plan_set_occ(orc_plan_handle* h, const float* xyz, int64_t n) { h->ops.setOcc(xyz, n); return 0; }
+int orc_plan_internal_space(orc_plan_handle* h, const float* seg_xyz, const int64_t* seg_offsets, int64_t nseg, const double* seg_ends6, int32_t inflate_num,
+                            double proj_interval, double thickness) {
+  for (int64_t s = 0; s < nseg; ++s)
+    h->ops.internalSpaceSegment(seg_xyz + 3 * seg_offsets[s], seg_offsets[s + 1] - seg_offsets[s], V3(seg_ends6[6 * s], seg_ends6[6 * s + 1], seg_ends6[6 * s + 2]),
+                                V3(seg_ends6[6 * s + 3], seg_ends6[6 * s + 4], seg_ends6[6 * s + 5]), inflate_num, proj_interval, thickness);
+  return 0;
+}
+int orc_plan_outer_check(orc_plan_handle* h, const double* outers6, int64_t n, double check_scale) { h->ops.outerCheck(outers6, n, check_scale); return 0; }
+int orc_plan_get_buffers(orc_plan_handle* h, int8_t* hc, int8_t* inflate, int8_t* internal) {
+  const size_t G = h->ops.g.inflate.size();
+  for (size_t i = 0; i < G; ++i) {
+    if (hc) hc[i] = (int8_t)h->ops.g.map.occupancy_buffer_hc_[i];
+    if (inflate) inflate[i] = (int8_t)h->ops.g.inflate[i];
+    if (internal) internal[i] = (int8_t)h->ops.g.map.occupancy_buffer_internal_[i];
+  }
+  return 0;
+}
+int64_t orc_plan_oob_writes(orc_plan_handle* h) { return h->ops.oob_writes; }
 int orc_plan_counters(orc_plan_handle* h, int64_t* out2) { out2[0] = h->ops.ctr.lookups; out2[1] = h->ops.ctr.cap_trips; return 0; }
 
 }  // extern "C"

@@ -12,6 +12,9 @@
 #include <cstdint>
 #include <iostream>
 #include <memory>
+#include <array>
+#include <atomic>
+#include <thread>
 #include <vector>
 
 #define private public   // normals_ of PerceptionUtils is read by ref_fov_normals
@@ -173,6 +176,24 @@ int ref_straight_line(const orc::PlanGrid* g, const double* p1, const double* p2
   }
   return safe ? 1 : 0;
 }
+// The marking loop of SDFMap::InternalSpace / OuterCheck (sdf_map.cpp:332-337, 379-384, 465-471) driving the reference's RayCaster:
+//   internal_cast_->input(a, b); internal_cast_->nextId(idx); while (internal_cast_->nextId(idx)) <touch idx>;
+// returns the number of voxels touched; the first `cap` of them as map indices in out[3 * k ..]
+int64_t ref_cast_marks(const orc::PlanGrid* g, const double* a, const double* b, int32_t* out, int64_t cap, int64_t max_calls, int32_t* capped) {
+  RayCaster rc;
+  rc.setParams(g->map.resolution_, ev(g->map.map_origin_));
+  Eigen::Vector3i idx;
+  int64_t k = 0, calls = 0;
+  *capped = 0;
+  rc.input(Eigen::Vector3d(a[0], a[1], a[2]), Eigen::Vector3d(b[0], b[1], b[2]));
+  rc.nextId(idx);
+  while (rc.nextId(idx)) {
+    if (++calls > max_calls) { *capped = 1; break; }
+    if (k < cap) { out[3 * k] = idx(0); out[3 * k + 1] = idx(1); out[3 * k + 2] = idx(2); }
+    ++k;
+  }
+  return k;
+}
 orc::PlanGrid* ref_plan_grid_create(const double* origin3, double res, const int32_t* dims3, const int8_t* hc, const int8_t* inflate, const int8_t* internal) {
   orc::PlanGrid* g = new orc::PlanGrid();
   const int d[3] = {dims3[0], dims3[1], dims3[2]};
@@ -213,17 +234,10 @@ int ref_set_model(ref_handle* h, const float* xyz, int64_t n) { h->model.assign(
 // One evaluator pass per pose with the reference's RayCaster and PerceptionUtils objects, driven
 // exactly as viewpoint_manager.cpp drives them (E1 358-425, E2 457-498, E3 822-875, E4 546-586).
 // Same contract as orc_evaluate (single thread).  counters4 = pair tests, rays, lookups, walk lookups.
-int ref_evaluate(ref_handle* h, int32_t stage, const double* pose5, int64_t n, const uint32_t* restrict_rows, int32_t* count,
-                 uint32_t* rows, int64_t* counters4) {
-  if (stage < 1 || stage > 4) return -1;
-  set_params(h->prm);
-  ros::NodeHandle nh;
-  RefEval e;
-  e.percep_utils_.init(nh);
-  e.raycaster_.setParams(h->map.resolution_, ev(h->map.map_origin_));     // viewpoint_manager.cpp:84-85
-  e.map = &h->map;
+static void ref_eval_range(ref_handle* h, RefEval& e, int32_t stage, const double* pose5, int64_t v0, int64_t v1, const uint32_t* restrict_rows, int32_t* count,
+                           uint32_t* rows) {
   const int64_t P = (int64_t)h->model.size() / 3, words = (P + 31) / 32;
-  for (int64_t v = 0; v < n; ++v) {
+  for (int64_t v = v0; v < v1; ++v) {
     const double* q = pose5 + 5 * v;
     const Eigen::Vector3d vp(q[0], q[1], q[2]);
     e.percep_utils_.setPose_PY(vp, q[3], q[4]);
@@ -254,7 +268,52 @@ int ref_evaluate(ref_handle* h, int32_t stage, const double* pose5, int64_t n, c
     }
     if (count) count[v] = c;
   }
+}
+
+int ref_evaluate(ref_handle* h, int32_t stage, const double* pose5, int64_t n, const uint32_t* restrict_rows, int32_t* count,
+                 uint32_t* rows, int64_t* counters4) {
+  if (stage < 1 || stage > 4) return -1;
+  set_params(h->prm);
+  ros::NodeHandle nh;
+  RefEval e;
+  e.percep_utils_.init(nh);
+  e.raycaster_.setParams(h->map.resolution_, ev(h->map.map_origin_));     // viewpoint_manager.cpp:84-85
+  e.map = &h->map;
+  ref_eval_range(h, e, stage, pose5, 0, n, restrict_rows, count, rows);
   if (counters4) { counters4[0] = e.pairs; counters4[1] = e.rays; counters4[2] = e.lookups; counters4[3] = e.walk; }
+  return 0;
+}
+
+// The same pass with the viewpoints handed out to `threads` host threads, each with its own RayCaster / PerceptionUtils objects
+// (the reference itself is single-threaded on this path; this is what "all host cores" means for bench.py --impl reference).
+int ref_evaluate_mt(ref_handle* h, int32_t stage, const double* pose5, int64_t n, const uint32_t* restrict_rows, int32_t* count, uint32_t* rows,
+                    int64_t* counters4, int32_t threads) {
+  if (stage < 1 || stage > 4) return -1;
+  if (threads < 1) threads = 1;
+  set_params(h->prm);
+  std::atomic<int64_t> next(0);
+  std::vector<std::array<int64_t, 4>> ctr((size_t)threads, std::array<int64_t, 4>{0, 0, 0, 0});
+  auto work = [&](int t) {
+    ros::NodeHandle nh;
+    RefEval e;
+    e.percep_utils_.init(nh);
+    e.raycaster_.setParams(h->map.resolution_, ev(h->map.map_origin_));
+    e.map = &h->map;
+    for (;;) {
+      const int64_t v = next.fetch_add(1);
+      if (v >= n) break;
+      ref_eval_range(h, e, stage, pose5, v, v + 1, restrict_rows, count, rows);
+    }
+    ctr[(size_t)t] = {e.pairs, e.rays, e.lookups, e.walk};
+  };
+  std::vector<std::thread> th;
+  for (int t = 1; t < threads; ++t) th.emplace_back(work, t);
+  work(0);
+  for (auto& t : th) t.join();
+  if (counters4) {
+    for (int k = 0; k < 4; ++k) counters4[k] = 0;
+    for (auto& c : ctr) for (int k = 0; k < 4; ++k) counters4[k] += c[(size_t)k];
+  }
   return 0;
 }
 

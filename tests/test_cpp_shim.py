@@ -27,7 +27,7 @@ def _build():
     return BIN
 
 
-def _write_inputs(tmp, prm, pts, nrm, vps):
+def _write_inputs(tmp, prm, pts, nrm, vps, gpus=1, drop=()):
     keys = {"viewpoint_manager/visible_range": prm.visible_range, "viewpoint_manager/viewpoints_distance": prm.viewpoints_distance,
             "viewpoint_manager/fov_h": prm.fov_h, "viewpoint_manager/fov_w": prm.fov_w, "viewpoint_manager/pitch_upper": prm.pitch_upper,
             "viewpoint_manager/pitch_lower": prm.pitch_lower, "viewpoint_manager/zGround": prm.z_ground, "viewpoint_manager/GroundPos": prm.ground_pos,
@@ -35,7 +35,9 @@ def _write_inputs(tmp, prm, pts, nrm, vps):
             "viewpoint_manager/max_iter_num": prm.max_iter_num, "viewpoint_manager/pose_update": prm.pose_update,
             "perception_utils/top_angle": prm.top_angle, "perception_utils/left_angle": prm.left_angle, "perception_utils/right_angle": prm.right_angle,
             "perception_utils/max_dist": prm.max_dist, "perception_utils/vis_dist": prm.vis_dist, "hcmap/resolution": prm.resolution,
-            "fcvm/seed": prm.seed}
+            "fcvm/seed": prm.seed, "fcvm/gpus": gpus}
+    for k in drop:
+        keys.pop(k)
     with open(os.path.join(tmp, "params.txt"), "w") as f:
         for k, v in keys.items():
             f.write(f"{k} {float(v)!r}\n")
@@ -92,3 +94,53 @@ def test_shim_sequence_matches_oracle(small_plant, oracle_mod, tmp_path):
     assert len(oi) > 5
     assert np.array_equal(fin["id"], oi) and np.array_equal(fin["pose"], op) and np.array_equal(fin["vox"], ox)
     assert np.array_equal(unc, orc.getUncoveredModelCloud())
+
+
+@pytest.mark.gpu
+def test_shim_on_two_gpus_in_one_process(small_plant, oracle_mod, tmp_path):
+    """`fcvm/gpus 2`: the drop-in class holds one library handle per GPU, joined by the library's own NCCL communicator and
+    driven by one host thread each; the planner's call sequence is unchanged and the result is the oracle's, bit for bit."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    exe = _build()
+    prm = small_plant["params"]
+    vps = small_plant["viewpoints"][:301]
+    _write_inputs(str(tmp_path), prm, small_plant["points"], small_plant["normals"], vps, gpus=2)
+    r = subprocess.run([exe, str(tmp_path / "params.txt"), str(tmp_path / "input.bin"), str(tmp_path / "out.bin")],
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
+    assert r.returncode == 0 and "ERROR" not in r.stderr, r.stderr
+    fin, unc = _read_outputs(tmp_path / "out.bin")
+    orc = oracle_mod.Oracle(prm)
+    orc.setMapPointCloud(small_plant["points"]); orc.setModel(small_plant["points"])
+    orc.setNormals(small_plant["points"].astype(np.float64), small_plant["normals"])
+    orc.setInitViewpoints(vps)
+    assert orc.updateViewpoints() == 0
+    oi, op, ox = orc.getUpdatedViewpoints()
+    assert len(oi) > 5
+    assert np.array_equal(fin["id"], oi) and np.array_equal(fin["pose"], op) and np.array_equal(fin["vox"], ox)
+    assert np.array_equal(unc, orc.getUncoveredModelCloud())
+
+
+@pytest.mark.gpu
+def test_shim_defaults_are_the_references(small_plant, oracle_mod, tmp_path):
+    """viewpoint_manager/max_iter_num and viewpoint_manager/pose_update left unset: the reference defaults to 0 and TRUE
+    (viewpoint_manager.cpp:46-47), so the E1 / E2 pose refinement runs and no uncovered-area round does."""
+    exe = _build()
+    prm = small_plant["params"]
+    vps = small_plant["viewpoints"][:150]
+    _write_inputs(str(tmp_path), prm, small_plant["points"], small_plant["normals"], vps, drop=("viewpoint_manager/max_iter_num", "viewpoint_manager/pose_update"))
+    r = subprocess.run([exe, str(tmp_path / "params.txt"), str(tmp_path / "input.bin"), str(tmp_path / "out.bin")],
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300)
+    assert r.returncode == 0 and r.stderr.strip() == "", r.stderr
+    fin, unc = _read_outputs(tmp_path / "out.bin")
+    import copy
+    p2 = copy.copy(prm)
+    p2.max_iter_num, p2.pose_update = 0, 1
+    orc = oracle_mod.Oracle(p2)
+    orc.setMapPointCloud(small_plant["points"]); orc.setModel(small_plant["points"])
+    orc.setNormals(small_plant["points"].astype(np.float64), small_plant["normals"])
+    orc.setInitViewpoints(vps)
+    assert orc.updateViewpoints() == 0
+    oi, op, ox = orc.getUpdatedViewpoints()
+    assert np.array_equal(fin["id"], oi) and np.array_equal(fin["pose"], op) and np.array_equal(fin["vox"], ox)

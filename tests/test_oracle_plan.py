@@ -90,3 +90,65 @@ def test_known_answers(oracle_mod):
     assert oracle_mod.PlanOracle([0, 0, 0], 0.5, dims, blk, None, None).safetyBox(np.array([[5.0, 5.0, 5.0]], np.float32), 1.0).tolist() == [0]
     internal2 = np.zeros_like(hc); internal2[10, 10, 10] = 1
     assert oracle_mod.PlanOracle([0, 0, 0], 0.5, dims, None, None, internal2).safetyBox(np.array([[5.0, 5.0, 5.0]], np.float32), 1.0).tolist() == [0]
+
+
+# ---- SDFMap::InternalSpace / OuterCheck (sdf_map.cpp:263-473), oracle/fcvm_oracle_plan.hpp ----------------------------------
+def test_internal_space_marking_loop_against_reference_raycaster(oracle_mod):
+    """The loop `input(a, b); nextId(idx); while (nextId(idx)) mark(idx)` of InternalSpace / OuterCheck: the voxels the oracle
+    marks for a single ray are exactly those the same loop touches when it drives the reference's own RayCaster."""
+    if not oracle_mod.ref_available():
+        pytest.skip("oracle/_ref is not built (no /root/reference here)")
+    origin, res, dims, _, _, _ = _grid()
+    ref = oracle_mod.RefPlanGrid(origin, res, dims)
+    rng = np.random.default_rng(5)
+    a, b = _segments(rng, origin + 2.0, res, dims - 10, 1500)        # keep most rays inside the map
+    G = int(np.prod(dims))
+    n_marked = n_cap = 0
+    for s, e in zip(a, b):
+        ids, capped = ref.cast_marks(s, e)
+        if capped:
+            n_cap += 1
+            continue
+        want = np.zeros(G, np.int8)
+        inside = np.all((ids >= 0) & (ids < dims), axis=1)
+        adr = (ids[inside, 0].astype(np.int64) * dims[1] + ids[inside, 1]) * dims[2] + ids[inside, 2]
+        want[adr] = 1
+        # OuterCheck with the ray's own direction and unit scale is one such loop (clearing); run it on an all-ones buffer
+        orc = oracle_mod.PlanOracle(origin, res, dims, None, None, np.ones(G, np.int8))
+        orc.OuterCheck(np.concatenate([s, e - s])[None], 1.0)
+        got = 1 - orc.buffers()[2]
+        # start + 1.0 * (e - s) can differ from e in the last bit: compare only when it reproduces e exactly
+        if not np.array_equal(s + 1.0 * (e - s), e):
+            continue
+        assert np.array_equal(got, want)
+        assert orc.oob_writes() == int((~inside).sum())
+        n_marked += int(want.sum())
+    assert n_marked > 5000 and n_cap < 400
+
+
+def test_internal_space_known_answers(oracle_mod):
+    """Hand-checkable InternalSpace: one segment along z, four cloud points."""
+    res, dims = 1.0, np.array([12, 12, 12], np.int32)
+    og = oracle_mod.PlanOracle(np.zeros(3), res, dims)
+    # segment from (5.5, 5.5, 2.5) to (5.5, 5.5, 6.5): length 4, interval 2 -> projection points at z = 2.5, 4.5 and the end 6.5
+    ends = np.array([[5.5, 5.5, 2.5, 5.5, 5.5, 6.5]])
+    cloud = np.array([[9.5, 5.5, 2.5],      # in the plane of the first projection point: ray (5.5,5.5,2.5) -> (9.5,5.5,2.5)
+                      [5.5, 1.5, 4.6],      # within thickness 0.2 of the second plane (z = 4.5)
+                      [2.5, 5.5, 5.5],      # no plane catches it: nearest projection point is z = 4.5 (distance sqrt(10)) vs z = 6.5 (same!) -> first minimum wins
+                      [5.5, 5.5, 9.5]], np.float32)   # beyond the end: nearest projection point is the end vertex
+    og.InternalSpace([cloud], ends, 1, 2.0, 0.2)
+    hc, inf, it = (b.reshape(tuple(dims)) for b in og.buffers())
+    assert hc.sum() == 4 and all(hc[tuple(np.floor(p).astype(int))] == 1 for p in cloud)
+    assert inf.sum() == 4 * 27                                      # four disjoint 3 x 3 x 3 cubes
+    # ray 1 runs along +x through voxels x = 5 .. 9 at (y, z) = (5, 2): the first (5) is discarded, the last (9) never reported
+    want = np.zeros_like(it)
+    want[6:9, 5, 2] = 1
+    # ray 2: (5.5, 5.5, 4.5) -> (5.5, 1.5, 4.6): along -y, voxels y = 5 .. 1 at x = 5, z = 4: marks y = 4, 3, 2
+    want[5, 2:5, 4] = 1
+    # ray 4: (5.5, 5.5, 6.5) -> (5.5, 5.5, 9.5): marks z = 7, 8
+    want[5, 5, 7:9] = 1
+    # ray 3: (5.5, 5.5, 4.5) -> (2.5, 5.5, 5.5): x from 5 down to 2, z from 4 up to 5; integer deltas (-3, 0, +1); its marks are whatever the
+    # marcher visits between the ends - at least the two interior x columns
+    got3 = it - want
+    assert got3.min() >= 0 and 2 <= got3.sum() <= 3 and got3[3:5, 5, 4:6].sum() == got3.sum()
+    assert it[5, 5, 2] == 0 and it[9, 5, 2] == 0                    # neither the projection point's voxel nor the cloud point's
