@@ -197,12 +197,14 @@ __device__ __forceinline__ bool birc(const GridDesc& g, double ax, double ay, do
     if (nflag) n.step(g);                                     \
     ret = pflag || nflag;                                     \
   }
-  bool more;
+  bool more, tripped = false;
   if (discard_first) { FCVM_BI_NEXT(more); }
   for (;;) {
     FCVM_BI_NEXT(more);
     if (!more) break;
-    if (--budget < 0) { st.trips++; break; }
+    // A marcher that has not arrived after Manhattan + 8 calls has run past its midpoint voxel and will never report "at
+    // end": the reference then walks on until an occCheck fails (an occupied voxel or the map's edge) and returns NOT visible.
+    if (--budget < 0) { st.trips++; tripped = true; break; }
     f = occ_free(g, pix, piy, piz, cp);
     r = occ_free(g, nix, niy, niz, cn);
     st.lookups += 2;
@@ -211,7 +213,7 @@ __device__ __forceinline__ bool birc(const GridDesc& g, double ax, double ay, do
 #undef FCVM_BI_NEXT
   f = occ_free(g, pix, piy, piz, cp);
   st.lookups += 1;
-  return f && r;
+  return f && r && !tripped;
 }
 
 // Surface-offset walk (viewpoint_manager.cpp:463-477 / 554-568): march point -> viewpoint with the

@@ -135,6 +135,7 @@ struct fcvm_handle {
   std::vector<int> vps_voxcount, vps_contri;   // host mirrors; voxcount is authoritative on the device during a stage
   int last_vps_num = 0;
   DevBuf<int> d_cover_contrib, d_contrib_id, d_voxcount;
+  DevBuf<int> d_snap_contrib, d_snap_id;       // MCI snapshot of an uncovered-area round (cpp:272-274)
   size_t voxcount_n = 0;      // logical length of vps_voxcount
   std::vector<FinalVp> final_vps;
   // ViewpointsPrune maps (viewpoint_manager.h:160-178).  They are members that are only ever
@@ -159,6 +160,8 @@ struct fcvm_handle {
   PinBuf<uint32_t> h_rows;
   PinBuf<int> h_count;
   PinBuf<VpRec> h_recs;
+  PinBuf<int> h_own_ids;
+  PinBuf<int4> h_own_sched;
   int64_t resident_n = 0;
   int64_t resident_W = 0;
   bool resident_e1 = false;                    // the first rows buffer holds the E1 rows of the resident batch
@@ -633,23 +636,27 @@ static int ownership(fcvm_handle* h, const DevBuf<uint32_t>& d_rows, int64_t n, 
 
   // id_at_pos[t] = viewpoint id of the t-th row in processing order; the local rows with a positive count, sorted by
   // key = (contri, ~position) descending, are what k_own_best walks
-  std::vector<int> id_at_pos(order.size());
-  std::vector<int4> sched;
+  // (page-locked staging owned by the handle: the copies below are still in flight when this function returns)
+  CU(h->h_own_ids.reserve(order.size()));
+  CU(h->h_own_sched.reserve(order.size()));
+  int* id_at_pos = h->h_own_ids.p;
+  int4* sched_buf = h->h_own_sched.p;
+  size_t nsched = 0;
   for (size_t t = 0; t < order.size(); ++t) {
     const int r = order[t];
     id_at_pos[t] = vp_ids[(size_t)r];
-    if (r >= lo && r < hi && count_host[r] > 0) sched.push_back(make_int4(r, count_host[r], (int)~(uint32_t)t, 0));
+    if (r >= lo && r < hi && count_host[r] > 0) sched_buf[nsched++] = make_int4(r, count_host[r], (int)~(uint32_t)t, 0);
   }
-  std::sort(sched.begin(), sched.end(), [](const int4& a, const int4& b) {
+  std::sort(sched_buf, sched_buf + nsched, [](const int4& a, const int4& b) {
     return a.y != b.y ? a.y > b.y : (uint32_t)a.z > (uint32_t)b.z;
   });
-  CU(h->d_ids.reserve(id_at_pos.size()));
-  CU(cudaMemcpyAsync(h->d_ids.p, id_at_pos.data(), id_at_pos.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
-  CU(h->d_sched.reserve(std::max<size_t>(sched.size(), 1)));
-  if (!sched.empty()) CU(cudaMemcpyAsync(h->d_sched.p, sched.data(), sched.size() * sizeof(int4), cudaMemcpyHostToDevice, h->stream));
+  CU(h->d_ids.reserve(order.size()));
+  CU(cudaMemcpyAsync(h->d_ids.p, id_at_pos, order.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  CU(h->d_sched.reserve(std::max<size_t>(nsched, 1)));
+  if (nsched) CU(cudaMemcpyAsync(h->d_sched.p, sched_buf, nsched * sizeof(int4), cudaMemcpyHostToDevice, h->stream));
   CU(h->d_best.reserve((size_t)h->P));
   CU(cudaMemsetAsync(h->d_best.p, 0, (size_t)h->P * sizeof(unsigned long long), h->stream));
-  CU(launch_own_best(d_rows.p, h->W, h->d_sched.p, (int)sched.size(), h->P, h->d_best.p, h->stream));
+  CU(launch_own_best(d_rows.p, h->W, h->d_sched.p, (int)nsched, h->P, h->d_best.p, h->stream));
   h->counters[5] += 1;
   if (h->world > 1) {
     rc = do_comm(h, FCVM_COMM_ALLREDUCE_MAX, h->d_best.p, h->P);     // keys are < 2^63: a signed MAX orders them like the unsigned one
@@ -657,8 +664,7 @@ static int ownership(fcvm_handle* h, const DevBuf<uint32_t>& d_rows, int64_t n, 
   }
   CU(launch_own_apply(h->d_best.p, h->d_ids.p, h->last_vps_num, h->P, h->d_cover_contrib.p, h->d_contrib_id.p, h->d_voxcount.p, h->stream));
   h->counters[5] += 1;
-  CU(cudaStreamSynchronize(h->stream));      // the host vectors above must outlive the copies
-  return FCVM_OK;
+  return FCVM_OK;       // not synchronised: everything that reads the cover state is ordered on the same stream
 }
 
 // vps_voxcount lives on the device while stages run; these move it
@@ -667,16 +673,20 @@ static int voxcount_resize(fcvm_handle* h, size_t n) {   // grow with zeros, kee
   if (n > h->d_voxcount.cap) {
     DevBuf<int> nb;
     CU(nb.reserve(std::max(n, h->d_voxcount.cap * 2)));
-    if (h->voxcount_n) CU(cudaMemcpy(nb.p, h->d_voxcount.p, h->voxcount_n * sizeof(int), cudaMemcpyDeviceToDevice));
+    if (h->voxcount_n) CU(cudaMemcpyAsync(nb.p, h->d_voxcount.p, h->voxcount_n * sizeof(int), cudaMemcpyDeviceToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));      // the old buffer is released next
     h->d_voxcount = std::move(nb);
   }
-  CU(cudaMemset(h->d_voxcount.p + h->voxcount_n, 0, (n - h->voxcount_n) * sizeof(int)));
+  CU(cudaMemsetAsync(h->d_voxcount.p + h->voxcount_n, 0, (n - h->voxcount_n) * sizeof(int), h->stream));
   h->voxcount_n = n;
   return FCVM_OK;
 }
 static int voxcount_download(fcvm_handle* h, std::vector<int>& out) {
   out.assign(h->voxcount_n, 0);
-  if (h->voxcount_n) CU(cudaMemcpy(out.data(), h->d_voxcount.p, h->voxcount_n * sizeof(int), cudaMemcpyDeviceToHost));
+  if (h->voxcount_n) {
+    CU(cudaMemcpyAsync(out.data(), h->d_voxcount.p, h->voxcount_n * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+  }
   return FCVM_OK;
 }
 static int voxcount_upload(fcvm_handle* h, const std::vector<int>& in) {
@@ -684,14 +694,17 @@ static int voxcount_upload(fcvm_handle* h, const std::vector<int>& in) {
   if (rc) return rc;
   rc = voxcount_resize(h, in.size());
   if (rc) return rc;
-  if (!in.empty()) CU(cudaMemcpy(h->d_voxcount.p, in.data(), in.size() * sizeof(int), cudaMemcpyHostToDevice));
+  if (!in.empty()) {
+    CU(cudaMemcpyAsync(h->d_voxcount.p, in.data(), in.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));      // `in` is the caller's
+  }
   return FCVM_OK;
 }
 static int cover_reset(fcvm_handle* h) {   // MCI reset, cpp:178-183
   CU(h->d_cover_contrib.reserve((size_t)h->P));
   CU(h->d_contrib_id.reserve((size_t)h->P));
-  CU(cudaMemset(h->d_cover_contrib.p, 0, (size_t)h->P * sizeof(int)));
-  CU(cudaMemset(h->d_contrib_id.p, 0xff, (size_t)h->P * sizeof(int)));   // -1
+  CU(cudaMemsetAsync(h->d_cover_contrib.p, 0, (size_t)h->P * sizeof(int), h->stream));
+  CU(cudaMemsetAsync(h->d_contrib_id.p, 0xff, (size_t)h->P * sizeof(int), h->stream));   // -1
   return FCVM_OK;
 }
 
@@ -1513,7 +1526,8 @@ static int update_impl(fcvm_handle* h) {
 
   auto uncovered = [&](std::vector<int>& ids) -> int {
     std::vector<int> cid((size_t)h->P);
-    CU(cudaMemcpy(cid.data(), h->d_contrib_id.p, (size_t)h->P * sizeof(int), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpyAsync(cid.data(), h->d_contrib_id.p, (size_t)h->P * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
     ids.clear();
     for (int i = 0; i < (int)h->P; ++i)
       if (cid[(size_t)i] < 0) ids.push_back(i);
@@ -1597,11 +1611,12 @@ static int update_impl(fcvm_handle* h) {
     }
 
     // snapshot of MCI (cpp:272-274)
-    DevBuf<int> snap_contrib, snap_id;
+    DevBuf<int>& snap_contrib = h->d_snap_contrib;
+    DevBuf<int>& snap_id = h->d_snap_id;
     CU(snap_contrib.reserve((size_t)h->P));
     CU(snap_id.reserve((size_t)h->P));
-    CU(cudaMemcpy(snap_contrib.p, h->d_cover_contrib.p, (size_t)h->P * sizeof(int), cudaMemcpyDeviceToDevice));
-    CU(cudaMemcpy(snap_id.p, h->d_contrib_id.p, (size_t)h->P * sizeof(int), cudaMemcpyDeviceToDevice));
+    CU(cudaMemcpyAsync(snap_contrib.p, h->d_cover_contrib.p, (size_t)h->P * sizeof(int), cudaMemcpyDeviceToDevice, h->stream));
+    CU(cudaMemcpyAsync(snap_id.p, h->d_contrib_id.p, (size_t)h->P * sizeof(int), cudaMemcpyDeviceToDevice, h->stream));
 
     const int oriVpNum = (int)h->vps_pose.size();
     h->last_vps_num = oriVpNum;
@@ -1624,10 +1639,8 @@ static int update_impl(fcvm_handle* h) {
     h->vps_pose.insert(h->vps_pose.end(), pose_set_unc.begin(), pose_set_unc.end());
 
     // restore MCI, swap the voxcounts (cpp:304-309)
-    CU(cudaMemcpy(h->d_cover_contrib.p, snap_contrib.p, (size_t)h->P * sizeof(int), cudaMemcpyDeviceToDevice));
-    CU(cudaMemcpy(h->d_contrib_id.p, snap_id.p, (size_t)h->P * sizeof(int), cudaMemcpyDeviceToDevice));
-    snap_contrib.free();
-    snap_id.free();
+    CU(cudaMemcpyAsync(h->d_cover_contrib.p, snap_contrib.p, (size_t)h->P * sizeof(int), cudaMemcpyDeviceToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->d_contrib_id.p, snap_id.p, (size_t)h->P * sizeof(int), cudaMemcpyDeviceToDevice, h->stream));
     rc = voxcount_download(h, temp_vps_voxcount);
     if (rc) return rc;
     rc = voxcount_upload(h, before_vps_voxcount);
@@ -1806,7 +1819,8 @@ int fcvm_set_model(fcvm_t* h, const float* xyz, int64_t n) {   // cpp:91-108
   std::vector<float4> pts((size_t)n);
   for (int64_t i = 0; i < n; ++i) pts[(size_t)i] = make_float4(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], 0.f);
   CU(h->d_points.reserve((size_t)n));
-  CU(cudaMemcpy(h->d_points.p, pts.data(), (size_t)n * sizeof(float4), cudaMemcpyHostToDevice));
+  CU(cudaMemcpyAsync(h->d_points.p, pts.data(), (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
   if (grown || !h->model_flag) {   // MCI resize (keeps values when the size is unchanged, like vector::resize)
     rc = cover_reset(h);
     if (rc) return rc;
@@ -1866,7 +1880,8 @@ int64_t fcvm_get_uncovered(fcvm_t* h, float* xyz, int64_t cap) {   // cpp:1138-1
   if (!h->device_ok || h->P == 0) return 0;
   std::vector<int> cid((size_t)h->P);
   if (ensure_device(h)) return FCVM_ECUDA;
-  if (cudaMemcpy(cid.data(), h->d_contrib_id.p, (size_t)h->P * sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess)
+  if (cudaMemcpyAsync(cid.data(), h->d_contrib_id.p, (size_t)h->P * sizeof(int), cudaMemcpyDeviceToHost, h->stream) != cudaSuccess ||
+      cudaStreamSynchronize(h->stream) != cudaSuccess)
     return fail(FCVM_ECUDA, "download of contrib_id failed");
   int64_t n = 0;
   for (int64_t i = 0; i < h->P; ++i)
@@ -1904,8 +1919,9 @@ int64_t fcvm_get_cover_state(fcvm_t* h, uint8_t* covered, int32_t* cover_contrib
   if (!h->device_ok || h->P == 0 || cap <= 0) return h->P;
   if (ensure_device(h)) return FCVM_ECUDA;
   std::vector<int> cc((size_t)h->P), ci((size_t)h->P);
-  if (cudaMemcpy(cc.data(), h->d_cover_contrib.p, (size_t)h->P * sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess ||
-      cudaMemcpy(ci.data(), h->d_contrib_id.p, (size_t)h->P * sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess)
+  if (cudaMemcpyAsync(cc.data(), h->d_cover_contrib.p, (size_t)h->P * sizeof(int), cudaMemcpyDeviceToHost, h->stream) != cudaSuccess ||
+      cudaMemcpyAsync(ci.data(), h->d_contrib_id.p, (size_t)h->P * sizeof(int), cudaMemcpyDeviceToHost, h->stream) != cudaSuccess ||
+      cudaStreamSynchronize(h->stream) != cudaSuccess)
     return fail(FCVM_ECUDA, "download of cover state failed");
   for (int64_t i = 0; i < h->P && i < cap; ++i) {
     if (covered) covered[i] = ci[(size_t)i] >= 0 ? 1 : 0;
@@ -1923,7 +1939,8 @@ int fcvm_get_grid(fcvm_t* h, double* origin3, int32_t* voxel_num3, uint8_t* bits
     int rc = ensure_device(h);
     if (rc) return rc;
     h->grid.bricks.resize(h->grid.nbricks());
-    CU(cudaMemcpy(h->grid.bricks.data(), h->d_bricks.p + h->brick_guard, h->grid.nbricks() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpyAsync(h->grid.bricks.data(), h->d_bricks.p + h->brick_guard, h->grid.nbricks() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
     h->grid.export_xmajor(bits);
     h->grid.bricks.clear();
     h->grid.bricks.shrink_to_fit();

@@ -145,6 +145,8 @@ struct Side {
 #define CONT_INRANGE 2      // E1: ray_length <= visible_range (ANDed into the verdict)
 #define CONT_PFREE 4        // every voxel the viewpoint-side half-ray can visit is free (summed-area-table certificate): that
                             // side is not marched; p.ix/iy/iz hold the midpoint voxel, p.rem its remaining biNextId calls
+#define CONT_SANE 8         // both half-rays start strictly inside their voxels on every moving axis: each stays in the box spanned
+                            // by its current and the midpoint voxel, so "the box between the two fronts is empty" ends the march
 
 struct Cont {
   Side p, n;
@@ -256,10 +258,11 @@ __device__ __forceinline__ bool prepare_ray(const GridDesc& g, const FovConst& f
     // occCheck look-ups are only counted.
     bool pfree = false;
     if (g.sat != nullptr) {
-      const double fx = sxf - floor(sxf), fy = syf - floor(syf), fz = szf - floor(szf);
-      const bool interior = (dx == 0 || (fx > 1e-9 && fx < 1.0 - 1e-9)) && (dy == 0 || (fy > 1e-9 && fy < 1.0 - 1e-9)) &&
-                            (dz == 0 || (fz > 1e-9 && fz < 1.0 - 1e-9));
-      if (interior)
+      auto interior = [](double f, int d) { const double fr = f - floor(f); return d == 0 || (fr > 1e-9 && fr < 1.0 - 1e-9); };
+      const bool p_in = interior(sxf, dx) && interior(syf, dy) && interior(szf, dz);
+      const bool n_in = interior(exf, mx - x1) && interior(eyf, my - y1) && interior(ezf, mz - z1);
+      if (p_in && n_in) c.flags |= CONT_SANE;
+      if (p_in)
         pfree = sat_box_count(g, min(pix, mix) >> 3, min(piy, miy) >> 3, min(piz, miz) >> 3, max(pix, mix) >> 3, max(piy, miy) >> 3, max(piz, miz) >> 3) == 0;
     }
     c.p.rem = abs(dx) + abs(dy) + abs(dz);
@@ -291,6 +294,7 @@ __device__ __forceinline__ bool prepare_ray(const GridDesc& g, const FovConst& f
     c.n.step_if(c.n.rem > 0);
     c.flags &= ~CONT_DISCARD;
   }
+  if (c.flags & CONT_PFREE) c.p.rem = max(0, c.p.rem - c.n.rem);      // calls left on the certified side once the target side has arrived
   return true;
 }
 
@@ -413,6 +417,7 @@ __global__ void __launch_bounds__(kWarps * 32, EVAL_MIN_CTAS) k_eval(const __gri
     constexpr int kKeep = EVAL_KEEP;
     Cont c;
     bool active = false;
+    unsigned tick = 0;
     int pkey = -1, nkey = -1;
     unsigned long long pword = 0ull, nword = 0ull;
     for (;;) {
@@ -437,18 +442,38 @@ __global__ void __launch_bounds__(kWarps * 32, EVAL_MIN_CTAS) k_eval(const __gri
       }
       // EVAL_UNROLL biNextId calls per refill / suspend check: the two ballots and the queue logic are
       // warp-wide overhead, a lane that finishes inside the group idles for at most EVAL_UNROLL - 1 steps
+      // Every EVAL_QUERY_PERIOD-th round every ray in flight asks the summed-area table whether the box between its two fronts
+      // (a certified viewpoint side's front is the midpoint voxel) still holds an occupied voxel.  If not, every look-up the
+      // reference would still make returns "free": the pair is visible, its remaining biNextId calls are only counted.
+      if (g.sat != nullptr && ((++tick) & (EVAL_QUERY_PERIOD - 1)) == 0) {
+        if (active && (c.flags & CONT_SANE)) {
+          const int n_empty = sat_box_count(g, min(c.p.ix, c.n.ix) >> 3, min(c.p.iy, c.n.iy) >> 3, min(c.p.iz, c.n.iz) >> 3, max(c.p.ix, c.n.ix) >> 3,
+                                            max(c.p.iy, c.n.iy) >> 3, max(c.p.iz, c.n.iz) >> 3);
+          if (n_empty == 0) {
+            const int calls = (c.flags & CONT_PFREE) ? c.n.rem + c.p.rem : max(c.p.rem, c.n.rem);
+            st.lookups += 2u * (unsigned)calls + 1u;
+            if (c.flags & CONT_INRANGE) set_bit(c.vp, c.pt);
+            active = false;
+          }
+        }
+      }
+      const bool any_full = __any_sync(0xffffffffu, active && !(c.flags & CONT_PFREE));
 #pragma unroll
       for (int u = 0; u < EVAL_UNROLL; ++u) {
         if (active) {
           // ---- one biNextId call and the loop body that follows it.  The call reports the voxels
           // BEFORE it steps, so they are looked up first and both sides advance afterwards.
-          const bool pflag = c.p.rem > 0, nflag = c.n.rem > 0;
+          // A certified viewpoint side (CONT_PFREE) is never marched: p.ix/iy/iz stay at the midpoint voxel and p.rem holds
+          // the number of biNextId calls that side would still make once the target side has arrived (each looks at two
+          // free voxels).  In a warp that holds only such rays (any_full == false, the common case) the viewpoint side's
+          // look-up and step are skipped altogether; in a mixed warp they run for every lane, harmlessly for the certified
+          // ones (their side reports the free midpoint voxel and does not move).
           const bool pfree = (c.flags & CONT_PFREE) != 0;
+          const bool pflag = !pfree && c.p.rem > 0, nflag = c.n.rem > 0;
           if (!(pflag || nflag)) {
             // the call returned false: visible_flag = occCheck(idx); visible_flag_rev keeps its last (true) value
-            bool f = true;                                              // certified side: the midpoint voxel lies in the free box
-            if (!pfree) f = occ_fast(g, c.p.ix, c.p.iy, c.p.iz, pkey, pword);
-            st.lookups += 1;
+            const bool f = occ_fast(g, c.p.ix, c.p.iy, c.p.iz, pkey, pword);
+            st.lookups += pfree ? 1u + 2u * (unsigned)c.p.rem : 1u;
             // Both sides must have met in the midpoint voxel.  If they have not, the reference's marcher never reports
             // "at end": it walks on until an occCheck fails (an occupied voxel, or the map's edge), so the pair is NOT
             // visible there; counted as a cap trip (0 on every scene and test so far).
@@ -456,18 +481,11 @@ __global__ void __launch_bounds__(kWarps * 32, EVAL_MIN_CTAS) k_eval(const __gri
             if (!met) st.trips++;
             if (met && f && (c.flags & CONT_INRANGE)) set_bit(c.vp, c.pt);
             active = false;
-          } else if (pfree && !nflag) {
-            // the target side already waits in the midpoint voxel (free: it lies in the certified box) and the viewpoint
-            // side is certified: the remaining calls each look at two free voxels
-            st.lookups += 2u * (unsigned)c.p.rem;
-            c.p.rem = 0;
           } else {
             bool f = true;
-            if (!pfree) {
+            if (any_full) {
               f = occ_fast(g, c.p.ix, c.p.iy, c.p.iz, pkey, pword);
               c.p.step_if(pflag);
-            } else {
-              c.p.rem -= pflag ? 1 : 0;
             }
             const bool r = occ_fast(g, c.n.ix, c.n.iy, c.n.iz, nkey, nword);
             st.lookups += 2;

@@ -21,6 +21,9 @@ namespace fcvm {
 #ifndef EVAL_UNROLL
 #define EVAL_UNROLL 2         // march: biNextId calls per refill / suspend check
 #endif
+#ifndef EVAL_QUERY_PERIOD
+#define EVAL_QUERY_PERIOD 4   // march: every this many rounds (of EVAL_UNROLL steps) the rays in flight test the box between their fronts (power of 2)
+#endif
 #ifndef EVAL_WAVES
 #define EVAL_WAVES 12         // CTA waves (over 148 SMs x EVAL_MIN_CTAS) the tiling aims at (3..96 measured: flat from 8 to 24, worse outside)
 #endif

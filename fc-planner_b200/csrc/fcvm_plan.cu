@@ -300,13 +300,43 @@ __global__ void __launch_bounds__(128) k_safety_box(GridDesc g, double res_inv, 
   if (counters && looks) atomicAdd(counters + 0, looks);
 }
 
-// search_Path's straight-line test (hcsolver.cpp:556-583) for every ordered pair (i, j) of n positions
-__global__ void __launch_bounds__(128) k_line_of_sight(GridDesc g, const double* __restrict__ pts, long long n, uint8_t* __restrict__ safe,
-                                                       double* __restrict__ dist, unsigned long long* __restrict__ counters) {
+// search_Path's straight-line test (hcsolver.cpp:556-583) for every ordered pair (i, j) of n positions.
+// Rays of very different lengths in one warp leave most lanes idle (11 of 32 active when thread = pair index, ncu r1n), so the
+// pairs are first binned by their voxel Manhattan length - the number of steps a free ray takes - with a counting sort
+// (k_los_bin, k_exscan, k_los_scatter) and the march kernel walks that order: a warp's 32 rays then end together unless
+// something blocks them earlier.  The results are indexed by pair, so the order inside a bin is immaterial.
+constexpr int kLosBins = 4096;
+__device__ __forceinline__ int los_length(const double* __restrict__ pts, long long n, long long t, double res) {
+  const long long i = t / n, j = t % n;
+  const int dx = (int)floor(pts[3 * j] / res) - (int)floor(pts[3 * i] / res);
+  const int dy = (int)floor(pts[3 * j + 1] / res) - (int)floor(pts[3 * i + 1] / res);
+  const int dz = (int)floor(pts[3 * j + 2] / res) - (int)floor(pts[3 * i + 2] / res);
+  return min(abs(dx) + abs(dy) + abs(dz), kLosBins - 1);
+}
+__global__ void __launch_bounds__(256) k_los_bin(const double* __restrict__ pts, long long n, double res, int* __restrict__ hist) {
+  __shared__ int sh[kLosBins];
+  for (int k = threadIdx.x; k < kLosBins; k += blockDim.x) sh[k] = 0;
+  __syncthreads();
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n * n; t += (long long)gridDim.x * blockDim.x)
+    atomicAdd(&sh[los_length(pts, n, t, res)], 1);
+  __syncthreads();
+  for (int k = threadIdx.x; k < kLosBins; k += blockDim.x)
+    if (sh[k]) atomicAdd(hist + k, sh[k]);
+}
+__global__ void __launch_bounds__(256) k_los_scatter(const double* __restrict__ pts, long long n, double res, const long long* __restrict__ start,
+                                                     int* __restrict__ fill, unsigned* __restrict__ order) {
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const bool valid = t < n * n;
+  if (t >= n * n) return;
+  const int b = los_length(pts, n, t, res);
+  order[start[b] + atomicAdd(fill + b, 1)] = (unsigned)t;
+}
+__global__ void __launch_bounds__(128) k_line_of_sight(GridDesc g, const double* __restrict__ pts, long long n, const unsigned* __restrict__ order,
+                                                       uint8_t* __restrict__ safe, double* __restrict__ dist, unsigned long long* __restrict__ counters) {
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid = tid < n * n;
   unsigned long long looks = 0, trips = 0;
   if (valid) {
+    const long long t = order ? (long long)order[tid] : tid;
     const long long i = t / n, j = t % n;
     const double ax = pts[3 * i], ay = pts[3 * i + 1], az = pts[3 * i + 2];
     const double bx = pts[3 * j], by = pts[3 * j + 1], bz = pts[3 * j + 2];
@@ -350,6 +380,9 @@ struct fcvm_grid_handle {
   DevBuf<unsigned long long> d_occ, d_inf, d_int;     // raw planes: occupancy_buffer_hc_ (= occ), occupancy_inflate_buffer_hc_, occupancy_buffer_internal_
   DevBuf<unsigned long long> d_sblk, d_pblk;          // derived planes, refreshed after every change of the raw ones
   DevBuf<unsigned char> d_visited;
+  DevBuf<int> d_hist;                 // 2 x kLosBins: histogram + fill counters of the line-of-sight counting sort
+  DevBuf<long long> d_binstart;
+  DevBuf<unsigned> d_order;
   DevBuf<double> d_in;
   DevBuf<float> d_in_f, d_rosa;
   DevBuf<uint8_t> d_u8;
@@ -461,7 +494,7 @@ void fcvm_grid_destroy(fcvm_grid_t* h) {
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   h->d_occ.free(); h->d_inf.free(); h->d_int.free(); h->d_sblk.free(); h->d_pblk.free(); h->d_visited.free(); h->d_in.free(); h->d_in_f.free(); h->d_rosa.free(); h->d_u8.free();
-  h->d_i32a.free(); h->d_i32b.free(); h->d_dist.free(); h->d_counters.free();
+  h->d_i32a.free(); h->d_i32b.free(); h->d_dist.free(); h->d_counters.free(); h->d_hist.free(); h->d_binstart.free(); h->d_order.free();
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -521,7 +554,21 @@ int fcvm_grid_line_of_sight(fcvm_grid_t* h, const double* p_xyz, int64_t n, uint
   GridDesc g;
   plan_desc(h, h->d_pblk.p, g);
   CU(cudaEventRecord(h->ev0, s));
-  k_line_of_sight<<<(unsigned)((n * n + 127) / 128), 128, 0, s>>>(g, h->d_in.p, n, h->d_u8.p, dist_nxn ? h->d_dist.p : nullptr, h->d_counters.p);
+  const unsigned* order = nullptr;
+  if (n * n >= 4096) {                 // counting sort of the pairs by voxel Manhattan length (see k_line_of_sight)
+    CU(h->d_hist.reserve(2 * kLosBins));
+    CU(h->d_binstart.reserve(kLosBins + 1));
+    CU(h->d_order.reserve((size_t)n * n));
+    CU(cudaMemsetAsync(h->d_hist.p, 0, 2 * kLosBins * sizeof(int), s));
+    k_los_bin<<<(unsigned)std::min<long long>(1184, (n * n + 255) / 256), 256, 0, s>>>(h->d_in.p, n, h->res, h->d_hist.p);
+    CU(cudaGetLastError());
+    CU(launch_exscan(h->d_hist.p, kLosBins, h->d_binstart.p, s));
+    k_los_scatter<<<(unsigned)((n * n + 255) / 256), 256, 0, s>>>(h->d_in.p, n, h->res, h->d_binstart.p, h->d_hist.p + kLosBins, h->d_order.p);
+    CU(cudaGetLastError());
+    order = h->d_order.p;
+    h->counters[2] += 3;
+  }
+  k_line_of_sight<<<(unsigned)((n * n + 127) / 128), 128, 0, s>>>(g, h->d_in.p, n, order, h->d_u8.p, dist_nxn ? h->d_dist.p : nullptr, h->d_counters.p);
   CU(cudaGetLastError());
   CU(cudaEventRecord(h->ev1, s));      // ev0 .. ev1 bracket the kernel alone
   CU(cudaMemcpyAsync(safe_nxn, h->d_u8.p, (size_t)n * n, cudaMemcpyDeviceToHost, s));

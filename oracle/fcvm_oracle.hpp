@@ -468,7 +468,9 @@ struct EvalContext {
       if (visible_flag == false || visible_flag_rev == false) break;
     }
     visible_flag = occ(idx);
-    if (raycaster_.capped) ctr.cap_trips++;
+    // A capped march has run past its midpoint voxel: the reference would walk on until an occCheck fails (an occupied voxel
+    // or the map's edge, where occCheck is false) and so return "not visible" (viewpoint_manager.cpp:388-396).
+    if (raycaster_.capped) { ctr.cap_trips++; return false; }
     return visible_flag == true && visible_flag_rev == true;
   }
   // surface-offset walk, viewpoint_manager.cpp:463-477 / 554-568

@@ -571,6 +571,8 @@ class PlanOracle:
         xyz = np.ascontiguousarray(xyz, np.float32).reshape(-1, 3)
         self.lib.orc_plan_set_occ(self.h, _ptr(xyz, c_f32p), ctypes.c_int64(len(xyz)))
 
+    SetOcc = setOcc
+
     def InternalSpace(self, seg_clouds, seg_ends, inflate_num, proj_interval, thickness):
         """seg_clouds: list of float32 [n_s, 3]; seg_ends: [nseg, 6] = (start xyz, end xyz) of each skeleton segment."""
         xyz = np.ascontiguousarray(np.concatenate(seg_clouds) if len(seg_clouds) else np.zeros((0, 3)), np.float32)
