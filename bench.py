@@ -604,11 +604,51 @@ def main():
         except Exception:
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
         achieved = b_alg / (kernel_ms * 1e-3) / 1e9
-        traffic = None
+        # Per-launch figures of one `ncu --set full` capture of this kernel (profiles/traffic.json, written by
+        # profiles/summarize_ncu.py), stamped with the hash of the kernel sources they were taken on: stale when that differs.
+        tr = {}
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("dram_bytes_per_launch")
+            tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
         except Exception:
             pass
+        build_id = None
+        try:
+            import importlib.util
+            spec = importlib.util.spec_from_file_location("fcvm_build", os.path.join(ROOT, "fc-planner_b200", "build.py"))
+            bm = importlib.util.module_from_spec(spec); spec.loader.exec_module(bm)
+            build_id = bm.kernel_build_id()
+        except Exception:
+            pass
+        traffic = tr.get("dram_bytes_per_launch")
+        stale = bool(tr) and (tr.get("kernel_build") != build_id or args.stage != 1 or V != 25000 or P != 1000000)
+        l2_peak, fp64_peak = None, None
+        try:
+            pk = json.load(open(os.path.join(ROOT, "profiles", "r2", "measured_peaks_l2_fp64.json")))
+            l2_peak = max(v for k, v in pk["read_gbs"].items() if int(k.split("_")[0]) <= 96)
+            fp64_peak = pk["fp64"]["dadd_tops"]
+        except Exception:
+            pass
+        sm_clock = (clocks.get("sm_mhz") or 1965.0) * 1e6
+        roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_stale": stale,
+                "kernel": f"k_eval<E{args.stage}>", "kernel_ms": kernel_ms, "algorithmic_bytes": b_alg, "peak_source": peak_src,
+                "kernel_build": build_id, "traffic_kernel_build": tr.get("kernel_build"),
+                "note": "achieved = ALGORITHMIC bytes (SURVEY.md 8d: 32 B per occCheck the reference makes + streamed points + records + bitset rows) per second; "
+                        "the kernel is built not to move them (bit-packed grid in L2, brick words in registers, certified half-rays counted instead of "
+                        "marched), so frac > 1 is possible and says nothing about DRAM utilisation - see dram / l2 / issue below"}
+        if tr:
+            l2b, ins = tr.get("l2_bytes_per_launch"), tr.get("warp_instructions")
+            roof["dram"] = {"bytes_per_launch": traffic, "achieved_gbs": (traffic / (kernel_ms * 1e-3) / 1e9) if traffic else None, "peak_gbs": peak,
+                            "frac": (traffic / (kernel_ms * 1e-3) / 1e9 / peak) if traffic else None}
+            roof["l2"] = {"bytes_per_launch": l2b, "achieved_gbs": (l2b / (kernel_ms * 1e-3) / 1e9) if l2b else None, "peak_gbs": l2_peak,
+                          "frac": (l2b / (kernel_ms * 1e-3) / 1e9 / l2_peak) if (l2b and l2_peak) else None, "hit_rate_pct": tr.get("l2_hit_rate_pct"),
+                          "peak_source": "profiles/scripts/peaks.cu: streaming 128-bit __ldcg reads of an L2-resident buffer, measured on this pool"}
+            roof["l1_sectors"] = tr.get("l1_sectors_global_ld_per_launch")
+            # the bound that actually binds: instruction issue.  warp instructions of the capture / live kernel time against 4 issue slots x SMs x clock
+            roof["issue"] = {"bound": "issue", "warp_instructions_per_launch": ins, "achieved_ginst_s": (ins / (kernel_ms * 1e-3) / 1e9) if ins else None,
+                             "peak_ginst_s": 148 * 4 * sm_clock / 1e9, "frac": (ins / (kernel_ms * 1e-3) / (148 * 4 * sm_clock)) if ins else None,
+                             "issue_active_pct_ncu": tr.get("issue_active_pct"), "warps_per_scheduler": tr.get("warps_per_scheduler"),
+                             "active_lanes_per_instruction": tr.get("active_lanes_per_instruction"), "top_stalls_pct": tr.get("top_stalls_pct"),
+                             "fp64_pipe_pct": tr.get("fp64_pipe_pct"), "fp64_dadd_peak_tops": fp64_peak}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -628,8 +668,7 @@ def main():
             "rays_per_step_per_gpu": rays_step, "pair_tests_per_step_per_gpu": pairs_step, "voxel_lookups_per_step_per_gpu": lookups_step,
             "viewpoint_evals_per_s": V * world * args.steps / (dev_ms_max * 1e-3),
             "other_evaluators_rank0": other_stages,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "kernel": f"k_eval<E{args.stage}>", "kernel_ms": kernel_ms, "algorithmic_bytes": b_alg, "peak_source": peak_src},
+            "roofline": roof,
         }
         if not args.no_cpu and world == 1:      # the CPU baseline is timed on rank 0 at N = 1 only
             threads = host_cores()

@@ -22,6 +22,16 @@ NVCC_FLAGS = [
 ]
 
 
+def kernel_build_id():
+    """Hash of the sources k_eval is compiled from: stamps ncu captures (profiles/traffic.json) so that bench.py can tell
+    whether the quoted traffic figures belong to the kernel it is timing."""
+    import hashlib
+    h = hashlib.sha1()
+    for name in ("fcvm_kernels.cu", "fcvm_device.cuh", "fcvm_kernels.h"):
+        h.update(open(os.path.join(CSRC, name), "rb").read())
+    return h.hexdigest()[:12]
+
+
 def needs_build():
     if not os.path.exists(OUT):
         return True

@@ -39,6 +39,7 @@ struct GridDesc {
   const int* sat;
   int sat_ny, sat_nz;                // (nby / 2 + 1), (nbz / 2 + 1)
   double res;                        // resolution_
+  double res_rcp;                    // RN(1 / resolution_), for div_exact
   double offx, offy, offz;           // RayCaster::offset_ = 0.5 - origin/res   (raycast.cpp:344)
   double orgx, orgy, orgz;           // map_origin_
 };
@@ -117,6 +118,28 @@ __device__ __forceinline__ double d_mod1(double value) {
   const double b = a + 1.0;
   return b - trunc(b);
 }
+// a / b, correctly rounded, from y = RN(1 / b): q0 = RN(a y), r = a - b q0 (exact, one fused multiply-add), q = RN(q0 + r y)
+// (Markstein's theorem; explicit fma intrinsics are not subject to -fmad=false).  Exact for every finite a, b as long as the
+// quotient is a normal number - which is all the marchers feed it (tests/ddmath_check.cpp re-checks it against the divider on
+// 2 10^8 arguments; the only miss there is a subnormal numerator).  The compiler's own FP64 division is ~70 instructions per
+// site, and the DDA set-up has 18 of them per ray.
+__device__ __forceinline__ double div_exact(double a, double b, double y) {
+  const double q0 = a * y;
+  const double r = __fma_rn(-b, q0, a);
+  return __fma_rn(r, y, q0);
+}
+// intbound (raycast.cpp:29-43) with the integer voxel delta the call sites pass ((double)(end - start)): the quotient
+// (1 - s) / |delta| has 2^-53 <= 1 - s <= 1 and 1 <= |delta|, so div_exact applies with y from the reciprocal table;
+// delta == 0 gives +inf like the division by zero it replaces.  |delta| must be below the table's size (the fast path's
+// guard_steps is clamped to it on the host).
+__device__ __forceinline__ double d_intbound_i(double s, int delta, const double* __restrict__ rcp_table) {
+  if (delta < 0) s = -s;
+  s = d_mod1(s);
+  const int ad = abs(delta);
+  const double a = 1 - s;
+  const double q = div_exact(a, (double)ad, __ldg(rcp_table + ad));
+  return ad == 0 ? __longlong_as_double(0x7ff0000000000000ll) : q;
+}
 __device__ __forceinline__ double d_intbound(double s, double ds) {
   if (ds < 0) { s = -s; ds = -ds; }       // intbound(-s, -ds): one level of recursion at most
   s = d_mod1(s);
@@ -168,7 +191,7 @@ struct RayStats {
 //   if (!f || !r) break; }  f = occ(idx);  visible = f && r.
 // a = viewpoint side (p-ray), b = target side (n-ray); both march to the midpoint voxel in lock
 // step, idx / idxR are the voxels BEFORE the step of that call.
-__device__ __forceinline__ bool birc(const GridDesc& g, double ax, double ay, double az, double bx, double by, double bz,
+static __device__ __noinline__ bool birc(const GridDesc& g, double ax, double ay, double az, double bx, double by, double bz,
                                      bool discard_first, RayStats& st) {
   const double res = g.res;
   // start_ = start / resolution_;  inter_ = (0.5*(start+end)) / resolution_;  end_ = end / resolution_
@@ -245,6 +268,25 @@ __device__ __forceinline__ void offset_target(const GridDesc& g, double px, doub
   tx = ((double)ix + 0.5) * res + g.orgx;
   ty = ((double)iy + 0.5) * res + g.orgy;
   tz = ((double)iz + 0.5) * res + g.orgz;
+}
+
+// ---------------------------------------------------------------------------------------------
+// One end of a ray as RayCaster::biInput sees it (raycast.cpp:394-396: start_ = start / resolution_): the three quotients,
+// computed ONCE per viewpoint / per model point instead of once per ray (IEEE division: the same bits wherever it runs), and
+// whether the end lies strictly inside its voxel on x / y / z (bits 0..2 of `inside`), which is what lets a half-ray be
+// certified (k_eval, CONT_SANE / CONT_PFREE).  32 bytes = one sector.
+// ---------------------------------------------------------------------------------------------
+struct alignas(32) RayEnd {
+  double sx, sy, sz;
+  double inside;            // 0..7 as a double
+};
+__host__ __device__ __forceinline__ RayEnd make_ray_end(double x, double y, double z, double res) {
+  RayEnd e;
+  e.sx = x / res; e.sy = y / res; e.sz = z / res;
+  const double fx = e.sx - floor(e.sx), fy = e.sy - floor(e.sy), fz = e.sz - floor(e.sz);
+  const int bits = ((fx > 1e-9 && fx < 1.0 - 1e-9) ? 1 : 0) | ((fy > 1e-9 && fy < 1.0 - 1e-9) ? 2 : 0) | ((fz > 1e-9 && fz < 1.0 - 1e-9) ? 4 : 0);
+  e.inside = (double)bits;
+  return e;
 }
 
 // ---------------------------------------------------------------------------------------------

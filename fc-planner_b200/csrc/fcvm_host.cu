@@ -149,6 +149,7 @@ struct fcvm_handle {
 
   // device scratch for a batch
   DevBuf<VpRec> d_recs;
+  DevBuf<RayEnd> d_vp_ends, d_pt_ends;         // record positions / model points divided by the resolution (k_ray_ends)
   DevBuf<uint32_t> d_rows1, d_rows2;
   DevBuf<int> d_count;
   DevBuf<int4> d_sched;
@@ -266,6 +267,7 @@ static void fill_grid_desc(const fcvm_handle* h, GridDesc& g) {
   g.nly = hg.ns[1] >> 1; g.nlz = hg.ns[2] >> 2;
   g.nbricks = (int)hg.nbricks();
   g.res = hg.res;
+  g.res_rcp = 1.0 / hg.res;
   // RayCaster::setParams (raycast.cpp:341-345): offset_ = half_ - origin / resolution_
   g.offx = 0.5 - hg.origin[0] / hg.res;
   g.offy = 0.5 - hg.origin[1] / hg.res;
@@ -307,6 +309,13 @@ static int launch_stage(fcvm_handle* h, int stage, const VpRec* d_recs, int64_t 
   a.P = h->P;
   a.recs = d_recs;
   a.V = n;
+  // the records' positions / resolution, once per viewpoint instead of once per ray (same slot as the record in its buffer)
+  const size_t rec0 = (size_t)(d_recs - h->d_recs.p);
+  if (d_recs < h->d_recs.p || rec0 + (size_t)n > h->d_recs.cap) return fail(FCVM_EINTERNAL, "records outside the handle's buffer");
+  CU(h->d_vp_ends.reserve(h->d_recs.cap));
+  CU(launch_ray_ends(reinterpret_cast<const double*>(d_recs), (int)(sizeof(VpRec) / sizeof(double)), nullptr, n, h->grid.res, h->d_vp_ends.p + rec0, s));
+  a.vp_ends = h->d_vp_ends.p + rec0;
+  a.pt_ends = h->d_pt_ends.p;
   a.rows = d_rows;
   a.restrict_rows = d_restrict;
   a.words = h->W;
@@ -1765,6 +1774,7 @@ int fcvm_set_map_cloud(fcvm_t* h, const float* xyz, int64_t n) {   // cpp:74-89
     // voxels of the map on every axis; its brick index then falls into [-guard, nbricks + guard), which is allocated
     // and reads 'occupied'.  Longer rays (none pass the range test) take the literal, bounds-checked marcher.
     h->guard_steps = 3 * ((int)std::ceil(std::max(h->prm.max_dist, h->prm.visible_range) / (2 * h->grid.res)) + 2);
+    h->guard_steps = std::min(h->guard_steps, EVAL_RCP_TABLE - 1);      // the fast path's reciprocal table (longer half-rays take the literal marcher)
     h->brick_guard = (size_t)brick_guard_words(h->guard_steps, h->grid.ns[1], h->grid.ns[2]);
     CU(h->d_bricks.reserve(h->grid.nbricks() + 2 * h->brick_guard));
     CU(cudaMemsetAsync(h->d_bricks.p, 0xFF, h->brick_guard * sizeof(unsigned long long), s));
@@ -1820,6 +1830,8 @@ int fcvm_set_model(fcvm_t* h, const float* xyz, int64_t n) {   // cpp:91-108
   for (int64_t i = 0; i < n; ++i) pts[(size_t)i] = make_float4(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], 0.f);
   CU(h->d_points.reserve((size_t)n));
   CU(cudaMemcpyAsync(h->d_points.p, pts.data(), (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, h->stream));
+  CU(h->d_pt_ends.reserve((size_t)n));
+  CU(launch_ray_ends(nullptr, 0, h->d_points.p, n, h->prm.resolution, h->d_pt_ends.p, h->stream));   // resolution_ = hcmap/resolution (sdf_map.cpp:128)
   CU(cudaStreamSynchronize(h->stream));
   if (grown || !h->model_flag) {   // MCI resize (keeps values when the size is unchanged, like vector::resize)
     rc = cover_reset(h);

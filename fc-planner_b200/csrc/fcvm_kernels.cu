@@ -206,10 +206,30 @@ __device__ __forceinline__ bool occ_fast(const GridDesc& g, int ix, int iy, int 
   return ((cword >> brick_bit_index(ix, iy, iz)) & 1ull) == 0ull;
 }
 
+// tDelta = step / delta with step = signum(delta) (raycast.cpp:412-434) is 1 / |delta| (NaN for 0 / 0): a table of the
+// reciprocals of 0 .. kRcpN - 1, filled once per device with the very division the reference makes
+constexpr int kRcpN = EVAL_RCP_TABLE;
+__device__ double g_rcp[kRcpN];
+__global__ void k_init_rcp() {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < kRcpN) g_rcp[k] = k == 0 ? (0.0 / (double)k) : (1.0 / (double)k);
+}
+__device__ __forceinline__ double t_delta(int delta) { return __ldg(&g_rcp[abs(delta)]); }   // |delta| < kRcpN on the fast path
+__global__ void __launch_bounds__(256) k_ray_ends(const double* __restrict__ xyz, int stride_d, const float4* __restrict__ pts, long long n, double res,
+                                                  RayEnd* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (xyz) out[i] = make_ray_end(xyz[i * stride_d], xyz[i * stride_d + 1], xyz[i * stride_d + 2], res);
+  else { const float4 q = pts[i]; out[i] = make_ray_end((double)q.x, (double)q.y, (double)q.z, res); }
+}
+
 // biInput (raycast.cpp:392-444) for one ray.  Returns true and fills `c` when the ray qualifies for
 // the fast path; otherwise the verdict is computed right here with the literal marcher (birc).
+// vpe / pte: the two ends divided by the resolution, precomputed per viewpoint / per model point (E2 / E4 aim at the
+// offset target instead of the point and divide here).
 template <int STAGE>
-__device__ __forceinline__ bool prepare_ray(const GridDesc& g, const FovConst& fc, const VpRec* __restrict__ recs, uint32_t v, uint32_t pti,
+__device__ __forceinline__ bool prepare_ray(const GridDesc& g, const FovConst& fc, const VpRec* __restrict__ recs, const RayEnd* __restrict__ vp_ends,
+                                            const RayEnd* __restrict__ pt_ends, long long gp, uint32_t v, uint32_t pti,
                                             float4 q, Cont& c, bool& slow_verdict, RayStats& st) {
   const double vx = __ldg(&recs[v].px), vy = __ldg(&recs[v].py), vz = __ldg(&recs[v].pz);
   const double qx = (double)q.x, qy = (double)q.y, qz = (double)q.z;
@@ -222,12 +242,23 @@ __device__ __forceinline__ bool prepare_ray(const GridDesc& g, const FovConst& f
   } else {
     flags |= CONT_INRANGE;
   }
-  if (STAGE == 2 || STAGE == 4) offset_target(g, qx, qy, qz, vx, vy, vz, bx, by, bz, st);
-
   const double res = g.res;
-  const double sxf = vx / res, syf = vy / res, szf = vz / res;
-  const double mxf = (0.5 * (vx + bx)) / res, myf = (0.5 * (vy + by)) / res, mzf = (0.5 * (vz + bz)) / res;
-  const double exf = bx / res, eyf = by / res, ezf = bz / res;
+  const double2 ve0 = __ldg(reinterpret_cast<const double2*>(vp_ends + v)), ve1 = __ldg(reinterpret_cast<const double2*>(vp_ends + v) + 1);
+  const double sxf = ve0.x, syf = ve0.y, szf = ve1.x;
+  int v_inside = (int)ve1.y, n_inside;
+  double exf, eyf, ezf;
+  if (STAGE == 2 || STAGE == 4) {
+    offset_target(g, qx, qy, qz, vx, vy, vz, bx, by, bz, st);
+    // the target is a voxel centre: finite, and strictly inside its voxel on every axis unless rounding says otherwise
+    exf = div_exact(bx, res, g.res_rcp); eyf = div_exact(by, res, g.res_rcp); ezf = div_exact(bz, res, g.res_rcp);
+    const double fx = exf - floor(exf), fy = eyf - floor(eyf), fz = ezf - floor(ezf);
+    n_inside = ((fx > 1e-9 && fx < 1.0 - 1e-9) ? 1 : 0) | ((fy > 1e-9 && fy < 1.0 - 1e-9) ? 2 : 0) | ((fz > 1e-9 && fz < 1.0 - 1e-9) ? 4 : 0);
+  } else {
+    const double2 pe0 = __ldg(reinterpret_cast<const double2*>(pt_ends + gp)), pe1 = __ldg(reinterpret_cast<const double2*>(pt_ends + gp) + 1);
+    exf = pe0.x; eyf = pe0.y; ezf = pe1.x; n_inside = (int)pe1.y;
+  }
+  // inter_ = 0.5 * (start + end) / resolution_: only its floor is used
+  const double mxf = div_exact(0.5 * (vx + bx), res, g.res_rcp), myf = div_exact(0.5 * (vy + by), res, g.res_rcp), mzf = div_exact(0.5 * (vz + bz), res, g.res_rcp);
   const int x0 = (int)floor(sxf), y0 = (int)floor(syf), z0 = (int)floor(szf);
   const int mx = (int)floor(mxf), my = (int)floor(myf), mz = (int)floor(mzf);
   const int x1 = (int)floor(exf), y1 = (int)floor(eyf), z1 = (int)floor(ezf);
@@ -239,7 +270,8 @@ __device__ __forceinline__ bool prepare_ray(const GridDesc& g, const FovConst& f
   // fast path <=> the map-index conversion is a pure shift between the corners (it is monotone, so
   // equal deltas at the ends mean unit increments in between) and all corners are inside the map
   // (the marcher never leaves the box spanned by its end voxels).
-  const bool fast = inside(pix, piy, piz) && inside(mix, miy, miz) && inside(nix, niy, niz) &&
+  const bool fast = (fabs(mxf) + fabs(myf)) + fabs(mzf) < 1.0e9 &&        // finite (an infinite or NaN end takes the literal path)
+                    inside(pix, piy, piz) && inside(mix, miy, miz) && inside(nix, niy, niz) &&
                     (mix - pix == mx - x0) && (miy - piy == my - y0) && (miz - piz == mz - z0) &&
                     (mix - nix == mx - x1) && (miy - niy == my - y1) && (miz - niz == mz - z1) &&
                     abs(mx - x0) + abs(my - y0) + abs(mz - z0) <= g.guard_steps && abs(mx - x1) + abs(my - y1) + abs(mz - z1) <= g.guard_steps;
@@ -258,9 +290,10 @@ __device__ __forceinline__ bool prepare_ray(const GridDesc& g, const FovConst& f
     // occCheck look-ups are only counted.
     bool pfree = false;
     if (g.sat != nullptr) {
-      auto interior = [](double f, int d) { const double fr = f - floor(f); return d == 0 || (fr > 1e-9 && fr < 1.0 - 1e-9); };
-      const bool p_in = interior(sxf, dx) && interior(syf, dy) && interior(szf, dz);
-      const bool n_in = interior(exf, mx - x1) && interior(eyf, my - y1) && interior(ezf, mz - z1);
+      // "strictly inside its voxel on every moving axis": idle axes do not matter
+      v_inside |= (dx == 0 ? 1 : 0) | (dy == 0 ? 2 : 0) | (dz == 0 ? 4 : 0);
+      n_inside |= (mx == x1 ? 1 : 0) | (my == y1 ? 2 : 0) | (mz == z1 ? 4 : 0);
+      const bool p_in = v_inside == 7, n_in = n_inside == 7;
       if (p_in && n_in) c.flags |= CONT_SANE;
       if (p_in)
         pfree = sat_box_count(g, min(pix, mix) >> 3, min(piy, miy) >> 3, min(piz, miz) >> 3, max(pix, mix) >> 3, max(piy, miy) >> 3, max(piz, miz) >> 3) == 0;
@@ -274,8 +307,8 @@ __device__ __forceinline__ bool prepare_ray(const GridDesc& g, const FovConst& f
     } else {
       c.p.ix = pix; c.p.iy = piy; c.p.iz = piz;
       c.p.sx = d_signum(dx); c.p.sy = d_signum(dy); c.p.sz = d_signum(dz);
-      c.p.tmx = d_intbound(sxf, (double)dx); c.p.tmy = d_intbound(syf, (double)dy); c.p.tmz = d_intbound(szf, (double)dz);
-      c.p.tdx = ((double)c.p.sx) / (double)dx; c.p.tdy = ((double)c.p.sy) / (double)dy; c.p.tdz = ((double)c.p.sz) / (double)dz;
+      c.p.tmx = d_intbound_i(sxf, dx, g_rcp); c.p.tmy = d_intbound_i(syf, dy, g_rcp); c.p.tmz = d_intbound_i(szf, dz, g_rcp);
+      c.p.tdx = t_delta(dx); c.p.tdy = t_delta(dy); c.p.tdz = t_delta(dz);
     }
   }
   {
@@ -283,8 +316,8 @@ __device__ __forceinline__ bool prepare_ray(const GridDesc& g, const FovConst& f
     c.n.ix = nix; c.n.iy = niy; c.n.iz = niz;
     c.n.rem = abs(dx) + abs(dy) + abs(dz);
     c.n.sx = d_signum(dx); c.n.sy = d_signum(dy); c.n.sz = d_signum(dz);
-    c.n.tmx = d_intbound(exf, (double)dx); c.n.tmy = d_intbound(eyf, (double)dy); c.n.tmz = d_intbound(ezf, (double)dz);
-    c.n.tdx = ((double)c.n.sx) / (double)dx; c.n.tdy = ((double)c.n.sy) / (double)dy; c.n.tdz = ((double)c.n.sz) / (double)dz;
+    c.n.tmx = d_intbound_i(exf, dx, g_rcp); c.n.tmy = d_intbound_i(eyf, dy, g_rcp); c.n.tmz = d_intbound_i(ezf, dz, g_rcp);
+    c.n.tdx = t_delta(dx); c.n.tdy = t_delta(dy); c.n.tdz = t_delta(dz);
   }
   if (flags & CONT_DISCARD) {
     // `raycaster_->biNextId(idx, idx_rev);` before the loop (cpp:387, 483, 845): both sides advance
@@ -393,7 +426,7 @@ __global__ void __launch_bounds__(kWarps * 32, EVAL_MIN_CTAS) k_eval(const __gri
       if (FCVM_CHECK(en - cnt + lane >= 0 && en - cnt + lane < kEntryQ && qe.pt < (uint32_t)npts && qe.vp < (uint32_t)a.V))
 #endif
       {
-        queued = prepare_ray<STAGE>(g, fc, a.recs, qe.vp, qe.pt, tile[qe.pt], c, verdict, st);
+        queued = prepare_ray<STAGE>(g, fc, a.recs, a.vp_ends, a.pt_ends, tile_base + qe.pt, qe.vp, qe.pt, tile[qe.pt], c, verdict, st);
         if (!queued && verdict) set_bit(qe.vp, qe.pt);
       }
     }
@@ -855,6 +888,9 @@ static cudaError_t launch_eval_t(const EvalArgs& a, dim3 grid, size_t smem, cuda
   if (dev < 0 || dev >= 64 || !attr_done[dev].load(std::memory_order_acquire)) {
     e = cudaFuncSetAttribute(k_eval<STAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)eval_smem_bytes(EVAL_MAX_TILE));
     if (e != cudaSuccess) return e;
+    k_init_rcp<<<(kRcpN + 255) / 256, 256, 0, s>>>();      // the device's reciprocal table (same stream: ordered before the first k_eval)
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
     if (dev >= 0 && dev < 64) attr_done[dev].store(true, std::memory_order_release);
   }
   k_eval<STAGE><<<grid, kWarps * 32, smem, s>>>(a);
@@ -880,6 +916,12 @@ cudaError_t launch_eval(int stage, const EvalArgs& a, cudaStream_t s) {
     case 4: return launch_eval_t<4>(a, grid, smem, s);
   }
   return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_ray_ends(const double* xyz, int stride_d, const float4* pts, long long n, double res, RayEnd* out, cudaStream_t s) {
+  if (n <= 0) return cudaSuccess;
+  k_ray_ends<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(xyz, stride_d, pts, n, res, out);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_popc_rows(const uint32_t* rows, long long n, long long words, int* count, cudaStream_t s) {

@@ -19,10 +19,13 @@ namespace fcvm {
 #define EVAL_KEEP 28          // march: suspend back to the FOV phase when fewer lanes than this are busy and the queue is empty
 #endif
 #ifndef EVAL_UNROLL
-#define EVAL_UNROLL 2         // march: biNextId calls per refill / suspend check
+#define EVAL_UNROLL 1         // march: biNextId calls per refill / suspend check (2 measured equal on E1, slower on E2 / E4: code size)
 #endif
 #ifndef EVAL_QUERY_PERIOD
 #define EVAL_QUERY_PERIOD 4   // march: every this many rounds (of EVAL_UNROLL steps) the rays in flight test the box between their fronts (power of 2)
+#endif
+#ifndef EVAL_RCP_TABLE
+#define EVAL_RCP_TABLE 1024   // reciprocals 1/k, k < this, for the DDA set-up of the fast path (half-rays of more voxel steps take the literal path)
 #endif
 #ifndef EVAL_WAVES
 #define EVAL_WAVES 12         // CTA waves (over 148 SMs x EVAL_MIN_CTAS) the tiling aims at (3..96 measured: flat from 8 to 24, worse outside)
@@ -40,6 +43,8 @@ struct EvalArgs {
   const float4* points;            // model cloud, float4 (x, y, z, 0) like pcl::PointXYZ; P entries
   long long P;
   const VpRec* recs;               // V viewpoint records
+  const RayEnd* vp_ends;           // V: the records' positions / resolution (k_ray_ends)
+  const RayEnd* pt_ends;           // P: the model points / resolution (k_ray_ends, once per setModel)
   long long V;
   uint32_t* rows;                  // V x words bitset rows, zeroed by the caller
   const uint32_t* restrict_rows;   // E2 only: V x words rows of the E1 pass
@@ -50,6 +55,8 @@ struct EvalArgs {
 };
 
 size_t eval_smem_bytes(int tile_pts);
+// RayEnd of n positions: xyz = doubles with `stride_d` doubles between positions (VpRec: 16) or, with xyz == nullptr, float4 points
+cudaError_t launch_ray_ends(const double* xyz, int stride_d, const float4* pts, long long n, double res, RayEnd* out, cudaStream_t s);
 cudaError_t launch_eval(int stage, const EvalArgs& a, cudaStream_t s);
 cudaError_t launch_popc_rows(const uint32_t* rows, long long n, long long words, int* count, cudaStream_t s);
 cudaError_t launch_exscan(const int* count, long long n, long long* offsets, cudaStream_t s);

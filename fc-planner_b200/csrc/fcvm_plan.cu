@@ -405,6 +405,7 @@ static void plan_desc(const fcvm_grid_handle* h, const unsigned long long* brick
   g.guard_steps = 0;
   g.sat = nullptr; g.sat_ny = g.sat_nz = 0;
   g.res = h->res;
+  g.res_rcp = 1.0 / h->res;
   g.offx = 0.5 - h->origin[0] / h->res;      // RayCaster::setParams (raycast.cpp:341-345; hcplanner.cpp:89, hcsolver.cpp:40)
   g.offy = 0.5 - h->origin[1] / h->res;
   g.offz = 0.5 - h->origin[2] / h->res;

@@ -43,3 +43,17 @@ def test_dd_asin_acos_certificate(seed):
     assert z["max_err_ulp_asin"] < 1e-3 and z["max_err_ulp_acos"] < 1e-3
     # about 12.5 % of the arguments are flagged (2 x margin)
     assert 0.08 < z["flagged_asin"] / z["n"] < 0.18 and 0.08 < z["flagged_acos"] / z["n"] < 0.18
+
+
+def test_division_from_reciprocal_is_exact(tmp_path):
+    """div_exact (fcvm_device.cuh): reciprocal-table division with two fused multiply-adds == the hardware divider."""
+    if not shutil.which("gcc"):
+        pytest.skip("no gcc")
+    if "fma" not in open("/proc/cpuinfo").read():
+        pytest.skip("host CPU without FMA")
+    exe = str(tmp_path / "div_exact_check")
+    r = subprocess.run(["gcc", "-O2", "-mfma", "-ffp-contract=off", os.path.join(HERE, "div_exact_check.c"), "-o", exe, "-lm"],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout
+    r = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
+    assert r.returncode == 0 and "mismatches 0" in r.stdout, r.stdout
