@@ -166,6 +166,17 @@ struct Marcher {
     tdx = ((double)sx) / dx; tdy = ((double)sy) / dy; tdz = ((double)sz) / dz;   // 0/0 = NaN on idle axes
     ix = to_map_index(x, g.offx); iy = to_map_index(y, g.offy); iz = to_map_index(z, g.offz);
   }
+  // the same set-up with every division taken from the reciprocal table (d_intbound_i, 1 / |delta|): the caller guarantees
+  // finite coordinates and |delta| < the table's size on every axis
+  __device__ __forceinline__ void init_table(double fx, double fy, double fz, int tx, int ty, int tz, const GridDesc& g, const double* __restrict__ rcp) {
+    x = (int)floor(fx); y = (int)floor(fy); z = (int)floor(fz);
+    ex = tx; ey = ty; ez = tz;
+    const int dx = ex - x, dy = ey - y, dz = ez - z;
+    sx = d_signum(dx); sy = d_signum(dy); sz = d_signum(dz);
+    tmx = d_intbound_i(fx, dx, rcp); tmy = d_intbound_i(fy, dy, rcp); tmz = d_intbound_i(fz, dz, rcp);
+    tdx = __ldg(rcp + abs(dx)); tdy = __ldg(rcp + abs(dy)); tdz = __ldg(rcp + abs(dz));   // rcp[0] = NaN = 0 / 0 on idle axes
+    ix = to_map_index(x, g.offx); iy = to_map_index(y, g.offy); iz = to_map_index(z, g.offz);
+  }
   __device__ __forceinline__ bool at_end() const { return x == ex && y == ey && z == ez; }
   __device__ __forceinline__ int manhattan() const { return abs(ex - x) + abs(ey - y) + abs(ez - z); }
   // the branch ladder of nextId / biNextId (raycast.cpp:455-476): strict '<', z on ties and NaN
@@ -242,13 +253,23 @@ static __device__ __noinline__ bool birc(const GridDesc& g, double ax, double ay
 // Surface-offset walk (viewpoint_manager.cpp:463-477 / 554-568): march point -> viewpoint with the
 // one-directional caster, stop at the 2nd free voxel (or at the viewpoint's voxel), return that
 // voxel's centre via indexToPos_hc (sdf_map.h:244-247).
+// With `rcp` (a table of 1 / k, k < rcp_n) the quotients point / res and viewpoint / res arrive precomputed (sxf .. ezf, the
+// very divisions, made once per point / per viewpoint) and the DDA set-up divides through the table (div_exact) whenever
+// the ray is finite and shorter than the table on every axis; otherwise, and with rcp == nullptr, it divides literally.
 __device__ __forceinline__ void offset_target(const GridDesc& g, double px, double py, double pz, double vx, double vy, double vz,
-                                              double& tx, double& ty, double& tz, RayStats& st) {
+                                              double& tx, double& ty, double& tz, RayStats& st, const double* __restrict__ rcp = nullptr, int rcp_n = 0,
+                                              double sxf = 0.0, double syf = 0.0, double szf = 0.0, double exf = 0.0, double eyf = 0.0, double ezf = 0.0) {
   const double res = g.res;
-  const double sxf = px / res, syf = py / res, szf = pz / res;
-  const double exf = vx / res, eyf = vy / res, ezf = vz / res;
+  if (rcp == nullptr) {
+    sxf = px / res; syf = py / res; szf = pz / res;
+    exf = vx / res; eyf = vy / res; ezf = vz / res;
+  }
   Marcher m;
-  m.init(sxf, syf, szf, (int)floor(exf), (int)floor(eyf), (int)floor(ezf), g);
+  const bool table = rcp != nullptr && ((fabs(sxf) + fabs(syf)) + fabs(szf)) + ((fabs(exf) + fabs(eyf)) + fabs(ezf)) < 1.0e9 &&
+                     abs((int)floor(exf) - (int)floor(sxf)) < rcp_n && abs((int)floor(eyf) - (int)floor(syf)) < rcp_n &&
+                     abs((int)floor(ezf) - (int)floor(szf)) < rcp_n;
+  if (table) m.init_table(sxf, syf, szf, (int)floor(exf), (int)floor(eyf), (int)floor(ezf), g, rcp);
+  else m.init(sxf, syf, szf, (int)floor(exf), (int)floor(eyf), (int)floor(ezf), g);
   int budget = m.manhattan() + 8;
   BrickCache c;
   c.reset();

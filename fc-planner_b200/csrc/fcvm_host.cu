@@ -1095,22 +1095,23 @@ static int get_pose_batch(fcvm_handle* h, const std::vector<D3>& pos, const std:
     }
     // averaged poses (cpp:427-447); (pitch, yaw, free_num) of every viewpoint reach every rank
     std::vector<double> avg3((size_t)cn * 3, 0.0);
-    for (int64_t i = lo; i < hi; ++i) {
-      if (free_num[(size_t)i] == 0) continue;     // free_num == 0: pose stays (pos, init_py), no E2, no ownership (cpp:427-436)
+    parallel_for(hi - lo, h->threads, [&](int64_t r) {
+      const int64_t i = lo + r;
+      if (free_num[(size_t)i] == 0) return;       // free_num == 0: pose stays (pos, init_py), no E2, no ownership (cpp:427-436)
       finish_average(h, sums[(size_t)2 * i], sums[(size_t)2 * i + 1], free_num[(size_t)i], seed[(size_t)i].init_yaw, avg3[(size_t)3 * i], avg3[(size_t)3 * i + 1]);
       avg3[(size_t)3 * i + 2] = (double)free_num[(size_t)i];
-    }
+    });
     rc = gather_doubles(h, avg3.data(), cn, 3);
     if (rc) return rc;
     std::vector<char> has_free((size_t)cn, 0);
-    for (int64_t i = 0; i < cn; ++i) {
-      if (avg3[(size_t)3 * i + 2] == 0.0) continue;
+    parallel_for(cn, h->threads, [&](int64_t i) {   // the E2 records (sin / cos of the averaged pose: libm, per viewpoint)
+      if (avg3[(size_t)3 * i + 2] == 0.0) return;
       const D3& vp = seed[(size_t)i].vp;
       poses_out[(size_t)(c0 + i)].v[3] = avg3[(size_t)3 * i];
       poses_out[(size_t)(c0 + i)].v[4] = avg3[(size_t)3 * i + 1];
       has_free[(size_t)i] = 1;
       h->cam.fill(h->h_recs.p[i], vp.x, vp.y, vp.z, avg3[(size_t)3 * i], avg3[(size_t)3 * i + 1]);
-    }
+    });
 
     // ---- E2 on the E1 sets (cpp:457-498) ---------------------------------------------------
     // viewpoints with free_num == 0 have all-zero E1 rows, so they contribute nothing here

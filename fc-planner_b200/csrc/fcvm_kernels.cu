@@ -248,7 +248,10 @@ __device__ __forceinline__ bool prepare_ray(const GridDesc& g, const FovConst& f
   int v_inside = (int)ve1.y, n_inside;
   double exf, eyf, ezf;
   if (STAGE == 2 || STAGE == 4) {
-    offset_target(g, qx, qy, qz, vx, vy, vz, bx, by, bz, st);
+    {
+      const double2 pe0 = __ldg(reinterpret_cast<const double2*>(pt_ends + gp)), pe1 = __ldg(reinterpret_cast<const double2*>(pt_ends + gp) + 1);
+      offset_target(g, qx, qy, qz, vx, vy, vz, bx, by, bz, st, g_rcp, kRcpN, pe0.x, pe0.y, pe1.x, sxf, syf, szf);
+    }
     // the target is a voxel centre: finite, and strictly inside its voxel on every axis unless rounding says otherwise
     exf = div_exact(bx, res, g.res_rcp); eyf = div_exact(by, res, g.res_rcp); ezf = div_exact(bz, res, g.res_rcp);
     const double fx = exf - floor(exf), fy = eyf - floor(eyf), fz = ezf - floor(ezf);
@@ -331,6 +334,30 @@ __device__ __forceinline__ bool prepare_ray(const GridDesc& g, const FovConst& f
   return true;
 }
 
+// Conservative whole-box cull, shared by the tile level (a lane = a viewpoint) and the group level (a lane = 32 consecutive
+// points): true when NO point of the axis-aligned box [lo, hi] can pass insideFOV for a viewpoint at (px, py, pz).  Either the
+// squared distance from the viewpoint to the box exceeds the range band (every point fails `dir.norm() > max_dist`), or the
+// whole box lies behind one of the four FOV planes: the largest d.n over the box is negative by a margin far above rounding,
+// so every point fails that plane's `dir.dot(n) >= 0`.  Skipping such a box is exact.  nrm(q, k) = component k of normal q.
+template <bool PLANES, class NormalAt>
+__device__ __forceinline__ bool box_outside(const FovConst& fc, double px, double py, double pz, double lo0, double lo1, double lo2, double hi0,
+                                            double hi1, double hi2, NormalAt nrm) {
+  const double lx = lo0 - px, ly = lo1 - py, lz = lo2 - pz;
+  const double hx = hi0 - px, hy = hi1 - py, hz = hi2 - pz;
+  const double cx = fmax(fmax(lx, -hx), 0.0), cy = fmax(fmax(ly, -hy), 0.0), cz = fmax(fmax(lz, -hz), 0.0);
+  bool culled = (cx * cx + cy * cy) + cz * cz > fc.md2_hi * 1.000001;
+  if (PLANES && !culled) {
+    const double margin = 1e-9 * ((fmax(fabs(lx), fabs(hx)) + fmax(fabs(ly), fabs(hy))) + fmax(fabs(lz), fabs(hz)) + 1.0);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const double n0 = nrm(q, 0), n1 = nrm(q, 1), n2 = nrm(q, 2);
+      const double best = (fmax(lx * n0, hx * n0) + fmax(ly * n1, hy * n1)) + fmax(lz * n2, hz * n2);
+      culled = culled || best < -margin;
+    }
+  }
+  return culled;
+}
+
 template <int STAGE>
 __global__ void __launch_bounds__(kWarps * 32, EVAL_MIN_CTAS) k_eval(const __grid_constant__ EvalArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
@@ -341,13 +368,14 @@ __global__ void __launch_bounds__(kWarps * 32, EVAL_MIN_CTAS) k_eval(const __gri
   QueueEntry* entries = reinterpret_cast<QueueEntry*>(ready_i + (size_t)kWarps * kContI * kReadyQ);
   __shared__ __align__(8) uint64_t bar;
   __shared__ int next_vp;
-  __shared__ float red[kWarps][6];
+  __shared__ float4 gbox[2 * (EVAL_MAX_TILE / 32)];   // min / max corner of every group of 32 consecutive points of the tile
   __shared__ double aabb[6];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const unsigned lt_mask = (1u << lane) - 1u;
   const long long tile_base = (long long)blockIdx.x * a.tile_pts;
   const int npts = (int)min((long long)a.tile_pts, a.P - tile_base);
+  const int ngroups = (npts + 31) >> 5;                // <= 32: one lane per group at the group-level cull
   const long long v_lo = (long long)blockIdx.y * a.vp_per_cta;
   const long long v_hi = min(v_lo + (long long)a.vp_per_cta, a.V);
 
@@ -365,31 +393,47 @@ __global__ void __launch_bounds__(kWarps * 32, EVAL_MIN_CTAS) k_eval(const __gri
   }
   mbar_wait(&bar, 0);
 
-  // ---- tile bounding box (for the conservative whole-tile range cull) ---------------------
+  // ---- bounding boxes: one per group of 32 consecutive points, and the tile's (for the two conservative culls).  A group
+  // that holds a non-finite coordinate gets an all-embracing box: such points are never culled (NaN compares false in the
+  // reference's range test, so it goes on to cast the ray).
   {
-    float mn[3] = {3.0e38f, 3.0e38f, 3.0e38f}, mx[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
-    for (int i = tid; i < npts; i += kWarps * 32) {
-      const float4 q = tile[i];
-      mn[0] = fminf(mn[0], q.x); mx[0] = fmaxf(mx[0], q.x);
-      mn[1] = fminf(mn[1], q.y); mx[1] = fmaxf(mx[1], q.y);
-      mn[2] = fminf(mn[2], q.z); mx[2] = fmaxf(mx[2], q.z);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        mn[c] = fminf(mn[c], __shfl_xor_sync(0xffffffffu, mn[c], o));
-        mx[c] = fmaxf(mx[c], __shfl_xor_sync(0xffffffffu, mx[c], o));
+    for (int gi = warp; gi < ngroups; gi += kWarps) {
+      const int i = gi * 32 + lane;
+      float mn[3] = {3.0e38f, 3.0e38f, 3.0e38f}, mx[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+      bool bad = false;
+      if (i < npts) {
+        const float4 q = tile[i];
+        mn[0] = mx[0] = q.x; mn[1] = mx[1] = q.y; mn[2] = mx[2] = q.z;
+        bad = !(fabsf(q.x) <= 3.0e38f && fabsf(q.y) <= 3.0e38f && fabsf(q.z) <= 3.0e38f);
       }
-    if (lane == 0) {
+      bad = __any_sync(0xffffffffu, bad);
 #pragma unroll
-      for (int c = 0; c < 3; ++c) { red[warp][c] = mn[c]; red[warp][3 + c] = mx[c]; }
+      for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          mn[c] = fminf(mn[c], __shfl_xor_sync(0xffffffffu, mn[c], o));
+          mx[c] = fmaxf(mx[c], __shfl_xor_sync(0xffffffffu, mx[c], o));
+        }
+      if (lane == 0) {
+        gbox[2 * gi] = bad ? make_float4(-3.0e38f, -3.0e38f, -3.0e38f, 0.f) : make_float4(mn[0], mn[1], mn[2], 0.f);
+        gbox[2 * gi + 1] = bad ? make_float4(3.0e38f, 3.0e38f, 3.0e38f, 0.f) : make_float4(mx[0], mx[1], mx[2], 0.f);
+      }
     }
     __syncthreads();
-    if (tid < 6) {
-      float r = red[0][tid];
-      for (int w = 1; w < kWarps; ++w) r = tid < 3 ? fminf(r, red[w][tid]) : fmaxf(r, red[w][tid]);
-      aabb[tid] = (double)r;
+    if (warp == 0) {
+      float4 lo = make_float4(3.0e38f, 3.0e38f, 3.0e38f, 0.f), hi = make_float4(-3.0e38f, -3.0e38f, -3.0e38f, 0.f);
+      if (lane < ngroups) { lo = gbox[2 * lane]; hi = gbox[2 * lane + 1]; }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        lo.x = fminf(lo.x, __shfl_xor_sync(0xffffffffu, lo.x, o)); lo.y = fminf(lo.y, __shfl_xor_sync(0xffffffffu, lo.y, o));
+        lo.z = fminf(lo.z, __shfl_xor_sync(0xffffffffu, lo.z, o));
+        hi.x = fmaxf(hi.x, __shfl_xor_sync(0xffffffffu, hi.x, o)); hi.y = fmaxf(hi.y, __shfl_xor_sync(0xffffffffu, hi.y, o));
+        hi.z = fmaxf(hi.z, __shfl_xor_sync(0xffffffffu, hi.z, o));
+      }
+      if (lane == 0) {
+        aabb[0] = (double)lo.x; aabb[1] = (double)lo.y; aabb[2] = (double)lo.z;
+        aabb[3] = (double)hi.x; aabb[4] = (double)hi.y; aabb[5] = (double)hi.z;
+      }
     }
     __syncthreads();
   }
@@ -533,12 +577,32 @@ __global__ void __launch_bounds__(kWarps * 32, EVAL_MIN_CTAS) k_eval(const __gri
     }
   };
 
+  // Viewpoints are taken from the CTA's counter `chunk` at a time and culled against the tile's box with one viewpoint per
+  // lane; the survivors are then culled against the 32-point groups' boxes with one group per lane, and only the groups
+  // that remain are tested point by point.  Both culls are exact (box_outside), so the pair tests they skip are counted.
+  const int chunk = max(1, min(32, a.vp_per_cta / (kWarps * 2)));
   for (;;) {
     int vi = 0;
-    if (lane == 0) vi = atomicAdd(&next_vp, 1);
+    if (lane == 0) vi = atomicAdd(&next_vp, chunk);
     vi = __shfl_sync(0xffffffffu, vi, 0);
-    const long long v = v_lo + vi;
-    if (v >= v_hi) break;
+    const long long vbase = v_lo + vi;
+    if (vbase >= v_hi) break;
+    unsigned vmask;
+    {
+      const long long vl = vbase + lane;
+      const bool mine = lane < chunk && vl < v_hi;
+      bool culled = true;
+      if (mine) {
+        const VpRec* r = a.recs + vl;
+        culled = box_outside<STAGE != 2>(fc, __ldg(&r->px), __ldg(&r->py), __ldg(&r->pz), aabb[0], aabb[1], aabb[2], aabb[3], aabb[4], aabb[5],
+                                         [&](int q, int k) { return __ldg(&r->n[q][k]); });
+        if (STAGE != 2 && culled) npairs += (unsigned long long)npts;
+      }
+      vmask = __ballot_sync(0xffffffffu, mine && !culled);
+    }
+   while (vmask != 0u) {
+    const long long v = vbase + (__ffs(vmask) - 1);
+    vmask &= vmask - 1u;
 
     // viewpoint record -> registers (uniform loads)
     VpRec rec;
@@ -549,38 +613,32 @@ __global__ void __launch_bounds__(kWarps * 32, EVAL_MIN_CTAS) k_eval(const __gri
       for (int k = 0; k < 8; ++k) dst[k] = __ldg(src + k);
     };
     load_rec();
-    // whole-tile cull: squared distance from the viewpoint to the tile's bounding box.  Every point
-    // of a culled tile fails `dir.norm() > max_dist` in the reference, so skipping is exact ...
-    {
-      const double cx = fmax(fmax(aabb[0] - rec.px, rec.px - aabb[3]), 0.0);
-      const double cy = fmax(fmax(aabb[1] - rec.py, rec.py - aabb[4]), 0.0);
-      const double cz = fmax(fmax(aabb[2] - rec.pz, rec.pz - aabb[5]), 0.0);
-      bool culled = (cx * cx + cy * cy) + cz * cz > fc.md2_hi * 1.000001;
-      if (!culled && STAGE != 2) {
-        // ... or the whole box lies behind one of the four FOV planes: the largest d.n over the box is negative by a
-        // margin far above rounding, so every point of the tile fails that plane's `dir.dot(n) >= 0` (exact skip)
-        const double lx = aabb[0] - rec.px, ly = aabb[1] - rec.py, lz = aabb[2] - rec.pz;
-        const double hx = aabb[3] - rec.px, hy = aabb[4] - rec.py, hz = aabb[5] - rec.pz;
-        const double margin = 1e-9 * ((fmax(fabs(lx), fabs(hx)) + fmax(fabs(ly), fabs(hy))) + fmax(fabs(lz), fabs(hz)) + 1.0);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const double best = (fmax(lx * rec.n[q][0], hx * rec.n[q][0]) + fmax(ly * rec.n[q][1], hy * rec.n[q][1])) +
-                              fmax(lz * rec.n[q][2], hz * rec.n[q][2]);
-          culled = culled || best < -margin;
-        }
-      }
-      if (culled) {
-        if (STAGE != 2) npairs += (lane == 0) ? (unsigned long long)npts : 0ull;
-        continue;
-      }
-    }
     const uint32_t* rrow = (STAGE == 2) ? a.restrict_rows + v * W + (tile_base >> 5) : nullptr;
-    for (int cb = 0; cb < npts; cb += 32) {
+    // groups worth a point-by-point test: E2 re-tests only what E1 found visible (a lane fetches its group's word of the E1
+    // row: one coalesced load instead of 32 uniform ones); the others drop the groups whose box is out of range or behind a plane
+    unsigned gmask;
+    uint32_t rw_mine = 0u;
+    if (STAGE == 2) {
+      if (lane < ngroups) rw_mine = __ldg(rrow + lane);
+      gmask = __ballot_sync(0xffffffffu, rw_mine != 0u);
+    } else {
+      bool keep = false;
+      if (lane < ngroups) {
+        const float4 lo = gbox[2 * lane], hi = gbox[2 * lane + 1];
+        keep = !box_outside<true>(fc, rec.px, rec.py, rec.pz, (double)lo.x, (double)lo.y, (double)lo.z, (double)hi.x, (double)hi.y, (double)hi.z,
+                                  [&](int q, int k) { return rec.n[q][k]; });
+        if (!keep) npairs += (unsigned long long)min(32, npts - 32 * lane);
+      }
+      gmask = __ballot_sync(0xffffffffu, keep);
+    }
+    while (gmask != 0u) {
+      const int grp = __ffs(gmask) - 1;
+      gmask &= gmask - 1u;
+      const int cb = grp << 5;
       const int i = cb + lane;
       bool valid = i < npts;
       if (STAGE == 2) {
-        const uint32_t rw = __ldg(rrow + (cb >> 5));   // only points E1 found visible are re-tested
-        if (rw == 0u) continue;
+        const uint32_t rw = __shfl_sync(0xffffffffu, rw_mine, grp);   // only points E1 found visible are re-tested
         valid = valid && ((rw >> lane) & 1u);
       }
       bool pass = false;
@@ -652,6 +710,7 @@ __global__ void __launch_bounds__(kWarps * 32, EVAL_MIN_CTAS) k_eval(const __gri
         load_rec();   // re-read instead of keeping 30 registers live across the ray phases
       }
     }
+   }
   }
   if (en > 0) prepare(en);   // en < 32 here
   march(true);
