@@ -47,10 +47,14 @@ def build(force=False, verbose=False):
     # tuning experiments: FCVM_DEFS="EVAL_UNROLL=2,EVAL_KEEP=16" FCVM_OUT=/path/variant.so (load with FCVM_LIB=...)
     defs = ["-D" + d for d in os.environ.get("FCVM_DEFS", "").split(",") if d]
     out = os.environ.get("FCVM_OUT", OUT)
-    cmd = [nvcc] + NVCC_FLAGS + defs + (["-Xptxas", "-v"] if verbose else []) + ["-o", out] + [os.path.join(CSRC, s) for s in SOURCES]
+    tmp = out + ".tmp%d" % os.getpid()     # the library appears atomically (a repo snapshot never sees a half-written file)
+    cmd = [nvcc] + NVCC_FLAGS + defs + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + [os.path.join(CSRC, s) for s in SOURCES]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
+        if os.path.exists(tmp):
+            os.remove(tmp)
         raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + r.stdout)
+    os.replace(tmp, out)
     if verbose:
         print(r.stdout)
     return out

@@ -78,7 +78,13 @@ __host__ __device__ __forceinline__ int brick_bit_index(int x, int y, int z) {
   return ((x & 3) << 4) | ((y & 3) << 2) | (z & 3);
 }
 
-// number of non-empty 8^3-voxel cells in the inclusive cell box [lo, hi] (coordinates already >> 3)
+// The summed-area table's cells are (1 << FCVM_SAT_SHIFT)^3 voxels: 3 = 2 x 2 x 2 bricks (6.4 MB at config 5), 2 = one brick, the default
+// (51 MB there, but a ray leaves the cells of its own surface patch after half as many steps).
+#ifndef FCVM_SAT_SHIFT
+#define FCVM_SAT_SHIFT 2
+#endif
+#define FCVM_SAT_BRICKS (1 << (FCVM_SAT_SHIFT - 2))     // bricks per cell and axis
+// number of non-empty cells in the inclusive cell box [lo, hi] (coordinates already >> FCVM_SAT_SHIFT)
 __device__ __forceinline__ int sat_box_count(const GridDesc& g, int x0, int y0, int z0, int x1, int y1, int z1) {
   const int* s = g.sat;
   const long long ny = g.sat_ny, nz = g.sat_nz;

@@ -106,6 +106,7 @@ struct fcvm_handle {
   // map
   HostGrid grid;                               // geometry; the bricks live on the device (downloaded on demand for the parity tap)
   DevBuf<unsigned long long> d_bricks;          // [guard | bricks | guard]; the guard words read 'occupied' (see occ_fast)
+  DevBuf<int> d_snap_vox;                       // vps_voxcount before an uncovered-area round (update_impl)
   DevBuf<int> d_sat;                            // summed-area table over 8^3-voxel cells (GridDesc::sat)
   bool use_sat = true;                          // FCVM_NO_PFREE=1 switches the half-ray certificate off (A/B)
   size_t brick_guard = 0;                       // guard words on each side
@@ -145,7 +146,6 @@ struct fcvm_handle {
   // call.  Only the key order of idx_viewpoints_ is observable, so it maps id -> slot here.
   std::unordered_map<D3, int, D3Hash, D3Eq> inverse_idx;
   std::unordered_map<int, int> idx_slot;
-  std::unordered_map<int, int> idx_ctrl_voxels;
 
   // device scratch for a batch
   DevBuf<VpRec> d_recs;
@@ -218,6 +218,19 @@ struct fcvm_handle {
 
 namespace fcvm {
 
+// f(i) for i in [0, n) on the handle's persistent worker pool (created on first use); n <= block runs on the caller.
+// (parallel_for of fcvm_hostutil.h spawns its threads per call, ~0.3 ms for 16: most of a shipped scene's per-call budget.)
+template <class F>
+static void pfor(fcvm_handle* h, int64_t n, int64_t block, F&& f) {
+  if (n <= 0) return;
+  if (h->threads <= 1 || n <= block) {
+    for (int64_t i = 0; i < n; ++i) f(i);
+    return;
+  }
+  if (!h->pool) h->pool.reset(new WorkerPool(h->threads));
+  h->pool->run(n, block, f);
+}
+
 // ------------------------------------------------------------------------------------------------
 // device bring-up (lazy: creating a handle and the host-only helpers work without a GPU)
 // ------------------------------------------------------------------------------------------------
@@ -261,7 +274,7 @@ static void fill_grid_desc(const fcvm_handle* h, GridDesc& g) {
   g.bricks = h->d_bricks.p + h->brick_guard;
   g.guard_steps = h->guard_steps;
   g.sat = h->use_sat ? h->d_sat.p : nullptr;
-  g.sat_ny = hg.ns[1] / 2 + 1; g.sat_nz = hg.ns[2] / 2 + 1;
+  g.sat_ny = hg.ns[1] / FCVM_SAT_BRICKS + 1; g.sat_nz = hg.ns[2] / FCVM_SAT_BRICKS + 1;
   g.nx = hg.dims[0]; g.ny = hg.dims[1]; g.nz = hg.dims[2];
   g.nbx = hg.ns[0]; g.nby = hg.ns[1]; g.nbz = hg.ns[2];
   g.nly = hg.ns[1] >> 1; g.nlz = hg.ns[2] >> 2;
@@ -432,10 +445,20 @@ static int eval_batch(fcvm_handle* h, int stage, const VpRec* recs, int64_t n, c
   // stream.  The host only waits for the (tiny) offsets of a finished sub-batch, with the next kernel already queued.
   bool csr_streamed = false;
   if (csr && !rows_out && h->world == 1 && n >= 2 * kPipeMinRows) {
-    // two sub-batches: every extra launch costs ~2.5 ms of load-balance tail, the index lists are only ~4 B per visible ray
-    const int pipe_subs = env().pipe_subs ? env().pipe_subs : 2;
-    const int64_t sub = std::max<int64_t>(kPipeMinRows, (n + pipe_subs - 1) / pipe_subs);
-    const size_t nsub = (size_t)((n + sub - 1) / sub);
+    // Sub-batches of decreasing size (55 / 30 / 15 %): what cannot overlap is the compaction and copy-out of the LAST one's
+    // lists, while every extra launch costs a load-balance tail of its own.  FCVM_PIPE_SUBS=k: k equal sub-batches instead.
+    std::vector<std::pair<int64_t, int64_t>> subs;      // (first row, rows)
+    if (env().pipe_subs) {
+      const int64_t sub = std::max<int64_t>(kPipeMinRows, (n + env().pipe_subs - 1) / env().pipe_subs);
+      for (int64_t s0 = 0; s0 < n; s0 += sub) subs.emplace_back(s0, std::min(sub, n - s0));
+    } else if (n >= 8 * kPipeMinRows) {
+      const int64_t a = (n * 55 / 100 + 31) & ~31ll, b = (n * 30 / 100 + 31) & ~31ll;
+      subs = {{0, a}, {a, b}, {a + b, n - a - b}};
+    } else {
+      const int64_t a = (n * 6 / 10 + 31) & ~31ll;
+      subs = {{0, a}, {a, n - a}};
+    }
+    const size_t nsub = subs.size();
     CU(h->d_offsets.reserve((size_t)n + nsub));
     CU(h->h_offsets.reserve((size_t)n + nsub));
     while (h->pipe_ev.size() < 2 * nsub) {
@@ -444,8 +467,8 @@ static int eval_batch(fcvm_handle* h, int stage, const VpRec* recs, int64_t n, c
       h->pipe_ev.push_back(e);
     }
     size_t k = 0;
-    for (int64_t s0 = 0; s0 < n; s0 += sub, ++k) {      // everything of the evaluation side is queued up front
-      const int64_t sn = std::min(sub, n - s0);
+    for (; k < nsub; ++k) {      // everything of the evaluation side is queued up front
+      const int64_t s0 = subs[k].first, sn = subs[k].second;
       rc = launch_stage(h, stage, h->d_recs.p + s0, sn, d_rows.p + s0 * W, d_restrict ? d_restrict + s0 * W : nullptr, h->stream, true);
       if (rc) return rc;
       CU(launch_popc_rows(d_rows.p + s0 * W, sn, W, h->d_count.p + s0, h->stream));
@@ -458,9 +481,8 @@ static int eval_batch(fcvm_handle* h, int stage, const VpRec* recs, int64_t n, c
     tmark("kernels queued");
     csr->offs.assign((size_t)n + 1, 0);
     long long base = 0;
-    k = 0;
-    for (int64_t s0 = 0; s0 < n; s0 += sub, ++k) {
-      const int64_t sn = std::min(sub, n - s0);
+    for (k = 0; k < nsub; ++k) {
+      const int64_t s0 = subs[k].first, sn = subs[k].second;
       long long* h_off = h->h_offsets.p + s0 + (int64_t)k;
       CU(cudaStreamWaitEvent(h->copy_stream, h->pipe_ev[2 * k], 0));
       CU(cudaMemcpyAsync(h_off, h->d_offsets.p + s0 + (int64_t)k, ((size_t)sn + 1) * sizeof(long long), cudaMemcpyDeviceToHost, h->copy_stream));
@@ -934,7 +956,7 @@ static int e1_with_pose_sums(fcvm_handle* h, int64_t lo, int64_t hi, const std::
       CU(cudaStreamSynchronize(ax));
       h->h_indices.note_use();
       Stopwatch sw2(h->t_sums);
-      parallel_for(sn, h->threads, [&](int64_t i) {
+      pfor(h, sn, 4, [&](int64_t i) {
         const long long cnt = h_off[i + 1] - h_off[i];
         if (cnt > 0) host_pose_sums(M, seed[(size_t)(r0 + i)], h->h_indices.p + h_off[i], cnt, sums[(size_t)2 * (r0 + i)], sums[(size_t)2 * (r0 + i) + 1]);
       });
@@ -1030,6 +1052,11 @@ static int get_pose_batch(fcvm_handle* h, const std::vector<D3>& pos, const std:
   if (n == 0) return FCVM_OK;
   const int64_t W = h->W;
   int rc;
+  const auto t_gp0 = std::chrono::steady_clock::now();
+  auto gmark = [&](const char* what) {
+    if (env().profile >= 2)
+      std::fprintf(stderr, "[fcvm]   getPose batch n=%lld: %s at %.3f ms\n", (long long)n, what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_gp0).count());
+  };
   for (int64_t c0 = 0; c0 < n; c0 += chunk_rows(h, n)) {
     const int64_t cn = std::min(chunk_rows(h, n), n - c0);
     std::vector<PoseSeed> seed((size_t)cn);
@@ -1037,7 +1064,7 @@ static int get_pose_batch(fcvm_handle* h, const std::vector<D3>& pos, const std:
     CU(h->h_recs.reserve((size_t)cn));
     CU(h->h_aux.reserve((size_t)cn));
     CU(h->h_count.reserve((size_t)cn));
-    parallel_for(cn, h->threads, [&](int64_t i) {
+    pfor(h, cn, 128, [&](int64_t i) {
       // fov_sample_ray = dir.normalized(); fov_yaw_ray = (x, y, 0).normalized(); init_py = PitchYaw
       PoseSeed& sd = seed[(size_t)i];
       sd.vp = pos[(size_t)(c0 + i)];
@@ -1081,6 +1108,7 @@ static int get_pose_batch(fcvm_handle* h, const std::vector<D3>& pos, const std:
     }
     std::vector<long long> free_num((size_t)cn, 0);
     std::vector<double> sums((size_t)2 * cn, 0.0);
+    gmark("records built and queued for upload");
     {
       Stopwatch sw(h->t_eval);
       rc = e1_with_pose_sums(h, lo, hi, seed, free_num, sums);
@@ -1088,6 +1116,7 @@ static int get_pose_batch(fcvm_handle* h, const std::vector<D3>& pos, const std:
       rc = fetch_counters(h);      // synchronises the main stream
       if (rc) return rc;
     }
+    gmark("E1 + pose sums");
     if (h->trace_on) {
       rc = fetch_rows_for_trace(h, h->d_rows1, cn);
       if (rc) return rc;
@@ -1095,7 +1124,7 @@ static int get_pose_batch(fcvm_handle* h, const std::vector<D3>& pos, const std:
     }
     // averaged poses (cpp:427-447); (pitch, yaw, free_num) of every viewpoint reach every rank
     std::vector<double> avg3((size_t)cn * 3, 0.0);
-    parallel_for(hi - lo, h->threads, [&](int64_t r) {
+    pfor(h, hi - lo, 1024, [&](int64_t r) {
       const int64_t i = lo + r;
       if (free_num[(size_t)i] == 0) return;       // free_num == 0: pose stays (pos, init_py), no E2, no ownership (cpp:427-436)
       finish_average(h, sums[(size_t)2 * i], sums[(size_t)2 * i + 1], free_num[(size_t)i], seed[(size_t)i].init_yaw, avg3[(size_t)3 * i], avg3[(size_t)3 * i + 1]);
@@ -1104,7 +1133,7 @@ static int get_pose_batch(fcvm_handle* h, const std::vector<D3>& pos, const std:
     rc = gather_doubles(h, avg3.data(), cn, 3);
     if (rc) return rc;
     std::vector<char> has_free((size_t)cn, 0);
-    parallel_for(cn, h->threads, [&](int64_t i) {   // the E2 records (sin / cos of the averaged pose: libm, per viewpoint)
+    pfor(h, cn, 128, [&](int64_t i) {   // the E2 records (sin / cos of the averaged pose: libm, per viewpoint)
       if (avg3[(size_t)3 * i + 2] == 0.0) return;
       const D3& vp = seed[(size_t)i].vp;
       poses_out[(size_t)(c0 + i)].v[3] = avg3[(size_t)3 * i];
@@ -1113,6 +1142,7 @@ static int get_pose_batch(fcvm_handle* h, const std::vector<D3>& pos, const std:
       h->cam.fill(h->h_recs.p[i], vp.x, vp.y, vp.z, avg3[(size_t)3 * i], avg3[(size_t)3 * i + 1]);
     });
 
+    gmark("averaged poses, E2 records");
     // ---- E2 on the E1 sets (cpp:457-498) ---------------------------------------------------
     // viewpoints with free_num == 0 have all-zero E1 rows, so they contribute nothing here
     {
@@ -1134,8 +1164,10 @@ static int get_pose_batch(fcvm_handle* h, const std::vector<D3>& pos, const std:
       for (int64_t i = 0; i < cn; ++i)
         if (has_free[(size_t)i]) record(h, 2, ids[(size_t)i], poses_out[(size_t)(c0 + i)], h->h_rows.p + i * W);
     }
+    gmark("E2");
     rc = ownership(h, h->d_rows2, cn, lo, hi, order, ids, h->h_count.p);
     if (rc) return rc;
+    gmark("ownership queued");
   }
   return FCVM_OK;
 }
@@ -1184,10 +1216,8 @@ static int viewpoints_prune(fcvm_handle* h, const std::vector<Pose5>& vps_pose, 
   };
   auto& inverse_idx = h->inverse_idx;
   auto& idx_slot = h->idx_slot;
-  auto& idx_ctrl_voxels = h->idx_ctrl_voxels;
   inverse_idx.clear();
   idx_slot.clear();
-  idx_ctrl_voxels.clear();
   std::vector<int> slot_id;
   std::vector<Pose5> slot_pose;
   std::vector<char> live, query;
@@ -1200,7 +1230,6 @@ static int viewpoints_prune(fcvm_handle* h, const std::vector<Pose5>& vps_pose, 
       vp_cloud.push_back(fx); vp_cloud.push_back(fyy); vp_cloud.push_back(fz);
       inverse_idx[D3{fx, fyy, fz}] = i;
       idx_slot[i] = (int)slot_id.size();
-      idx_ctrl_voxels[i] = sub_voxcount[(size_t)i];
       slot_id.push_back(i);
       slot_pose.push_back(q);
       live.push_back(1);
@@ -1209,8 +1238,12 @@ static int viewpoints_prune(fcvm_handle* h, const std::vector<Pose5>& vps_pose, 
   }
   if (vp_cloud.empty()) return FCVM_OK;   // "No need prune viewpoints!" cpp:651-655
 
-  // sort by ctrl voxels, descending, over the unordered_map's own iteration order (cpp:658-662)
-  std::vector<std::pair<int, int>> ctrlVector(idx_ctrl_voxels.begin(), idx_ctrl_voxels.end());
+  // sort by ctrl voxels, descending, over the unordered_map's own iteration order (cpp:658-662).  The reference's
+  // idx_ctrl_voxels_ receives the same keys in the same order, and is cleared at the same moments, as idx_viewpoints_ (idx_slot
+  // here): libstdc++'s iteration order depends on nothing else, so one map stands for both.
+  std::vector<std::pair<int, int>> ctrlVector;
+  ctrlVector.reserve(idx_slot.size());
+  for (const auto& kv : idx_slot) ctrlVector.emplace_back(kv.first, sub_voxcount[(size_t)kv.first]);
   std::sort(ctrlVector.begin(), ctrlVector.end(), [](const std::pair<int, int>& a, const std::pair<int, int>& b) { return a.second > b.second; });
 
   CellIndex vps_tree;
@@ -1362,7 +1395,7 @@ static int viewpoints_prune(fcvm_handle* h, const std::vector<Pose5>& vps_pose, 
       }
       std::vector<double> upd((size_t)cn * 2, 0.0);
       const auto t_sums0 = std::chrono::steady_clock::now();
-      parallel_for(my_hi - my_lo, h->threads, [&](int64_t r) {
+      pfor(h, my_hi - my_lo, 1, [&](int64_t r) {
         const int64_t i = my_lo + r;
         const Grav& gq = grav[(size_t)(c0 + i)];
         double avg_pitch = gq.upi, avg_yaw = gq.uy;
@@ -1498,6 +1531,11 @@ static int update_impl(fcvm_handle* h) {
   if (rc) return rc;
   const fcvm_params& prm = h->prm;
   const float* M = h->model.data();
+  const auto t_upd0 = std::chrono::steady_clock::now();
+  auto umark = [&](const char* what) {
+    if (env().profile >= 2)
+      std::fprintf(stderr, "[fcvm] updateViewpoints: %s at %.3f ms\n", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_upd0).count());
+  };
   if (!h->viewpoints_flag) {
     // "No input viewpoints!! Use normals gengerate viewpoints!!" (cpp:145-171)
     if (!h->map_flag || !h->model_flag || !h->normal_flag) return fail(FCVM_ENOTREADY, "Not ready: map, model and normals are required");
@@ -1514,12 +1552,15 @@ static int update_impl(fcvm_handle* h) {
       q.push_back(vx); q.push_back(vy); q.push_back(vz);
     }
     std::vector<uint8_t> safe;
+    umark("candidates from the normals");
     rc = safety_batch(h, q, 0, safe);                  // viewpointSafetyCheck of every candidate (cpp:159-160), one launch
     if (rc) return rc;
     for (size_t i = 0; i < all.size(); ++i)
       if (safe[i]) vps.push_back(all[i]);
+    umark("their safety check");
     rc = set_init_viewpoints_impl(h, vps);
     if (rc && rc != FCVM_EINVAL) return rc;
+    umark("setInitViewpoints (getPose of all)");
   }
   if (!(h->map_flag && h->model_flag && h->viewpoints_flag && h->normal_flag)) return fail(FCVM_ENOTREADY, "[ViewpointManager] Not ready");
 
@@ -1531,8 +1572,10 @@ static int update_impl(fcvm_handle* h) {
   if (rc) return rc;
   rc = voxcount_upload(h, std::vector<int>(std::max((size_t)h->P, h->vps_pose.size()), 0));   // resize(P) in the reference; A.9
   if (rc) return rc;
+  umark("cover reset, voxcount swap");
   rc = viewpoints_prune(h, h->vps_pose, temp_vps_voxcount);
   if (rc) return rc;
+  umark("first prune");
 
   auto uncovered = [&](std::vector<int>& ids) -> int {
     std::vector<int> cid((size_t)h->P);
@@ -1546,6 +1589,7 @@ static int update_impl(fcvm_handle* h) {
   std::vector<int> uncoveredID;
   rc = uncovered(uncoveredID);
   if (rc) return rc;
+  umark("uncovered ids");
 
   // cpp:206-221: candidate library for the uncovered points.
   // The points are independent (candidate q of the c-th call draws from engines seeded seed + 8c + k): the library is one
@@ -1592,6 +1636,7 @@ static int update_impl(fcvm_handle* h) {
     tmark("library complete");
   }
 
+  umark("candidate library");
   int unc_iter = 0, last_unc_num = -1;
   while ((int)uncoveredID.size() > 0 && unc_iter < prm.max_iter_num && last_unc_num != (int)uncoveredID.size()) {
     last_unc_num = (int)uncoveredID.size();
@@ -1634,9 +1679,10 @@ static int update_impl(fcvm_handle* h) {
     if (rc) return rc;
     h->vps_contri.resize(h->vps_contri.size() + cand.size(), 0);
     if (h->vps_contri.size() < (size_t)oriVpNum + cand.size()) h->vps_contri.resize((size_t)oriVpNum + cand.size(), 0);
-    std::vector<int> before_vps_voxcount;
-    rc = voxcount_download(h, before_vps_voxcount);
-    if (rc) return rc;
+    // before_vps_voxcount (cpp:276): kept on the device, it only ever comes back as the vector's contents (cpp:307)
+    const size_t before_n = h->voxcount_n;
+    CU(h->d_snap_vox.reserve(std::max<size_t>(before_n, 1)));
+    if (before_n) CU(cudaMemcpyAsync(h->d_snap_vox.p, h->d_voxcount.p, before_n * sizeof(int), cudaMemcpyDeviceToDevice, h->stream));
 
     std::vector<D3> pos(cand.size()), dir(cand.size());
     for (size_t i = 0; i < cand.size(); ++i) {
@@ -1644,8 +1690,10 @@ static int update_impl(fcvm_handle* h) {
       dir[i] = D3{cand[i].nx, cand[i].ny, cand[i].nz};
     }
     std::vector<Pose5> pose_set_unc;
+    umark("  iteration: candidates drawn, snapshots");
     rc = get_pose_batch(h, pos, dir, oriVpNum, pose_set_unc);
     if (rc) return rc;      // the snapshots are released by their destructors
+    umark("  iteration: getPose of the candidates");
     h->vps_pose.insert(h->vps_pose.end(), pose_set_unc.begin(), pose_set_unc.end());
 
     // restore MCI, swap the voxcounts (cpp:304-309)
@@ -1653,12 +1701,15 @@ static int update_impl(fcvm_handle* h) {
     CU(cudaMemcpyAsync(h->d_contrib_id.p, snap_id.p, (size_t)h->P * sizeof(int), cudaMemcpyDeviceToDevice, h->stream));
     rc = voxcount_download(h, temp_vps_voxcount);
     if (rc) return rc;
-    rc = voxcount_upload(h, before_vps_voxcount);
-    if (rc) return rc;
+    if (h->voxcount_n != before_n) return fail(FCVM_EINTERNAL, "vps_voxcount changed its size inside getPose");
+    if (before_n) CU(cudaMemcpyAsync(h->d_voxcount.p, h->d_snap_vox.p, before_n * sizeof(int), cudaMemcpyDeviceToDevice, h->stream));
+    umark("  iteration: state restored");
     rc = viewpoints_prune(h, h->vps_pose, temp_vps_voxcount);
     if (rc) return rc;
+    umark("  iteration: prune");
     rc = uncovered(uncoveredID);
     if (rc) return rc;
+    umark("  iteration: uncovered ids");
     unc_iter++;
   }
   return voxcount_download(h, h->vps_voxcount);
@@ -1726,7 +1777,7 @@ int fcvm_reset(fcvm_t* h) {   // cpp:64-72
   h->last_vps_num = 0; h->voxcount_n = 0;
   h->pt_normal_pairs.clear();
   h->final_vps.clear();
-  h->inverse_idx.clear(); h->idx_slot.clear(); h->idx_ctrl_voxels.clear();   // VPP.reset(): clear(), buckets kept
+  h->inverse_idx.clear(); h->idx_slot.clear();   // VPP.reset(): clear(), buckets kept
   h->n_map = 0;
   h->trace.clear();
   for (int k = 0; k < FCVM_NCOUNTERS; ++k) h->counters[k] = 0;
@@ -1783,7 +1834,7 @@ int fcvm_set_map_cloud(fcvm_t* h, const float* xyz, int64_t n) {   // cpp:74-89
     CU(cudaMemsetAsync(h->d_bricks.p + h->brick_guard + h->grid.nbricks(), 0xFF, h->brick_guard * sizeof(unsigned long long), s));
     CU(launch_voxelise(h->d_map_xyz.p, n, g, h->d_bricks.p + h->brick_guard, s));
     CU(launch_mark_padding(h->d_bricks.p + h->brick_guard, h->grid.dims, h->grid.ns, s));
-    CU(h->d_sat.reserve((size_t)(h->grid.ns[0] / 2 + 1) * (h->grid.ns[1] / 2 + 1) * (h->grid.ns[2] / 2 + 1)));
+    CU(h->d_sat.reserve((size_t)(h->grid.ns[0] / FCVM_SAT_BRICKS + 1) * (h->grid.ns[1] / FCVM_SAT_BRICKS + 1) * (h->grid.ns[2] / FCVM_SAT_BRICKS + 1)));
     CU(launch_build_sat(h->d_bricks.p + h->brick_guard, h->grid.ns, h->d_sat.p, s));
     h->counters[5] += 7;
 
@@ -2004,7 +2055,7 @@ int fcvm_evaluate(fcvm_t* h, int32_t stage, const double* pose5, int64_t n, cons
   for (int64_t c0 = 0; c0 < n; c0 += chunk_rows(h, n)) {
     const int64_t cn = std::min(chunk_rows(h, n), n - c0);
     CU(h->h_recs.reserve((size_t)cn));
-    parallel_for(cn, h->threads, [&](int64_t i) {
+    pfor(h, cn, 128, [&](int64_t i) {
       const double* p = pose5 + 5 * (c0 + i);
       h->cam.fill(h->h_recs.p[i], p[0], p[1], p[2], p[3], p[4]);
     });
@@ -2027,7 +2078,7 @@ int64_t fcvm_evaluate_csr(fcvm_t* h, int32_t stage, const double* pose5, int64_t
   for (int64_t c0 = 0; c0 < n; c0 += chunk_rows(h, n)) {
     const int64_t cn = std::min(chunk_rows(h, n), n - c0);
     CU(h->h_recs.reserve((size_t)cn));
-    parallel_for(cn, h->threads, [&](int64_t i) {
+    pfor(h, cn, 128, [&](int64_t i) {
       const double* p = pose5 + 5 * (c0 + i);
       h->cam.fill(h->h_recs.p[i], p[0], p[1], p[2], p[3], p[4]);
     });
@@ -2050,7 +2101,7 @@ int fcvm_stage_poses(fcvm_t* h, const double* pose5, int64_t n) {
   int rc = ensure_device(h);
   if (rc) return rc;
   CU(h->h_recs.reserve((size_t)n));
-  parallel_for(n, h->threads, [&](int64_t i) { h->cam.fill(h->h_recs.p[i], pose5[5 * i], pose5[5 * i + 1], pose5[5 * i + 2], pose5[5 * i + 3], pose5[5 * i + 4]); });
+  pfor(h, n, 128, [&](int64_t i) { h->cam.fill(h->h_recs.p[i], pose5[5 * i], pose5[5 * i + 1], pose5[5 * i + 2], pose5[5 * i + 3], pose5[5 * i + 4]); });
   CU(h->d_recs.reserve((size_t)n));
   CU(h->d_rows1.reserve((size_t)n * h->W));
   CU(h->d_count.reserve((size_t)n));

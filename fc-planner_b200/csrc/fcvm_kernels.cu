@@ -299,7 +299,8 @@ __device__ __forceinline__ bool prepare_ray(const GridDesc& g, const FovConst& f
       const bool p_in = v_inside == 7, n_in = n_inside == 7;
       if (p_in && n_in) c.flags |= CONT_SANE;
       if (p_in)
-        pfree = sat_box_count(g, min(pix, mix) >> 3, min(piy, miy) >> 3, min(piz, miz) >> 3, max(pix, mix) >> 3, max(piy, miy) >> 3, max(piz, miz) >> 3) == 0;
+        pfree = sat_box_count(g, min(pix, mix) >> FCVM_SAT_SHIFT, min(piy, miy) >> FCVM_SAT_SHIFT, min(piz, miz) >> FCVM_SAT_SHIFT, max(pix, mix) >> FCVM_SAT_SHIFT,
+                              max(piy, miy) >> FCVM_SAT_SHIFT, max(piz, miz) >> FCVM_SAT_SHIFT) == 0;
     }
     c.p.rem = abs(dx) + abs(dy) + abs(dz);
     if (pfree) {
@@ -524,8 +525,8 @@ __global__ void __launch_bounds__(kWarps * 32, EVAL_MIN_CTAS) k_eval(const __gri
       // reference would still make returns "free": the pair is visible, its remaining biNextId calls are only counted.
       if (g.sat != nullptr && ((++tick) & (EVAL_QUERY_PERIOD - 1)) == 0) {
         if (active && (c.flags & CONT_SANE)) {
-          const int n_empty = sat_box_count(g, min(c.p.ix, c.n.ix) >> 3, min(c.p.iy, c.n.iy) >> 3, min(c.p.iz, c.n.iz) >> 3, max(c.p.ix, c.n.ix) >> 3,
-                                            max(c.p.iy, c.n.iy) >> 3, max(c.p.iz, c.n.iz) >> 3);
+          const int n_empty = sat_box_count(g, min(c.p.ix, c.n.ix) >> FCVM_SAT_SHIFT, min(c.p.iy, c.n.iy) >> FCVM_SAT_SHIFT, min(c.p.iz, c.n.iz) >> FCVM_SAT_SHIFT,
+                                            max(c.p.ix, c.n.ix) >> FCVM_SAT_SHIFT, max(c.p.iy, c.n.iy) >> FCVM_SAT_SHIFT, max(c.p.iz, c.n.iz) >> FCVM_SAT_SHIFT);
           if (n_empty == 0) {
             const int calls = (c.flags & CONT_PFREE) ? c.n.rem + c.p.rem : max(c.p.rem, c.n.rem);
             st.lookups += 2u * (unsigned)calls + 1u;

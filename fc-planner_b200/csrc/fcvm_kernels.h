@@ -117,7 +117,7 @@ cudaError_t launch_cloud_minmax(const float* xyz, long long n, float* partial, i
 cudaError_t launch_voxelise(const float* xyz, long long n, const MapGeom& g, unsigned long long* bricks, cudaStream_t s);
 // voxels of the padded brick array beyond map_voxel_num_ read 'occupied' (occCheck is false outside the map)
 cudaError_t launch_mark_padding(unsigned long long* bricks, const int dims[3], const int nb[3], cudaStream_t s);
-// summed-area table over 2 x 2 x 2-brick cells; sat must hold (nb[0]/2 + 1) * (nb[1]/2 + 1) * (nb[2]/2 + 1) ints
+// summed-area table over cells of FCVM_SAT_BRICKS^3 bricks; sat must hold (nb[0]/B + 1) * (nb[1]/B + 1) * (nb[2]/B + 1) ints
 cudaError_t launch_build_sat(const unsigned long long* bricks, const int nb[3], int* sat, cudaStream_t s);
 cudaError_t launch_cell_count(const float* xyz, long long n, const CellGeom& cg, int* count, cudaStream_t s);
 cudaError_t launch_cell_fill(const float* xyz, long long n, const CellGeom& cg, const long long* start, int* fill, float4* sorted, cudaStream_t s);

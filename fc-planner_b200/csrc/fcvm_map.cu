@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(256) k_mark_padding(unsigned long long* __rest
   bricks[i] |= m;
 }
 
-// ---- summed-area table of "cell has an occupied voxel" over 2 x 2 x 2-brick cells (GridDesc::sat) ------------------
+// ---- summed-area table of "cell has an occupied voxel" over cells of FCVM_SAT_BRICKS^3 bricks (GridDesc::sat) ------------------
 // flags into sat[(x + 1, y + 1, z + 1)] (the table is zeroed first), then one inclusive prefix pass per axis.
 __global__ void __launch_bounds__(256) k_sat_flags(const unsigned long long* __restrict__ bricks, int nby, int nbz, int cx, int cy, int cz, int* __restrict__ sat) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -78,11 +78,12 @@ __global__ void __launch_bounds__(256) k_sat_flags(const unsigned long long* __r
   const int z = (int)(i % cz), y = (int)((i / cz) % cy), x = (int)(i / ((long long)cz * cy));
   unsigned long long any = 0ull;
 #pragma unroll
-  for (int a = 0; a < 2; ++a)
+  for (int a = 0; a < FCVM_SAT_BRICKS; ++a)
 #pragma unroll
-    for (int b = 0; b < 2; ++b)
+    for (int b = 0; b < FCVM_SAT_BRICKS; ++b)
 #pragma unroll
-      for (int c = 0; c < 2; ++c) any |= __ldg(bricks + ((long long)(2 * x + a) * nby + (2 * y + b)) * nbz + (2 * z + c));
+      for (int c = 0; c < FCVM_SAT_BRICKS; ++c)
+        any |= __ldg(bricks + ((long long)(FCVM_SAT_BRICKS * x + a) * nby + (FCVM_SAT_BRICKS * y + b)) * nbz + (FCVM_SAT_BRICKS * z + c));
   sat[((long long)(x + 1) * (cy + 1) + (y + 1)) * (cz + 1) + (z + 1)] = any ? 1 : 0;
 }
 // axis 0 / 1 / 2 = prefix along x / y / z; one thread per line of the other two axes
@@ -236,7 +237,7 @@ cudaError_t launch_mark_padding(unsigned long long* bricks, const int dims[3], c
 }
 
 cudaError_t launch_build_sat(const unsigned long long* bricks, const int nb[3], int* sat, cudaStream_t s) {
-  const int cx = nb[0] / 2, cy = nb[1] / 2, cz = nb[2] / 2;
+  const int cx = nb[0] / FCVM_SAT_BRICKS, cy = nb[1] / FCVM_SAT_BRICKS, cz = nb[2] / FCVM_SAT_BRICKS;
   const long long n = (long long)(cx + 1) * (cy + 1) * (cz + 1);
   cudaError_t e = cudaMemsetAsync(sat, 0, (size_t)n * sizeof(int), s);
   if (e != cudaSuccess) return e;
