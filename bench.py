@@ -517,10 +517,12 @@ def main():
     barrier()
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = int(vm.counters()[5])
     ev0.record()
     for _ in range(args.steps):
         vm.evaluate_resident(args.stage, stream=stream, sync=False)
     ev1.record()
+    launches_timed = int(vm.counters()[5]) - launches0      # the library's own count: k_ray_ends + k_eval + k_popc_rows per step
     barrier()
     clocks = sampler.stop()
     dev_ms = ev0.elapsed_time(ev1)
@@ -664,7 +666,7 @@ def main():
             "e2e_rows": {"value": rays_step / (e2e_rows_s / args.steps), "unit": UNIT, "ms_per_step": 1e3 * e2e_rows_s / args.steps,
                          "d2h_bytes_per_step": int(V * 4 + V * words * 4), "note": "rank 0's own rate",
                          "call": "fcvm_evaluate(...) -> counts + raw bitset rows"},
-            "gpu_launches": 2 * args.steps,
+            "gpu_launches": launches_timed,
             "rays_per_step_per_gpu": rays_step, "pair_tests_per_step_per_gpu": pairs_step, "voxel_lookups_per_step_per_gpu": lookups_step,
             "viewpoint_evals_per_s": V * world * args.steps / (dev_ms_max * 1e-3),
             "other_evaluators_rank0": other_stages,

@@ -7,10 +7,10 @@
 // IBM Accurate Mathematical Library code behind them evaluates to ~70 bits and rounds once).  So a device
 // implementation cannot reproduce glibc bit for bit by itself, but it can compute the CORRECTLY ROUNDED value
 // together with a certificate: the double-double result (hi, lo) is accurate to < 2^-12 ulp, and when
-// hi + lo is farther than kFlagMargin = 1/16 ulp from every rounding midpoint, glibc's value must equal hi.
-// Rays inside the margin (12.5 % of them) are flagged and their arguments go to the host, which calls the
+// hi + lo is farther than kFlagMargin = 1/32 ulp from every rounding midpoint, glibc's value must equal hi.
+// Rays inside the margin (6.25 % of them) are flagged and their arguments go to the host, which calls the
 // real glibc function for exactly those (fcvm_host.cu, pose_sums_*).  Nothing here is approximate in effect:
-// the summed pitch / yaw are bit-identical to the reference's, the host's libm work drops by ~16x.
+// the summed pitch / yaw are bit-identical to the reference's, the host's libm work drops by ~16x (32x per function).
 //
 // Algorithm (x in [0, 1]; odd / reflection symmetry outside):  theta ~ asin(x) in plain double picks
 // k = rint(64 theta), theta_k = k / 64 (exact), and with s = sqrt(1 - x^2) in double-double
@@ -95,7 +95,11 @@ FCVM_HD DD dd_sqrt_1mx2(double x) {
   return fast_two_sum(s0, r / (2.0 * s0));
 }
 
-constexpr double kFlagMargin = 0.0625;   // in ulps; glibc 2.39 deviates from correct rounding only within 0.021 ulp of a midpoint
+// in ulps.  glibc 2.39's asin / acos (IBM Accurate Mathematical Library without its former slow paths) evaluate to well below
+// 0.03 ulp before their single rounding: the largest distance from a midpoint at which their value was NOT the correctly rounded
+// one is 0.0153 ulp (asin) / 0.0217 ulp (acos), and the maximum is reached within the first few million samples and does not move
+// over billions (profiles/r2_ddmath_check.json) - a bound of the approximation, not a tail.  1/32 leaves 1.4x on top of it.
+constexpr double kFlagMargin = 0.03125;
 
 // true when hi + lo is within kFlagMargin ulp of a rounding midpoint next to hi (conservative at powers of two)
 FCVM_HD bool near_midpoint(DD r) {

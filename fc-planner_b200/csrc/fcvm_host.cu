@@ -108,6 +108,7 @@ struct fcvm_handle {
   DevBuf<unsigned long long> d_bricks;          // [guard | bricks | guard]; the guard words read 'occupied' (see occ_fast)
   DevBuf<int> d_snap_vox;                       // vps_voxcount before an uncovered-area round (update_impl)
   DevBuf<int> d_sat;                            // summed-area table over 8^3-voxel cells (GridDesc::sat)
+  bool sat_built = false;                       // false: the grid is too large for the table's 32-bit offsets
   bool use_sat = true;                          // FCVM_NO_PFREE=1 switches the half-ray certificate off (A/B)
   size_t brick_guard = 0;                       // guard words on each side
   int guard_steps = 0;                          // longest half-ray (voxel steps) the fast path accepts
@@ -168,6 +169,10 @@ struct fcvm_handle {
   bool resident_e1 = false;                    // the first rows buffer holds the E1 rows of the resident batch
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;          // D2H of finished sub-batches while the next one is evaluated
+  std::vector<cudaStream_t> sub_streams;       // sub-batch k of an evaluator pass runs on sub_streams[k]: priorities fall with k, so the block
+                                               // scheduler finishes the sub-batches in order while the tail of one overlaps the head of the next
+  cudaEvent_t sub_start = nullptr;             // "the batch's inputs are on the device" (recorded on the main stream)
+  int pri_lo = 0, pri_hi = 0;                  // cudaDeviceGetStreamPriorityRange: least, greatest
   cudaStream_t aux_stream = nullptr;           // pose-sum pipeline of a finished E1 sub-batch while the next one is evaluated (high priority)
   std::vector<cudaEvent_t> pipe_ev;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -177,6 +182,7 @@ struct fcvm_handle {
   // device time per evaluator stage: event pairs recorded around every k_eval launch, read after the next stream sync
   struct StageEv { cudaEvent_t a, b; int stage; };
   std::vector<StageEv> stage_ev_pending, stage_ev_free;
+  StageEv span_ev{nullptr, nullptr, 0};         // the pair of a pass made of overlapping sub-batches (launch_stage, span)
   double stage_ms[4] = {0, 0, 0, 0};
 
   // ownership as a per-point arg-max (k_own_best / k_own_apply)
@@ -248,11 +254,14 @@ static int ensure_device(fcvm_handle* h) {
                                     " (this library has no CPU fallback)");
   CU(cudaSetDevice(h->prm.device));
   CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-  CU(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
   {
     int lo_pri = 0, hi_pri = 0;
     CU(cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri));
+    // the copy stream also runs the compaction kernels of finished sub-batches: they must not queue behind the evaluator's CTAs
+    CU(cudaStreamCreateWithPriority(&h->copy_stream, cudaStreamNonBlocking, hi_pri));
     CU(cudaStreamCreateWithPriority(&h->aux_stream, cudaStreamNonBlocking, hi_pri));
+    h->pri_lo = lo_pri; h->pri_hi = hi_pri;
+    CU(cudaEventCreateWithFlags(&h->sub_start, cudaEventDisableTiming));
   }
   {
     // the stream-ordered allocator keeps what the pose-sum pipeline frees (default: returned to the OS at the next sync)
@@ -269,11 +278,26 @@ static int ensure_device(fcvm_handle* h) {
   return FCVM_OK;
 }
 
+// Stream of sub-batch k: one below the pose-sum pipeline's priority for k = 0, falling with k (numerically rising) down to the
+// device's least priority.  Kernels of several sub-batches are resident at once; the block scheduler dispatches the CTAs of the
+// highest-priority kernel first, so sub-batch k completes before k + 1 although nothing serialises them, and the SMs that the
+// tail of k leaves idle are taken by k + 1 at once.
+static int sub_stream(fcvm_handle* h, size_t k, cudaStream_t& out) {
+  while (h->sub_streams.size() <= k) {
+    const int pri = std::min(h->pri_lo, h->pri_hi + 1 + (int)h->sub_streams.size());
+    cudaStream_t st;
+    CU(cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, pri));
+    h->sub_streams.push_back(st);
+  }
+  out = h->sub_streams[k];
+  return FCVM_OK;
+}
+
 static void fill_grid_desc(const fcvm_handle* h, GridDesc& g) {
   const HostGrid& hg = h->grid;
   g.bricks = h->d_bricks.p + h->brick_guard;
   g.guard_steps = h->guard_steps;
-  g.sat = h->use_sat ? h->d_sat.p : nullptr;
+  g.sat = (h->use_sat && h->sat_built) ? h->d_sat.p : nullptr;
   g.sat_ny = hg.ns[1] / FCVM_SAT_BRICKS + 1; g.sat_nz = hg.ns[2] / FCVM_SAT_BRICKS + 1;
   g.nx = hg.dims[0]; g.ny = hg.dims[1]; g.nz = hg.dims[2];
   g.nbx = hg.ns[0]; g.nby = hg.ns[1]; g.nbz = hg.ns[2];
@@ -313,8 +337,10 @@ static void choose_tiling(int64_t P, int64_t V, int& tile_pts, int& vp_per_cta) 
 
 // One evaluator launch over recs[0..n) already on the device -> rows (zeroed here).  Adds the
 // kernel's counters to the handle when `count_stats`.
+// span: 0 = a launch of its own; 1 / 2 / 3 = first / middle / last sub-batch of one pass whose kernels overlap on priority
+// streams - the per-stage device time (fcvm_get_timers) then runs from the first kernel's start to the last one's end.
 static int launch_stage(fcvm_handle* h, int stage, const VpRec* d_recs, int64_t n, uint32_t* d_rows, const uint32_t* d_restrict,
-                        cudaStream_t s, bool count_stats) {
+                        cudaStream_t s, bool count_stats, int span = 0) {
   EvalArgs a;
   fill_grid_desc(h, a.grid);
   fill_fov_const(h, a.fov);
@@ -337,16 +363,18 @@ static int launch_stage(fcvm_handle* h, int stage, const VpRec* d_recs, int64_t 
   CU(cudaMemsetAsync(d_rows, 0, (size_t)n * h->W * sizeof(uint32_t), s));
   CU(cudaEventRecord(h->ev0, s));      // ev0..ev1 bracket the visibility kernel alone (roofline timing)
   fcvm_handle::StageEv se{nullptr, nullptr, stage};
-  if (count_stats) {                   // per-stage device time of the manager-level calls (fcvm_get_timers)
+  if (count_stats && span <= 1) {      // per-stage device time of the manager-level calls (fcvm_get_timers)
     if (!h->stage_ev_free.empty()) { se = h->stage_ev_free.back(); h->stage_ev_free.pop_back(); se.stage = stage; }
     else { CU(cudaEventCreate(&se.a)); CU(cudaEventCreate(&se.b)); }
     CU(cudaEventRecord(se.a, s));
+    if (span == 1) h->span_ev = se;
   }
   CU(launch_eval(stage, a, s));
-  if (count_stats) { CU(cudaEventRecord(se.b, s)); h->stage_ev_pending.push_back(se); }
+  if (count_stats && span == 0) { CU(cudaEventRecord(se.b, s)); h->stage_ev_pending.push_back(se); }
+  if (count_stats && span == 3) { CU(cudaEventRecord(h->span_ev.b, s)); h->stage_ev_pending.push_back(h->span_ev); }
   CU(cudaEventRecord(h->ev1, s));
   h->timed = true;
-  h->counters[5] += 1;
+  h->counters[5] += 2;                 // k_ray_ends + k_eval
   h->counters[6] += n;
   return FCVM_OK;
 }
@@ -467,15 +495,23 @@ static int eval_batch(fcvm_handle* h, int stage, const VpRec* recs, int64_t n, c
       h->pipe_ev.push_back(e);
     }
     size_t k = 0;
-    for (; k < nsub; ++k) {      // everything of the evaluation side is queued up front
+    CU(cudaEventRecord(h->sub_start, h->stream));
+    for (; k < nsub; ++k) {      // everything of the evaluation side is queued up front, one priority stream per sub-batch
       const int64_t s0 = subs[k].first, sn = subs[k].second;
-      rc = launch_stage(h, stage, h->d_recs.p + s0, sn, d_rows.p + s0 * W, d_restrict ? d_restrict + s0 * W : nullptr, h->stream, true);
+      cudaStream_t ss;
+      rc = sub_stream(h, k, ss);
       if (rc) return rc;
-      CU(launch_popc_rows(d_rows.p + s0 * W, sn, W, h->d_count.p + s0, h->stream));
-      CU(launch_exscan(h->d_count.p + s0, sn, h->d_offsets.p + s0 + (int64_t)k, h->stream));
+      CU(cudaStreamWaitEvent(ss, h->sub_start, 0));
+      if ((int)k >= std::max(1, h->pri_lo - h->pri_hi)) CU(cudaStreamWaitEvent(ss, h->pipe_ev[2 * (k - 1)], 0));   // out of priority levels
+      rc = launch_stage(h, stage, h->d_recs.p + s0, sn, d_rows.p + s0 * W, d_restrict ? d_restrict + s0 * W : nullptr, ss, true,
+                        nsub == 1 ? 0 : (k == 0 ? 1 : (k + 1 == nsub ? 3 : 2)));
+      if (rc) return rc;
+      CU(launch_popc_rows(d_rows.p + s0 * W, sn, W, h->d_count.p + s0, ss));
+      CU(launch_exscan(h->d_count.p + s0, sn, h->d_offsets.p + s0 + (int64_t)k, ss));
       h->counters[5] += 2;
-      CU(cudaEventRecord(h->pipe_ev[2 * k], h->stream));
+      CU(cudaEventRecord(h->pipe_ev[2 * k], ss));
     }
+    for (k = 0; k < nsub; ++k) CU(cudaStreamWaitEvent(h->stream, h->pipe_ev[2 * k], 0));    // the main stream continues after all of them
     const bool vprof = env().profile >= 3;
     auto tmark = [&](const char* what) { if (vprof) std::fprintf(stderr, "[fcvm]     %s at %.2f ms\n", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - verbose.t0).count()); };
     tmark("kernels queued");
@@ -901,7 +937,8 @@ static int e1_with_pose_sums(fcvm_handle* h, int64_t lo, int64_t hi, const std::
   const int64_t W = h->W, ln = hi - lo;
   if (ln <= 0) return FCVM_OK;
   int rc;
-  const int want = env().pipe_subs ? env().pipe_subs : (int)std::min<int64_t>(8, std::max<int64_t>(1, ln / 6144));
+  const int levels = std::max(1, h->pri_lo - h->pri_hi);       // priority levels below the pose-sum pipeline's
+  const int want = env().pipe_subs ? env().pipe_subs : (int)std::min<int64_t>(std::min(8, levels), std::max<int64_t>(1, ln / 6144));
   const int64_t sub = std::max<int64_t>(std::min<int64_t>(kPipeMinRows, ln), (ln + want - 1) / want);
   const size_t nsub = (size_t)((ln + sub - 1) / sub);
   CU(h->d_offsets.reserve((size_t)ln + nsub));
@@ -915,17 +952,25 @@ static int e1_with_pose_sums(fcvm_handle* h, int64_t lo, int64_t hi, const std::
     CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     h->pipe_ev.push_back(e);
   }
-  // everything of the evaluation side is queued up front on the main stream
+  // everything of the evaluation side is queued up front, one priority stream per sub-batch (sub_stream): they finish in
+  // order, the tail of one overlapping the head of the next
   size_t k = 0;
+  CU(cudaEventRecord(h->sub_start, h->stream));
   for (int64_t s0 = 0; s0 < ln; s0 += sub, ++k) {
     const int64_t sn = std::min(sub, ln - s0), r0 = lo + s0;
-    rc = launch_stage(h, FCVM_STAGE_E1, h->d_recs.p + r0, sn, h->d_rows1.p + r0 * W, nullptr, h->stream, true);
+    cudaStream_t ss;
+    rc = sub_stream(h, k, ss);
     if (rc) return rc;
-    CU(launch_popc_rows(h->d_rows1.p + r0 * W, sn, W, h->d_count.p + r0, h->stream));
-    CU(launch_exscan(h->d_count.p + r0, sn, h->d_offsets.p + s0 + (int64_t)k, h->stream));
+    CU(cudaStreamWaitEvent(ss, h->sub_start, 0));
+    if ((int)k >= levels) CU(cudaStreamWaitEvent(ss, h->pipe_ev[k - 1], 0));     // out of priority levels: plain serialisation
+    rc = launch_stage(h, FCVM_STAGE_E1, h->d_recs.p + r0, sn, h->d_rows1.p + r0 * W, nullptr, ss, true, nsub == 1 ? 0 : (k == 0 ? 1 : (k + 1 == nsub ? 3 : 2)));
+    if (rc) return rc;
+    CU(launch_popc_rows(h->d_rows1.p + r0 * W, sn, W, h->d_count.p + r0, ss));
+    CU(launch_exscan(h->d_count.p + r0, sn, h->d_offsets.p + s0 + (int64_t)k, ss));
     h->counters[5] += 2;
-    CU(cudaEventRecord(h->pipe_ev[k], h->stream));
+    CU(cudaEventRecord(h->pipe_ev[k], ss));
   }
+  for (k = 0; k < nsub; ++k) CU(cudaStreamWaitEvent(h->stream, h->pipe_ev[k], 0));      // the main stream continues after all of them
   const float* M = h->model.data();
   cudaStream_t ax = h->aux_stream;
   k = 0;
@@ -964,7 +1009,7 @@ static int e1_with_pose_sums(fcvm_handle* h, int64_t lo, int64_t hi, const std::
     }
     CU(h->d_valp.reserve((size_t)total, ax));
     CU(h->d_valy.reserve((size_t)total, ax));
-    unsigned long long cap = (unsigned long long)total / 5 + 4096;       // ~12.5 % of the rays are flagged per function
+    unsigned long long cap = (unsigned long long)total / 10 + 4096;      // ~6.25 % of the rays are flagged per function
     unsigned long long np = 0, ny = 0;
     for (int attempt = 0; attempt < 2; ++attempt) {
       CU(h->d_keyp.reserve((size_t)cap, ax)); CU(h->d_argp.reserve((size_t)cap, ax));
@@ -1757,6 +1802,8 @@ void fcvm_destroy(fcvm_t* h) {
   for (int q = 0; q < fcvm_handle::kRing; ++q) { if (h->ring_d2h[q]) cudaEventDestroy(h->ring_d2h[q]); if (h->ring_h2d[q]) cudaEventDestroy(h->ring_h2d[q]); }
   h->pool.reset();
   if (h->aux_stream) cudaStreamDestroy(h->aux_stream);
+  for (cudaStream_t st : h->sub_streams) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
+  if (h->sub_start) cudaEventDestroy(h->sub_start);
   h->d_map_xyz.free(); h->d_map_sorted.free(); h->d_cell_start.free(); h->d_cell_count.free(); h->d_minmax.free();
   h->d_cand.free(); h->d_ok.free(); h->d_looks.free(); h->d_gather.free();
   h->d_bricks.free(); h->d_points.free(); h->d_cover_contrib.free(); h->d_contrib_id.free(); h->d_voxcount.free();
@@ -1834,8 +1881,13 @@ int fcvm_set_map_cloud(fcvm_t* h, const float* xyz, int64_t n) {   // cpp:74-89
     CU(cudaMemsetAsync(h->d_bricks.p + h->brick_guard + h->grid.nbricks(), 0xFF, h->brick_guard * sizeof(unsigned long long), s));
     CU(launch_voxelise(h->d_map_xyz.p, n, g, h->d_bricks.p + h->brick_guard, s));
     CU(launch_mark_padding(h->d_bricks.p + h->brick_guard, h->grid.dims, h->grid.ns, s));
-    CU(h->d_sat.reserve((size_t)(h->grid.ns[0] / FCVM_SAT_BRICKS + 1) * (h->grid.ns[1] / FCVM_SAT_BRICKS + 1) * (h->grid.ns[2] / FCVM_SAT_BRICKS + 1)));
-    CU(launch_build_sat(h->d_bricks.p + h->brick_guard, h->grid.ns, h->d_sat.p, s));
+    // the free-space table; a grid so large that its offsets would not fit 32 bits goes without (every ray is then marched)
+    const size_t n_sat = (size_t)(h->grid.ns[0] / FCVM_SAT_BRICKS + 1) * (h->grid.ns[1] / FCVM_SAT_BRICKS + 1) * (h->grid.ns[2] / FCVM_SAT_BRICKS + 1);
+    h->sat_built = n_sat < ((size_t)1 << 31);
+    if (h->sat_built) {
+      CU(h->d_sat.reserve(n_sat));
+      CU(launch_build_sat(h->d_bricks.p + h->brick_guard, h->grid.ns, h->d_sat.p, s));
+    }
     h->counters[5] += 7;
 
     // uniform cell index over the map cloud for nearCheck: cells well below the radius so that far cells are never visited

@@ -7,7 +7,7 @@
 // acos are not correctly rounded, so a device libm cannot stand in for them).  Here:
 //   k_pose_terms   one warp per viewpoint walks its index list; every lane evaluates one ray with exactly the host's
 //                  operation order (FP64, no contraction) and obtains asin / acos from fcvm_ddmath.h: the correctly
-//                  rounded value plus a flag when the true result is within 1/16 ulp of a rounding midpoint - the only
+//                  rounded value plus a flag when the true result is within 1/32 ulp of a rounding midpoint - the only
 //                  place glibc can differ.  Values go to per-ray arrays, flagged arguments (~12 %) to a compact list.
 //   host           calls the real glibc asin / acos on the flagged arguments only (fcvm_host.cu).
 //   k_pose_patch   writes those values over the flagged rays.
