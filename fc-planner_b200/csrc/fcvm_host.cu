@@ -172,6 +172,7 @@ struct fcvm_handle {
   std::vector<cudaStream_t> sub_streams;       // sub-batch k of an evaluator pass runs on sub_streams[k]: priorities fall with k, so the block
                                                // scheduler finishes the sub-batches in order while the tail of one overlaps the head of the next
   cudaEvent_t sub_start = nullptr;             // "the batch's inputs are on the device" (recorded on the main stream)
+  int64_t rows_cap_bytes = 4ll << 30;          // manager-level rows buffer cap (ensure_device: from the device's memory size)
   int pri_lo = 0, pri_hi = 0;                  // cudaDeviceGetStreamPriorityRange: least, greatest
   cudaStream_t aux_stream = nullptr;           // pose-sum pipeline of a finished E1 sub-batch while the next one is evaluated (high priority)
   std::vector<cudaEvent_t> pipe_ev;
@@ -269,6 +270,11 @@ static int ensure_device(fcvm_handle* h) {
     CU(cudaDeviceGetDefaultMemPool(&pool, h->prm.device));
     uint64_t keep = ~0ull;
     CU(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+  }
+  {
+    size_t free_b = 0, total_b = 0;
+    CU(cudaMemGetInfo(&free_b, &total_b));
+    h->rows_cap_bytes = std::max<int64_t>(4ll << 30, std::min<int64_t>(32ll << 30, (int64_t)(total_b / 6)));
   }
   CU(cudaEventCreate(&h->ev0));
   CU(cudaEventCreate(&h->ev1));
@@ -414,10 +420,13 @@ static int do_comm(fcvm_handle* h, int32_t op, void* buf_dev, int64_t n) {
 
 constexpr int64_t kPipeMinRows = 1024;   // smallest sub-batch worth a launch of its own
 
-// rows per batch chunk so that one rows buffer stays <= 4 GiB (two such buffers live on the device;
-// a B200 has 180 GB, the cap only bounds the pinned staging of the traced / CSR paths)
-static int64_t chunk_rows(const fcvm_handle* h, int64_t n) {
-  const int64_t per = std::max<int64_t>(1, (int64_t)(4ll << 30) / (h->W * 4));
+// rows per batch chunk.  The evaluator-level entries (rows / index lists go to the host) keep one rows buffer <= 4 GiB, which
+// bounds their page-locked staging; the manager-level batches (rows never leave the device) use a sixth of the device's memory
+// per buffer, at most 32 GiB - two such buffers live on the device - so that configs[4] (200 000 viewpoints x 125 KB) is ONE
+// chunk on a 180 GB B200: one ownership pass, no pipeline refill between chunks, and a sharded run's GPUs each get a large block.
+static int64_t chunk_rows(const fcvm_handle* h, int64_t n, bool manager = false) {
+  const int64_t cap = manager ? h->rows_cap_bytes : (int64_t)(4ll << 30);
+  const int64_t per = std::max<int64_t>(1, cap / (h->W * 4));
   return std::min(n, per);
 }
 
@@ -480,8 +489,15 @@ static int eval_batch(fcvm_handle* h, int stage, const VpRec* recs, int64_t n, c
       const int64_t sub = std::max<int64_t>(kPipeMinRows, (n + env().pipe_subs - 1) / env().pipe_subs);
       for (int64_t s0 = 0; s0 < n; s0 += sub) subs.emplace_back(s0, std::min(sub, n - s0));
     } else if (n >= 8 * kPipeMinRows) {
-      const int64_t a = (n * 55 / 100 + 31) & ~31ll, b = (n * 30 / 100 + 31) & ~31ll;
-      subs = {{0, a}, {a, b}, {a + b, n - a - b}};
+      static const std::vector<int> kFracs = {55, 30, 15};
+      const std::vector<int>& fr = env().pipe_fracs.empty() ? kFracs : env().pipe_fracs;
+      int64_t s0 = 0;
+      for (size_t i = 0; i < fr.size() && s0 < n; ++i) {
+        const int64_t sn = i + 1 == fr.size() ? n - s0 : std::min<int64_t>(n - s0, (int64_t)((n * fr[i] / 100 + 31) & ~31ll));
+        if (sn > 0) subs.emplace_back(s0, sn);
+        s0 += sn;
+      }
+      if (s0 < n) subs.emplace_back(s0, n - s0);
     } else {
       const int64_t a = (n * 6 / 10 + 31) & ~31ll;
       subs = {{0, a}, {a, n - a}};
@@ -1102,8 +1118,8 @@ static int get_pose_batch(fcvm_handle* h, const std::vector<D3>& pos, const std:
     if (env().profile >= 2)
       std::fprintf(stderr, "[fcvm]   getPose batch n=%lld: %s at %.3f ms\n", (long long)n, what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_gp0).count());
   };
-  for (int64_t c0 = 0; c0 < n; c0 += chunk_rows(h, n)) {
-    const int64_t cn = std::min(chunk_rows(h, n), n - c0);
+  for (int64_t c0 = 0; c0 < n; c0 += chunk_rows(h, n, true)) {
+    const int64_t cn = std::min(chunk_rows(h, n, true), n - c0);
     std::vector<PoseSeed> seed((size_t)cn);
     std::vector<double> ip((size_t)cn);
     CU(h->h_recs.reserve((size_t)cn));
@@ -1222,8 +1238,8 @@ static int update_info_batch(fcvm_handle* h, const std::vector<int>& ids, const 
   const int64_t n = (int64_t)ids.size();
   const int64_t W = h->W;
   int rc;
-  for (int64_t c0 = 0; c0 < n; c0 += chunk_rows(h, n)) {
-    const int64_t cn = std::min(chunk_rows(h, n), n - c0);
+  for (int64_t c0 = 0; c0 < n; c0 += chunk_rows(h, n, true)) {
+    const int64_t cn = std::min(chunk_rows(h, n, true), n - c0);
     CU(h->h_recs.reserve((size_t)cn));
     CU(h->h_count.reserve((size_t)cn));
     std::vector<int> cid((size_t)cn), order((size_t)cn);
@@ -1422,8 +1438,8 @@ static int viewpoints_prune(fcvm_handle* h, const std::vector<Pose5>& vps_pose, 
     const float* M = h->model.data();
     const double pu = h->pitch_upper * M_PI / 180.0, pl = h->pitch_lower * M_PI / 180.0;
     const int64_t n = (int64_t)grav.size();
-    for (int64_t c0 = 0; c0 < n; c0 += chunk_rows(h, n)) {
-      const int64_t cn = std::min(chunk_rows(h, n), n - c0);
+    for (int64_t c0 = 0; c0 < n; c0 += chunk_rows(h, n, true)) {
+      const int64_t cn = std::min(chunk_rows(h, n, true), n - c0);
       CU(h->h_recs.reserve((size_t)cn));
       for (int64_t i = 0; i < cn; ++i) {
         const Grav& gq = grav[(size_t)(c0 + i)];

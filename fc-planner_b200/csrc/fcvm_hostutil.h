@@ -40,7 +40,15 @@ struct EnvSettings {
   bool host_sums = false;   // FCVM_HOST_SUMS=1: pitch / yaw sums of getPose entirely on the host (the round-1 path; A/B and cross-check)
   bool own_sweep = false;   // FCVM_OWN_SWEEP=1: ownership by the ordered row sweep instead of the per-point arg-max (single GPU only)
   bool no_pfree = false;    // FCVM_NO_PFREE=1: k_eval marches the viewpoint-side half-ray even where the summed-area table certifies it free
+  std::vector<int> pipe_fracs;   // FCVM_PIPE_FRACS=40,25,15,12,8: sub-batch sizes of the CSR path in per cent (tuning; the default is built in)
   EnvSettings() {
+    if (const char* e = std::getenv("FCVM_PIPE_FRACS")) {
+      int v = 0; bool any = false;
+      for (const char* c = e;; ++c) {
+        if (*c >= '0' && *c <= '9') { v = v * 10 + (*c - '0'); any = true; }
+        else { if (any && v > 0) pipe_fracs.push_back(v); v = 0; any = false; if (!*c) break; }
+      }
+    }
     if (const char* e = std::getenv("FCVM_PROFILE")) profile = atoi(e);
     if (const char* e = std::getenv("FCVM_PIPE_SUBS")) pipe_subs = std::max(1, atoi(e));
     if (const char* e = std::getenv("FCVM_HOST_SUMS")) host_sums = atoi(e) != 0;
