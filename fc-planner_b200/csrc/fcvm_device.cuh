@@ -85,15 +85,17 @@ __host__ __device__ __forceinline__ int brick_bit_index(int x, int y, int z) {
 #endif
 #define FCVM_SAT_BRICKS (1 << (FCVM_SAT_SHIFT - 2))     // bricks per cell and axis
 // number of non-empty cells in the inclusive cell box [lo, hi] (coordinates already >> FCVM_SAT_SHIFT)
-__device__ __forceinline__ int sat_box_count(const GridDesc& g, int x0, int y0, int z0, int x1, int y1, int z1) {
+__device__ __forceinline__ int sat_box_count(const int* __restrict__ s, int ny, int nz, int x0, int y0, int z0, int x1, int y1, int z1) {
   // the table has fewer than 2^31 entries (fcvm_set_map_cloud checks), so the eight offsets are 32-bit arithmetic: four row
   // bases, each read at z0 and z1 + 1
-  const int* s = g.sat;
-  const int ny = g.sat_ny, nz = g.sat_nz;
   const int r00 = (x0 * ny + y0) * nz, r01 = (x0 * ny + (y1 + 1)) * nz, r10 = ((x1 + 1) * ny + y0) * nz, r11 = ((x1 + 1) * ny + (y1 + 1)) * nz;
   const int* lo = s + z0;
   const int* hi = s + (z1 + 1);
   return ((__ldg(hi + r11) - __ldg(hi + r01)) - (__ldg(hi + r10) - __ldg(hi + r00))) - ((__ldg(lo + r11) - __ldg(lo + r01)) - (__ldg(lo + r10) - __ldg(lo + r00)));
+}
+
+__device__ __forceinline__ int sat_box_count(const GridDesc& g, int x0, int y0, int z0, int x1, int y1, int z1) {
+  return sat_box_count(g.sat, g.sat_ny, g.sat_nz, x0, y0, z0, x1, y1, z1);
 }
 
 // One-entry register cache of the last brick a ray touched.

@@ -831,6 +831,8 @@ static int safety_batch(fcvm_handle* h, const float* xyz, int64_t n, int mode, s
   for (int c = 0; c < 3; ++c) { a.geom.org[c] = h->grid.origin[c]; a.geom.dims[c] = h->grid.dims[c]; a.geom.nb[c] = h->grid.ns[c]; }
   a.geom.res_inv = h->grid.res_inv;
   a.bricks = h->d_bricks.p + h->brick_guard;
+  a.sat = (h->use_sat && h->sat_built) ? h->d_sat.p : nullptr;
+  a.sat_ny = h->grid.ns[1] / FCVM_SAT_BRICKS + 1; a.sat_nz = h->grid.ns[2] / FCVM_SAT_BRICKS + 1;
   a.cells = h->cells;
   a.cell_start = h->d_cell_start.p;
   a.sorted = h->d_map_sorted.p;
@@ -1698,6 +1700,14 @@ static int update_impl(fcvm_handle* h) {
   }
 
   umark("candidate library");
+  // the 8 safety verdicts of every library record as one byte: the candidate pool of a round is counted and walked over these
+  // 1-byte masks (the 200-byte records are only touched for the <= 100 candidates actually drawn)
+  std::vector<uint8_t> lib_mask((size_t)std::max<int64_t>(1, n_lib), 0);
+  pfor(h, n_lib, 4096, [&](int64_t k) {
+    uint8_t m = 0;
+    for (int c = 0; c < 8; ++c) m |= lib[(size_t)k].safe[c] ? (uint8_t)(1u << c) : (uint8_t)0;
+    lib_mask[(size_t)k] = m;
+  });
   int unc_iter = 0, last_unc_num = -1;
   while ((int)uncoveredID.size() > 0 && unc_iter < prm.max_iter_num && last_unc_num != (int)uncoveredID.size()) {
     last_unc_num = (int)uncoveredID.size();
@@ -1706,19 +1716,20 @@ static int update_impl(fcvm_handle* h) {
     std::vector<PtNormal> cand;
     {
       size_t pool_size = 0;
-      for (int p : uncoveredID) {
-        const uint8_t* sf = lib[(size_t)lib_slot[(size_t)p]].safe;
-        for (int c = 0; c < 8; ++c) pool_size += sf[c] ? 1 : 0;
-      }
+      for (int p : uncoveredID) pool_size += (size_t)__builtin_popcount(lib_mask[(size_t)lib_slot[(size_t)p]]);
       std::vector<size_t> pick;
       const bool all = pool_size <= 100;
       if (!all) pick = random_sample_positions(h, pool_size, 100);
       size_t pos = 0, next = 0;
       for (int p : uncoveredID) {
         if (!all && next >= pick.size()) break;
-        const LibRec& rec = lib[(size_t)lib_slot[(size_t)p]];
+        const int slot = lib_slot[(size_t)p];
+        const unsigned m = lib_mask[(size_t)slot];
+        const size_t cnt = (size_t)__builtin_popcount(m);
+        if (!all && pick[next] >= pos + cnt) { pos += cnt; continue; }      // none of this point's candidates is drawn
+        const LibRec& rec = lib[(size_t)slot];
         for (int c = 0; c < 8; ++c) {
-          if (!rec.safe[c]) continue;
+          if (!((m >> c) & 1u)) continue;
           if (all) cand.push_back(rec.c[c]);
           else if (next < pick.size() && pick[next] == pos) { cand.push_back(rec.c[c]); ++next; }
           ++pos;

@@ -99,6 +99,8 @@ struct CellGeom {           // uniform cell index over the map cloud
 struct SafetyArgs {
   MapGeom geom;
   const unsigned long long* bricks;
+  const int* sat;                  // summed-area table of occupied cells (GridDesc::sat), may be null
+  int sat_ny, sat_nz;
   CellGeom cells;
   const long long* cell_start;     // [ncell + 1]
   const float4* sorted;            // map points grouped by cell

@@ -145,6 +145,21 @@ __global__ void __launch_bounds__(256) k_safety(const __grid_constant__ SafetyAr
   const double vx = (double)fx, vy = (double)fy, vz = (double)fz;
   bool ok = true;
   unsigned long long looks = 0;
+  // Free-space certificate: the box of voxels around the candidate that reaches one voxel beyond +- safe_radius on every axis
+  // lies inside the map and holds no occupied voxel (summed-area table, 8 loads).  Every probe of the lattice falls into that
+  // box, so all of them are "inside the map and free"; every map point lies in an occupied voxel (k_voxelise marks the voxel
+  // of each), so none is within safe_radius either.  Both loops are then only counted.  Candidates are generated
+  // viewpoints_distance away from the surface, so this is the common case.
+  bool certified = false;
+  if (a.sat != nullptr && fabs(vx) < 1e15 && fabs(vy) < 1e15 && fabs(vz) < 1e15) {      // false for NaN
+    const double r = a.sr * 1.0001 + 1e-6;
+    const int x0 = (int)floor((vx - r - a.geom.org[0]) * a.geom.res_inv) - 1, x1 = (int)floor((vx + r - a.geom.org[0]) * a.geom.res_inv) + 1;
+    const int y0 = (int)floor((vy - r - a.geom.org[1]) * a.geom.res_inv) - 1, y1 = (int)floor((vy + r - a.geom.org[1]) * a.geom.res_inv) + 1;
+    const int z0 = (int)floor((vz - r - a.geom.org[2]) * a.geom.res_inv) - 1, z1 = (int)floor((vz + r - a.geom.org[2]) * a.geom.res_inv) + 1;
+    if (x0 >= 0 && y0 >= 0 && z0 >= 0 && x1 < a.geom.dims[0] && y1 < a.geom.dims[1] && z1 < a.geom.dims[2])
+      certified = sat_box_count(a.sat, a.sat_ny, a.sat_nz, x0 >> FCVM_SAT_SHIFT, y0 >> FCVM_SAT_SHIFT, z0 >> FCVM_SAT_SHIFT, x1 >> FCVM_SAT_SHIFT,
+                                y1 >> FCVM_SAT_SHIFT, z1 >> FCVM_SAT_SHIFT) == 0;
+  }
   if (a.mode == 0) {
     if (a.z_ground && vz < a.ground_limit) ok = false;                               // viewpoint_manager.cpp:891-892
     if (ok && a.safe_voxel <= 0) ok = false;                                          // reference: infinite loop
@@ -153,7 +168,7 @@ __global__ void __launch_bounds__(256) k_safety(const __grid_constant__ SafetyAr
                 nz = lattice_steps(vz, a.sr, a.res, a.safe_voxel);
       const long long total = (long long)nx * ny * nz;      // up to 4096^3: 64-bit
       looks = (unsigned long long)total;
-      for (long long base = 0; base < total; base += 32) {
+      for (long long base = 0; base < total && !certified; base += 32) {
         const long long t = base + lane;
         bool bad = false;
         if (t < total) {
@@ -170,7 +185,7 @@ __global__ void __launch_bounds__(256) k_safety(const __grid_constant__ SafetyAr
     }
   }
   // nearCheck (viewpoint_manager.cpp:916-946) with vox_num > 1: fails when the nearest map point is closer than safe_radius
-  if (ok) {
+  if (ok && !(certified && a.n_map > 0)) {
     if (!(isfinite(vx) && isfinite(vy) && isfinite(vz)) || a.n_map == 0) {
       ok = false;
     } else if (fabs(vx) >= 1e15 || fabs(vy) >= 1e15 || fabs(vz) >= 1e15) {
