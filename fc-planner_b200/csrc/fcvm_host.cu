@@ -145,7 +145,6 @@ struct fcvm_handle {
   // arrays - and with them the iteration order that decides the prune order among equal counts,
   // the E4 processing order and the order of final_vps_ - carry over from call to
   // call.  Only the key order of idx_viewpoints_ is observable, so it maps id -> slot here.
-  std::unordered_map<D3, int, D3Hash, D3Eq> inverse_idx;
   std::unordered_map<int, int> idx_slot;
 
   // device scratch for a batch
@@ -1270,6 +1269,47 @@ static int update_info_batch(fcvm_handle* h, const std::vector<int>& ids, const 
 // viewpointsPrune (viewpoint_manager.cpp:620-710) with updatePoseGravitation (712-887) split into
 // the sequential host flag chain and one batched E3 launch.
 // ------------------------------------------------------------------------------------------------
+// Stand-in for the reference's inverse_idx_ (unordered_map keyed by the candidate's float position, cpp:643: the LAST candidate
+// inserted at a position owns it).  It is only ever looked up (cpp:739), so its iteration order is not
+// observable: an open-addressing table over the slots' positions, with the map's key equality (operator== per component,
+// so -0 == +0 and a NaN position equals nothing, itself included).
+struct PosTable {
+  std::vector<int> tab;
+  const float* cloud = nullptr;
+  uint32_t mask = 0;
+  static inline uint32_t bits(float f) { if (f == 0.0f) return 0u; uint32_t u; std::memcpy(&u, &f, 4); return u; }
+  static inline uint32_t hash3(const float* q) {
+    uint64_t x = ((uint64_t)bits(q[0]) * 0x9E3779B97F4A7C15ull) ^ ((uint64_t)bits(q[1]) * 0xC2B2AE3D27D4EB4Full) ^ ((uint64_t)bits(q[2]) * 0x165667B19E3779F9ull);
+    x ^= x >> 29; x *= 0xBF58476D1CE4E5B9ull; x ^= x >> 32;
+    return (uint32_t)x;
+  }
+  void build(const float* c, int n) {
+    cloud = c;
+    uint32_t cap = 16;
+    while (cap < 2u * (uint32_t)std::max(n, 1)) cap <<= 1;
+    mask = cap - 1;
+    tab.assign(cap, -1);
+    for (int sl = 0; sl < n; ++sl) {
+      const float* q = c + 3 * (size_t)sl;
+      uint32_t i = hash3(q) & mask;
+      for (;; i = (i + 1) & mask) {
+        const int o = tab[i];
+        if (o < 0) { tab[i] = sl; break; }
+        const float* p = c + 3 * (size_t)o;
+        if (p[0] == q[0] && p[1] == q[1] && p[2] == q[2]) { tab[i] = sl; break; }     // same key: the later insertion owns it
+      }
+    }
+  }
+  int find(const float* q, int self) const {          // the slot that owns position q (self if the key matches nothing: NaN)
+    for (uint32_t i = hash3(q) & mask;; i = (i + 1) & mask) {
+      const int o = tab[i];
+      if (o < 0) return self;
+      const float* p = cloud + 3 * (size_t)o;
+      if (p[0] == q[0] && p[1] == q[1] && p[2] == q[2]) return o;
+    }
+  }
+};
+
 static int viewpoints_prune(fcvm_handle* h, const std::vector<Pose5>& vps_pose, const std::vector<int>& sub_voxcount) {
   const fcvm_params& prm = h->prm;
   const auto t_prune0 = std::chrono::steady_clock::now();
@@ -1277,9 +1317,7 @@ static int viewpoints_prune(fcvm_handle* h, const std::vector<Pose5>& vps_pose, 
     if (env().profile >= 2)
       std::fprintf(stderr, "[fcvm]   viewpointsPrune: %s at %.2f ms\n", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_prune0).count());
   };
-  auto& inverse_idx = h->inverse_idx;
   auto& idx_slot = h->idx_slot;
-  inverse_idx.clear();
   idx_slot.clear();
   std::vector<int> slot_id;
   std::vector<Pose5> slot_pose;
@@ -1291,7 +1329,6 @@ static int viewpoints_prune(fcvm_handle* h, const std::vector<Pose5>& vps_pose, 
       const Pose5& q = vps_pose[(size_t)i];
       const float fx = (float)q.v[0], fyy = (float)q.v[1], fz = (float)q.v[2];
       vp_cloud.push_back(fx); vp_cloud.push_back(fyy); vp_cloud.push_back(fz);
-      inverse_idx[D3{fx, fyy, fz}] = i;
       idx_slot[i] = (int)slot_id.size();
       slot_id.push_back(i);
       slot_pose.push_back(q);
@@ -1340,13 +1377,15 @@ static int viewpoints_prune(fcvm_handle* h, const std::vector<Pose5>& vps_pose, 
   std::vector<std::vector<int>> arena((size_t)nblk);
   std::vector<int64_t> nb_off((size_t)nslot, 0);
   std::vector<int> nb_cnt((size_t)nslot, -1);
+  PosTable pos_table;
+  pos_table.build(vp_cloud.data(), nslot);
   if (!h->pool) h->pool.reset(new WorkerPool(h->threads));
   h->pool->run(nblk, 1, [&](int64_t bk) {
     std::vector<int> found;
     std::vector<int>& ar = arena[(size_t)bk];
     for (int sl = (int)bk * kBlock; sl < std::min(nslot, ((int)bk + 1) * kBlock); ++sl) {
       const float* q = &vp_cloud[3 * (size_t)sl];
-      canon[(size_t)sl] = slot_of_id[(size_t)(inverse_idx.find(D3{q[0], q[1], q[2]})->second - id0)];
+      canon[(size_t)sl] = pos_table.find(q, sl);
       if (!(slot_vox[(size_t)sl] > 1 && near_ok[(size_t)sl])) continue;
       vps_tree.radius_search(q, bubble_radius, found);
       nb_off[(size_t)sl] = (int64_t)ar.size();
@@ -1851,7 +1890,7 @@ int fcvm_reset(fcvm_t* h) {   // cpp:64-72
   h->last_vps_num = 0; h->voxcount_n = 0;
   h->pt_normal_pairs.clear();
   h->final_vps.clear();
-  h->inverse_idx.clear(); h->idx_slot.clear();   // VPP.reset(): clear(), buckets kept
+  h->idx_slot.clear();   // VPP.reset(): clear(), buckets kept
   h->n_map = 0;
   h->trace.clear();
   for (int k = 0; k < FCVM_NCOUNTERS; ++k) h->counters[k] = 0;

@@ -17,19 +17,22 @@ def _free_port():
 
 @pytest.mark.parametrize("world", [2, 3])
 def test_sharded_exchange_over_gloo(world, oracle_mod):
-    port = _free_port()
     env = dict(os.environ, MASTER_ADDR="127.0.0.1", GLOO_SOCKET_IFNAME="lo")
-    procs = [subprocess.Popen([sys.executable, os.path.join(HERE, "_gloo_worker.py"), str(r), str(world), str(port)],
-                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env) for r in range(world)]
-    outs = []
-    for p in procs:
-        try:
-            out, _ = p.communicate(timeout=240)
-        except subprocess.TimeoutExpired:
-            for q in procs:
-                q.kill()
-            raise
-        outs.append(out)
+    for attempt in range(4):        # the port from bind(0) can be taken again before rank 0 listens on it: try another
+        port = _free_port()
+        procs = [subprocess.Popen([sys.executable, os.path.join(HERE, "_gloo_worker.py"), str(r), str(world), str(port)],
+                                  stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env) for r in range(world)]
+        outs = []
+        for p in procs:
+            try:
+                out, _ = p.communicate(timeout=240)
+            except subprocess.TimeoutExpired:
+                for q in procs:
+                    q.kill()
+                raise
+            outs.append(out)
+        if all(p.returncode == 0 for p in procs) or not any("EADDRINUSE" in o or "address already in use" in o for o in outs):
+            break
     for r, (p, out) in enumerate(zip(procs, outs)):
         assert p.returncode == 0, f"rank {r} failed:\n{out}"
         assert f"rank {r} ok" in out

@@ -21,12 +21,15 @@ def _ngpu():
 def test_sharded_update_matches_oracle(world, comm, oracle_mod):
     if _ngpu() < world:
         pytest.skip(f"needs {world} GPUs")
-    with socket.socket() as s:
-        s.bind(("127.0.0.1", 0))
-        port = s.getsockname()[1]
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
-           "--master-port", str(port), os.path.join(HERE, "_nccl_worker.py"), comm]
-    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    for attempt in range(4):        # a port handed out by bind(0) can still be taken by the time torchrun listens on it: try another
+        with socket.socket() as s:
+            s.bind(("127.0.0.1", 0))
+            port = s.getsockname()[1]
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+               "--master-port", str(port), os.path.join(HERE, "_nccl_worker.py"), comm]
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+        if r.returncode == 0 or "EADDRINUSE" not in r.stdout:
+            break
     assert r.returncode == 0, r.stdout[-4000:]
     for k in range(world):
         assert f"rank {k}/{world} ok" in r.stdout, r.stdout[-4000:]
