@@ -1692,61 +1692,59 @@ static int update_impl(fcvm_handle* h) {
   rc = uncovered(uncoveredID);
   if (rc) return rc;
   umark("uncovered ids");
+  const std::vector<int> uncoveredID0 = uncoveredID;      // the library below is indexed by position in this first list
 
   // cpp:206-221: candidate library for the uncovered points.
-  // The points are independent (candidate q of the c-th call draws from engines seeded seed + 8c + k): the library is one
-  // flat array of 8 candidates + 8 safety verdicts per uncovered point, built by all host threads (RNG + libm) and one
-  // k_safety launch; a sharded run builds only its block of the points and all-gathers the records (200 B per point).
-  struct LibRec { PtNormal c[8]; uint8_t safe[8]; };
-  static_assert(sizeof(LibRec) == 200, "LibRec is exchanged between ranks as raw bytes");
+  // The points are independent (candidate q of the c-th call draws from engines seeded seed + 8c + k), and a candidate is a
+  // pure function of its point and its call number.  What the rounds below need of the library is, per uncovered point, which
+  // of its 8 candidates passed viewpointSafetyCheck - one byte; the <= 100 candidates a round actually draws are regenerated on
+  // the spot.  So the library is a byte per point: all host threads generate the candidates of this rank's block of the points
+  // (RNG + libm), one k_safety launch checks them, and a sharded run all-gathers the bytes (round 2 before: 200-byte records).
   const int64_t n_lib = (int64_t)uncoveredID.size();
   const int64_t lib_per = (n_lib + h->world - 1) / h->world;
-  std::unique_ptr<LibRec[]> lib(new LibRec[(size_t)std::max<int64_t>(1, lib_per * h->world)]);     // not value-initialised: 60 MB at 300 000 points
+  std::vector<uint8_t> lib_mask((size_t)std::max<int64_t>(1, lib_per * h->world), 0);
   std::vector<int> lib_slot((size_t)h->P, -1);
+  const int64_t call0 = h->unc_calls;
+  h->unc_calls += n_lib;
+  auto candidates_of = [&](int64_t k, PtNormal c8[8]) {       // the 8 candidates of the k-th uncovered point (uncNeighVps, cpp:948-1131)
+    const int p = uncoveredID0[(size_t)k];
+    auto it = h->pt_normal_pairs.find(D3{M[3 * p], M[3 * p + 1], M[3 * p + 2]});
+    const D3 nd = it == h->pt_normal_pairs.end() ? D3{0, 0, 1} : it->second;
+    const float nrm[3] = {(float)nd.x, (float)nd.y, (float)nd.z};
+    unc_neigh_vps(h, &M[3 * p], nrm, c8, call0 + k);
+  };
   {
     Stopwatch sw_unc(h->t_unc);
     const bool vprof = env().profile >= 3;
     const auto t_unc0 = std::chrono::steady_clock::now();
     auto tmark = [&](const char* what) { if (vprof) std::fprintf(stderr, "[fcvm]     unc: %s at %.2f ms\n", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_unc0).count()); };
     tmark("start");
-    const int64_t call0 = h->unc_calls;
-    h->unc_calls += n_lib;
-    for (int64_t k = 0; k < n_lib; ++k) lib_slot[(size_t)uncoveredID[(size_t)k]] = (int)k;
+    for (int64_t k = 0; k < n_lib; ++k) lib_slot[(size_t)uncoveredID0[(size_t)k]] = (int)k;
     int64_t lo = 0, hi = n_lib;
     if (h->world > 1) shard_of(h, n_lib, lo, hi);
     std::unique_ptr<float[]> q(new float[(size_t)std::max<int64_t>(1, 24 * (hi - lo))]);
-    if (!h->pool) h->pool.reset(new WorkerPool(h->threads));
     tmark("buffers ready");
-    h->pool->run(hi - lo, 64, [&](int64_t r) {
-      const int64_t k = lo + r;
-      const int p = uncoveredID[(size_t)k];
-      auto it = h->pt_normal_pairs.find(D3{M[3 * p], M[3 * p + 1], M[3 * p + 2]});
-      const D3 nd = it == h->pt_normal_pairs.end() ? D3{0, 0, 1} : it->second;
-      const float nrm[3] = {(float)nd.x, (float)nd.y, (float)nd.z};
-      LibRec& rec = lib[(size_t)k];
-      unc_neigh_vps(h, &M[3 * p], nrm, rec.c, call0 + k);
-      for (int c = 0; c < 8; ++c) { q[(size_t)24 * r + 3 * c] = rec.c[c].x; q[(size_t)24 * r + 3 * c + 1] = rec.c[c].y; q[(size_t)24 * r + 3 * c + 2] = rec.c[c].z; }
+    pfor(h, hi - lo, 64, [&](int64_t r) {
+      PtNormal c8[8];
+      candidates_of(lo + r, c8);
+      for (int c = 0; c < 8; ++c) { q[(size_t)24 * r + 3 * c] = c8[c].x; q[(size_t)24 * r + 3 * c + 1] = c8[c].y; q[(size_t)24 * r + 3 * c + 2] = c8[c].z; }
     });
     tmark("candidates generated");
     std::vector<uint8_t> safe;
     rc = safety_batch(h, q.get(), 8 * (hi - lo), 0, safe);
     if (rc) return rc;
     tmark("safety batch done");
-    for (int64_t r = 0; r < hi - lo; ++r) std::memcpy(lib[(size_t)(lo + r)].safe, &safe[(size_t)8 * r], 8);
-    rc = gather_records(h, lib.get(), n_lib, (int64_t)sizeof(LibRec));
+    for (int64_t r = 0; r < hi - lo; ++r) {
+      uint8_t m = 0;
+      for (int c = 0; c < 8; ++c) m |= safe[(size_t)8 * r + c] ? (uint8_t)(1u << c) : (uint8_t)0;
+      lib_mask[(size_t)(lo + r)] = m;
+    }
+    rc = gather_records(h, lib_mask.data(), n_lib, 1);
     if (rc) return rc;
     tmark("library complete");
   }
 
   umark("candidate library");
-  // the 8 safety verdicts of every library record as one byte: the candidate pool of a round is counted and walked over these
-  // 1-byte masks (the 200-byte records are only touched for the <= 100 candidates actually drawn)
-  std::vector<uint8_t> lib_mask((size_t)std::max<int64_t>(1, n_lib), 0);
-  pfor(h, n_lib, 4096, [&](int64_t k) {
-    uint8_t m = 0;
-    for (int c = 0; c < 8; ++c) m |= lib[(size_t)k].safe[c] ? (uint8_t)(1u << c) : (uint8_t)0;
-    lib_mask[(size_t)k] = m;
-  });
   int unc_iter = 0, last_unc_num = -1;
   while ((int)uncoveredID.size() > 0 && unc_iter < prm.max_iter_num && last_unc_num != (int)uncoveredID.size()) {
     last_unc_num = (int)uncoveredID.size();
@@ -1766,11 +1764,12 @@ static int update_impl(fcvm_handle* h) {
         const unsigned m = lib_mask[(size_t)slot];
         const size_t cnt = (size_t)__builtin_popcount(m);
         if (!all && pick[next] >= pos + cnt) { pos += cnt; continue; }      // none of this point's candidates is drawn
-        const LibRec& rec = lib[(size_t)slot];
+        PtNormal c8[8];
+        candidates_of(slot, c8);
         for (int c = 0; c < 8; ++c) {
           if (!((m >> c) & 1u)) continue;
-          if (all) cand.push_back(rec.c[c]);
-          else if (next < pick.size() && pick[next] == pos) { cand.push_back(rec.c[c]); ++next; }
+          if (all) cand.push_back(c8[c]);
+          else if (next < pick.size() && pick[next] == pos) { cand.push_back(c8[c]); ++next; }
           ++pos;
         }
       }
