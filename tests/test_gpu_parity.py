@@ -49,6 +49,45 @@ def test_evaluator_masks_bit_exact(small_plant, oracle_mod, stage):
     assert c1[4] == 0 and octr[4] == 0
 
 
+@pytest.mark.parametrize("n_points,order", [(4999, "shuffled"), (1023, "shuffled"), (4133, "sorted_z"), (33, "as_is")])
+def test_culls_exact_for_any_point_order(small_plant, oracle_mod, n_points, order):
+    """The tile- and group-level box culls (k_eval: one viewpoint / one 32-point group per lane) must drop nothing the
+    reference would test positively, whatever the order of the model cloud and however ragged the last tile and group
+    are: shuffled clouds (every box spans the scene: nothing culled), z-sorted clouds (thin slabs: most culled), sizes
+    that leave partial groups and a single partial tile.  Masks, counts and the algorithmic counters against the oracle."""
+    from fc_planner_b200.manager import ViewpointManager
+    rng = np.random.default_rng(n_points)
+    pts = small_plant["points"][rng.choice(len(small_plant["points"]), n_points, replace=False)]
+    if order == "sorted_z":
+        pts = pts[np.argsort(pts[:, 2], kind="stable")]
+    elif order == "as_is":
+        pts = np.sort(pts, axis=0)[:n_points]
+    pts = np.ascontiguousarray(pts)
+    prm = small_plant["params"]
+    vm, orc = ViewpointManager(prm), oracle_mod.Oracle(prm)
+    for m in (vm, orc):
+        m.setMapPointCloud(small_plant["points"])        # the full plant occludes
+        m.setModel(pts)
+    poses = _perturbed_poses(small_plant, n=200, seed=n_points)
+    W = (n_points + 31) // 32
+    rows1 = None
+    for stage in (1, 2, 3, 4):
+        c0 = vm.counters()
+        if stage == 2:
+            cnt, rows = vm.evaluate(2, poses, restrict_rows=rows1)
+            ocnt, orows, octr = orc.evaluate(2, poses, restrict_rows=rows1[:, :W])
+        else:
+            cnt, rows = vm.evaluate(stage, poses)
+            ocnt, orows, octr = orc.evaluate(stage, poses)
+        c1 = vm.counters() - c0
+        assert np.array_equal(rows[:, :W], orows) and not rows[:, W:].any(), stage
+        assert np.array_equal(cnt, ocnt), stage
+        assert np.array_equal(c1[:5], octr[:5]), (stage, c1[:5], octr[:5])
+        if stage == 1:
+            rows1 = rows
+            assert cnt.sum() > 50
+
+
 def test_e2_restricted_to_e1_rows(small_plant, oracle_mod):
     vm, orc, _ = _mk(small_plant, oracle_mod)
     poses = _perturbed_poses(small_plant)
