@@ -106,6 +106,13 @@ def host_cores():
         return os.cpu_count() or 1
 
 
+_THREADS_PER_RANK = None      # set by main() when the ranks are bound to their GPUs' NUMA nodes
+
+
+def threads_per_rank(world):
+    return _THREADS_PER_RANK or max(1, host_cores() // max(1, world))
+
+
 def cpu_evaluator(prm, pts, kind):
     """kind 'reference': the reference's own RayCaster / PerceptionUtils (raycast.cpp, perception_utils.cpp compiled from
     /root/reference into oracle/_ref, driven by viewpoint_manager.cpp's loops); 'port': the oracle's restatement."""
@@ -140,7 +147,7 @@ def pruning_leg(args, device, with_cpu, world=1, rank=0):
     from fc_planner_b200.manager import ViewpointManager
     pts, nrm, prims = scenes.make_plant(n_points=args.prune_points, scale=0.5, seed=0)
     # the ranks of one box share its cores: each rank reduces only its own shard of the viewpoints on its share of the threads
-    prm = launch_params("synthetic", seed=0, resolution=0.2, device=device, host_threads=max(1, host_cores() // max(1, world)))
+    prm = launch_params("synthetic", seed=0, resolution=0.2, device=device, host_threads=threads_per_rank(world))
     vps = scenes.plant_viewpoints(pts, nrm, prims, args.prune_views, prm.viewpoints_distance, seed=5)
 
     def run(m):
@@ -209,7 +216,7 @@ def pruning_full_leg(args, device, world=1, rank=0):
     from fc_planner_b200 import launch_params, scenes
     from fc_planner_b200.manager import ViewpointManager
     pts, nrm, prims = scenes.make_plant(n_points=args.points, scale=args.scale, seed=0)
-    prm = launch_params("synthetic", seed=0, resolution=args.resolution, device=device, host_threads=max(1, host_cores() // max(1, world)))
+    prm = launch_params("synthetic", seed=0, resolution=args.resolution, device=device, host_threads=threads_per_rank(world))
     vps = scenes.plant_viewpoints(pts, nrm, prims, args.full_views, prm.viewpoints_distance, seed=100)
     vm = ViewpointManager(prm)
     if world > 1:
@@ -485,6 +492,12 @@ def main():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        # one rank per GPU on one box: keep each rank, and with it its page-locked staging buffers, on its GPU's NUMA node
+        from fc_planner_b200.distributed import bind_to_gpu_numa_node
+        global _THREADS_PER_RANK
+        _THREADS_PER_RANK = bind_to_gpu_numa_node(local_rank, world)
+        print(f"[bench] rank {rank}: {'bound to its GPU node, ' + str(len(os.sched_getaffinity(0))) + ' cores, ' + str(_THREADS_PER_RANK) + ' host threads' if _THREADS_PER_RANK else 'NUMA topology not readable, not bound'}",
+              file=sys.stderr, flush=True)
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the one JSON line
@@ -493,6 +506,8 @@ def main():
     from fc_planner_b200.manager import ViewpointManager
     pts, nrm, prm, poses = build_scene(args, rank)
     prm.device = local_rank
+    if world > 1:
+        prm.host_threads = threads_per_rank(world)
     vm = ViewpointManager(prm)
     vm.setMapPointCloud(pts)
     vm.setModel(pts)

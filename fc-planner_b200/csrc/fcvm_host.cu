@@ -32,6 +32,7 @@
 #include <random>
 #include <string>
 #include <thread>
+#include <sched.h>
 #include <unordered_map>
 #include <vector>
 
@@ -1844,7 +1845,12 @@ fcvm_t* fcvm_create(const fcvm_params* p) {
   if (p->attitude == FCVM_ATTITUDE_YAW) { h->pitch_upper = 0.0; h->pitch_lower = 0.0; }   // cpp:50-54
   h->fov_base = std::min(p->fov_h, p->fov_w) * M_PI / 360.0;                               // cpp:55
   h->cam.init(*p);
-  int t = p->host_threads > 0 ? p->host_threads : (int)std::thread::hardware_concurrency();
+  int t = p->host_threads;
+  if (t <= 0) {      // default: the CPUs this process may run on (a rank bound to its GPU's NUMA node gets that node's cores)
+    cpu_set_t set;
+    CPU_ZERO(&set);
+    t = sched_getaffinity(0, sizeof(set), &set) == 0 ? CPU_COUNT(&set) : (int)std::thread::hardware_concurrency();
+  }
   h->threads = std::max(1, std::min(t, 64));
   const EnvSettings e = env_now();
   h->host_sums = e.host_sums;

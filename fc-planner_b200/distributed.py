@@ -146,3 +146,35 @@ def sum_over_ranks(values, device=None, group=None):
     if dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
     return [float(x) for x in t]
+
+
+
+def bind_to_gpu_numa_node(device_index, local_world=1):
+    """Pin this process to the cores of the NUMA node its GPU hangs off (sysfs: the PCI device's `numa_node`, the node's
+    `cpulist`), before any page-locked buffer is allocated: page-locked memory lands on the node of the allocating thread, and
+    a rank whose staging buffers sit on the other socket pays the inter-socket link for every D2H byte - with 8 ranks each
+    copying 0.5 GB of index lists per evaluator pass that link, not PCIe, sets the pace.  Returns the number of host threads
+    this rank should use (the node's cores shared between the `local_world` ranks whose GPUs sit on the same node), or None
+    when the topology cannot be read (nothing is changed then)."""
+    import os
+    try:
+        import torch
+        def node_of(i):
+            p = torch.cuda.get_device_properties(i)
+            bus = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+            return int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read().strip())
+        node = node_of(device_index)
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        sharing = sum(1 for i in range(min(local_world, torch.cuda.device_count())) if node_of(i) == node)
+        return max(1, len(cpus) // max(1, sharing))
+    except Exception:
+        return None
