@@ -1367,50 +1367,58 @@ static int viewpoints_prune(fcvm_handle* h, const std::vector<Pose5>& vps_pose, 
   // Tables that stand in for the reference's per-neighbour map look-ups inside the chain (cpp:733-745): the slot of an id,
   // the ctrl-voxel count of a slot, and - because inverse_idx_ is keyed by the float position, so coincident candidates
   // collapse to the LAST inserted id - the slot the reference actually reaches from cloud point s.
-  // The radius searches (cpp:685) read only the original float cloud, so they are independent of the chain's state and run
-  // up front on all host threads, for exactly the candidates that can reach them (count > 1 and nearCheck passed).
+  // The radius searches (cpp:685) read only the original float cloud, so they are independent of the chain's state; their
+  // results are only ever used for a candidate that is still alive at its turn (cpp:688) - a few hundred of 200 000 at
+  // configs[4], the rest having been absorbed by a stronger neighbour.  So they run lazily, in waves: when the chain reaches a
+  // live candidate without a list, the lists of the next kWave live candidates in chain order are computed on all host threads
+  // (some of those die before their turn: wasted, harmless).
   const int nslot = (int)slot_id.size();
   const int id0 = h->last_vps_num;
   std::vector<int> slot_of_id(vps_pose.size() - (size_t)id0, -1), slot_vox((size_t)nslot), canon((size_t)nslot);
   for (int sl = 0; sl < nslot; ++sl) { slot_of_id[(size_t)(slot_id[(size_t)sl] - id0)] = sl; slot_vox[(size_t)sl] = sub_voxcount[(size_t)slot_id[(size_t)sl]]; }
-  constexpr int kBlock = 512;
-  const int nblk = (nslot + kBlock - 1) / kBlock;
-  std::vector<std::vector<int>> arena((size_t)nblk);
-  std::vector<int64_t> nb_off((size_t)nslot, 0);
-  std::vector<int> nb_cnt((size_t)nslot, -1);
   PosTable pos_table;
   pos_table.build(vp_cloud.data(), nslot);
-  if (!h->pool) h->pool.reset(new WorkerPool(h->threads));
-  h->pool->run(nblk, 1, [&](int64_t bk) {
-    std::vector<int> found;
-    std::vector<int>& ar = arena[(size_t)bk];
-    for (int sl = (int)bk * kBlock; sl < std::min(nslot, ((int)bk + 1) * kBlock); ++sl) {
-      const float* q = &vp_cloud[3 * (size_t)sl];
-      canon[(size_t)sl] = pos_table.find(q, sl);
-      if (!(slot_vox[(size_t)sl] > 1 && near_ok[(size_t)sl])) continue;
-      vps_tree.radius_search(q, bubble_radius, found);
-      nb_off[(size_t)sl] = (int64_t)ar.size();
-      nb_cnt[(size_t)sl] = (int)found.size();
-      ar.insert(ar.end(), found.begin(), found.end());
+  pfor(h, nslot, 2048, [&](int64_t sl) { canon[(size_t)sl] = pos_table.find(&vp_cloud[3 * (size_t)sl], (int)sl); });
+  std::vector<std::vector<int>> lists;          // radiusSearch results, (distance, index)-sorted
+  std::vector<int> list_of((size_t)nslot, -1);  // slot -> index into `lists`, -1 = not searched (yet)
+  std::vector<int> wave;
+  const size_t kWave = (size_t)std::max(32, 4 * h->threads);
+  auto qualifies = [&](int sl) { return slot_vox[(size_t)sl] > 1 && near_ok[(size_t)sl]; };
+  auto search_wave = [&](size_t from) {
+    wave.clear();
+    for (size_t j = from; j < ctrlVector.size() && wave.size() < kWave; ++j) {
+      const int sl = slot_of_id[(size_t)(ctrlVector[j].first - id0)];
+      if (live[(size_t)sl] && qualifies(sl) && list_of[(size_t)sl] < 0) wave.push_back(sl);
     }
-  });
-  pmark("neighbour lists ready");
+    const size_t base = lists.size();
+    lists.resize(base + wave.size());
+    pfor(h, (int64_t)wave.size(), 1, [&](int64_t w) {
+      std::vector<int> found;
+      vps_tree.radius_search(&vp_cloud[3 * (size_t)wave[(size_t)w]], bubble_radius, found);
+      lists[base + (size_t)w] = std::move(found);
+    });
+    for (size_t w = 0; w < wave.size(); ++w) list_of[(size_t)wave[w]] = (int)(base + w);
+  };
+  pmark("position table, canonical slots");
 
   struct Grav { int slot; D3 up; double upi, uy; };
   std::vector<Grav> grav;
   struct Pulled { int slot; D3 up; D3 cur; };
   std::vector<Pulled> pulled;                 // positions whose viewpointSafetyCheck (cpp:805-810) is resolved after the chain
   std::vector<int> updated;                   // slots absorbed by the current candidate
-  for (const auto& pr : ctrlVector) {
-    const int c = pr.first;
+  for (size_t ci = 0; ci < ctrlVector.size(); ++ci) {
+    const int c = ctrlVector[ci].first;
     const int cs = slot_of_id[(size_t)(c - id0)];
     const Pose5 cur_pose = slot_pose[(size_t)cs];
     const D3 cur_position{cur_pose.v[0], cur_pose.v[1], cur_pose.v[2]};
     const int cur_vox = slot_vox[(size_t)cs];
-    if (!(cur_vox > 1 && near_ok[(size_t)cs])) { live[(size_t)cs] = 0; continue; }     // nearCheck(cur_position, cur_vox)
-    const int* neigh = arena[(size_t)(cs / kBlock)].data() + nb_off[(size_t)cs];      // radiusSearch result, (distance, index)-sorted
-    const int n_neigh = nb_cnt[(size_t)cs];
-    if (!(live[(size_t)cs] && n_neigh > 1)) continue;
+    if (!qualifies(cs)) { live[(size_t)cs] = 0; continue; }                           // nearCheck(cur_position, cur_vox)
+    if (!live[(size_t)cs]) continue;                                                   // its search result would not be used (cpp:688)
+    if (list_of[(size_t)cs] < 0) search_wave(ci);
+    const std::vector<int>& nlist = lists[(size_t)list_of[(size_t)cs]];
+    const int* neigh = nlist.data();
+    const int n_neigh = (int)nlist.size();
+    if (n_neigh <= 1) continue;
 
     // ---- updatePoseGravitation, host part (cpp:714-810) -----------------------------------
     query[(size_t)cs] = 1;
