@@ -62,6 +62,9 @@ __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarr
 #ifndef EVAL_ASM_STEP
 #define EVAL_ASM_STEP 1
 #endif
+#ifndef EVAL_STATS
+#define EVAL_STATS 0          // 1 / 2: measurement builds that reuse the walk / trips counters of an E1 pass (profiles/march_stats.py)
+#endif
 #ifndef EVAL_STAGED_FOV
 #define EVAL_STAGED_FOV 1
 #endif
@@ -532,6 +535,11 @@ __global__ void __launch_bounds__(kWarps * 32, EVAL_MIN_CTAS) k_eval(const __gri
             st.lookups += 2u * (unsigned)calls + 1u;
             if (c.flags & CONT_INRANGE) set_bit(c.vp, c.pt);
             active = false;
+#if EVAL_STATS == 1
+            st.trips++;                               // measurement build: rays ended by the in-flight certificate
+#elif EVAL_STATS == 2
+            st.walk += (unsigned)calls;               // measurement build: biNextId calls the certificate saved
+#endif
           }
         }
       }
@@ -568,9 +576,15 @@ __global__ void __launch_bounds__(kWarps * 32, EVAL_MIN_CTAS) k_eval(const __gri
             const bool r = occ_fast(g, c.n.ix, c.n.iy, c.n.iz, nkey, nword);
             st.lookups += 2;
             c.n.step_if(nflag);
+#if EVAL_STATS == 1
+            st.walk++;                                // measurement build: lane-steps marched
+#endif
             if (!f || !r) {
               st.lookups += 1;                        // the re-check after the break (same voxel, same answer)
               active = false;
+#if EVAL_STATS == 2
+              st.trips++;                             // measurement build: rays ended by an occupied voxel
+#endif
             }
           }
         }

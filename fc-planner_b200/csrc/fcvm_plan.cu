@@ -22,6 +22,8 @@
 // No CPU fallback.
 #include <cfloat>
 #include <cstring>
+#include <limits>
+#include <vector>
 
 #include "fcvm_hostutil.h"
 #include "fcvm_kernels.h"
@@ -300,72 +302,204 @@ __global__ void __launch_bounds__(128) k_safety_box(GridDesc g, double res_inv, 
   if (counters && looks) atomicAdd(counters + 0, looks);
 }
 
-// search_Path's straight-line test (hcsolver.cpp:556-583) for every ordered pair (i, j) of n positions.
-// Rays of very different lengths in one warp leave most lanes idle (11 of 32 active when thread = pair index, ncu r1n), so the
-// pairs are first binned by their voxel Manhattan length - the number of steps a free ray takes - with a counting sort
-// (k_los_bin, k_exscan, k_los_scatter) and the march kernel walks that order: a warp's 32 rays then end together unless
-// something blocks them earlier.  The results are indexed by pair, so the order inside a bin is immaterial.
-constexpr int kLosBins = 4096;
-__device__ __forceinline__ int los_length(const double* __restrict__ pts, long long n, long long t, double res) {
-  const long long i = t / n, j = t % n;
-  const int dx = (int)floor(pts[3 * j] / res) - (int)floor(pts[3 * i] / res);
-  const int dy = (int)floor(pts[3 * j + 1] / res) - (int)floor(pts[3 * i + 1] / res);
-  const int dz = (int)floor(pts[3 * j + 2] / res) - (int)floor(pts[3 * i + 2] / res);
-  return min(abs(dx) + abs(dy) + abs(dz), kLosBins - 1);
+// search_Path's straight-line test (hcsolver.cpp:556-583) for every ordered pair (i, j) of n positions:
+//   raycaster_->input(p1, p2); while (raycaster_->nextId(idx)) if (inflate[idx] == 1 || internal[idx] == 1) -> not safe
+// Thread = pair left 11 of 32 lanes busy (ncu r1n: rays of very different lengths share a warp), binning the pairs by length
+// (round 2, first try) 15 of 32 at the price of a 0.9 ms scatter: a blocked ray ends anywhere.  Now three steps:
+//   k_los_ends      per POSITION: p / resolution (the reference's own division), its voxel, its map index, whether it lies
+//                   strictly inside its voxel - 6 FP64 divisions per pair become 3 per position
+//   k_los_classify  per PAIR, full warps: rays on the fast path (below) whose whole box of voxels is free by the summed-area
+//                   table of the pblk plane are safe without a march (8 loads); the other fast rays are appended to a list;
+//                   the few rays off the fast path run the literal marcher on the spot
+//   k_los_march     persistent warps over the list: a lane that finishes takes the next listed ray (refill in groups, so the
+//                   set-up runs several lanes wide); the DDA set-up divides through a reciprocal table (div_exact), the step is
+//                   predicated, and every 4 steps a ray asks the table whether the box from its front to its end is free.
+// Fast path = both end voxels inside the map, the map-index conversion a pure shift between them, every |delta| below the
+// reciprocal table's size, and the start strictly inside its voxel (by 1e-9) on every moving axis.  Such a marcher makes exactly
+// |dx| + |dy| + |dz| steps and never leaves the box spanned by its end voxels (the direction is the INTEGER voxel delta,
+// raycast.cpp:412-434, so the crossings it needs all have t < 1 and all others t > 1, by margins no rounding bridges; the
+// reference's runaway marchers start ON a lattice plane).  So "the box is free" means every voxel nextId reports is free,
+// whatever their exact sequence: the verdict and the look-up count (one per step) are the reference's.
+constexpr int kLosRcpN = 1024;
+struct LosEnd {
+  double fx, fy, fz;     // position / resolution
+  int vx, vy, vz;        // floor of it (world-anchored voxel)
+  int ix, iy, iz;        // the voxel as a map index, `(int)(v + offset_)`
+  int flags;             // bits 0-2: strictly inside the voxel on x / y / z; bit 3: finite and the voxel is inside the map
+  int pad[3];
+};
+static_assert(sizeof(LosEnd) == 64, "LosEnd layout");
+
+__global__ void __launch_bounds__(256) k_los_ends(GridDesc g, const double* __restrict__ pts, long long n, LosEnd* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  LosEnd e;
+  e.fx = pts[3 * i] / g.res; e.fy = pts[3 * i + 1] / g.res; e.fz = pts[3 * i + 2] / g.res;
+  const bool finite = (fabs(e.fx) + fabs(e.fy)) + fabs(e.fz) < 1.0e9;         // false for NaN / inf
+  const double flx = floor(e.fx), fly = floor(e.fy), flz = floor(e.fz);
+  e.vx = finite ? (int)flx : 0; e.vy = finite ? (int)fly : 0; e.vz = finite ? (int)flz : 0;
+  e.ix = to_map_index(e.vx, g.offx); e.iy = to_map_index(e.vy, g.offy); e.iz = to_map_index(e.vz, g.offz);
+  const double rx = e.fx - flx, ry = e.fy - fly, rz = e.fz - flz;              // exact
+  e.flags = ((rx > 1e-9 && rx < 1.0 - 1e-9) ? 1 : 0) | ((ry > 1e-9 && ry < 1.0 - 1e-9) ? 2 : 0) | ((rz > 1e-9 && rz < 1.0 - 1e-9) ? 4 : 0);
+  if (finite && (unsigned)e.ix < (unsigned)g.nx && (unsigned)e.iy < (unsigned)g.ny && (unsigned)e.iz < (unsigned)g.nz) e.flags |= 8;
+  for (int k = 0; k < 3; ++k) e.pad[k] = 0;
+  out[i] = e;
 }
-__global__ void __launch_bounds__(256) k_los_bin(const double* __restrict__ pts, long long n, double res, int* __restrict__ hist) {
-  __shared__ int sh[kLosBins];
-  for (int k = threadIdx.x; k < kLosBins; k += blockDim.x) sh[k] = 0;
-  __syncthreads();
-  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n * n; t += (long long)gridDim.x * blockDim.x)
-    atomicAdd(&sh[los_length(pts, n, t, res)], 1);
-  __syncthreads();
-  for (int k = threadIdx.x; k < kLosBins; k += blockDim.x)
-    if (sh[k]) atomicAdd(hist + k, sh[k]);
+
+// the literal loop (every pair took it before round 2): Marcher of fcvm_device.cuh, bounds-checked look-ups, step cap
+__device__ __noinline__ bool los_literal(const GridDesc& g, double ax, double ay, double az, double bx, double by, double bz,
+                                         unsigned long long& looks, unsigned long long& trips) {
+  const double res = g.res;
+  Marcher m;
+  m.init(ax / res, ay / res, az / res, (int)floor(bx / res), (int)floor(by / res), (int)floor(bz / res), g);
+  int budget = m.manhattan() + 8;
+  BrickCache c;
+  c.reset();
+  for (;;) {
+    const int ix = m.ix, iy = m.iy, iz = m.iz;     // nextId reports the voxel before stepping ...
+    if (m.at_end()) return true;                    // ... and returns false at the end voxel (which is never tested)
+    if (--budget < 0) { trips++; return false; }
+    m.step(g);
+    looks++;
+    if (!occ_free(g, ix, iy, iz, c)) return false; // blocked, or outside the map
+  }
 }
-__global__ void __launch_bounds__(256) k_los_scatter(const double* __restrict__ pts, long long n, double res, const long long* __restrict__ start,
-                                                     int* __restrict__ fill, unsigned* __restrict__ order) {
+
+__device__ __forceinline__ bool los_fast(const LosEnd& a, const LosEnd& b, int& dx, int& dy, int& dz) {
+  dx = b.vx - a.vx; dy = b.vy - a.vy; dz = b.vz - a.vz;
+  const int inside = a.flags | (dx == 0 ? 1 : 0) | (dy == 0 ? 2 : 0) | (dz == 0 ? 4 : 0);     // idle axes do not matter
+  return (a.flags & b.flags & 8) && (inside & 7) == 7 && (b.ix - a.ix == dx) && (b.iy - a.iy == dy) && (b.iz - a.iz == dz) &&
+         abs(dx) < kLosRcpN && abs(dy) < kLosRcpN && abs(dz) < kLosRcpN;
+}
+
+__global__ void __launch_bounds__(256) k_los_classify(GridDesc g, const double* __restrict__ pts, const LosEnd* __restrict__ ends, long long n,
+                                                      uint8_t* __restrict__ safe, double* __restrict__ dist, unsigned* __restrict__ list,
+                                                      int* __restrict__ cursor, unsigned long long* __restrict__ counters) {
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= n * n) return;
-  const int b = los_length(pts, n, t, res);
-  order[start[b] + atomicAdd(fill + b, 1)] = (unsigned)t;
-}
-__global__ void __launch_bounds__(128) k_line_of_sight(GridDesc g, const double* __restrict__ pts, long long n, const unsigned* __restrict__ order,
-                                                       uint8_t* __restrict__ safe, double* __restrict__ dist, unsigned long long* __restrict__ counters) {
-  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const bool valid = tid < n * n;
+  const bool valid = t < n * n;
   unsigned long long looks = 0, trips = 0;
+  bool listed = false;
+  unsigned packed = 0u;
   if (valid) {
-    const long long t = order ? (long long)order[tid] : tid;
-    const long long i = t / n, j = t % n;
-    const double ax = pts[3 * i], ay = pts[3 * i + 1], az = pts[3 * i + 2];
-    const double bx = pts[3 * j], by = pts[3 * j + 1], bz = pts[3 * j + 2];
-    const double res = g.res;
-    Marcher m;
-    m.init(ax / res, ay / res, az / res, (int)floor(bx / res), (int)floor(by / res), (int)floor(bz / res), g);
-    int budget = m.manhattan() + 8;
-    BrickCache c;
-    c.reset();
-    bool ok = true;
-    for (;;) {
-      const int ix = m.ix, iy = m.iy, iz = m.iz;     // nextId reports the voxel before stepping ...
-      if (m.at_end()) break;                          // ... and returns false at the end voxel (which is never tested)
-      if (--budget < 0) { trips++; ok = false; break; }
-      m.step(g);
-      looks++;
-      if (!occ_free(g, ix, iy, iz, c)) { ok = false; break; }   // blocked, or outside the map
+    const unsigned i = (unsigned)(t / n), j = (unsigned)(t % n);
+    const LosEnd a = ends[i], b = ends[j];
+    int dx, dy, dz;
+    if (los_fast(a, b, dx, dy, dz)) {
+      const int steps = abs(dx) + abs(dy) + abs(dz);
+      if (steps == 0 ||
+          sat_box_count(g, min(a.ix, b.ix) >> FCVM_SAT_SHIFT, min(a.iy, b.iy) >> FCVM_SAT_SHIFT, min(a.iz, b.iz) >> FCVM_SAT_SHIFT,
+                        max(a.ix, b.ix) >> FCVM_SAT_SHIFT, max(a.iy, b.iy) >> FCVM_SAT_SHIFT, max(a.iz, b.iz) >> FCVM_SAT_SHIFT) == 0) {
+        safe[t] = 1;
+        looks = (unsigned long long)steps;
+      } else {
+        listed = true;
+        packed = (i << 16) | j;                       // n <= 46340 < 2^16
+      }
+    } else {
+      safe[t] = los_literal(g, pts[3 * i], pts[3 * i + 1], pts[3 * i + 2], pts[3 * j], pts[3 * j + 1], pts[3 * j + 2], looks, trips) ? 1 : 0;
     }
-    safe[t] = ok ? 1 : 0;
     if (dist) {
-      const double dx = ax - bx, dy = ay - by, dz = az - bz;
-      dist[t] = sqrt((dx * dx + dy * dy) + dz * dz);            // (p1 - p2).norm(), Eigen order
+      const double ex = pts[3 * i] - pts[3 * j], ey = pts[3 * i + 1] - pts[3 * j + 1], ez = pts[3 * i + 2] - pts[3 * j + 2];
+      dist[t] = sqrt((ex * ex + ey * ey) + ez * ez);  // (p1 - p2).norm(), Eigen order
     }
   }
-  if (counters) {                                     // one atomic per warp
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) { looks += __shfl_xor_sync(0xffffffffu, looks, o); trips += __shfl_xor_sync(0xffffffffu, trips, o); }
-    if ((threadIdx.x & 31) == 0) { if (looks) atomicAdd(counters + 0, looks); if (trips) atomicAdd(counters + 1, trips); }
+  const unsigned m = __ballot_sync(0xffffffffu, listed);
+  const int lane = threadIdx.x & 31;
+  if (m != 0u) {
+    int base = 0;
+    if (lane == 0) base = atomicAdd(cursor, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (listed) list[base + __popc(m & ((1u << lane) - 1u))] = packed;
   }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { looks += __shfl_xor_sync(0xffffffffu, looks, o); trips += __shfl_xor_sync(0xffffffffu, trips, o); }
+  if (lane == 0) { if (looks) atomicAdd(counters + 0, looks); if (trips) atomicAdd(counters + 1, trips); }
+}
+
+#ifndef LOS_REFILL
+#define LOS_REFILL 8          // k_los_march: idle lanes of a warp take new rays once at least this many are idle
+#endif
+#ifndef LOS_QUERY_PERIOD
+#define LOS_QUERY_PERIOD 4    // k_los_march: steps between two free-box queries of a ray
+#endif
+__global__ void __launch_bounds__(256) k_los_march(GridDesc g, const LosEnd* __restrict__ ends, long long n, const double* __restrict__ rcp,
+                                                   const unsigned* __restrict__ list, int* __restrict__ cursor, uint8_t* __restrict__ safe,
+                                                   unsigned long long* __restrict__ counters) {
+  const int lane = threadIdx.x & 31;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  const int count = cursor[0];                       // rays listed by k_los_classify; cursor[1] = next one to hand out
+  unsigned long long looks = 0;
+  bool active = false, more = true;
+  int ix = 0, iy = 0, iz = 0, ex = 0, ey = 0, ez = 0, sx = 0, sy = 0, sz = 0, rem = 0, key = -1;
+  double tmx = 0, tmy = 0, tmz = 0, tdx = 0, tdy = 0, tdz = 0;
+  unsigned long long word = 0ull;
+  long long t = 0;
+  for (;;) {
+    const unsigned idle = __ballot_sync(0xffffffffu, !active);
+    if (more && (__popc(idle) >= LOS_REFILL)) {
+      int base = 0;
+      if (lane == 0) base = atomicAdd(cursor + 1, __popc(idle));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (base + __popc(idle) >= count) more = false;
+      const int mine = base + __popc(idle & lt_mask);
+      if (!active && mine < count) {
+        const unsigned pk = __ldg(list + mine);
+        const unsigned i = pk >> 16, j = pk & 0xffffu;
+        const LosEnd* a = ends + i;
+        const LosEnd* b = ends + j;
+        const int avx = __ldg(&a->vx), avy = __ldg(&a->vy), avz = __ldg(&a->vz);
+        const int dx = __ldg(&b->vx) - avx, dy = __ldg(&b->vy) - avy, dz = __ldg(&b->vz) - avz;
+        ix = __ldg(&a->ix); iy = __ldg(&a->iy); iz = __ldg(&a->iz);
+        ex = __ldg(&b->ix); ey = __ldg(&b->iy); ez = __ldg(&b->iz);
+        sx = d_signum(dx); sy = d_signum(dy); sz = d_signum(dz);
+        rem = abs(dx) + abs(dy) + abs(dz);
+        tmx = d_intbound_i(__ldg(&a->fx), dx, rcp); tmy = d_intbound_i(__ldg(&a->fy), dy, rcp); tmz = d_intbound_i(__ldg(&a->fz), dz, rcp);
+        tdx = __ldg(rcp + abs(dx)); tdy = __ldg(rcp + abs(dy)); tdz = __ldg(rcp + abs(dz));     // rcp[0] = NaN = 0 / 0 on idle axes
+        t = (long long)i * n + j;
+        key = -1;
+        active = true;
+      }
+    }
+    if (__ballot_sync(0xffffffffu, active) == 0u) {
+      if (!more) break;
+      continue;
+    }
+    if (active) {
+      bool blocked = false;
+#pragma unroll
+      for (int u = 0; u < LOS_QUERY_PERIOD; ++u) {
+        if (rem > 0 && !blocked) {
+          // nextId reports the voxel BEFORE it steps; the reference tests that voxel
+          const int k = ((ix >> 2) * g.nby + (iy >> 2)) * g.nbz + (iz >> 2);
+          if (k != key) { key = k; word = __ldg(g.bricks + k); }
+          blocked = ((word >> brick_bit_index(ix, iy, iz)) & 1ull) != 0ull;
+          looks++;
+          // the branch ladder of nextId (raycast.cpp:455-476): strict '<', z on ties and NaN
+          if (tmx < tmy) {
+            if (tmx < tmz) { ix += sx; tmx += tdx; } else { iz += sz; tmz += tdz; }
+          } else {
+            if (tmy < tmz) { iy += sy; tmy += tdy; } else { iz += sz; tmz += tdz; }
+          }
+          rem--;
+        }
+      }
+      if (blocked) {
+        safe[t] = 0;
+        active = false;
+      } else if (rem == 0) {
+        safe[t] = 1;
+        active = false;
+      } else if (sat_box_count(g, min(ix, ex) >> FCVM_SAT_SHIFT, min(iy, ey) >> FCVM_SAT_SHIFT, min(iz, ez) >> FCVM_SAT_SHIFT,
+                               max(ix, ex) >> FCVM_SAT_SHIFT, max(iy, ey) >> FCVM_SAT_SHIFT, max(iz, ez) >> FCVM_SAT_SHIFT) == 0) {
+        looks += (unsigned long long)rem;             // every voxel still to be reported is free: one look-up per remaining step
+        safe[t] = 1;
+        active = false;
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) looks += __shfl_xor_sync(0xffffffffu, looks, o);
+  if (lane == 0 && looks) atomicAdd(counters + 0, looks);
 }
 
 }  // namespace fcvm
@@ -380,9 +514,12 @@ struct fcvm_grid_handle {
   DevBuf<unsigned long long> d_occ, d_inf, d_int;     // raw planes: occupancy_buffer_hc_ (= occ), occupancy_inflate_buffer_hc_, occupancy_buffer_internal_
   DevBuf<unsigned long long> d_sblk, d_pblk;          // derived planes, refreshed after every change of the raw ones
   DevBuf<unsigned char> d_visited;
-  DevBuf<int> d_hist;                 // 2 x kLosBins: histogram + fill counters of the line-of-sight counting sort
-  DevBuf<long long> d_binstart;
-  DevBuf<unsigned> d_order;
+  DevBuf<int> d_sat;                  // summed-area table of non-empty bricks of the pblk plane (line-of-sight certificate)
+  bool sat_ok = false;                //   ... rebuilt lazily after the planes changed
+  DevBuf<double> d_rcp;               // 1 / k, k < kLosRcpN (the divisions of the DDA set-up)
+  DevBuf<LosEnd> d_ends;
+  DevBuf<unsigned> d_list;            // rays k_los_classify left for k_los_march, (i << 16) | j
+  DevBuf<int> d_cursor;               // [0] rays listed, [1] next one handed out
   DevBuf<double> d_in;
   DevBuf<float> d_in_f, d_rosa;
   DevBuf<uint8_t> d_u8;
@@ -420,6 +557,7 @@ static void plane_geom(const fcvm_grid_handle* h, PlaneGeom& g) {
 static int plan_derive(fcvm_grid_handle* h) {
   k_derive_planes<<<(unsigned)((h->nbricks + 255) / 256), 256, 0, h->stream>>>(h->d_occ.p, h->d_inf.p, h->d_int.p, h->nbricks, h->d_sblk.p, h->d_pblk.p);
   CU(cudaGetLastError());
+  h->sat_ok = false;
   return FCVM_OK;
 }
 
@@ -495,7 +633,7 @@ void fcvm_grid_destroy(fcvm_grid_t* h) {
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   h->d_occ.free(); h->d_inf.free(); h->d_int.free(); h->d_sblk.free(); h->d_pblk.free(); h->d_visited.free(); h->d_in.free(); h->d_in_f.free(); h->d_rosa.free(); h->d_u8.free();
-  h->d_i32a.free(); h->d_i32b.free(); h->d_dist.free(); h->d_counters.free(); h->d_hist.free(); h->d_binstart.free(); h->d_order.free();
+  h->d_i32a.free(); h->d_i32b.free(); h->d_dist.free(); h->d_counters.free(); h->d_sat.free(); h->d_rcp.free(); h->d_ends.free(); h->d_list.free(); h->d_cursor.free();
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -554,23 +692,41 @@ int fcvm_grid_line_of_sight(fcvm_grid_t* h, const double* p_xyz, int64_t n, uint
   CU(cudaMemcpyAsync(h->d_in.p, p_xyz, (size_t)3 * n * sizeof(double), cudaMemcpyHostToDevice, s));
   GridDesc g;
   plan_desc(h, h->d_pblk.p, g);
-  CU(cudaEventRecord(h->ev0, s));
-  const unsigned* order = nullptr;
-  if (n * n >= 4096) {                 // counting sort of the pairs by voxel Manhattan length (see k_line_of_sight)
-    CU(h->d_hist.reserve(2 * kLosBins));
-    CU(h->d_binstart.reserve(kLosBins + 1));
-    CU(h->d_order.reserve((size_t)n * n));
-    CU(cudaMemsetAsync(h->d_hist.p, 0, 2 * kLosBins * sizeof(int), s));
-    k_los_bin<<<(unsigned)std::min<long long>(1184, (n * n + 255) / 256), 256, 0, s>>>(h->d_in.p, n, h->res, h->d_hist.p);
-    CU(cudaGetLastError());
-    CU(launch_exscan(h->d_hist.p, kLosBins, h->d_binstart.p, s));
-    k_los_scatter<<<(unsigned)((n * n + 255) / 256), 256, 0, s>>>(h->d_in.p, n, h->res, h->d_binstart.p, h->d_hist.p + kLosBins, h->d_order.p);
-    CU(cudaGetLastError());
-    order = h->d_order.p;
-    h->counters[2] += 3;
+  if (!h->d_rcp.p) {                   // 1 / k by the divider the reference uses (IEEE, same bits on host and device); 0 / 0 for k = 0
+    std::vector<double> rcp(kLosRcpN);
+    for (int k = 0; k < kLosRcpN; ++k) rcp[(size_t)k] = k == 0 ? std::numeric_limits<double>::quiet_NaN() : 1.0 / (double)k;
+    CU(h->d_rcp.reserve(kLosRcpN));
+    CU(cudaMemcpyAsync(h->d_rcp.p, rcp.data(), kLosRcpN * sizeof(double), cudaMemcpyHostToDevice, s));
+    CU(cudaStreamSynchronize(s));      // `rcp` goes out of scope
   }
-  k_line_of_sight<<<(unsigned)((n * n + 127) / 128), 128, 0, s>>>(g, h->d_in.p, n, order, h->d_u8.p, dist_nxn ? h->d_dist.p : nullptr, h->d_counters.p);
+  const int sat_dims[3] = {h->nb[0] / FCVM_SAT_BRICKS + 1, h->nb[1] / FCVM_SAT_BRICKS + 1, h->nb[2] / FCVM_SAT_BRICKS + 1};
+  if ((long long)sat_dims[0] * sat_dims[1] * sat_dims[2] >= (1ll << 31)) return fail(FCVM_EINVAL, "grid too large for the free-box table");
+  if (!h->sat_ok) {                    // the planes changed since the table was built
+    CU(h->d_sat.reserve((size_t)sat_dims[0] * sat_dims[1] * sat_dims[2]));
+    CU(launch_build_sat(h->d_pblk.p, h->nb, h->d_sat.p, s));
+    h->sat_ok = true;
+    h->counters[2] += 4;
+  }
+  g.sat = h->d_sat.p; g.sat_ny = sat_dims[1]; g.sat_nz = sat_dims[2];
+  CU(h->d_ends.reserve((size_t)n));
+  CU(h->d_list.reserve((size_t)n * n));
+  CU(h->d_cursor.reserve(2));
+  CU(cudaEventRecord(h->ev0, s));
+  CU(cudaMemsetAsync(h->d_cursor.p, 0, 2 * sizeof(int), s));
+  k_los_ends<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(g, h->d_in.p, n, h->d_ends.p);
   CU(cudaGetLastError());
+  k_los_classify<<<(unsigned)((n * n + 255) / 256), 256, 0, s>>>(g, h->d_in.p, h->d_ends.p, n, h->d_u8.p, dist_nxn ? h->d_dist.p : nullptr, h->d_list.p,
+                                                               h->d_cursor.p, h->d_counters.p);
+  CU(cudaGetLastError());
+  {
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+    const long long want = (n * n + 255) / 256;                       // never more warps than rays
+    k_los_march<<<(unsigned)std::max<long long>(1, std::min<long long>((long long)sms * 4, want)), 256, 0, s>>>(g, h->d_ends.p, n, h->d_rcp.p, h->d_list.p,
+                                                                                                             h->d_cursor.p, h->d_u8.p, h->d_counters.p);
+    CU(cudaGetLastError());
+  }
+  h->counters[2] += 3;
   CU(cudaEventRecord(h->ev1, s));      // ev0 .. ev1 bracket the kernel alone
   CU(cudaMemcpyAsync(safe_nxn, h->d_u8.p, (size_t)n * n, cudaMemcpyDeviceToHost, s));
   if (dist_nxn) CU(cudaMemcpyAsync(dist_nxn, h->d_dist.p, (size_t)n * n * sizeof(double), cudaMemcpyDeviceToHost, s));
