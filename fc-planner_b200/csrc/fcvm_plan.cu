@@ -3,7 +3,7 @@
 //
 //   hierarchical_coverage_planner/src/hcplanner.cpp:805-863   lightStateDet      -> k_light_state
 //   hierarchical_coverage_planner/src/hcplanner.cpp:658-692   candidate safety box -> k_safety_box
-//   hierarchical_coverage_planner/src/hcsolver.cpp:556-583    search_Path, straight-line part -> k_line_of_sight
+//   hierarchical_coverage_planner/src/hcsolver.cpp:556-583    search_Path, straight-line part -> k_los_ends, k_los_classify, k_los_march
 //
 // The planner's SDFMap holds three char buffers (sdf_map.h:217-227).  They are uploaded once and packed into the
 // bricked 1-bit layout of fcvm_device.cuh as the three planes these loops test:
