@@ -280,6 +280,23 @@ static int ensure_device(fcvm_handle* h) {
   CU(cudaEventCreate(&h->ev1));
   CU(h->d_counters.reserve(8));
   CU(cudaMemset(h->d_counters.p, 0, 8 * sizeof(unsigned long long)));
+  {
+    // Once per device and process: load the path's kernels now (the driver loads a kernel at its first launch otherwise, and a
+    // first updateViewpoints launches ~25 different ones), and let the stream-ordered pool own a first block of memory so that
+    // the handle's buffers are carved out of it instead of costing a driver allocation each.
+    static std::atomic<bool> warmed[64];
+    const int dev = h->prm.device;
+    if (dev < 0 || dev >= 64 || !warmed[dev].exchange(true)) {
+      CU(preload_eval_kernels());
+      CU(preload_pose_kernels());
+      CU(preload_map_kernels());
+      void* block = nullptr;
+      if (cudaMallocAsync(&block, (size_t)64 << 20, h->stream) == cudaSuccess) CU(cudaFreeAsync(block, h->stream));
+      else (void)cudaGetLastError();
+      CU(cudaStreamSynchronize(h->stream));
+    }
+  }
+  if (!h->pool) h->pool.reset(new WorkerPool(h->threads));
   h->device_ok = true;
   return FCVM_OK;
 }

@@ -971,6 +971,18 @@ static cudaError_t launch_eval_t(const EvalArgs& a, dim3 grid, size_t smem, cuda
   return cudaGetLastError();
 }
 
+cudaError_t preload_eval_kernels() {
+  cudaFuncAttributes fa;
+  const void* fns[] = {(const void*)k_init_rcp, (const void*)k_ray_ends, (const void*)k_eval<1>, (const void*)k_eval<2>, (const void*)k_eval<3>,
+                       (const void*)k_eval<4>, (const void*)k_popc_rows, (const void*)k_exscan, (const void*)k_compact_rows, (const void*)k_own_sweep,
+                       (const void*)k_own_best, (const void*)k_own_apply};
+  for (const void* f : fns) {
+    const cudaError_t e = cudaFuncGetAttributes(&fa, f);
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
+}
+
 size_t eval_smem_bytes(int tile_pts) {
   return (size_t)tile_pts * sizeof(float4) + (size_t)kWarps * kReadyQ * (kContD * sizeof(double) + kContI * sizeof(int)) +
          (size_t)kWarps * kEntryQ * sizeof(QueueEntry);

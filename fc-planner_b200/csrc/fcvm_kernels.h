@@ -125,4 +125,10 @@ cudaError_t launch_cell_count(const float* xyz, long long n, const CellGeom& cg,
 cudaError_t launch_cell_fill(const float* xyz, long long n, const CellGeom& cg, const long long* start, int* fill, float4* sorted, cudaStream_t s);
 cudaError_t launch_safety(const SafetyArgs& a, cudaStream_t s);
 
+// Loads every kernel of the viewpoint path into the current device's context (cudaFuncGetAttributes), so that the first
+// updateViewpoints does not pay the driver's lazy module loading launch by launch (~0.2 ms per kernel); called once per device.
+cudaError_t preload_eval_kernels();
+cudaError_t preload_pose_kernels();
+cudaError_t preload_map_kernels();
+
 }  // namespace fcvm

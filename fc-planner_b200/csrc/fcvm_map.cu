@@ -237,6 +237,17 @@ __global__ void __launch_bounds__(256) k_safety(const __grid_constant__ SafetyAr
 }
 
 // ---- launchers ---------------------------------------------------------------------------------------------------
+cudaError_t preload_map_kernels() {
+  cudaFuncAttributes fa;
+  const void* fns[] = {(const void*)k_cloud_minmax, (const void*)k_voxelise, (const void*)k_mark_padding, (const void*)k_sat_flags, (const void*)k_sat_scan,
+                       (const void*)k_cell_count, (const void*)k_cell_fill, (const void*)k_safety};
+  for (const void* f : fns) {
+    const cudaError_t e = cudaFuncGetAttributes(&fa, f);
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
+}
+
 cudaError_t launch_cloud_minmax(const float* xyz, long long n, float* partial, int blocks, cudaStream_t s) {
   k_cloud_minmax<<<blocks, 256, 0, s>>>(xyz, n, partial);
   return cudaGetLastError();

@@ -112,6 +112,16 @@ __global__ void __launch_bounds__(256) k_pose_sum(const long long* __restrict__ 
   if (lane == 0) { sums[2 * (long long)r] = sp; sums[2 * (long long)r + 1] = sy; }
 }
 
+cudaError_t preload_pose_kernels() {
+  cudaFuncAttributes fa;
+  const void* fns[] = {(const void*)k_pose_terms, (const void*)k_pose_patch, (const void*)k_pose_sum};
+  for (const void* f : fns) {
+    const cudaError_t e = cudaFuncGetAttributes(&fa, f);
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
+}
+
 cudaError_t launch_pose_terms(const float4* points, const PoseAux* aux, const long long* offsets, const uint32_t* indices, int nrows, double* val_p,
                               double* val_y, unsigned long long* key_p, double* arg_p, unsigned long long* key_y, double* arg_y,
                               unsigned long long* nflag, unsigned long long cap, cudaStream_t s) {
