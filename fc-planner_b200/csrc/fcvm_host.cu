@@ -789,17 +789,6 @@ static int voxcount_download(fcvm_handle* h, std::vector<int>& out) {
   }
   return FCVM_OK;
 }
-static int voxcount_upload(fcvm_handle* h, const std::vector<int>& in) {
-  int rc = voxcount_resize(h, 0);
-  if (rc) return rc;
-  rc = voxcount_resize(h, in.size());
-  if (rc) return rc;
-  if (!in.empty()) {
-    CU(cudaMemcpyAsync(h->d_voxcount.p, in.data(), in.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
-    CU(cudaStreamSynchronize(h->stream));      // `in` is the caller's
-  }
-  return FCVM_OK;
-}
 static int cover_reset(fcvm_handle* h) {   // MCI reset, cpp:178-183
   CU(h->d_cover_contrib.reserve((size_t)h->P));
   CU(h->d_contrib_id.reserve((size_t)h->P));
@@ -1698,7 +1687,8 @@ static int update_impl(fcvm_handle* h) {
   if (rc) return rc;
   rc = voxcount_download(h, temp_vps_voxcount);
   if (rc) return rc;
-  rc = voxcount_upload(h, std::vector<int>(std::max((size_t)h->P, h->vps_pose.size()), 0));   // resize(P) in the reference; A.9
+  rc = voxcount_resize(h, 0);                                                                  // resize(P) in the reference; A.9:
+  if (!rc) rc = voxcount_resize(h, std::max((size_t)h->P, h->vps_pose.size()));                 // all zeros, by a memset on the device
   if (rc) return rc;
   umark("cover reset, voxcount swap");
   rc = viewpoints_prune(h, h->vps_pose, temp_vps_voxcount);

@@ -63,7 +63,7 @@ __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarr
 #define EVAL_ASM_STEP 1
 #endif
 #ifndef EVAL_STATS
-#define EVAL_STATS 0          // 1 / 2: measurement builds that reuse the walk / trips counters of an E1 pass (profiles/march_stats.py)
+#define EVAL_STATS 0          // 1 / 2 / 3: measurement builds that reuse the walk / trips counters of an E1 pass (profiles/march_stats.py)
 #endif
 #ifndef EVAL_STAGED_FOV
 #define EVAL_STAGED_FOV 1
@@ -501,6 +501,9 @@ __global__ void __launch_bounds__(kWarps * 32, EVAL_MIN_CTAS) k_eval(const __gri
     unsigned tick = 0;
     int pkey = -1, nkey = -1;
     unsigned long long pword = 0ull, nword = 0ull;
+#if EVAL_STATS == 3
+    int age = 0;                                      // measurement build: biNextId calls since the ray was (re)loaded
+#endif
     for (;;) {
       const unsigned idle = __ballot_sync(0xffffffffu, !active);
       if (idle != 0u && rn > 0) {
@@ -509,6 +512,9 @@ __global__ void __launch_bounds__(kWarps * 32, EVAL_MIN_CTAS) k_eval(const __gri
           cont_load(rqd, rqi, rn - 1 - r, c);
           active = true;
           pkey = -1; nkey = -1;
+#if EVAL_STATS == 3
+          age = 0;
+#endif
         }
         rn -= min(__popc(idle), rn);
         __syncwarp();
@@ -578,12 +584,17 @@ __global__ void __launch_bounds__(kWarps * 32, EVAL_MIN_CTAS) k_eval(const __gri
             c.n.step_if(nflag);
 #if EVAL_STATS == 1
             st.walk++;                                // measurement build: lane-steps marched
+#elif EVAL_STATS == 3
+            age++;
 #endif
             if (!f || !r) {
               st.lookups += 1;                        // the re-check after the break (same voxel, same answer)
               active = false;
 #if EVAL_STATS == 2
               st.trips++;                             // measurement build: rays ended by an occupied voxel
+#elif EVAL_STATS == 3
+              if (age == 1) st.walk++;                // measurement build: ... at the first call after loading / within the first three
+              if (age <= 3) st.trips++;
 #endif
             }
           }

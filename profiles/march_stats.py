@@ -1,8 +1,8 @@
 #!/usr/bin/env python
 """How far do the rays of the bench scene's E1 pass really march?  Runs the pass with the two measurement builds
-(FCVM_DEFS=EVAL_STATS=1 / 2, see k_eval) and prints, per ray: biNextId calls of the reference, lane-steps marched by
+(FCVM_DEFS=EVAL_STATS=1 / 2 / 3, see k_eval) and prints, per ray: biNextId calls of the reference, lane-steps marched by
 the kernel, rays ended by the in-flight free-box certificate / by an occupied voxel.
-    FCVM_LIB=<variant.so> python profiles/march_stats.py <1|2> [views]"""
+    FCVM_LIB=<variant.so> python profiles/march_stats.py <1|2|3> [views]"""
 import json
 import os
 import sys
@@ -29,6 +29,8 @@ out = {"mode": mode, "views": views, "rays": int(c[1]), "lookups": int(c[2]), "v
        "calls_per_ray": float(c[2]) / 2 / max(1, int(c[1]))}
 if mode == 1:
     out.update(lane_steps=int(c[3]), ended_by_certificate=int(c[4]), lane_steps_per_ray=float(c[3]) / max(1, int(c[1])))
-else:
+elif mode == 2:
     out.update(calls_saved_by_certificate=int(c[3]), ended_by_occupied_voxel=int(c[4]))
+else:
+    out.update(blocked_at_first_call_after_loading=int(c[3]), blocked_within_3_calls_of_loading=int(c[4]))
 print(json.dumps(out))
