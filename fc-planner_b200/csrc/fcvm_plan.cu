@@ -420,7 +420,7 @@ __global__ void __launch_bounds__(256) k_los_classify(GridDesc g, const double* 
 #define LOS_REFILL 8          // k_los_march: idle lanes of a warp take new rays once at least this many are idle
 #endif
 #ifndef LOS_QUERY_PERIOD
-#define LOS_QUERY_PERIOD 4    // k_los_march: steps between two free-box queries of a ray
+#define LOS_QUERY_PERIOD 8    // k_los_march: steps between two free-box queries of a ray
 #endif
 __global__ void __launch_bounds__(256) k_los_march(GridDesc g, const LosEnd* __restrict__ ends, long long n, const double* __restrict__ rcp,
                                                    const unsigned* __restrict__ list, int* __restrict__ cursor, uint8_t* __restrict__ safe,
