@@ -338,7 +338,7 @@ def coverage_leg(args, device, with_cpu):
         pass
     out = {"workload": f"MBS shipped trajectory: {m} poses x {n} points, 640x480 pin-hole image; CoverageEvaluation (rate + visible_group per pose)",
            "gpu_ms": 1e3 * best, "kernel_ms": kern, "scan_kernel_ms": scan, "coverage_rate": rate, "group_ids": int(len(ids)),
-           "pair_tests": int(c[0]), "projections": int(c[1]), "chunks_scanned": int(c[4]), "chunks_total": int(m * ((n + 1023) // 1024)),
+           "pair_tests": int(c[0]), "projections": int(c[1]), "chunks_scanned": int(c[4]), "chunks_total": int(m * ((n + ce.chunk_points() - 1) // ce.chunk_points())), "chunk_points": ce.chunk_points(),
            "pair_tests_per_s": c[0] / (scan * 1e-3), "kernel_launches": int(c[3]),
            "matches_fixture": bool(rate == float(z["rate"]) and np.array_equal(offs, z["group_offsets"]) and np.array_equal(ids, z["group_ids"])),
            "reference_output_agreement": {"same": int(z["agreement"][0]), "only_reference": int(z["agreement"][1]),
@@ -346,7 +346,7 @@ def coverage_leg(args, device, with_cpu):
                                           "note": "vs the reference's shipped solution/Traj/CloudInfoMBS.txt; its poses are printed with 6 decimals"},
            "roofline": {"bound": "hbm", "kernel": "k_cov_scan", "achieved": b_alg / (scan * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                         "frac": b_alg / (scan * 1e-3) / 1e9 / peak, "algorithmic_bytes": b_alg,
-                        "note": "algorithmic = what the reference loop touches; whole 1024-point chunks are culled exactly, so fewer bytes move"}}
+                        "note": "algorithmic = what the reference loop touches; whole chunks of consecutive points are culled exactly, so fewer bytes move"}}
     if with_cpu:
         from oracle import oracle
         orc = oracle.CoverageOracle(prm, cam)

@@ -86,6 +86,7 @@ SYMBOLS = {
     "fcvm_cov_evaluate": (i64, [vp, f64p, i64, f64p, i64p, i32p, i64, u8p]),
     "fcvm_cov_fetch_ids": (i64, [vp, i32p, i64]),
     "fcvm_cov_counters": (ctypes.c_int, [vp, i64p]),
+    "fcvm_cov_chunk_points": (ctypes.c_int32, []),
     "fcvm_cov_last_kernel_ms": (f64, [vp]),
     "fcvm_cov_last_scan_ms": (f64, [vp]),
 }

@@ -75,6 +75,10 @@ class CoverageEvaluator:
         total = check(self.lib.fcvm_cov_evaluate(self.h, ptr(pose5, f64p), m, ctypes.byref(rate), ptr(offsets, i64p), None, 0, ptr(ever, u8p)))
         return rate.value, offsets, self._fetch(total), ever
 
+    def chunk_points(self):
+        """points per culling chunk (counters()[4] counts chunks scanned)"""
+        return int(self.lib.fcvm_cov_chunk_points())
+
     def counters(self):
         """[pair tests, projections, out-of-image, kernels launched, chunks scanned, duplicate-pixel slow paths]"""
         out = np.zeros(6, np.int64)

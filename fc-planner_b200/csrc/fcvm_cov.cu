@@ -49,14 +49,32 @@
 namespace fcvm {
 
 constexpr int kCovThreads = 256;
-constexpr int kCovPer = 4;                        // points per thread per chunk
-constexpr int kCovChunk = kCovThreads * kCovPer;  // 1024 points, walked in index order
+#ifndef COV_PER
+#define COV_PER 1           // points per thread per chunk
+#endif
+constexpr int kCovPer = COV_PER;
+constexpr int kCovChunk = kCovThreads * kCovPer;  // 256 points, walked in index order; one bounding box each
 #ifndef COV_CTAS
-#define COV_CTAS 4          // resident CTAs per SM the register allocation is capped for
+#define COV_CTAS 3          // resident CTAs per SM (74 KB of shared memory each)
 #endif
 constexpr int kCovCtasPerSm = COV_CTAS;
-constexpr int kCovHash = 2048;                    // pixel-collision detector slots (per chunk)
+#ifndef COV_GROUP
+#define COV_GROUP 2         // live chunks tested per barrier
+#endif
+constexpr int kCovGroup = COV_GROUP;
+#ifndef COV_BATCH
+#define COV_BATCH 2048      // projected points a CTA collects (over several chunks) before it resolves their pixels
+#endif
+constexpr int kCovBatch = COV_BATCH;
+constexpr int kCovPerBatch = kCovBatch / kCovThreads;
+#ifndef COV_HASH
+#define COV_HASH (2 * COV_BATCH)
+#endif
+constexpr int kCovHash = COV_HASH;                // pixel -> chain table slots (open addressing, load <= 0.5); a power of two
+static_assert((kCovHash & (kCovHash - 1)) == 0 && kCovHash > kCovBatch && kCovHash <= 32768, "table size");
+constexpr int kCovLivePass = 8192;                // chunks culled per pass (bitmap in shared memory)
 constexpr unsigned long long kEmpty = ~0ull;
+static_assert(kCovBatch % kCovThreads == 0 && kCovBatch >= 2 * kCovGroup * kCovChunk && kCovBatch <= 32767, "batch size");
 
 struct alignas(16) CovPose {
   VpRec rec;          // position + 4 world FOV normals (setPose_PY)
@@ -98,15 +116,27 @@ __device__ __forceinline__ int floor_to_int(double v) {
   return (int)f;
 }
 
+size_t cov_smem_bytes() {
+  return (size_t)kCovBatch * (sizeof(double) + 2 * sizeof(int) + 2 * sizeof(short)) + (size_t)kCovHash * 2 * sizeof(int);
+}
+
+// Round 2: the projected points of SEVERAL chunks are collected in shared memory and their pixels resolved together.  The
+// predicate "holds the pixel at the time the reference scans it" only compares point indices, so it applies to any batch that
+// is a contiguous piece of the scan.  A pose whose projections all fit one batch (the usual case: ~860 per pose on the shipped
+// trajectories) is resolved entirely in shared memory - the z-buffer slot in HBM, its four dependent L2 round trips and three
+// of the four barriers per chunk (round 1: 23 chunks per pose) are gone; a pose that overflows the batch takes the z-buffer
+// path for all its batches.
 __global__ void __launch_bounds__(kCovThreads, kCovCtasPerSm) k_cov_scan(const __grid_constant__ CovArgs a) {
-  __shared__ double s_dist[kCovChunk];
-  __shared__ int s_pix[kCovChunk];         // pixel of each point of the chunk, -1 = not in the image
-  __shared__ short s_next[kCovChunk];      // chain of the chunk's points that share a pixel
-  __shared__ short s_bucket[kCovChunk];    // the table slot of the point's pixel
-  __shared__ int t_key[kCovHash];          // open-addressing table pixel -> chain head (per chunk)
-  __shared__ int t_head[kCovHash];
-  __shared__ uint32_t s_live[1024];        // surviving-chunk bitmap, 32768 chunks per pass
-  __shared__ int s_pose, s_ntouched;
+  extern __shared__ __align__(16) unsigned char cov_smem[];
+  double* s_dist = reinterpret_cast<double*>(cov_smem);                 // camera distance of each collected point
+  int* s_pix = reinterpret_cast<int*>(s_dist + kCovBatch);              // its pixel
+  int* s_idx = s_pix + kCovBatch;                                       // its index in the cloud (scan position)
+  int* t_key = s_idx + kCovBatch;                                       // open-addressing table pixel -> chain head
+  int* t_head = t_key + kCovHash;
+  short* s_next = reinterpret_cast<short*>(t_head + kCovHash);          // chain of the batch's points that share a pixel
+  short* s_bucket = s_next + kCovBatch;                                 // the table slot of the point's pixel
+  __shared__ uint32_t s_live[kCovLivePass / 32];                        // surviving-chunk bitmap of a pass
+  __shared__ int s_pose, s_ntouched, s_count;
   __shared__ CovPose s_ps;
 
   const int tid = threadIdx.x, lane = tid & 31;
@@ -121,12 +151,12 @@ __global__ void __launch_bounds__(kCovThreads, kCovCtasPerSm) k_cov_scan(const _
 
   for (;;) {
     __syncthreads();
-    if (tid == 0) { s_pose = atomicAdd(a.next_pose, 1); s_ntouched = 0; }
+    if (tid == 0) { s_pose = atomicAdd(a.next_pose, 1); s_ntouched = 0; s_count = 0; }
     __syncthreads();
     const int k = s_pose;
     if (k >= a.m) break;
 
-    // the pose record lives in shared memory (broadcast reads): 28 doubles per thread would halve the occupancy
+    // the pose record lives in shared memory (broadcast reads): 28 doubles per thread would cost the occupancy
     if (tid < (int)(sizeof(CovPose) / 16))
       reinterpret_cast<double2*>(&s_ps)[tid] = __ldg(reinterpret_cast<const double2*>(a.poses + k) + tid);
     __syncthreads();
@@ -134,9 +164,145 @@ __global__ void __launch_bounds__(kCovThreads, kCovCtasPerSm) k_cov_scan(const _
     const VpRec& rec = ps.rec;
     uint32_t* vrow = a.vis_rows + (long long)k * a.words;
     uint32_t* drow = a.disp_rows ? a.disp_rows + (long long)k * a.words : nullptr;
+    bool spilled = false;          // the pose overflowed a batch: its pixels live in the z-buffer slot
 
-    for (int c0 = 0; c0 < a.nchunks; c0 += 32768) {
-      const int cn = min(32768, a.nchunks - c0);
+    // CameraModelProjection (hcplanner.cpp:1196-1211) of the n collected points: pixel (-1 = not in the image), camera distance,
+    // and the point joins its pixel's chain
+    auto project = [&](int n) {
+#pragma unroll 1
+      for (int u = 0; u < kCovPerBatch; ++u) {
+        const int e = u * kCovThreads + tid;
+        if (e >= n) break;
+        const float4 q = __ldg(a.points + s_idx[e]);
+        const double dx = (double)q.x - rec.px, dy = (double)q.y - rec.py, dz = (double)q.z - rec.pz;
+        const double dd = sqrt((dx * dx + dy * dy) + dz * dz);
+        const double pc0 = (ps.M[0] * dx + ps.M[1] * dy) + ps.M[2] * dz;
+        const double pc1 = (ps.M[3] * dx + ps.M[4] * dy) + ps.M[5] * dz;
+        const double pc2 = (ps.M[6] * dx + ps.M[7] * dy) + ps.M[8] * dz;
+        const double camX = cc.fx * pc1 / (1000.0 * pc0) - cc.ldc0;
+        const double camY = cc.fy * pc2 / (1000.0 * pc0) - cc.ldc1;
+        const int xi = floor_to_int(camX / cc.xRes), yi = floor_to_int(camY / cc.yRes);
+        n_proj++;
+        int px = -1;
+        if (xi >= 0 && yi >= 0) {
+          if (xi >= cc.xPixel || yi >= cc.yPixel) {
+            n_out++;
+          } else {
+            px = xi * cc.yPixel + yi;
+            s_dist[e] = dd;
+            int hb = (int)(((unsigned)px * 0x9E3779B1u) >> 16) & (kCovHash - 1);
+            for (;;) {
+              const int old = atomicCAS(&t_key[hb], -1, px);
+              if (old == -1 || old == px) break;
+              hb = (hb + 1) & (kCovHash - 1);
+            }
+            s_next[e] = (short)atomicExch(&t_head[hb], e);
+            s_bucket[e] = (short)hb;
+          }
+        }
+        s_pix[e] = px;
+      }
+      __syncthreads();
+    };
+
+    // Resolve the n collected points against the z-buffer slot (the pose has more projections than one batch holds).
+    auto flush_zbuffer = [&](int n) {
+      project(n);
+      unsigned held = 0u, fresh = 0u;          // bit u: entry u holds its pixel / the pixel was empty before this batch
+#pragma unroll 1
+      for (int u = 0; u < kCovPerBatch; ++u) {
+        const int e = u * kCovThreads + tid;
+        if (e >= n) break;
+        const int px = s_pix[e];
+        if (px < 0) continue;
+        const double dd = s_dist[e];
+        const unsigned long long before = __ldcg(zdist + px);
+        if (before == kEmpty) fresh |= 1u << u;
+        if ((unsigned long long)__double_as_longlong(dd) < before) {
+          bool h = true;
+          const int me = s_idx[e];
+          int j = t_head[s_bucket[e]];
+          n_slow += (j != e || s_next[e] >= 0);
+          for (; j >= 0; j = s_next[j])
+            if (s_idx[j] < me && s_dist[j] <= dd) { h = false; break; }
+          if (h) held |= 1u << u;
+        }
+      }
+      __syncthreads();
+      if (tid == 0) s_count = 0;
+      // the pixel's new minimum
+#pragma unroll 1
+      for (int u = 0; u < kCovPerBatch; ++u) {
+        const int e = u * kCovThreads + tid;
+        if ((held >> u) & 1u) atomicMin(zdist + s_pix[e], (unsigned long long)__double_as_longlong(s_dist[e]));
+      }
+      __syncthreads();
+      // occupant hand-over; displaced marks; the chain table is wiped
+#pragma unroll 1
+      for (int u = 0; u < kCovPerBatch; ++u) {
+        const int e = u * kCovThreads + tid;
+        if (e >= n) break;
+        const int px = s_pix[e];
+        if (px < 0) continue;
+        const int hb = s_bucket[e];
+        t_key[hb] = -1;
+        t_head[hb] = -1;
+        if (!((held >> u) & 1u)) continue;
+        const int me = s_idx[e];
+        if (__ldcg(zdist + px) == (unsigned long long)__double_as_longlong(s_dist[e])) {
+          if ((fresh >> u) & 1u) {
+            touched[atomicAdd(&s_ntouched, 1)] = px;
+          } else if (drow) {
+            const int old = __ldcg(zidx + px);
+            atomicOr(drow + (old >> 5), 1u << (old & 31));
+          }
+          __stcg(zidx + px, me);
+        } else if (drow) {
+          atomicOr(drow + (me >> 5), 1u << (me & 31));
+        }
+      }
+      __syncthreads();      // the table is clean before the next chunk inserts
+    };
+
+    // Resolve the n collected points of a pose that fits one batch, in shared memory alone.  Per pixel chain: a point holds
+    // the pixel when it is scanned iff no earlier point of the chain is at least as near; of the holders, the one no point of
+    // the chain is strictly nearer than is the occupant at the end of the scan (visible), the others were displaced.
+    auto flush_local = [&](int n) {
+      project(n);
+#pragma unroll 1
+      for (int u = 0; u < kCovPerBatch; ++u) {
+        const int e = u * kCovThreads + tid;
+        if (e >= n) break;
+        if (s_pix[e] < 0) continue;
+        const double dd = s_dist[e];
+        const int me = s_idx[e];
+        bool held = true, last = true;
+        int j = t_head[s_bucket[e]];
+        n_slow += (j != e || s_next[e] >= 0);
+        for (; j >= 0; j = s_next[j]) {
+          const double dj = s_dist[j];
+          if (s_idx[j] < me && dj <= dd) { held = false; break; }
+          if (dj < dd) last = false;
+        }
+        if (held) {
+          if (last) atomicOr(vrow + (me >> 5), 1u << (me & 31));
+          else if (drow) atomicOr(drow + (me >> 5), 1u << (me & 31));
+        }
+      }
+      __syncthreads();
+      if (tid == 0) s_count = 0;
+#pragma unroll 1
+      for (int u = 0; u < kCovPerBatch; ++u) {
+        const int e = u * kCovThreads + tid;
+        if (e >= n || s_pix[e] < 0) continue;
+        const int hb = s_bucket[e];
+        t_key[hb] = -1;
+        t_head[hb] = -1;
+      }
+    };
+
+    for (int c0 = 0; c0 < a.nchunks; c0 += kCovLivePass) {
+      const int cn = min(kCovLivePass, a.nchunks - c0);
       // ---- chunk cull: out of range, or the whole box behind one FOV plane ------------------
       __syncthreads();
       for (int cb = 0; cb < cn; cb += kCovThreads) {
@@ -163,122 +329,78 @@ __global__ void __launch_bounds__(kCovThreads, kCovCtasPerSm) k_cov_scan(const _
       }
       __syncthreads();
 
-      // ---- surviving chunks in index order --------------------------------------------------
-      for (int w = 0; w < (cn + 31) / 32; ++w) {
-        uint32_t bits = s_live[w];
-        while (bits) {
-          const int c = c0 + w * 32 + (__ffs(bits) - 1);
-          bits &= bits - 1;
-          const long long base = (long long)c * kCovChunk;
+      // ---- surviving chunks in index order ---------------------------------------------------------------------------
+      const int nw = (cn + 31) / 32;
+      int w = 0;
+      uint32_t bits = s_live[0];
+      auto next_chunk = [&]() -> int {
+        while (bits == 0u) {
+          if (++w >= nw) return -1;
+          bits = s_live[w];
+        }
+        const int c = c0 + w * 32 + (__ffs(bits) - 1);
+        bits &= bits - 1;
+        return c;
+      };
+      for (;;) {
+        // kCovGroup live chunks per barrier: culling stays fine-grained, the barrier (and the batch-overflow check) is per group
+        int cs[kCovGroup];
+        float4 pts[kCovGroup][kCovPer];
+#pragma unroll
+        for (int g = 0; g < kCovGroup; ++g) {
+          cs[g] = next_chunk();
+          if (cs[g] >= 0) {
+            const long long base = (long long)cs[g] * kCovChunk;
+#pragma unroll
+            for (int u = 0; u < kCovPer; ++u) {
+              const long long gi = base + u * kCovThreads + tid;
+              if (gi < a.P) pts[g][u] = __ldg(a.points + gi);
+            }
+          }
+        }
+        if (cs[0] < 0) break;
+        // FOV test of the chunks' points; the ones inside join the batch by index.  Their projection (three divisions and a
+        // square root each) waits for the batch to be resolved, where it runs on all threads evenly: done here, the few
+        // threads whose point is inside kept the whole CTA waiting at the barrier below (27 % of the stall samples).
+#pragma unroll
+        for (int g = 0; g < kCovGroup; ++g) {
+          if (cs[g] < 0) continue;
           n_chunks += (tid == 0);
-
-          // phase 1: FOV + projection of 4 points per thread.  All per-point state lives in shared memory and the
-          // loops over a thread's points are not unrolled: registers buy occupancy here, the kernel waits on L2.
-          bool any = false;
-#pragma unroll 1
+          const long long base = (long long)cs[g] * kCovChunk;
+#pragma unroll
           for (int u = 0; u < kCovPer; ++u) {
-            const int slot = u * kCovThreads + tid;
-            int px = -1;
-            if (base + slot < a.P) {
-              const float4 q = __ldg(a.points + base + slot);
-              const double qx = (double)q.x, qy = (double)q.y, qz = (double)q.z;
-              if (inside_fov(rec, fc, qx, qy, qz)) {
-                // CameraModelProjection (hcplanner.cpp:1196-1211)
-                const double dx = qx - rec.px, dy = qy - rec.py, dz = qz - rec.pz;
-                const double dd = sqrt((dx * dx + dy * dy) + dz * dz);
-                const double pc0 = (ps.M[0] * dx + ps.M[1] * dy) + ps.M[2] * dz;
-                const double pc1 = (ps.M[3] * dx + ps.M[4] * dy) + ps.M[5] * dz;
-                const double pc2 = (ps.M[6] * dx + ps.M[7] * dy) + ps.M[8] * dz;
-                const double camX = cc.fx * pc1 / (1000.0 * pc0) - cc.ldc0;
-                const double camY = cc.fy * pc2 / (1000.0 * pc0) - cc.ldc1;
-                const int xi = floor_to_int(camX / cc.xRes), yi = floor_to_int(camY / cc.yRes);
-                n_proj++;
-                if (xi >= 0 && yi >= 0) {
-                  if (xi >= cc.xPixel || yi >= cc.yPixel) {
-                    n_out++;
-                  } else {
-                    px = xi * cc.yPixel + yi;
-                    any = true;
-                    s_dist[slot] = dd;
-                    int hb = (int)((px * 0x9E3779B1u) >> 21);
-                    for (;;) {
-                      const int old = atomicCAS(&t_key[hb], -1, px);
-                      if (old == -1 || old == px) break;
-                      hb = (hb + 1) & (kCovHash - 1);
-                    }
-                    s_next[slot] = (short)atomicExch(&t_head[hb], slot);
-                    s_bucket[slot] = (short)hb;
-                  }
-                }
-              }
-            }
-            s_pix[slot] = px;
-          }
-          if (!__syncthreads_or(any)) continue;
-
-          // phase 2: does the point hold its pixel at the time the reference scans it?
-          unsigned held = 0u, fresh = 0u;          // bit u: point u holds its pixel / the pixel was empty before this chunk
-#pragma unroll 1
-          for (int u = 0; u < kCovPer; ++u) {
-            const int slot = u * kCovThreads + tid;
-            const int px = s_pix[slot];
-            if (px < 0) continue;
-            const double dd = s_dist[slot];
-            const unsigned long long before = __ldcg(zdist + px);
-            if (before == kEmpty) fresh |= 1u << u;
-            if ((unsigned long long)__double_as_longlong(dd) < before) {
-              bool h = true;
-              int j = t_head[s_bucket[slot]];
-              n_slow += (j != slot || s_next[slot] >= 0);
-              for (; j >= 0; j = s_next[j])
-                if (j < slot && s_dist[j] <= dd) { h = false; break; }
-              if (h) held |= 1u << u;
+            const long long gi = base + u * kCovThreads + tid;
+            if (gi < a.P) {
+              const float4 q = pts[g][u];
+              if (inside_fov(rec, fc, (double)q.x, (double)q.y, (double)q.z)) s_idx[atomicAdd(&s_count, 1)] = (int)gi;   // < kCovBatch, see below
             }
           }
-          __syncthreads();
-          // phase 3: the pixel's new minimum
-#pragma unroll 1
-          for (int u = 0; u < kCovPer; ++u) {
-            const int slot = u * kCovThreads + tid;
-            if ((held >> u) & 1u) atomicMin(zdist + s_pix[slot], (unsigned long long)__double_as_longlong(s_dist[slot]));
-          }
-          __syncthreads();
-          // phase 4: occupant hand-over; displaced marks; the chain table is wiped
-#pragma unroll 1
-          for (int u = 0; u < kCovPer; ++u) {
-            const int slot = u * kCovThreads + tid;
-            const int px = s_pix[slot];
-            if (px < 0) continue;
-            const int hb = s_bucket[slot];
-            t_key[hb] = -1;
-            t_head[hb] = -1;
-            if (!((held >> u) & 1u)) continue;
-            const int me = (int)(base + slot);
-            if (__ldcg(zdist + px) == (unsigned long long)__double_as_longlong(s_dist[slot])) {
-              if ((fresh >> u) & 1u) {
-                touched[atomicAdd(&s_ntouched, 1)] = px;
-              } else if (drow) {
-                const int old = __ldcg(zidx + px);
-                atomicOr(drow + (old >> 5), 1u << (old & 31));
-              }
-              __stcg(zidx + px, me);
-            } else if (drow) {
-              atomicOr(drow + (me >> 5), 1u << (me & 31));
-            }
-          }
-          __syncthreads();      // the table is clean before the next chunk inserts
+        }
+        __syncthreads();
+        const int n = s_count;
+        if (n > kCovBatch - kCovGroup * kCovChunk) {       // the next group might not fit
+          spilled = true;
+          flush_zbuffer(n);
         }
       }
     }
 
-    // ---- occupants -> visible row; z-buffer slot back to 'empty' -----------------------------
+    // ---- end of the scan ----------------------------------------------------------------------
     __syncthreads();
-    const int nt = s_ntouched;
-    for (int t = tid; t < nt; t += kCovThreads) {
-      const int p = touched[t];
-      const int id = __ldcg(zidx + p);
-      atomicOr(vrow + (id >> 5), 1u << (id & 31));
-      __stcg(zdist + p, kEmpty);
+    const int n = s_count;
+    if (!spilled) {
+      if (n > 0) flush_local(n);
+    } else {
+      if (n > 0) flush_zbuffer(n);
+      // occupants -> visible row; z-buffer slot back to 'empty'
+      __syncthreads();
+      const int nt = s_ntouched;
+      for (int t = tid; t < nt; t += kCovThreads) {
+        const int p = touched[t];
+        const int id = __ldcg(zidx + p);
+        atomicOr(vrow + (id >> 5), 1u << (id & 31));
+        __stcg(zdist + p, kEmpty);
+      }
     }
   }
 
@@ -407,6 +529,7 @@ static int cov_ensure_device(fcvm_cov_handle* h) {
   CU(h->d_counters.reserve(4));
   CU(cudaMemset(h->d_counters.p, 0, 4 * sizeof(unsigned long long)));
   CU(h->d_next.reserve(1));
+  CU(cudaFuncSetAttribute(k_cov_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cov_smem_bytes()));   // 72 KB: opt-in, per device
   // z-buffer slots: one per resident CTA
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->prm.device);
@@ -469,7 +592,7 @@ static int cov_batch(fcvm_cov_handle* h, const double* pose5, int64_t mb, bool e
   a.counters = h->d_counters.p;
   const int grid = (int)std::min<int64_t>(mb, h->slots);
   CU(cudaEventRecord(h->ev0, s));
-  k_cov_scan<<<grid, kCovThreads, 0, s>>>(a);
+  k_cov_scan<<<grid, kCovThreads, cov_smem_bytes(), s>>>(a);
   CU(cudaGetLastError());
   CU(cudaEventRecord(h->evm, s));
   {
@@ -655,6 +778,7 @@ int64_t fcvm_cov_fetch_ids(fcvm_cov_t* h, int32_t* ids, int64_t cap) {
   return n;
 }
 
+int32_t fcvm_cov_chunk_points(void) { return kCovChunk; }
 int fcvm_cov_counters(fcvm_cov_t* h, int64_t* out6) {
   if (!h || !out6) return fail(FCVM_EINVAL, "bad arguments");
   for (int k = 0; k < 6; ++k) out6[k] = h->counters[k];

@@ -264,9 +264,12 @@ int64_t     fcvm_cov_evaluate(fcvm_cov_t* c, const double* pose5, int64_t m, dou
  * not know the size calls once with ids = NULL and then fetches): copies at most cap ids, returns their number */
 int64_t     fcvm_cov_fetch_ids(fcvm_cov_t* c, int32_t* ids, int64_t cap);
 /* counters since create: [0] pair tests (insideFOV) [1] projections [2] out-of-image projections (undefined
- * behaviour in the reference: unchecked Eigen index; skipped here) [3] kernels launched [4] 1024-point
- * chunks scanned (the rest were culled whole) [5] duplicate-pixel slow paths taken */
+ * behaviour in the reference: unchecked Eigen index; skipped here) [3] kernels launched [4] chunks of
+ * fcvm_cov_chunk_points() consecutive points scanned (the rest were culled whole) [5] points that shared their pixel with
+ * another point of the same batch */
 int         fcvm_cov_counters(fcvm_cov_t* c, int64_t* out6);
+/* points per culling chunk (one bounding box each) */
+int32_t     fcvm_cov_chunk_points(void);
 /* device time of all kernels of the most recent pinhole / evaluate call, in ms (CUDA events) */
 double      fcvm_cov_last_kernel_ms(fcvm_cov_t* c);
 /* of which k_cov_scan (FOV + projection + z-buffer), the dominant kernel */

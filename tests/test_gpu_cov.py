@@ -56,7 +56,8 @@ def test_shipped_trajectories_bit_exact(oracle_mod, scene):
     ctr = ce.counters()
     assert ctr[0] == 2 * len(z["poses"]) * len(zs["map_cloud"])
     assert ctr[1] == 2 * z["counters"][1] and ctr[2] == 2 * z["counters"][2]
-    assert ctr[4] < 0.5 * 2 * len(z["poses"]) * ((len(zs["map_cloud"]) + 1023) // 1024)    # the chunk cull does cull
+    cp = ce.chunk_points()
+    assert ctr[4] < 0.5 * 2 * len(z["poses"]) * ((len(zs["map_cloud"]) + cp - 1) // cp)    # the chunk cull does cull
 
 
 def test_dense_collisions_small_image(oracle_mod, small_plant):
