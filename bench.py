@@ -235,7 +235,7 @@ def pruning_full_leg(args, device, world=1, rank=0):
         return t1 - t0, t2 - t1
 
     first = run()                                   # device allocations, page-locking, NCCL channel set-up
-    init_s, upd_s = run()
+    init_s, upd_s = min((run() for _ in range(2)), key=sum)     # the host-serial parts pick up the noise of a shared box: best of two
     tm, st, c = vm.timers(), vm.comm_stats(), vm.counters()
     gi, gp, gx = vm.final_arrays()
     cov, con, cid = vm.cover_state()

@@ -40,6 +40,7 @@ struct EnvSettings {
   bool host_sums = false;   // FCVM_HOST_SUMS=1: pitch / yaw sums of getPose entirely on the host (the round-1 path; A/B and cross-check)
   bool own_sweep = false;   // FCVM_OWN_SWEEP=1: ownership by the ordered row sweep instead of the per-point arg-max (single GPU only)
   bool no_pfree = false;    // FCVM_NO_PFREE=1: k_eval marches the viewpoint-side half-ray even where the summed-area table certifies it free
+  bool plain_alloc = false; // FCVM_PLAIN_ALLOC=1: handle buffers from cudaMalloc instead of the stream-ordered pool (A/B)
   std::vector<int> pipe_fracs;   // FCVM_PIPE_FRACS=40,25,15,12,8: sub-batch sizes of the CSR path in per cent (tuning; the default is built in)
   EnvSettings() {
     if (const char* e = std::getenv("FCVM_PIPE_FRACS")) {
@@ -54,6 +55,7 @@ struct EnvSettings {
     if (const char* e = std::getenv("FCVM_HOST_SUMS")) host_sums = atoi(e) != 0;
     if (const char* e = std::getenv("FCVM_OWN_SWEEP")) own_sweep = atoi(e) != 0;
     if (const char* e = std::getenv("FCVM_NO_PFREE")) no_pfree = atoi(e) != 0;
+    if (const char* e = std::getenv("FCVM_PLAIN_ALLOC")) plain_alloc = atoi(e) != 0;
   }
 };
 inline EnvSettings env_now() { return EnvSettings(); }
@@ -183,7 +185,7 @@ struct DevBuf {
     if (n <= cap) return cudaSuccess;
     if (p) cudaFree(p);
     p = nullptr; cap = 0;
-    cudaError_t e = cudaMallocAsync((void**)&p, std::max<size_t>(n, 1) * sizeof(T), (cudaStream_t)0);
+    cudaError_t e = env().plain_alloc ? cudaErrorNotSupported : cudaMallocAsync((void**)&p, std::max<size_t>(n, 1) * sizeof(T), (cudaStream_t)0);
     if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)0);
     if (e != cudaSuccess) {                   // e.g. a device without memory pools: the plain allocator
       (void)cudaGetLastError();
