@@ -65,6 +65,9 @@ __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarr
 #ifndef EVAL_STATS
 #define EVAL_STATS 0          // 1 / 2 / 3: measurement builds that reuse the walk / trips counters of an E1 pass (profiles/march_stats.py)
 #endif
+#ifndef EVAL_HANDOFF
+#define EVAL_HANDOFF 1        // freshly prepared rays enter the march in registers, not through the shared-memory queue
+#endif
 #ifndef EVAL_STAGED_FOV
 #define EVAL_STAGED_FOV 1
 #endif
@@ -461,9 +464,8 @@ __global__ void __launch_bounds__(kWarps * 32, EVAL_MIN_CTAS) k_eval(const __gri
 
   // Pop `cnt` (<= 32) entries, run biInput for each on its own lane at full warp width, push the
   // rays that qualify for the fast path onto the ready queue; the rest are finished on the spot.
-  auto prepare = [&](int cnt) {
+  auto prepare = [&](int cnt, Cont& c) -> bool {
     bool queued = false;
-    Cont c;
     if (lane < cnt) {
       const QueueEntry qe = eq[en - cnt + lane];
       nrays++;
@@ -483,6 +485,10 @@ __global__ void __launch_bounds__(kWarps * 32, EVAL_MIN_CTAS) k_eval(const __gri
     if (queued && c.p.rem == 123456789) set_bit(c.vp, c.pt);   // timing experiment: rays dropped after prepare
     queued = false;
 #endif
+    return queued;
+  };
+  // prepared rays onto the ready queue
+  auto enqueue = [&](bool queued, const Cont& c) {
     const unsigned m = __ballot_sync(0xffffffffu, queued);
     if (queued && FCVM_CHECK(rn + __popc(m & lt_mask) < kReadyQ)) cont_store(rqd, rqi, rn + __popc(m & lt_mask), c);
     rn += __popc(m);
@@ -494,10 +500,10 @@ __global__ void __launch_bounds__(kWarps * 32, EVAL_MIN_CTAS) k_eval(const __gri
   // once, so the warp stays full while rays of very different lengths finish.  Unless draining,
   // the warp suspends (writes the rays in flight back as continuations) as soon as the queue is
   // empty and fewer than `kKeep` lanes are busy, and goes back to testing FOV pairs.
-  auto march = [&](bool drain) {
+  // EVAL_HANDOFF: the rays a warp has just prepared enter the march in the registers of their lanes (`active` / `c` on entry)
+  // instead of through the queue; the idle lanes take queued (suspended) rays as before.
+  auto march = [&](bool drain, bool active, Cont& c) {
     constexpr int kKeep = EVAL_KEEP;
-    Cont c;
-    bool active = false;
     unsigned tick = 0;
     int pkey = -1, nkey = -1;
     unsigned long long pword = 0ull, nword = 0ull;
@@ -731,15 +737,31 @@ __global__ void __launch_bounds__(kWarps * 32, EVAL_MIN_CTAS) k_eval(const __gri
       en += __popc(m);
       __syncwarp();
       if (en >= 32) {
-        prepare(32);
-        if (rn >= 32) march(false);
+        Cont c;
+        const bool queued = prepare(32, c);
+#if EVAL_HANDOFF
+        if (rn + __popc(__ballot_sync(0xffffffffu, queued)) >= 32) march(false, queued, c);
+        else enqueue(queued, c);
+#else
+        enqueue(queued, c);
+        if (rn >= 32) march(false, false, c);
+#endif
         load_rec();   // re-read instead of keeping 30 registers live across the ray phases
       }
     }
    }
   }
-  if (en > 0) prepare(en);   // en < 32 here
-  march(true);
+  {
+    Cont c;
+    bool queued = false;
+    if (en > 0) queued = prepare(en, c);   // en < 32 here
+#if EVAL_HANDOFF
+    march(true, queued, c);
+#else
+    enqueue(queued, c);
+    march(true, false, c);
+#endif
+  }
 
   // ---- counters -------------------------------------------------------------------------
   if (a.counters) {
