@@ -19,10 +19,10 @@ namespace fcvm {
 #define EVAL_KEEP 28          // march: suspend back to the FOV phase when fewer lanes than this are busy and the queue is empty
 #endif
 #ifndef EVAL_UNROLL
-#define EVAL_UNROLL 1         // march: biNextId calls per refill / suspend check (2 measured equal on E1, slower on E2 / E4: code size)
+#define EVAL_UNROLL 2         // march: biNextId calls per refill / suspend check (with the hand-off build: 1 -> 24.1 ms per E1 step, 2 -> 23.1, 4 -> 22.9)
 #endif
 #ifndef EVAL_QUERY_PERIOD
-#define EVAL_QUERY_PERIOD 4   // march: every this many rounds (of EVAL_UNROLL steps) the rays in flight test the box between their fronts (power of 2)
+#define EVAL_QUERY_PERIOD 2   // march: every this many rounds (of EVAL_UNROLL steps) the rays in flight test the box between their fronts (power of 2)
 #endif
 #ifndef EVAL_RCP_TABLE
 #define EVAL_RCP_TABLE 1024   // reciprocals 1/k, k < this, for the DDA set-up of the fast path (half-rays of more voxel steps take the literal path)
