@@ -574,6 +574,7 @@ static int cov_batch(fcvm_cov_handle* h, const double* pose5, int64_t mb, bool e
   a.fov.md2_hi = md2 * (1.0 + 1e-12);
   a.fov.plane_eps = 1e-10 * std::max(h->prm.max_dist, 1.0);
   a.fov.visible_range = h->prm.visible_range;
+  a.fov.vr2_lo = a.fov.vr2_hi = h->prm.visible_range * h->prm.visible_range;      // (E1 only; unused here)
   a.cam = h->cc;
   a.points = h->d_points.p;
   a.P = h->P;

@@ -337,6 +337,7 @@ struct FovConst {
   double md2_lo, md2_hi;  // max_dist^2 * (1 -/+ 1e-12): outside this band the sqrt is not needed
   double plane_eps;       // |d.n| below this (unnormalised) -> take the exact normalised path
   double visible_range;   // viewpoint_manager/visible_range (E1 only)
+  double vr2_lo, vr2_hi;  // visible_range^2 * (1 -/+ 1e-12): outside this band `ray_length <= visible_range` needs no sqrt
 };
 
 // PerceptionUtils::insideFOV (perception_utils.cpp:115-124), Eigen order:

@@ -342,6 +342,9 @@ static void fill_fov_const(const fcvm_handle* h, FovConst& f) {
   f.md2_hi = md2 * (1.0 + 1e-12);
   f.plane_eps = 1e-10 * std::max(h->prm.max_dist, 1.0);
   f.visible_range = h->prm.visible_range;
+  const double vr2 = h->prm.visible_range * h->prm.visible_range;
+  f.vr2_lo = vr2 * (1.0 - 1e-12);
+  f.vr2_hi = vr2 * (1.0 + 1e-12);
 }
 
 // choose the CTA decomposition: tiles of points x chunks of viewpoints, aiming at >= 4 waves of

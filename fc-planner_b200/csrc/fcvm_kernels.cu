@@ -68,6 +68,9 @@ __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarr
 #ifndef EVAL_HANDOFF
 #define EVAL_HANDOFF 1        // freshly prepared rays enter the march in registers, not through the shared-memory queue
 #endif
+#ifndef EVAL_RANGE_SQ
+#define EVAL_RANGE_SQ 1         // E1's `ray_length <= visible_range` from the squared length outside a rounding band
+#endif
 #ifndef EVAL_STAGED_FOV
 #define EVAL_STAGED_FOV 1
 #endif
@@ -244,7 +247,14 @@ __device__ __forceinline__ bool prepare_ray(const GridDesc& g, const FovConst& f
   if (STAGE == 1) {
     // ray_length <= visible_range (viewpoint_manager.cpp:402-403), tested by the reference after the cast
     const double dx = qx - vx, dy = qy - vy, dz = qz - vz;
+#if EVAL_RANGE_SQ
+    // sqrt is monotone and correctly rounded: outside a 1e-12 relative band around visible_range^2 the squared length decides
+    // (NaN fails both compares and takes the literal test, which it fails as in the reference)
+    const double n2 = (dx * dx + dy * dy) + dz * dz;
+    if (n2 < fc.vr2_lo || (!(n2 > fc.vr2_hi) && sqrt(n2) <= fc.visible_range)) flags |= CONT_INRANGE;
+#else
     if (sqrt((dx * dx + dy * dy) + dz * dz) <= fc.visible_range) flags |= CONT_INRANGE;
+#endif
   } else {
     flags |= CONT_INRANGE;
   }

@@ -49,6 +49,37 @@ def test_evaluator_masks_bit_exact(small_plant, oracle_mod, stage):
     assert c1[4] == 0 and octr[4] == 0
 
 
+def test_e1_visible_range_band(small_plant, oracle_mod):
+    """E1's `ray_length <= visible_range` is decided from the squared length outside a 1e-12 band around visible_range^2 and by
+    the literal sqrt inside it: viewpoints placed at visible_range (1 + k 2e-14) from a point they see, k = -20 .. 20."""
+    vr = 6.0
+    vm, orc, prm = _mk(small_plant, oracle_mod, visible_range=vr)
+    base = _perturbed_poses(small_plant, n=120, seed=5)
+    _, rows0 = vm.evaluate(1, base)                       # with the short range: who sees what, roughly
+    wide_vm, _, _ = _mk(small_plant, oracle_mod)          # default range (= max_dist): the visible sets to pick targets from
+    cnt_w, rows_w = wide_vm.evaluate(1, base)
+    pts = small_plant["points"].astype(np.float64)
+    poses, in_band = [], 0
+    for i in np.flatnonzero(cnt_w > 0)[:40]:
+        seen = np.flatnonzero(np.unpackbits(rows_w[i].view(np.uint8), bitorder="little"))
+        j = int(seen[len(seen) // 2])
+        d = pts[j] - base[i, :3]
+        u = d / np.linalg.norm(d)
+        for k in range(-20, 21):
+            p = base[i].copy()
+            p[:3] = pts[j] - u * (vr * (1.0 + k * 2e-14))
+            poses.append(p)
+            dd = pts[j] - p[:3]
+            n2 = (dd[0] * dd[0] + dd[1] * dd[1]) + dd[2] * dd[2]
+            in_band += abs(n2 / (vr * vr) - 1.0) < 1e-12
+    poses = np.array(poses)
+    assert in_band > 200                                   # the literal path is exercised
+    cnt, rows = vm.evaluate(1, poses)
+    ocnt, orows, _ = orc.evaluate(1, poses)
+    assert np.array_equal(rows[:, :orows.shape[1]], orows) and np.array_equal(cnt, ocnt)
+    assert 0 < cnt.sum()
+
+
 @pytest.mark.parametrize("n_points,order", [(4999, "shuffled"), (1023, "shuffled"), (4133, "sorted_z"), (33, "as_is")])
 def test_culls_exact_for_any_point_order(small_plant, oracle_mod, n_points, order):
     """The tile- and group-level box culls (k_eval: one viewpoint / one 32-point group per lane) must drop nothing the
