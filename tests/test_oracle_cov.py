@@ -87,6 +87,33 @@ def test_oracle_reproduces_the_shipped_reference_output(oracle_mod, scene):
     assert len(rids) > 20_000                                      # not vacuous
 
 
+def test_residue_is_the_size_of_the_pose_printing_error(oracle_mod):
+    """The 15 ids (MBS) on which the oracle and the reference's shipped output differ: the reference evaluated the poses it had
+    in memory and printed them with 6 decimals; moving every pose component by a random amount within that printing error
+    (+-5e-7) changes the oracle's own groups by about as many ids, and hits ids of the residue
+    (profiles/cov_pose_rounding_sensitivity.py runs more trials and the other scenes)."""
+    prm, zs = load_golden("mbs")
+    z = np.load(os.path.join(GOLDEN, "cov_mbs.npz"))
+
+    def groups(poses):
+        ce = _cov(oracle_mod, launch_params("mbs"), launch_camera("mbs"))
+        ce.setCloud(zs["map_cloud"])
+        _, offs, ids, _ = ce.CoverageEvaluation(poses)
+        return {(k, int(i)) for k in range(len(poses)) for i in ids[offs[k]:offs[k + 1]]}
+
+    base = groups(z["poses"])
+    ref = {(k, int(i)) for k in range(len(z["poses"])) for i in z["ref_ids"][z["ref_offsets"][k]:z["ref_offsets"][k + 1]]}
+    residue = base ^ ref
+    assert len(residue) == 15
+    rng = np.random.default_rng(0)
+    flips, sizes = set(), []
+    for _ in range(3):
+        d = base ^ groups(z["poses"] + rng.uniform(-5e-7, 5e-7, z["poses"].shape))
+        sizes.append(len(d)); flips |= d
+    assert 3 <= min(sizes) and max(sizes) <= 3 * len(residue)     # same order of magnitude as the residue
+    assert len(residue & flips) >= 3                               # and the very same (pose, point) pairs are among the flips
+
+
 def test_pinhole_golden_and_threads(oracle_mod):
     prm, zs = load_golden("pipe")
     z = np.load(os.path.join(GOLDEN, "cov_pipe.npz"))
