@@ -71,6 +71,9 @@ __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarr
 #ifndef EVAL_RANGE_SQ
 #define EVAL_RANGE_SQ 1         // E1's `ray_length <= visible_range` from the squared length outside a rounding band
 #endif
+#ifndef EVAL_FAST_WALK
+#define EVAL_FAST_WALK 1         // E2 / E4: the surface-offset walk on the fast marcher where that is legal
+#endif
 #ifndef EVAL_STAGED_FOV
 #define EVAL_STAGED_FOV 1
 #endif
@@ -266,7 +269,46 @@ __device__ __forceinline__ bool prepare_ray(const GridDesc& g, const FovConst& f
   if (STAGE == 2 || STAGE == 4) {
     {
       const double2 pe0 = __ldg(reinterpret_cast<const double2*>(pt_ends + gp)), pe1 = __ldg(reinterpret_cast<const double2*>(pt_ends + gp) + 1);
-      offset_target(g, qx, qy, qz, vx, vy, vz, bx, by, bz, st, g_rcp, kRcpN, pe0.x, pe0.y, pe1.x, sxf, syf, szf);
+      bool walked = false;
+#if EVAL_FAST_WALK
+      // The surface-offset walk (point -> viewpoint, stop at the 2nd free voxel) on the fast marcher: map indices tracked
+      // directly, steps counted down, unchecked brick fetch.  Legal when both end voxels are inside the map, the map-index
+      // conversion is a pure shift between them, every |delta| is below the reciprocal table's size and the point lies strictly
+      // inside its voxel on every moving axis: such a marcher arrives after exactly |dx| + |dy| + |dz| steps and never leaves
+      // the box of its end voxels (see the certificates below).  Everything else takes the literal walk (offset_target).
+      if (((fabs(pe0.x) + fabs(pe0.y)) + fabs(pe1.x)) + ((fabs(sxf) + fabs(syf)) + fabs(szf)) < 1.0e9) {
+        const int wx = (int)floor(pe0.x), wy = (int)floor(pe0.y), wz = (int)floor(pe1.x);
+        const int ux = (int)floor(sxf), uy = (int)floor(syf), uz = (int)floor(szf);
+        const int ddx = ux - wx, ddy = uy - wy, ddz = uz - wz;
+        const int wix = to_map_index(wx, g.offx), wiy = to_map_index(wy, g.offy), wiz = to_map_index(wz, g.offz);
+        const int uix = to_map_index(ux, g.offx), uiy = to_map_index(uy, g.offy), uiz = to_map_index(uz, g.offz);
+        const int in_bits = (int)pe1.y | (ddx == 0 ? 1 : 0) | (ddy == 0 ? 2 : 0) | (ddz == 0 ? 4 : 0);
+        if (in_bits == 7 && (unsigned)wix < (unsigned)g.nx && (unsigned)wiy < (unsigned)g.ny && (unsigned)wiz < (unsigned)g.nz &&
+            (unsigned)uix < (unsigned)g.nx && (unsigned)uiy < (unsigned)g.ny && (unsigned)uiz < (unsigned)g.nz &&
+            uix - wix == ddx && uiy - wiy == ddy && uiz - wiz == ddz && abs(ddx) < kRcpN && abs(ddy) < kRcpN && abs(ddz) < kRcpN) {
+          Side w;
+          w.ix = wix; w.iy = wiy; w.iz = wiz;
+          w.rem = abs(ddx) + abs(ddy) + abs(ddz);
+          w.sx = d_signum(ddx); w.sy = d_signum(ddy); w.sz = d_signum(ddz);
+          w.tmx = d_intbound_i(pe0.x, ddx, g_rcp); w.tmy = d_intbound_i(pe0.y, ddy, g_rcp); w.tmz = d_intbound_i(pe1.x, ddz, g_rcp);
+          w.tdx = t_delta(ddx); w.tdy = t_delta(ddy); w.tdz = t_delta(ddz);
+          int key = -1, count = 0, tix, tiy, tiz;
+          unsigned long long word = 0ull;
+          for (;;) {
+            tix = w.ix; tiy = w.iy; tiz = w.iz;          // nextId reports the voxel before stepping
+            if (w.rem == 0) break;                        // ... and returns false at the end voxel
+            w.step_if(true);
+            st.lookups += 1; st.walk += 1;
+            if (occ_fast(g, tix, tiy, tiz, key, word) && ++count == 2) break;
+          }
+          bx = ((double)tix + 0.5) * res + g.orgx;       // indexToPos_hc (sdf_map.h:244-247)
+          by = ((double)tiy + 0.5) * res + g.orgy;
+          bz = ((double)tiz + 0.5) * res + g.orgz;
+          walked = true;
+        }
+      }
+#endif
+      if (!walked) offset_target(g, qx, qy, qz, vx, vy, vz, bx, by, bz, st, g_rcp, kRcpN, pe0.x, pe0.y, pe1.x, sxf, syf, szf);
     }
     // the target is a voxel centre: finite, and strictly inside its voxel on every axis unless rounding says otherwise
     exf = div_exact(bx, res, g.res_rcp); eyf = div_exact(by, res, g.res_rcp); ezf = div_exact(bz, res, g.res_rcp);

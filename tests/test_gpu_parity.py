@@ -268,6 +268,40 @@ def test_lattice_aligned_viewpoints(small_plant, oracle_mod):
     print(f"lattice-aligned: {clean} clean viewpoints bit-exact, {capped} with capped rays (oracle), gpu cap trips {gpu_trips}")
 
 
+def test_offset_walk_with_lattice_aligned_and_border_points(oracle_mod):
+    """E2 / E4's surface-offset walk starts at the model point: points exactly on voxel-lattice planes (the fast walk must not
+    take them: the literal marcher decides), points in general position, and viewpoints outside the map, on a 0.5 m grid
+    where the lattice is exact in float32.  Masks, counts and the walk's look-up counter against the oracle."""
+    from fc_planner_b200 import launch_params, scenes
+    from fc_planner_b200.manager import ViewpointManager
+    pts, nrm, prims = scenes.make_plant(n_points=4000, scale=0.4, seed=2)
+    pts = pts.copy()
+    pts[:1200] = np.round(pts[:1200] / 0.5) * 0.5                # on lattice corners / edges / faces
+    pts[1200:1800, 0] = np.round(pts[1200:1800, 0] / 0.5) * 0.5  # on x planes only
+    prm = launch_params("mbs", z_ground=0, seed=7, resolution=0.5)
+    vps = scenes.plant_viewpoints(pts, nrm, prims, 200, prm.viewpoints_distance, seed=1)
+    poses = scenes.poses_from_viewpoints(vps)
+    rng = np.random.default_rng(9)
+    poses[:, :3] += rng.normal(0, 0.3, (len(poses), 3))
+    poses[:8, :3] += 60.0                                        # outside the map: the walk's end voxel is not in the grid
+    vm, orc = ViewpointManager(prm), oracle_mod.Oracle(prm)
+    for m in (vm, orc):
+        m.setMapPointCloud(pts); m.setModel(pts); m.setNormals(pts.astype(np.float64), nrm)
+    _, e1 = vm.evaluate(1, poses)
+    for stage, restrict in ((4, None), (2, e1)):
+        c0 = vm.counters()
+        cnt, rows = vm.evaluate(stage, poses, restrict_rows=restrict)
+        c1 = vm.counters() - c0
+        ocnt, orows, octr = orc.evaluate(stage, poses, restrict_rows=None if restrict is None else restrict[:, :(orc.P + 31) // 32])
+        W = orows.shape[1]
+        ok = octr[4] == 0                                         # no capped march on the oracle's side: everything must match
+        assert c1[4] == octr[4]
+        if ok:
+            assert np.array_equal(rows[:, :W], orows) and np.array_equal(cnt, ocnt), stage
+            assert c1[1] == octr[1] and c1[2] == octr[2] and c1[3] == octr[3], stage
+        assert cnt.sum() > 500
+
+
 def test_safety_check_batch_matches_oracle(small_plant, oracle_mod):
     """viewpointSafetyCheck on the device (k_safety): verdicts and the number of safety_check probes (early exit
     included) against the oracle, for positions near, inside, far from and outside the map, with and without ground."""
