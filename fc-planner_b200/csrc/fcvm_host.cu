@@ -455,6 +455,20 @@ static int64_t chunk_rows(const fcvm_handle* h, int64_t n, bool manager = false)
 // buffer (must hold n x W words).
 // gather_rows (sharded runs only): true = every rank ends up with all rows and counts (the evaluator-level API); false = rows
 // and counts of the other ranks' blocks stay zero (the manager: nothing it does needs foreign rows, see ownership()).
+// f(j) for every set bit j of a bitset row, ascending
+template <class F>
+static void for_each_bit(const uint32_t* row, int64_t words, F&& f) {
+  for (int64_t w = 0; w < words; ++w) {
+    uint32_t x = row[w];
+    while (x) {
+      const int b = __builtin_ctz(x);
+      x &= x - 1;
+      f((int)(w * 32 + b));
+    }
+  }
+}
+
+constexpr int64_t kSmallRowsWords = 16384;      // 64 KB of bitset rows: below this a batch is summed / listed on the host (one wait)
 static int eval_batch(fcvm_handle* h, int stage, const VpRec* recs, int64_t n, const uint32_t* restrict_host, uint32_t* rows_out,
                       int* count_out, DevBuf<uint32_t>& d_rows, bool restrict_resident = false, CsrOut* csr = nullptr, bool gather_rows = true) {
   int rc = ensure_device(h);
@@ -649,6 +663,33 @@ static int eval_batch(fcvm_handle* h, int stage, const VpRec* recs, int64_t n, c
   h->counters[5] += 1;
   const int64_t c_lo = csr ? std::max<long long>(0, csr->lo) : 0, c_hi = csr ? (csr->hi < 0 ? n : std::min<long long>(n, csr->hi)) : 0;
   const int64_t c_n = std::max<int64_t>(0, c_hi - c_lo);
+  if (csr && !rows_out && !sharded && n * W <= kSmallRowsWords) {
+    // a small batch (E3 of a handful of gravitated viewpoints): the rows themselves go to the host with the counts, one wait
+    // instead of "offsets, wait, lists, wait", and the index lists are read off the rows there
+    CU(h->h_rows.reserve((size_t)(n * W)));
+    CU(cudaMemcpyAsync(h->h_rows.p, d_rows.p, (size_t)(n * W) * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+    if (count_out) CU(cudaMemcpyAsync(count_out, h->d_count.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    rc = fetch_counters(h);   // synchronises the stream
+    if (rc) return rc;
+    h->h_rows.note_use();
+    csr->offs.assign((size_t)c_n + 1, 0);
+    long long total = 0;
+    for (int64_t i = 0; i < c_n; ++i) {
+      const uint32_t* row = h->h_rows.p + (c_lo + i) * W;
+      for (int64_t w = 0; w < W; ++w) total += __builtin_popcount(row[w]);
+      csr->offs[(size_t)i + 1] = total;
+    }
+    CU(h->h_indices.reserve((size_t)std::max<long long>(total, 1)));
+    uint32_t* out = h->h_indices.p;
+    for (int64_t i = 0; i < c_n; ++i) for_each_bit(h->h_rows.p + (c_lo + i) * W, W, [&](int j) { *out++ = (uint32_t)j; });
+    csr->idx = h->h_indices.p;
+    if (h->timed) {
+      float ms = 0.f;
+      CU(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+      h->last_kernel_ms = ms;
+    }
+    return FCVM_OK;
+  }
   if (csr) {
     CU(h->d_offsets.reserve((size_t)c_n + 1));
     CU(h->h_offsets.reserve((size_t)c_n + 1));
@@ -807,18 +848,6 @@ static void record(fcvm_handle* h, int stage, int vp_id, const Pose5& pose, cons
   h->trace.push_back(std::move(e));
 }
 
-template <class F>
-static void for_each_bit(const uint32_t* row, int64_t words, F&& f) {
-  for (int64_t w = 0; w < words; ++w) {
-    uint32_t x = row[w];
-    while (x) {
-      const int b = __builtin_ctz(x);
-      x &= x - 1;
-      f((int)(w * 32 + b));
-    }
-  }
-}
-
 // ------------------------------------------------------------------------------------------------
 // viewpointSafetyCheck / nearCheck (viewpoint_manager.cpp:889-946)
 // ------------------------------------------------------------------------------------------------
@@ -964,6 +993,30 @@ static int e1_with_pose_sums(fcvm_handle* h, int64_t lo, int64_t hi, const std::
   const int64_t W = h->W, ln = hi - lo;
   if (ln <= 0) return FCVM_OK;
   int rc;
+  if (ln * W <= kSmallRowsWords && !h->host_sums) {
+    // A small batch (the <= 100 candidates of an uncovered-area round on the shipped scenes): the device pipeline's four
+    // waits (offsets, flag counts, flagged arguments out and back, sums) cost more than its work.  The rows themselves go to
+    // the host - at most 64 KB, one wait - and the sums are the reference's own loop there (host_pose_sums, every ray through
+    // libm: identical by construction to what the device pipeline reproduces).
+    rc = launch_stage(h, FCVM_STAGE_E1, h->d_recs.p + lo, ln, h->d_rows1.p + lo * W, nullptr, h->stream, true);
+    if (rc) return rc;
+    CU(h->h_rows.reserve((size_t)(ln * W)));
+    CU(cudaMemcpyAsync(h->h_rows.p, h->d_rows1.p + lo * W, (size_t)(ln * W) * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    h->h_rows.note_use();
+    Stopwatch sw(h->t_sums);
+    const float* Mh = h->model.data();
+    pfor(h, ln, 8, [&](int64_t i) {
+      const uint32_t* row = h->h_rows.p + i * W;
+      thread_local std::vector<uint32_t> idx;
+      idx.clear();
+      for_each_bit(row, W, [&](int j) { idx.push_back((uint32_t)j); });
+      free_num[(size_t)(lo + i)] = (long long)idx.size();
+      if (!idx.empty())
+        host_pose_sums(Mh, seed[(size_t)(lo + i)], idx.data(), (long long)idx.size(), sums[(size_t)2 * (lo + i)], sums[(size_t)2 * (lo + i) + 1]);
+    });
+    return FCVM_OK;
+  }
   const int levels = std::max(1, h->pri_lo - h->pri_hi);       // priority levels below the pose-sum pipeline's
   const int want = env().pipe_subs ? env().pipe_subs : (int)std::min<int64_t>(std::min(8, levels), std::max<int64_t>(1, ln / 6144));
   const int64_t sub = std::max<int64_t>(std::min<int64_t>(kPipeMinRows, ln), (ln + want - 1) / want);
