@@ -163,6 +163,17 @@ struct Stopwatch {
 
 // Device buffer that only grows.  Owns its allocation (freed by the destructor on the device that was current when it
 // was made: every public entry point selects the handle's device first); movable, not copyable.
+// the library's allocation stream of the current device (see DevBuf::reserve); nullptr if it cannot be created
+inline cudaStream_t alloc_stream() {
+  static std::mutex m;
+  static cudaStream_t streams[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) { (void)cudaGetLastError(); return nullptr; }
+  std::lock_guard<std::mutex> g(m);
+  if (!streams[dev] && cudaStreamCreateWithFlags(&streams[dev], cudaStreamNonBlocking) != cudaSuccess) { (void)cudaGetLastError(); streams[dev] = nullptr; }
+  return streams[dev];
+}
+
 template <class T>
 struct DevBuf {
   T* p = nullptr;
@@ -178,15 +189,19 @@ struct DevBuf {
   ~DevBuf() { free(); }
   // From the device's default stream-ordered pool (its release threshold is raised in ensure_device, so it keeps what is
   // freed): a first-time buffer is carved out of memory the pool already owns instead of costing a driver allocation
-  // (~0.1-0.3 ms each, ~35 of them on a first updateViewpoints).  The allocation is made on the legacy default stream and
-  // that stream is synchronised (nothing else is ever queued on it), so the buffer is usable on every stream at once;
-  // cudaFree of such a pointer synchronises the device like before.
+  // (~0.1-0.3 ms each, ~35 of them on a first updateViewpoints).  The allocation is made on a private stream of the library
+  // (one per device, never used for anything else) and that stream is synchronised, so the buffer is usable on every stream
+  // at once and nothing of the host application is waited for; cudaFree of such a pointer synchronises the device like before.
   cudaError_t reserve(size_t n) {
     if (n <= cap) return cudaSuccess;
     if (p) cudaFree(p);
     p = nullptr; cap = 0;
-    cudaError_t e = env().plain_alloc ? cudaErrorNotSupported : cudaMallocAsync((void**)&p, std::max<size_t>(n, 1) * sizeof(T), (cudaStream_t)0);
-    if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)0);
+    cudaError_t e = cudaErrorNotSupported;
+    cudaStream_t as = env().plain_alloc ? nullptr : alloc_stream();
+    if (as) {
+      e = cudaMallocAsync((void**)&p, std::max<size_t>(n, 1) * sizeof(T), as);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(as);
+    }
     if (e != cudaSuccess) {                   // e.g. a device without memory pools: the plain allocator
       (void)cudaGetLastError();
       p = nullptr;
