@@ -981,41 +981,23 @@ __global__ void __launch_bounds__(128) k_own_sweep(const uint32_t* __restrict__ 
 // first row that sees a point is its local winner, so a thread only has to remember which of its 32 points are taken.
 // The thread IS a 32-point word column: consecutive lanes read consecutive words of a row (128-byte coalesced loads,
 // every row word read exactly once), stores happen once per point.
-// Round 2, late: the schedule is cut into chunks of kOwnChunk rows (grid.y); a thread owns one 32-point column of one chunk.
-// The rows arrive sorted by key, descending, so the first row of a chunk that sees a point holds that chunk's best key for it,
-// and the best over all rows is the atomic MAX of the chunks' bests.  One thread per column over the whole schedule (round 1 /
-// early round 2) was a chain of 200 000 / 8 dependent loads at configs[4] on 31 250 threads: 40 ms that setInitViewpoints
-// left queued for updateViewpoints to wait on.  A chunk first drops the points whose key already beats its first (largest)
-// one - chunks are scheduled roughly in order, so the later ones mostly find nothing left to do.
-constexpr int kOwnChunk = 4096;
 __global__ void __launch_bounds__(256) k_own_best(const uint32_t* __restrict__ rows, long long words, const int4* __restrict__ sched, int nsched,
                                                   long long P, unsigned long long* __restrict__ best) {
   const long long col = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (col * 32 >= P) return;
-  const int t_lo = (int)blockIdx.y * kOwnChunk, t_hi = min(nsched, t_lo + kOwnChunk);
-  if (t_lo >= t_hi) return;
   uint32_t taken = 0u;
-  if (blockIdx.y > 0) {
-    const int4 s0 = __ldg(sched + t_lo);
-    const unsigned long long k0 = ((unsigned long long)(uint32_t)s0.y << 32) | (unsigned long long)(uint32_t)s0.z;
-    for (int bit = 0; bit < 32; ++bit) {
-      const long long j = col * 32 + bit;
-      if (j >= P || __ldcg(best + j) >= k0) taken |= 1u << bit;      // (a stale read only means less skipping)
-    }
-    if (taken == 0xffffffffu) return;
-  }
   constexpr int kAhead = 8;
-  for (int t0 = t_lo; t0 < t_hi; t0 += kAhead) {
+  for (int t0 = 0; t0 < nsched; t0 += kAhead) {
     int4 sv[kAhead];
     uint32_t wv[kAhead];
 #pragma unroll
     for (int u = 0; u < kAhead; ++u) {
-      sv[u] = __ldg(sched + min(t0 + u, t_hi - 1));
+      sv[u] = __ldg(sched + min(t0 + u, nsched - 1));
       wv[u] = __ldg(rows + (long long)sv[u].x * words + col);
     }
 #pragma unroll
     for (int u = 0; u < kAhead; ++u) {
-      if (t0 + u >= t_hi) break;
+      if (t0 + u >= nsched) break;
       uint32_t w = wv[u] & ~taken;
       if (w == 0u) continue;
       taken |= w;
@@ -1024,7 +1006,7 @@ __global__ void __launch_bounds__(256) k_own_best(const uint32_t* __restrict__ r
         const int bit = __ffs(w) - 1;
         w &= w - 1;
         const long long j = col * 32 + bit;
-        if (j < P) atomicMax(best + j, key);
+        if (j < P) best[j] = key;
       }
     }
     if (taken == 0xffffffffu) break;
@@ -1144,9 +1126,7 @@ cudaError_t launch_own_sweep(const uint32_t* rows, long long words, const int4* 
 cudaError_t launch_own_best(const uint32_t* rows, long long words, const int4* sched, int nsched, long long P, unsigned long long* best, cudaStream_t s) {
   if (nsched <= 0 || P <= 0) return cudaSuccess;
   const long long cols = (P + 31) / 32;
-  const dim3 grid((unsigned)((cols + 255) / 256), (unsigned)((nsched + kOwnChunk - 1) / kOwnChunk));     // nsched < 2^31 / kOwnChunk rows: grid.y <= 65535 up to 2.7e8 rows
-  if (grid.y > 65535u) return cudaErrorInvalidConfiguration;
-  k_own_best<<<grid, 256, 0, s>>>(rows, words, sched, nsched, P, best);
+  k_own_best<<<(unsigned)((cols + 255) / 256), 256, 0, s>>>(rows, words, sched, nsched, P, best);
   return cudaGetLastError();
 }
 
