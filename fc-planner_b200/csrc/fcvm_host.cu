@@ -2083,6 +2083,17 @@ int fcvm_set_model(fcvm_t* h, const float* xyz, int64_t n) {   // cpp:91-108
     rc = cover_reset(h);
     if (rc) return rc;
   }
+  if (n <= (1 << 16)) {
+    // The page-locked staging a first updateViewpoints would otherwise allocate call by call (one candidate viewpoint per model
+    // point is what the reference generates, cpp:145-171): cudaMallocHost costs 0.1 - 3 ms apiece, tens of ms on a loaded host.
+    // Reserved here, where the model size becomes known; larger models allocate on demand (their first call is dominated by work).
+    const size_t v = (size_t)n + 128;
+    CU(h->h_recs.reserve(v)); CU(h->h_aux.reserve(v)); CU(h->h_count.reserve(v)); CU(h->h_offsets.reserve(v + 16));
+    CU(h->h_own_ids.reserve(v)); CU(h->h_own_sched.reserve(v)); CU(h->h_sums.reserve(2 * v)); CU(h->h_nflag.reserve(2));
+    CU(h->h_rows.reserve((size_t)kSmallRowsWords));
+    CU(h->h_indices.reserve((size_t)64 * v));
+    for (int q = 0; q < fcvm_handle::kRing; ++q) CU(h->h_ring[q].reserve((size_t)16 * v));
+  }
   h->model_flag = true;
   return FCVM_OK;
 }
