@@ -46,8 +46,12 @@ class Exchange:
     """`fcvm_comm_fn` over torch.distributed: op 0 = in-place all-gather of `world` equal byte slices, op 1 = in-place
     all-reduce MAX over int64 values."""
 
-    def __init__(self, group=None, host_buffers=None):
+    def __init__(self, group=None, host_buffers=None, staged=False):
         self.group = group
+        # staged=True: the library's DEVICE pointers with a CPU backend (gloo): every collective is staged through host memory.
+        # Slow by design - it exists so that the sharded path can be verified with several ranks on ONE GPU
+        # (tests/test_multi_gpu.py::test_sharded_update_on_one_gpu), where NCCL refuses two ranks on the same device.
+        self.staged = staged
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
         self.on_device = dist.get_backend(group) == "nccl"
@@ -67,6 +71,18 @@ class Exchange:
             mine = whole[self.rank * bytes_per_rank:(self.rank + 1) * bytes_per_rank]
             with torch.cuda.stream(self._stream(stream)):
                 dist.all_gather_into_tensor(whole, mine, group=self.group)   # in place: slice r of the output is rank r's input
+        elif self.staged:
+            st = self._stream(stream)
+            whole = torch.as_tensor(_DevBuf(buf_ptr, total), device=torch.device("cuda", torch.cuda.current_device()))
+            with torch.cuda.stream(st):
+                host = whole.cpu()                       # ordered after everything the library has queued on its stream
+            st.synchronize()
+            mine = host[self.rank * bytes_per_rank:(self.rank + 1) * bytes_per_rank].clone()
+            parts = [torch.empty_like(mine) for _ in range(self.world)]
+            dist.all_gather(parts, mine, group=self.group)
+            with torch.cuda.stream(st):
+                whole.copy_(torch.cat(parts))
+            st.synchronize()
         else:
             host = np.ctypeslib.as_array(ctypes.cast(buf_ptr, ctypes.POINTER(ctypes.c_uint8)), shape=(total,))
             whole = torch.from_numpy(host)
@@ -84,6 +100,16 @@ class Exchange:
             t = torch.as_tensor(_DevBuf(buf_ptr, count, "<i8"), device=torch.device("cuda", torch.cuda.current_device()))
             with torch.cuda.stream(self._stream(stream)):
                 dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+        elif self.staged:
+            st = self._stream(stream)
+            t = torch.as_tensor(_DevBuf(buf_ptr, count, "<i8"), device=torch.device("cuda", torch.cuda.current_device()))
+            with torch.cuda.stream(st):
+                host = t.cpu()
+            st.synchronize()
+            dist.all_reduce(host, op=dist.ReduceOp.MAX, group=self.group)
+            with torch.cuda.stream(st):
+                t.copy_(host)
+            st.synchronize()
         else:
             host = np.ctypeslib.as_array(ctypes.cast(buf_ptr, ctypes.POINTER(ctypes.c_int64)), shape=(count,))
             t = torch.from_numpy(host)
@@ -113,10 +139,11 @@ def broadcast_unique_id(group=None):
     return payload[0]
 
 
-def attach(manager, group=None, native=True):
+def attach(manager, group=None, native=True, staged=False):
     """Shard `manager` (a fc_planner_b200.manager.ViewpointManager) over the ranks of `group`.
     native=True: the library's own NCCL communicator (one per handle).  native=False: collectives through torch.distributed;
-    the library always passes DEVICE pointers, so that needs the nccl backend."""
+    the library always passes DEVICE pointers, so that needs the nccl backend - or staged=True, which copies every collective
+    through host memory and works with any backend (several ranks on one GPU: verification only)."""
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     if world == 1:
         manager.set_shard(0, 1, None)
@@ -124,8 +151,8 @@ def attach(manager, group=None, native=True):
     if native:
         manager.set_shard_nccl(broadcast_unique_id(group), rank, world)
         return None
-    ex = Exchange(group, host_buffers=False)
-    if not ex.on_device:
+    ex = Exchange(group, host_buffers=False, staged=staged)
+    if not ex.on_device and not staged:
         raise RuntimeError("fcvm hands device pointers to the collectives callback: attach(native=False) needs the nccl backend "
                            f"(got {dist.get_backend(group)}); use attach(native=True) or a CUDA-aware backend")
     manager.set_shard(ex.rank, ex.world, ex)

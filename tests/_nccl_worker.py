@@ -1,8 +1,9 @@
 """Per-rank body of tests/test_multi_gpu.py: launched by torch.distributed.run, one rank per GPU.
 Viewpoints sharded over the ranks, grid + model replicated; per stage an all-gather of the per-viewpoint results and one
 all-reduce MAX of the per-point ownership keys (fc-planner_b200/distributed.py); every rank must reproduce the oracle's
-result bit for bit.  argv[1] = "native" (the library's own NCCL communicator, default) or "torch" (collectives through
-torch.distributed via the fcvm_comm_fn callback)."""
+result bit for bit.  argv[1] = "native" (the library's own NCCL communicator, default), "torch" (collectives through
+torch.distributed via the fcvm_comm_fn callback) or "staged" (every rank on device 0, gloo backend, each collective staged
+through host memory: the sharded algorithm verified on a box with ONE GPU)."""
 import os
 import sys
 
@@ -16,8 +17,14 @@ def main():
     import torch
     import torch.distributed as dist
     rank, local, world = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"]), int(os.environ["WORLD_SIZE"])
-    torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    one_gpu = len(sys.argv) > 1 and sys.argv[1] == "staged"       # every rank on device 0, gloo, collectives staged through the host
+    if one_gpu:
+        local = 0
+        torch.cuda.set_device(0)
+        dist.init_process_group("gloo")
+    else:
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from fc_planner_b200 import distributed as fd, launch_params, scenes
     from fc_planner_b200.manager import ViewpointManager
     from oracle import oracle
@@ -26,8 +33,8 @@ def main():
     prm = launch_params("mbs", z_ground=0, seed=7, device=local)
     vps = scenes.plant_viewpoints(pts, nrm, prims, 401, prm.viewpoints_distance, seed=0)   # odd: exercises shard padding
     vm, orc = ViewpointManager(prm), oracle.Oracle(prm)
-    native = not (len(sys.argv) > 1 and sys.argv[1] == "torch")
-    fd.attach(vm, native=native)
+    native = not (len(sys.argv) > 1 and sys.argv[1] in ("torch", "staged"))
+    fd.attach(vm, native=native, staged=one_gpu)
     for m in (vm, orc):
         m.setMapPointCloud(pts); m.setModel(pts); m.setNormals(pts.astype(np.float64), nrm)
     poses = scenes.poses_from_viewpoints(vps)
@@ -56,7 +63,7 @@ def main():
         gprm, z = load_golden(scene)
         gprm.device = local
         gm = ViewpointManager(gprm)
-        fd.attach(gm, native=native)
+        fd.attach(gm, native=native, staged=one_gpu)
         run_sequence(gm, z, trace=False)
         ids, pose, vox = gm.final_arrays()
         c = gm.counters()
@@ -64,14 +71,14 @@ def main():
         assert np.array_equal(gm.vps_pose(), z["vps_pose"]) and np.array_equal(gm.getUncoveredModelCloud(), z["uncovered"])
         cov, con, cid = gm.cover_state()
         assert np.array_equal(cov, z["covered"]) and np.array_equal(con, z["cover_contrib"]) and np.array_equal(cid, z["contrib_id"])
-        t = torch.tensor([int(c[1]), int(c[2])], dtype=torch.int64, device="cuda")
+        t = torch.tensor([int(c[1]), int(c[2])], dtype=torch.int64, device="cpu" if one_gpu else "cuda")
         dist.all_reduce(t)                                  # rays and lookups are per rank: their sum is the fixture's count
         assert int(t[0]) == int(z["counters"][1]) and int(t[1]) == int(z["counters"][2]), f"{scene}: ray / lookup totals differ"
         gm.close()
     st = vm.comm_stats()
     assert st[0] > calls_eval and st[2] > 0                  # all-gathers of per-viewpoint results + all-reduces of the ownership keys
     dist.barrier()
-    print(f"rank {rank}/{world} ok ({'native NCCL' if native else 'torch.distributed'}): {len(gi)} final viewpoints, {int(st[0])} all-gathers "
+    print(f"rank {rank}/{world} ok ({'native NCCL' if native else ('gloo, staged through the host, one GPU' if one_gpu else 'torch.distributed')}): {len(gi)} final viewpoints, {int(st[0])} all-gathers "
           f"({st[1] / 1e6:.1f} MB), {int(st[2])} all-reduces ({st[3] / 1e6:.1f} MB)", flush=True)
     dist.destroy_process_group()
 
